@@ -1,0 +1,404 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see so_common.hpp).
+// Restates the default key path of analyze_audio (lib.rs:961-1559): key STFT, soft harmonic
+// time mask (chroma/extractor.rs:1246-1349), HPCP (extractor.rs:529-680, 1097-1150), median
+// smoothing (chroma/smoothing.rs:37-94), frame weights (lib.rs:1236-1287), segment voting
+// (lib.rs:1332-1436), detect_key_weighted (key/detector.rs:68-313), clarity (key_clarity.rs:51-93)
+// and the Krumhansl-Kessler templates (key/templates.rs:64-143).
+#include <algorithm>
+#include <cmath>
+
+#include "so_common.hpp"
+
+namespace so {
+
+static const float EPSILON = 1e-10f;
+
+// smooth_spectrogram_time + harmonic_spectrogram_time_mask — extractor.rs:1246-1349
+Spec harmonic_spectrogram_time_mask(const Spec& K, size_t margin, float power) {
+    Spec out;
+    if (K.frames == 0) return out;
+    out.frames = K.frames;
+    out.bins = K.bins;
+    out.d.assign(K.d.size(), 0.0f);
+    const size_t nf = K.frames, nb = K.bins;
+    const float p = fmax_rs(power, 1.0f), eps = 1e-12f;
+    std::vector<float> prefix(nf + 1);
+    for (size_t b = 0; b < nb; ++b) {
+        prefix[0] = 0.0f;
+        for (size_t t = 0; t < nf; ++t) prefix[t + 1] = prefix[t] + K.d[t * nb + b];  // :1277-1279 sequential f32 prefix
+        for (size_t t = 0; t < nf; ++t) {
+            float h_est;
+            if (margin == 0) {
+                h_est = K.d[t * nb + b];  // smooth_spectrogram_time returns the input when margin == 0
+            } else {
+                size_t st = t >= margin ? t - margin : 0, en = std::min(t + margin + 1, nf);
+                float sum = prefix[en] - prefix[st];
+                float denom = (float)std::max<size_t>(en - st, 1);
+                h_est = sum / denom;
+            }
+            float x = fmax_rs(K.d[t * nb + b], 0.0f);
+            float h = fmax_rs(h_est, 0.0f);
+            float r = fmax_rs(x - h, 0.0f);
+            float hp = powf(h, p), rp = powf(r, p);
+            float m = hp / (hp + rp + eps);
+            out.d[t * nb + b] = x * m;
+        }
+    }
+    return out;
+}
+
+// rem_euclid for f32 (Rust): r = fmod(a,b); if r < 0 { r += |b| }
+static float rem_euclid(float a, float b) {
+    float r = fmodf(a, b);
+    return r < 0.0f ? r + fabsf(b) : r;
+}
+
+// frame_to_hpcp_tuned_band — extractor.rs:529-680 with whitening off, tuning 0, band 100..5000 Hz.
+// Top-K ordering: `select_nth_unstable_by` leaves the K selected peaks in an unspecified order
+// (which only changes f32 accumulation order).  The oracle fixes it as: selected set = the K
+// largest by (magnitude desc, bin asc); accumulation in ascending bin order.
+static void frame_to_hpcp(const float* mag, size_t nb, uint32_t sr, size_t fft_size, const Config& c, float pc[12]) {
+    for (int i = 0; i < 12; ++i) pc[i] = 0.0f;
+    if (nb == 0 || sr == 0 || fft_size == 0) return;
+    float res = (float)sr / (float)fft_size;
+    float fmin = fmax_rs(100.0f, 20.0f), fmax = fmin_rs(5000.0f, (float)sr / 2.0f);
+    if (fmax <= fmin) return;
+    std::vector<std::pair<size_t, float>> peaks;
+    for (size_t b = 1; b + 1 < nb; ++b) {
+        float f = (float)b * res;
+        if (f < fmin) continue;
+        if (f > fmax) break;
+        float m = mag[b];
+        if (m <= mag[b - 1] || m < mag[b + 1]) continue;
+        peaks.emplace_back(b, m);
+    }
+    if (peaks.empty()) return;
+    size_t k = std::min(std::max<size_t>(c.key_hpcp_peaks_per_frame, 1), peaks.size());
+    if (peaks.size() > k) {
+        std::vector<std::pair<size_t, float>> byv = peaks;
+        std::stable_sort(byv.begin(), byv.end(), [](const std::pair<size_t, float>& a, const std::pair<size_t, float>& b) { return a.second > b.second; });
+        byv.resize(k);
+        std::sort(byv.begin(), byv.end(), [](const std::pair<size_t, float>& a, const std::pair<size_t, float>& b) { return a.first < b.first; });
+        peaks.swap(byv);
+    }
+    float sigma = fmax_rs(c.soft_mapping_sigma, 1e-6f);
+    size_t hmax = std::max<size_t>(c.key_hpcp_num_harmonics, 1);
+    float decay = clamp_rs(c.key_hpcp_harmonic_decay, 0.0f, 1.0f);
+    float p = clamp_rs(c.key_hpcp_mag_power, 0.05f, 1.0f);
+    for (auto& pk : peaks) {
+        float f0 = (float)pk.first * res;
+        if (f0 <= 0.0f) continue;
+        float w0 = powf(fmax_rs(mag[pk.first], 0.0f), p);
+        if (w0 <= 0.0f) continue;
+        for (size_t h = 1; h <= hmax; ++h) {
+            float fh = f0 * (float)h;
+            if (fh > fmax) break;
+            if (fh < fmin) continue;
+            float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f - 0.0f;
+            float spc = rem_euclid(semitone, 12.0f);
+            float ppc = rem_euclid(roundf(spc), 12.0f);
+            int primary = as_i32(ppc);
+            // decay.powi(h-1): repeated multiplication (powi lowers to llvm.powi: x*x*...)
+            float dp = 1.0f;
+            for (size_t i = 1; i < h; ++i) dp *= decay;
+            float hw = dp / (float)h;
+            float contrib = w0 * hw;
+            for (int off = -1; off <= 1; ++off) {
+                int tc = ((primary + off) % 12 + 12) % 12;
+                float dist = fabsf(spc - (float)tc);
+                dist = fmin_rs(dist, 12.0f - dist);
+                float wgt = expf(-dist * dist / (2.0f * sigma * sigma));
+                pc[tc] += contrib * wgt;
+            }
+        }
+    }
+    float ss = 0.0f;
+    for (int i = 0; i < 12; ++i) ss += pc[i] * pc[i];
+    float norm = sqrtf(ss);
+    if (norm > EPSILON)
+        for (int i = 0; i < 12; ++i) pc[i] /= norm;
+}
+
+// extract_hpcp_from_spectrogram_with_options_and_energy_tuned — extractor.rs:1097-1150
+void extract_hpcp(const Spec& K, uint32_t sr, size_t fft_size, const Config& c, std::vector<float>& chroma, std::vector<float>& energy) {
+    chroma.assign(K.frames * 12, 0.0f);
+    energy.assign(K.frames, 0.0f);
+    for (size_t t = 0; t < K.frames; ++t) {
+        const float* r = K.row(t);
+        float e = 0.0f;
+        for (size_t b = 0; b < K.bins; ++b) e += r[b] * r[b];
+        energy[t] = e;
+        frame_to_hpcp(r, K.bins, sr, fft_size, c, &chroma[t * 12]);
+    }
+}
+
+// smooth_chroma (median) — smoothing.rs:37-94
+void smooth_chroma(std::vector<float>& chroma, size_t frames, size_t window) {
+    if (frames == 0 || window <= 1) return;
+    if (window % 2 == 0) window += 1;
+    long half = (long)(window / 2);
+    std::vector<float> out(chroma.size());
+    for (size_t t = 0; t < frames; ++t)
+        for (int s = 0; s < 12; ++s) {
+            float vals[16];
+            int n = 0;
+            for (long off = 0; off < (long)window && n < 16; ++off) {
+                long ft = (long)t + (off - half);
+                if (ft >= 0 && (size_t)ft < frames) vals[n++] = chroma[(size_t)ft * 12 + s];
+            }
+            if (n > 0) {
+                std::stable_sort(vals, vals + n);
+                out[t * 12 + s] = vals[n / 2];
+            } else
+                out[t * 12 + s] = chroma[t * 12 + s];
+        }
+    chroma.swap(out);
+}
+
+// KeyTemplates::new_krumhansl_kessler — templates.rs:64-143
+void key_templates(float major[12][12], float minor[12][12]) {
+    const float cmaj[12] = {6.35f, 2.23f, 3.48f, 2.33f, 4.38f, 4.09f, 2.52f, 5.19f, 2.39f, 3.66f, 2.29f, 2.88f};
+    const float cmin[12] = {6.33f, 2.68f, 3.52f, 5.38f, 2.60f, 3.53f, 2.54f, 4.75f, 3.98f, 2.69f, 3.34f, 3.17f};
+    for (int k = 0; k < 12; ++k)
+        for (int s = 0; s < 12; ++s) {
+            major[k][s] = cmaj[(s + 12 - k) % 12];
+            minor[k][s] = cmin[(s + 12 - k) % 12];
+        }
+    auto l2 = [](float* v) {
+        float ss = 0.0f;
+        for (int i = 0; i < 12; ++i) ss += v[i] * v[i];
+        float n = sqrtf(ss);
+        if (n > 1e-12f)
+            for (int i = 0; i < 12; ++i) v[i] /= n;
+    };
+    for (int k = 0; k < 12; ++k) {
+        l2(major[k]);
+        l2(minor[k]);
+    }
+}
+
+// compute_key_clarity — key_clarity.rs:51-93 (scores in ranked order)
+float compute_key_clarity(const float* sc, size_t n) {
+    if (n < 2) return 0.0f;
+    float best = sc[0], sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) sum += sc[i];
+    float avg = sum / (float)n;
+    float mn = sc[0], mx = sc[0];
+    for (size_t i = 1; i < n; ++i) {
+        if (sc[i] < mn) mn = sc[i];   // min_by: first minimal
+        if (sc[i] >= mx) mx = sc[i];  // max_by: last maximal (same value either way)
+    }
+    float range = mx - mn;
+    if (range > 1e-10f) return clamp_rs((best - avg) / range, 0.0f, 1.0f);
+    return 0.0f;
+}
+
+// detect_key_weighted — detector.rs:68-313.  Key ids: 0..11 major, 12..23 minor.
+Error detect_key_weighted(const float* chroma, size_t frames, const float* w, KeyScores& out) {
+    if (frames == 0) return Error{INVALID_INPUT, "Empty chroma vectors"};
+    float maj[12][12], mnr[12][12];
+    key_templates(maj, mnr);
+    float sc[24];
+    for (int k = 0; k < 24; ++k) {
+        const float* tpl = k < 12 ? maj[k] : mnr[k - 12];
+        float acc = 0.0f;
+        for (size_t t = 0; t < frames; ++t) {  // weighted_sum_dot :984-1001
+            const float* ch = chroma + t * 12;
+            if (w) {
+                if (w[t] > 0.0f) {
+                    float dot = 0.0f;
+                    for (int i = 0; i < 12; ++i) dot += ch[i] * tpl[i];
+                    acc += w[t] * dot;
+                }
+            } else {
+                float dot = 0.0f;
+                for (int i = 0; i < 12; ++i) dot += ch[i] * tpl[i];
+                acc += dot;
+            }
+        }
+        sc[k] = acc;
+    }
+    float mxM = 0.0f, mxm = 0.0f;
+    for (int k = 0; k < 12; ++k) mxM = fmax_rs(mxM, sc[k]);
+    for (int k = 12; k < 24; ++k) mxm = fmax_rs(mxm, sc[k]);
+    if (mxM > 1e-9f && mxm > 1e-9f) {
+        for (int k = 0; k < 12; ++k) sc[k] /= mxM;
+        for (int k = 12; k < 24; ++k) sc[k] /= mxm;
+    }
+    const int cof[12] = {0, 7, 2, 9, 4, 11, 6, 1, 8, 3, 10, 5};
+    int pos_of[12];
+    for (int i = 0; i < 12; ++i) pos_of[cof[i]] = i;
+    // top key per mode: max_by -> last maximal (:177-198)
+    int topM = 0, topm = 12;
+    for (int k = 0; k < 12; ++k)
+        if (sc[k] >= sc[topM]) topM = k;
+    for (int k = 12; k < 24; ++k)
+        if (sc[k] >= sc[topm]) topm = k;
+    float refined[24];
+    for (int k = 0; k < 24; ++k) {
+        refined[k] = sc[k];
+        int ref = k < 12 ? topM : topm;
+        float ref_score = sc[ref];
+        if (ref_score > 1e-9f) {
+            int tp = pos_of[k % 12], rp = pos_of[ref % 12];
+            int d = std::abs(tp - rp);
+            int dist = std::min(d, 12 - d);
+            if (dist <= 2) {
+                float bonus = 0.20f * (1.0f - (float)dist * 0.5f);
+                refined[k] += ref_score * bonus;
+            }
+        }
+    }
+    int order[24];
+    for (int k = 0; k < 24; ++k) order[k] = k;
+    std::stable_sort(order, order + 24, [&](int a, int b) { return refined[a] > refined[b]; });
+    for (int i = 0; i < 24; ++i) {
+        out.keys[i] = order[i];
+        out.scores[i] = refined[order[i]];
+    }
+    // weighted top-3 voting (:254-275): the three keys are distinct, so each vote is
+    // score/best and the best key wins unless scores tie exactly (HashMap order in the
+    // reference; first-ranked here).
+    int final_key = out.keys[0];
+    float final_score = out.scores[0];
+    float best_other = out.scores[1];
+    out.key = final_key;
+    out.confidence = final_score > 0.0f ? clamp_rs((final_score - best_other) / final_score, 0.0f, 1.0f) : 0.0f;
+    return Error{};
+}
+
+static float chroma_tonalness(const float* ch) {  // lib.rs:1236-1251
+    float sum = 0.0f;
+    for (int i = 0; i < 12; ++i) sum += ch[i];
+    if (sum <= 1e-12f) return 0.0f;
+    float ent = 0.0f;
+    for (int i = 0; i < 12; ++i) {
+        float p = ch[i] / sum;
+        if (p > 1e-12f) ent -= p * logf(p);
+    }
+    float t = 1.0f - (ent / logf(12.0f));
+    return clamp_rs(t, 0.0f, 1.0f);
+}
+
+// Key section of analyze_audio — lib.rs:961-1559, default-config branches only.
+Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, const Spec& S_base, Result& r, Dump* dump) {
+    r.key_is_minor = 0;
+    r.key_index = 0;
+    r.key_confidence = 0.0f;
+    r.key_clarity = 0.0f;
+    if (n < c.frame_size) return Error{};
+    size_t kfft = c.enable_key_stft_override ? std::max<size_t>(c.key_stft_frame_size, 256) : c.frame_size;
+    size_t khop = c.enable_key_stft_override ? std::max<size_t>(c.key_stft_hop_size, 1) : c.hop_size;
+    Spec Kown;
+    if (c.enable_key_stft_override) Kown = compute_stft(s, n, kfft, khop);
+    const Spec& K = c.enable_key_stft_override ? Kown : S_base;
+    Spec masked;
+    const Spec* forkey = &K;
+    if (!K.empty() && c.enable_key_harmonic_mask) {
+        masked = harmonic_spectrogram_time_mask(K, c.key_spectrogram_smooth_margin, c.key_harmonic_mask_power);
+        forkey = &masked;
+    }
+    std::vector<float> chroma, energy;
+    extract_hpcp(*forkey, sr, kfft, c, chroma, energy);
+    size_t nf = forkey->frames;
+    if (dump) {
+        dump->f["key.hpcp_raw"] = chroma;
+        dump->f["key.energy"] = energy;
+    }
+    if (nf > 5) smooth_chroma(chroma, nf, 5);
+    if (dump) dump->f["key.hpcp_smooth"] = chroma;
+
+    std::vector<float> weights;
+    bool have_w = false;
+    if (c.enable_key_frame_weighting && nf > 0) {  // lib.rs:1253-1287
+        std::vector<float> sorted = energy;
+        std::stable_sort(sorted.begin(), sorted.end());
+        float median = fmax_rs(sorted[sorted.size() / 2], 1e-12f);
+        weights.resize(nf);
+        for (size_t t = 0; t < nf; ++t) {
+            float tonal = chroma_tonalness(&chroma[t * 12]);
+            if (tonal < c.key_min_tonalness) tonal = 0.0f;
+            float en = fmax_rs(energy[t] / median, 0.0f);
+            float wt = powf(tonal, fmax_rs(c.key_tonalness_power, 0.0f));
+            float we = powf(en, fmax_rs(c.key_energy_power, 0.0f));
+            weights[t] = fmax_rs(wt * we, 0.0f);
+        }
+        float sw = 0.0f;
+        size_t used = 0;
+        for (float x : weights) {
+            sw += x;
+            if (x > 0.0f) ++used;
+        }
+        have_w = !(sw <= 1e-12f || used < 10);
+    }
+    if (dump && have_w) dump->f["key.weights"] = weights;
+    const float* wp = have_w ? weights.data() : nullptr;
+
+    KeyScores ks;
+    float all_scores[24];
+    int all_keys[24];
+    float confidence;
+    int key;
+    bool voted = false;
+    if (c.enable_key_segment_voting && nf >= std::max<size_t>(c.key_segment_len_frames, 1) && c.key_segment_len_frames >= 120 &&
+        c.key_segment_hop_frames >= 1) {  // lib.rs:1332-1436
+        size_t seg_len = std::min(c.key_segment_len_frames, nf);
+        size_t hop = std::max<size_t>(std::min(c.key_segment_hop_frames, seg_len), 1);
+        float min_cl = clamp_rs(c.key_segment_min_clarity, 0.0f, 1.0f);
+        float acc[24];
+        for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
+        size_t used = 0;
+        std::vector<float> seg_dump;
+        for (size_t st = 0; st + seg_len <= nf; st += hop) {
+            if (Error e = detect_key_weighted(&chroma[st * 12], seg_len, wp ? wp + st : nullptr, ks)) return e;
+            float cl = compute_key_clarity(ks.scores, 24);
+            if (dump) {
+                seg_dump.push_back((float)ks.keys[0]);
+                seg_dump.push_back(cl);
+            }
+            if (cl >= min_cl) {
+                ++used;
+                for (int i = 0; i < 24; ++i) acc[ks.keys[i]] += ks.scores[i] * cl;
+            }
+        }
+        if (dump) dump->f["key.segments"] = seg_dump;
+        if (used > 0) {
+            int order[24];
+            for (int k = 0; k < 24; ++k) order[k] = k;
+            std::stable_sort(order, order + 24, [&](int a, int b) { return acc[a] > acc[b]; });
+            for (int i = 0; i < 24; ++i) {
+                all_keys[i] = order[i];
+                all_scores[i] = acc[order[i]];
+            }
+            key = all_keys[0];
+            confidence = all_scores[0] > 0.0f ? clamp_rs((all_scores[0] - all_scores[1]) / all_scores[0], 0.0f, 1.0f) : 0.0f;
+            voted = true;
+        }
+    }
+    if (!voted) {
+        if (Error e = detect_key_weighted(chroma.data(), nf, wp, ks)) {
+            // chroma extraction/key detection failure degrades to the default key (lib.rs:1542-1551)
+            return Error{};
+        }
+        for (int i = 0; i < 24; ++i) {
+            all_keys[i] = ks.keys[i];
+            all_scores[i] = ks.scores[i];
+        }
+        key = ks.key;
+        confidence = ks.confidence;
+    }
+    float clarity = compute_key_clarity(all_scores, 24);
+    r.key_is_minor = key >= 12;
+    r.key_index = (uint32_t)(key % 12);
+    r.key_confidence = confidence;
+    r.key_clarity = clarity;
+    if (dump) {
+        std::vector<float> a(all_scores, all_scores + 24), b;
+        for (int i = 0; i < 24; ++i) b.push_back((float)all_keys[i]);
+        dump->f["key.scores"] = a;
+        dump->f["key.order"] = b;
+    }
+    return Error{};
+}
+
+}  // namespace so
