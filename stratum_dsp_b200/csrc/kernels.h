@@ -1,0 +1,97 @@
+// Host-side launch interface of the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+// Values of StratumConfig that kernels read (copied by value into launches).
+struct DevCfg {
+    float min_bpm, max_bpm, bpm_resolution;
+    float silence_thr_linear;     // 10^(min_amplitude_db/20), silence.rs:141
+    uint32_t silence_min_ms;      // 500, lib.rs:134
+    float energy_thr_mul;         // 10^(-20/20), energy_flux.rs:160
+    float target_peak;            // 10^(-1/20), normalization.rs:290
+    int32_t normalization, enable_normalization, enable_trim, enable_consensus;
+    float onset_pct;
+    uint32_t consensus_tol_ms;
+    float cons_w[4];
+    uint32_t sf_k, mel_k;
+    float nov_ws, nov_we, nov_wh;
+    uint32_t nov_lmw, nov_smw;
+    int32_t band_fusion, mel_enabled, seed_only;
+    float w_full, w_low, w_mid, w_high, w_mel;
+    float support_thr, consensus_bonus;
+    uint32_t base_top_n, mr_top_k, mr_aux_k;
+    float mr_w512, mr_w256, mr_w1024, mr_dt, mr_margin;
+    int32_t mr_human_prior, mr_enabled;
+    int32_t force_legacy, legacy_guardrails;
+    float lg_pmin, lg_pmax, lg_smin, lg_smax, lg_mp, lg_ms, lg_me;
+    // key
+    uint32_t key_margin;
+    float key_mask_power;
+    int32_t key_mask, key_weighting, key_voting;
+    float key_min_tonal, key_tonal_pow, key_energy_pow;
+    uint32_t key_seg_len, key_seg_hop;
+    float key_seg_min_clarity;
+    uint32_t hpcp_peaks, hpcp_harm;
+    float hpcp_decay, hpcp_pow, hpcp_sigma;
+};
+
+// Per-sample-rate tables (band edges, mel filterbank) — novelty.rs:72-190, tempogram.rs:364-372.
+struct SrTables {
+    uint32_t sr;
+    uint32_t b0, b_low, b_mid, b_hi;  // band edges in bins of the 2048-point STFT
+    uint32_t variant_mask;            // bit v set when variant v (full, low, mid, high, mel) is active
+    uint32_t n_mels;
+    const int32_t* mel_m;             // [1025][2] mel index per contribution (-1 = none)
+    const float* mel_w;               // [1025][2]
+    uint32_t key_bin_lo, key_bin_hi;  // HPCP peak search range in the key STFT (extractor.rs:584-591)
+};
+
+struct WaveCtx {
+    cudaStream_t stream;
+    const float* samples;  // device
+    float* fa;             // float arena
+    int32_t* ia;           // int arena
+    TrackDev* tracks;      // device
+    const SrTables* srtab; // device array, tracks index it through sr_index
+    const int32_t* sr_index;  // per track
+    int n_tracks;
+    Tables tab;
+    DevCfg cfg;
+    // maxima over the wave (grid sizing upper bounds)
+    uint32_t max_F[N_HOPS], max_Fk, max_Fsil;
+    uint64_t max_n;
+    uint32_t max_beat_cap;
+};
+
+struct Launcher;  // counts launches + optional stage timing (engine.cu)
+void count_launch(const char* stage);
+
+// k_preprocess.cu
+void launch_peak_gain(const WaveCtx& c);
+void launch_silence_trim(const WaveCtx& c);
+// k_stft.cu
+void launch_stft_hop(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);
+void launch_stft_key(const WaveCtx& c);
+void launch_stft_raw(cudaStream_t s, const float* d_samples, uint64_t n, uint32_t frame_size, uint32_t hop, float gain, const Tables& tab,
+                     float* d_out, uint32_t frames);
+// k_onset.cu
+void launch_energy_onsets(const WaveCtx& c);
+void launch_spec_features(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);
+void launch_spectral_onsets_consensus(const WaveCtx& c);
+// k_tempo.cu
+void launch_tempogram(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);
+void launch_escalation_gate(const WaveCtx& c);
+void launch_multires_fusion(const WaveCtx& c, const int32_t* d_list, int n_list);
+void launch_final_bpm(const WaveCtx& c);
+// k_legacy.cu
+void launch_legacy_bpm(const WaveCtx& c);
+// k_beat.cu
+void launch_beat_tracking(const WaveCtx& c);
+// k_key.cu
+void launch_key_path(const WaveCtx& c);
+// k_synth.cu
+void launch_synth(cudaStream_t s, float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sr, const float* d_params5);
+
+}  // namespace sb
