@@ -197,6 +197,10 @@ int32_t stratum_b200_device_count(void);
 /* Frees the per-process device contexts. */
 void stratum_b200_shutdown(void);
 
+/* sizeof(StratumConfig) / sizeof(StratumResult) / sizeof(StratumConfidence) for which = 0 / 1 / 2:
+ * lets an FFI binding assert that its mirror of the structs matches this build. */
+size_t stratum_b200_sizeof(int32_t which);
+
 /* ---- stage-level entry points (kernel parity tests and bench instrumentation) ------------------ */
 
 /* compute_stft (src/features/chroma/extractor.rs:301-359) on the device: `samples` host pointer,

@@ -1,0 +1,1417 @@
+// Host engine + C ABI (include/stratum_b200.h) of the B200 analysis path.
+//
+// Execution model: a batch is cut into WAVES of tracks whose work areas fit the device arena
+// (spectrograms are the bulk: 64 MB for the 2048/512 STFT and 254 MB for the 8192/512 key STFT of a
+// 3-minute track).  Every stage of the reference's analyze_audio (lib.rs:86-1635) is one or a few
+// kernels launched over the whole wave; per-track state lives in a TrackDev record on the device.
+// The only host round trip inside a wave is the escalation decision (lib.rs:412-459): the records
+// are read back, the tracks that need the multi-resolution pass are given arena slots for their
+// hop-256 / hop-1024 spectrograms and processed as a compacted sub-batch.
+// There is no CPU fallback: without a usable CUDA device every compute entry point fails.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.h"
+
+namespace sb {
+
+// ---- errors ---------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+
+#define CUDA_OK(expr)                                                                                 \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr);           \
+            return STRATUM_PROCESSING_ERROR;                                                          \
+        }                                                                                             \
+    } while (0)
+
+// ---- launch accounting / stage timing ----------------------------------------------------------------
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_timing{0};
+static std::mutex g_stage_mu;
+static std::map<std::string, double> g_stage_ms;
+static std::vector<std::string> g_stage_order;
+
+void count_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct StageTimer {  // device time of a group of launches, accumulated per stage name
+    cudaStream_t s;
+    const char* name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(cudaStream_t s_, const char* n) : s(s_), name(n) {
+        if (g_timing.load()) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, s);
+        }
+    }
+    ~StageTimer() {
+        if (!a) return;
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, a, b);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        if (!g_stage_ms.count(name)) g_stage_order.push_back(name);
+        g_stage_ms[name] += ms;
+    }
+};
+
+// ---- debug capture (single-track calls) -----------------------------------------------------------------
+static std::atomic<int> g_debug{0};
+static std::mutex g_debug_mu;
+static std::map<std::string, std::vector<float>> g_debug_arrays;
+
+// ---- per-device context ------------------------------------------------------------------------------
+struct DeviceCtx {
+    int device = -1;
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    Tables tab{};
+    std::vector<void*> owned;                 // table allocations
+    std::map<uint32_t, float2*> tw_tables;    // size -> TW table (Stockham twiddles, oracle/so_fft.cpp)
+    std::vector<SrTables> sr_host;
+    SrTables* d_srtab = nullptr;
+    static constexpr int MAX_SR = 32;
+    float* fa = nullptr;
+    size_t fa_cap = 0;  // floats
+    float* oa = nullptr;
+    size_t oa_cap = 0;
+    int32_t* ia = nullptr;
+    size_t ia_cap = 0;
+    TrackDev* d_tracks = nullptr;
+    int32_t* d_sr_index = nullptr;
+    int32_t* d_list = nullptr;
+    size_t tr_cap = 0;
+    float* d_stage = nullptr;  // staging for host-sample batches
+    size_t stage_cap = 0;
+    std::mutex mu;
+};
+
+static std::mutex g_ctx_mu;
+static std::map<int, DeviceCtx*> g_ctx;
+
+template <class T>
+static T* dev_upload(DeviceCtx& c, const std::vector<T>& v) {
+    T* p = nullptr;
+    if (cudaMalloc(&p, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    c.owned.push_back(p);
+    return p;
+}
+
+static std::vector<float2> make_tw(uint32_t M) {  // TW[t] = (cos, -sin)(2 pi t / M) in double, rounded once
+    std::vector<float2> tw(M);
+    for (uint32_t t = 0; t < M; ++t) {
+        const double a = 2.0 * M_PI * (double)t / (double)M;
+        tw[t] = make_float2((float)cos(a), (float)(-sin(a)));
+    }
+    return tw;
+}
+
+static std::vector<float> make_hann(uint32_t n) {  // chroma/extractor.rs:318-323, f32
+    std::vector<float> w(n);
+    const float pi = 3.14159265358979323846f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float x = 2.0f * pi * (float)i / (float)(n - 1);
+        w[i] = 0.5f * (1.0f - cosf(x));
+    }
+    return w;
+}
+
+static void make_key_templates(std::vector<float>& major, std::vector<float>& minor) {  // key/templates.rs:64-143
+    const float cmaj[12] = {6.35f, 2.23f, 3.48f, 2.33f, 4.38f, 4.09f, 2.52f, 5.19f, 2.39f, 3.66f, 2.29f, 2.88f};
+    const float cmin[12] = {6.33f, 2.68f, 3.52f, 5.38f, 2.60f, 3.53f, 2.54f, 4.75f, 3.98f, 2.69f, 3.34f, 3.17f};
+    major.assign(144, 0.0f);
+    minor.assign(144, 0.0f);
+    for (int k = 0; k < 12; ++k) {
+        for (int s = 0; s < 12; ++s) {
+            major[k * 12 + s] = cmaj[(s + 12 - k) % 12];
+            minor[k * 12 + s] = cmin[(s + 12 - k) % 12];
+        }
+        for (std::vector<float>* v : {&major, &minor}) {
+            float ss = 0.0f;
+            for (int i = 0; i < 12; ++i) ss += (*v)[k * 12 + i] * (*v)[k * 12 + i];
+            const float n = sqrtf(ss);
+            if (n > 1e-12f)
+                for (int i = 0; i < 12; ++i) (*v)[k * 12 + i] /= n;
+        }
+    }
+}
+
+static const float2* get_tw(DeviceCtx& c, uint32_t M) {
+    auto it = c.tw_tables.find(M);
+    if (it != c.tw_tables.end()) return it->second;
+    float2* p = dev_upload(c, make_tw(M));
+    c.tw_tables[M] = p;
+    return p;
+}
+
+static int ctx_init(DeviceCtx& c, int device) {
+    CUDA_OK(cudaSetDevice(device));
+    c.device = device;
+    CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.tab.tw1024 = get_tw(c, 1024);
+    c.tab.tw4096 = get_tw(c, 4096);
+    c.tab.rw2048 = get_tw(c, 2048);  // RW_N[k] = TW_N[k], k <= N/2
+    c.tab.rw8192 = get_tw(c, 8192);
+    c.tab.win2048 = dev_upload(c, make_hann(2048));
+    c.tab.win8192 = dev_upload(c, make_hann(8192));
+    std::vector<float> mj, mn;
+    make_key_templates(mj, mn);
+    c.tab.key_major = dev_upload(c, mj);
+    c.tab.key_minor = dev_upload(c, mn);
+    CUDA_OK(cudaMalloc(&c.d_srtab, sizeof(SrTables) * DeviceCtx::MAX_SR));
+    if (!c.tab.tw1024 || !c.tab.tw4096 || !c.tab.rw2048 || !c.tab.rw8192 || !c.tab.win2048 || !c.tab.win8192 || !c.tab.key_major || !c.tab.key_minor) {
+        set_error("device table allocation failed");
+        return STRATUM_PROCESSING_ERROR;
+    }
+    c.ready = true;
+    return STRATUM_OK;
+}
+
+static DeviceCtx* get_ctx(int device, int* status) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        set_error("no CUDA device is usable (stratum_b200 has no CPU fallback)");
+        *status = STRATUM_PROCESSING_ERROR;
+        return nullptr;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= n) {
+        set_error("device id out of range");
+        *status = STRATUM_INVALID_INPUT;
+        return nullptr;
+    }
+    DeviceCtx*& c = g_ctx[device];
+    if (!c) c = new DeviceCtx();
+    if (!c->ready) {
+        const int st = ctx_init(*c, device);
+        if (st != STRATUM_OK) {
+            *status = st;
+            return nullptr;
+        }
+    }
+    *status = STRATUM_OK;
+    return c;
+}
+
+// ---- per-sample-rate tables ------------------------------------------------------------------------------
+static long f32_as_isize(float x) {
+    if (!(x == x)) return 0;
+    if (x >= 9.2233715e18f) return INT64_MAX;
+    if (x <= -9.2233715e18f) return INT64_MIN;
+    return (long)x;
+}
+static uint32_t hz_to_bin(float hz, float res, uint32_t n_bins) {  // period/tempogram.rs:279-289
+    if (!std::isfinite(hz) || hz <= 0.0f || !std::isfinite(res) || res <= 0.0f) return 0;
+    long b = f32_as_isize(roundf(hz / res));
+    long hi = (long)n_bins - 1;
+    if (hi < 0) hi = 0;
+    return (uint32_t)std::max<long>(0, std::min<long>(b, hi));
+}
+
+static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slot_out) {
+    for (size_t i = 0; i < c.sr_host.size(); ++i)
+        if (c.sr_host[i].sr == sr) {
+            *slot_out = (int)i;
+            return STRATUM_OK;
+        }
+    if ((int)c.sr_host.size() >= DeviceCtx::MAX_SR) {
+        set_error("too many distinct sample rates in one process (max 32)");
+        return STRATUM_NOT_IMPLEMENTED;
+    }
+    SrTables st{};
+    st.sr = sr;
+    const uint32_t n_bins = 1025;
+    const float freq_res = (float)sr / 2048.0f;
+    uint32_t vm = 1u;  // full
+    // band edges — period/tempogram.rs:356-372
+    const uint32_t b0 = 1;
+    const uint32_t b_low = std::max(hz_to_bin(cfg.tempogram_band_low_max_hz, freq_res, n_bins), b0);
+    const uint32_t b_mid = std::max(hz_to_bin(cfg.tempogram_band_mid_max_hz, freq_res, n_bins), b_low + 1);
+    uint32_t b_hi = cfg.tempogram_band_high_max_hz > 0.0f ? std::max(hz_to_bin(cfg.tempogram_band_high_max_hz, freq_res, n_bins), b_mid + 1) : n_bins;
+    b_hi = std::min(b_hi, n_bins);
+    st.b0 = b0;
+    st.b_low = std::min(b_low, n_bins);
+    st.b_mid = std::min(b_mid, n_bins);
+    st.b_hi = b_hi;
+    if (cfg.enable_tempogram_band_fusion) {
+        const uint32_t s[3] = {st.b0, st.b_low, st.b_mid}, e[3] = {st.b_low, st.b_mid, st.b_hi};
+        const float w[3] = {cfg.tempogram_band_w_low, cfg.tempogram_band_w_mid, cfg.tempogram_band_w_high};
+        for (int b = 0; b < 3; ++b)
+            if (std::isfinite(w[b]) && w[b] > 0.0f && e[b] > s[b] + 1) vm |= 1u << (1 + b);
+    }
+    // mel filterbank — period/novelty.rs:72-190
+    std::vector<int32_t> mel_m(n_bins * 2, -1);
+    std::vector<float> mel_w(n_bins * 2, 0.0f);
+    st.n_mels = 0;
+    if (cfg.enable_tempogram_mel_novelty) {
+        const uint32_t n_mels = std::max<uint32_t>(cfg.tempogram_mel_n_mels, 4);
+        if (n_mels > 40) {
+            set_error("tempogram_mel_n_mels > 40 is not supported");
+            return STRATUM_NOT_IMPLEMENTED;
+        }
+        auto mel_of = [](float hz) { return 2595.0f * log10f(1.0f + hz / 700.0f); };
+        auto inv_mel = [](float m) { return 700.0f * (powf(10.0f, m / 2595.0f) - 1.0f); };
+        const float nyq = (float)sr * 0.5f;
+        const float fmin = fminf(fmaxf(cfg.tempogram_mel_fmin_hz, 0.0f), fmaxf(nyq, 1.0f));
+        float fmax = cfg.tempogram_mel_fmax_hz;
+        if (!(std::isfinite(fmax) && fmax > 0.0f)) fmax = nyq;
+        {
+            const float lo = fmin + 1.0f;
+            if (fmax < lo) fmax = lo;
+            if (fmax > nyq) fmax = nyq;
+        }
+        const float res = (float)sr / 2048.0f;
+        const float mmin = mel_of(fmin), mmax = mel_of(fmax);
+        const float step = (mmax - mmin) / (float)(n_mels + 1);
+        std::vector<uint32_t> pts(n_mels + 2);
+        for (uint32_t i = 0; i < n_mels + 2; ++i) {
+            const float hz = inv_mel(mmin + step * (float)i);
+            long b = f32_as_isize(roundf(hz / res));
+            b = std::max<long>(0, std::min<long>(b, (long)n_bins - 1));
+            pts[i] = (uint32_t)b;
+        }
+        for (size_t i = 1; i < pts.size(); ++i)
+            if (pts[i] <= pts[i - 1]) pts[i] = std::min(pts[i - 1] + 1, n_bins - 1);
+        std::vector<int> fill(n_bins, 0);
+        bool overflow = false;
+        auto push = [&](uint32_t b, uint32_t m, float w) {
+            if (fill[b] >= 2) {
+                overflow = true;
+                return;
+            }
+            mel_m[b * 2 + fill[b]] = (int32_t)m;
+            mel_w[b * 2 + fill[b]] = w;
+            ++fill[b];
+        };
+        for (uint32_t m = 0; m < n_mels; ++m) {
+            const uint32_t l = pts[m], cc = pts[m + 1], r = pts[m + 2];
+            if (!(l < cc && cc < r)) continue;
+            for (uint32_t b = l; b <= cc; ++b) {
+                const float w = (b == l) ? 0.0f : ((float)b - (float)l) / ((float)cc - (float)l);
+                if (w > 0.0f) push(b, m, w);
+            }
+            for (uint32_t b = cc; b <= r; ++b) {
+                const float w = (b == r) ? 0.0f : ((float)r - (float)b) / ((float)r - (float)cc);
+                if (w > 0.0f) push(b, m, w);
+            }
+        }
+        if (overflow) {
+            set_error("mel filterbank with more than two contributions per bin is not supported");
+            return STRATUM_NOT_IMPLEMENTED;
+        }
+        st.n_mels = n_mels;
+        vm |= 1u << 4;
+    }
+    st.variant_mask = vm;
+    st.mel_m = dev_upload(c, mel_m);
+    st.mel_w = dev_upload(c, mel_w);
+    // HPCP band in key-STFT bins — chroma/extractor.rs:584-591 (b from 1 to n_bins-2)
+    {
+        const float res = (float)sr / 8192.0f;
+        const float fmin = fmaxf(100.0f, 20.0f), fmax = fminf(5000.0f, (float)sr / 2.0f);
+        uint32_t lo = 1, hi = 0;
+        if (fmax > fmin) {
+            lo = 0;
+            for (uint32_t b = 1; b + 1 < 4097; ++b) {
+                const float f = (float)b * res;
+                if (f < fmin) continue;
+                if (f > fmax) break;
+                if (lo == 0) lo = b;
+                hi = b;
+            }
+            if (lo == 0) {
+                lo = 1;
+                hi = 0;
+            }
+        }
+        st.key_bin_lo = lo;
+        st.key_bin_hi = hi;
+    }
+    c.sr_host.push_back(st);
+    *slot_out = (int)c.sr_host.size() - 1;
+    if (cudaMemcpy(c.d_srtab, c.sr_host.data(), sizeof(SrTables) * c.sr_host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("sr table upload failed");
+        return STRATUM_PROCESSING_ERROR;
+    }
+    return STRATUM_OK;
+}
+
+// ---- configuration -----------------------------------------------------------------------------------------
+static void config_default(StratumConfig* c) {  // src/config.rs:594-744
+    memset(c, 0, sizeof *c);
+    c->abi_version = STRATUM_B200_ABI_VERSION;
+    c->min_amplitude_db = -40.0f;
+    c->normalization = STRATUM_NORM_PEAK;
+    c->enable_normalization = 1;
+    c->enable_silence_trimming = 1;
+    c->enable_onset_consensus = 1;
+    c->onset_threshold_percentile = 0.80f;
+    c->onset_consensus_tolerance_ms = 50;
+    for (int i = 0; i < 4; ++i) c->onset_consensus_weights[i] = 0.25f;
+    c->enable_legacy_bpm_guardrails = 1;
+    c->enable_tempogram_multi_resolution = 1;
+    c->tempogram_multi_res_top_k = 25;
+    c->tempogram_multi_res_w512 = 0.45f;
+    c->tempogram_multi_res_w256 = 0.35f;
+    c->tempogram_multi_res_w1024 = 0.20f;
+    c->tempogram_multi_res_structural_discount = 0.85f;
+    c->tempogram_multi_res_double_time_512_factor = 0.92f;
+    c->tempogram_multi_res_margin_threshold = 0.08f;
+    c->enable_tempogram_band_fusion = 1;
+    c->tempogram_band_low_max_hz = 200.0f;
+    c->tempogram_band_mid_max_hz = 2000.0f;
+    c->tempogram_band_high_max_hz = 8000.0f;
+    c->tempogram_band_w_full = 0.40f;
+    c->tempogram_band_w_low = 0.25f;
+    c->tempogram_band_w_mid = 0.20f;
+    c->tempogram_band_w_high = 0.15f;
+    c->tempogram_band_seed_only = 1;
+    c->tempogram_band_support_threshold = 0.25f;
+    c->tempogram_band_consensus_bonus = 0.08f;
+    c->tempogram_novelty_w_spectral = 0.30f;
+    c->tempogram_novelty_w_energy = 0.35f;
+    c->tempogram_novelty_w_hfc = 0.35f;
+    c->tempogram_novelty_local_mean_window = 16;
+    c->tempogram_novelty_smooth_window = 5;
+    c->enable_tempogram_mel_novelty = 1;
+    c->tempogram_mel_n_mels = 40;
+    c->tempogram_mel_fmin_hz = 30.0f;
+    c->tempogram_mel_fmax_hz = 8000.0f;
+    c->tempogram_mel_max_filter_bins = 2;
+    c->tempogram_mel_weight = 0.15f;
+    c->tempogram_superflux_max_filter_bins = 4;
+    c->tempogram_candidates_top_n = 10;
+    c->legacy_bpm_preferred_min = 72.0f;
+    c->legacy_bpm_preferred_max = 168.0f;
+    c->legacy_bpm_soft_min = 60.0f;
+    c->legacy_bpm_soft_max = 210.0f;
+    c->legacy_bpm_conf_mul_preferred = 1.30f;
+    c->legacy_bpm_conf_mul_soft = 0.70f;
+    c->legacy_bpm_conf_mul_extreme = 0.01f;
+    c->min_bpm = 40.0f;
+    c->max_bpm = 240.0f;
+    c->bpm_resolution = 1.0f;
+    c->frame_size = 2048;
+    c->hop_size = 512;
+    c->soft_mapping_sigma = 0.5f;
+    c->key_spectrogram_smooth_margin = 12;
+    c->enable_key_frame_weighting = 1;
+    c->key_min_tonalness = 0.0f;
+    c->key_tonalness_power = 2.0f;
+    c->key_energy_power = 0.50f;
+    c->enable_key_harmonic_mask = 1;
+    c->key_harmonic_mask_power = 2.0f;
+    c->enable_key_stft_override = 1;
+    c->key_stft_frame_size = 8192;
+    c->key_stft_hop_size = 512;
+    c->enable_key_segment_voting = 1;
+    c->key_segment_len_frames = 1024;
+    c->key_segment_hop_frames = 512;
+    c->key_segment_min_clarity = 0.20f;
+    c->enable_key_hpcp = 1;
+    c->key_hpcp_peaks_per_frame = 24;
+    c->key_hpcp_num_harmonics = 4;
+    c->key_hpcp_harmonic_decay = 0.60f;
+    c->key_hpcp_mag_power = 0.50f;
+    c->chroma_sharpening_power = 1.0f;
+}
+
+// Rejects configurations whose branch is not built instead of silently ignoring them.
+static int config_validate(const StratumConfig& c) {
+    auto ni = [](const char* what) {
+        set_error(std::string("not implemented in the B200 path: ") + what);
+        return (int)STRATUM_NOT_IMPLEMENTED;
+    };
+    if (c.abi_version != STRATUM_B200_ABI_VERSION) {
+        set_error("StratumConfig.abi_version mismatch");
+        return STRATUM_INVALID_INPUT;
+    }
+    if (c.enable_normalization && c.normalization != STRATUM_NORM_PEAK) return ni("normalization = RMS / Loudness");
+    if (c.enable_hpss_onsets) return ni("enable_hpss_onsets");
+    if (c.enable_bpm_fusion) return ni("enable_bpm_fusion");
+    if (c.enable_tempogram_percussive_fallback) return ni("enable_tempogram_percussive_fallback");
+    if (c.emit_tempogram_candidates) return ni("emit_tempogram_candidates");
+    if (!c.tempogram_band_seed_only) return ni("tempogram_band_seed_only = false");
+    if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
+    if (!c.enable_key_stft_override || c.key_stft_frame_size != 8192 || c.key_stft_hop_size != 512) return ni("key STFT other than 8192/512");
+    if (!c.enable_key_hpcp) return ni("enable_key_hpcp = false (plain chroma folding)");
+    if (c.key_spectrogram_smooth_margin > 15) return ni("key_spectrogram_smooth_margin > 15");
+    if (c.key_hpcp_peaks_per_frame > 32) return ni("key_hpcp_peaks_per_frame > 32");
+    if (c.key_hpcp_num_harmonics > 8) return ni("key_hpcp_num_harmonics > 8");
+    if (c.tempogram_superflux_max_filter_bins > 8) return ni("tempogram_superflux_max_filter_bins > 8");
+    if (c.tempogram_multi_res_top_k > 32) return ni("tempogram_multi_res_top_k > 32");
+    if (c.enable_key_hpss_harmonic || c.enable_key_log_frequency || c.enable_key_beat_synchronous || c.enable_key_multi_scale || c.enable_key_ensemble ||
+        c.enable_key_median || c.enable_key_tuning_compensation || c.enable_key_edge_trim || c.enable_key_mode_heuristic || c.enable_key_hpcp_whitening ||
+        c.enable_key_hpcp_bass_blend || c.enable_key_minor_harmonic_bonus)
+        return ni("optional key-path variants (hpss/log-frequency/beat-sync/multi-scale/ensemble/median/tuning/edge-trim/mode-heuristic/whitening/bass-blend/minor-bonus)");
+    if (c.chroma_sharpening_power > 1.0f) return ni("chroma_sharpening_power > 1");
+    if (!(c.min_bpm > 0.0f) || !(c.max_bpm > c.min_bpm) || !(c.bpm_resolution > 0.0f)) {
+        set_error("Invalid BPM range");
+        return STRATUM_INVALID_INPUT;
+    }
+    if ((c.max_bpm - c.min_bpm) / c.bpm_resolution > 250.0f) return ni("more than 256 BPM hypotheses");
+    if (!(c.onset_threshold_percentile >= 0.0f && c.onset_threshold_percentile <= 1.0f)) {
+        set_error("Threshold percentile must be in [0, 1]");
+        return STRATUM_INVALID_INPUT;
+    }
+    if (c.onset_consensus_tolerance_ms == 0) {
+        set_error("Tolerance must be > 0");
+        return STRATUM_INVALID_INPUT;
+    }
+    return STRATUM_OK;
+}
+
+static DevCfg make_devcfg(const StratumConfig& c) {
+    DevCfg d{};
+    d.min_bpm = c.min_bpm;
+    d.max_bpm = c.max_bpm;
+    d.bpm_resolution = c.bpm_resolution;
+    d.silence_thr_linear = powf(10.0f, c.min_amplitude_db / 20.0f);
+    d.silence_min_ms = 500;
+    d.energy_thr_mul = powf(10.0f, -20.0f / 20.0f);
+    d.target_peak = powf(10.0f, (0.0f - 1.0f) / 20.0f);
+    d.normalization = c.normalization;
+    d.enable_normalization = c.enable_normalization;
+    d.enable_trim = c.enable_silence_trimming;
+    d.enable_consensus = c.enable_onset_consensus;
+    d.onset_pct = c.onset_threshold_percentile;
+    d.consensus_tol_ms = c.onset_consensus_tolerance_ms;
+    for (int i = 0; i < 4; ++i) d.cons_w[i] = c.onset_consensus_weights[i];
+    d.sf_k = c.tempogram_superflux_max_filter_bins;
+    d.mel_k = c.tempogram_mel_max_filter_bins;
+    d.nov_ws = c.tempogram_novelty_w_spectral;
+    d.nov_we = c.tempogram_novelty_w_energy;
+    d.nov_wh = c.tempogram_novelty_w_hfc;
+    d.nov_lmw = c.tempogram_novelty_local_mean_window;
+    d.nov_smw = c.tempogram_novelty_smooth_window;
+    d.band_fusion = c.enable_tempogram_band_fusion;
+    d.mel_enabled = c.enable_tempogram_mel_novelty;
+    d.seed_only = c.tempogram_band_seed_only;
+    d.w_full = c.tempogram_band_w_full;
+    d.w_low = c.tempogram_band_w_low;
+    d.w_mid = c.tempogram_band_w_mid;
+    d.w_high = c.tempogram_band_w_high;
+    d.w_mel = c.tempogram_mel_weight;
+    d.support_thr = c.tempogram_band_support_threshold;
+    d.consensus_bonus = c.tempogram_band_consensus_bonus;
+    // lib.rs:382-385 / multi_resolution.rs:230-234
+    const uint32_t base_top_n = std::max(std::max(c.tempogram_candidates_top_n, c.tempogram_multi_res_top_k), 10u);
+    d.base_top_n = c.enable_tempogram_multi_resolution ? base_top_n : 0;
+    d.mr_top_k = std::max(c.tempogram_multi_res_top_k, 1u);
+    d.mr_aux_k = std::min(std::max(d.mr_top_k * 4, 25u), 200u);
+    d.mr_w512 = c.tempogram_multi_res_w512;
+    d.mr_w256 = c.tempogram_multi_res_w256;
+    d.mr_w1024 = c.tempogram_multi_res_w1024;
+    d.mr_dt = c.tempogram_multi_res_double_time_512_factor;
+    d.mr_margin = c.tempogram_multi_res_margin_threshold;
+    d.mr_human_prior = c.tempogram_multi_res_use_human_prior;
+    d.mr_enabled = c.enable_tempogram_multi_resolution;
+    d.force_legacy = c.force_legacy_bpm;
+    d.legacy_guardrails = c.enable_legacy_bpm_guardrails;
+    d.lg_pmin = c.legacy_bpm_preferred_min;
+    d.lg_pmax = c.legacy_bpm_preferred_max;
+    d.lg_smin = c.legacy_bpm_soft_min;
+    d.lg_smax = c.legacy_bpm_soft_max;
+    d.lg_mp = c.legacy_bpm_conf_mul_preferred;
+    d.lg_ms = c.legacy_bpm_conf_mul_soft;
+    d.lg_me = c.legacy_bpm_conf_mul_extreme;
+    d.key_margin = c.key_spectrogram_smooth_margin;
+    d.key_mask_power = c.key_harmonic_mask_power;
+    d.key_mask = c.enable_key_harmonic_mask;
+    d.key_weighting = c.enable_key_frame_weighting;
+    d.key_voting = c.enable_key_segment_voting;
+    d.key_min_tonal = c.key_min_tonalness;
+    d.key_tonal_pow = c.key_tonalness_power;
+    d.key_energy_pow = c.key_energy_power;
+    d.key_seg_len = c.key_segment_len_frames;
+    d.key_seg_hop = c.key_segment_hop_frames;
+    d.key_seg_min_clarity = c.key_segment_min_clarity;
+    d.hpcp_peaks = c.key_hpcp_peaks_per_frame;
+    d.hpcp_harm = c.key_hpcp_num_harmonics;
+    d.hpcp_decay = c.key_hpcp_harmonic_decay;
+    d.hpcp_pow = c.key_hpcp_mag_power;
+    d.hpcp_sigma = c.soft_mapping_sigma;
+    return d;
+}
+
+// ---- arena planning -----------------------------------------------------------------------------------------
+static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+static inline uint32_t frames_of(uint64_t n, uint32_t frame, uint32_t hop) { return n >= frame ? (uint32_t)((n - frame) / hop + 1) : 0; }
+
+struct Bump {
+    uint64_t pos = 0;
+    uint64_t take(uint64_t n, uint64_t al = 32) {
+        pos = align_up(pos, al);
+        const uint64_t p = pos;
+        pos += n;
+        return p;
+    }
+};
+
+static void plan_hop(Bump& fa, HopLayout& H, uint32_t fcap, uint32_t hop) {
+    H.fmax = fcap;
+    H.hop = hop;
+    H.fft_cap = std::max<uint32_t>(next_pow2_u32(fcap > 1 ? fcap - 1 : 1), 4);
+    H.spec = fa.take((uint64_t)fcap * 1025);
+    H.frame = fa.take((uint64_t)FRAME_Q * fcap);
+    H.pair = fa.take((uint64_t)PAIR_Q * fcap);
+    H.nov = fa.take((uint64_t)MAX_VARIANTS * fcap);
+    H.tgfft = fa.take((uint64_t)MAX_VARIANTS * (H.fft_cap / 2 + 1));
+    H.tgac = fa.take((uint64_t)MAX_VARIANTS * AC_CAP);
+    H.tgwork = fa.take((uint64_t)MAX_VARIANTS * 2 * H.fft_cap);
+    H.tgtw = nullptr;
+    H.pad_ = 0;
+}
+
+// Base (always needed) work areas of one track.
+static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumConfig& cfg) {
+    const uint64_t n = T.n;
+    const uint32_t F512 = frames_of(n, 2048, 512), F256 = frames_of(n, 2048, 256), F1024 = frames_of(n, 2048, 1024);
+    const uint32_t Fk = frames_of(n, 8192, 512);
+    const uint32_t Fsil = n >= 2048 ? frames_of(n, 2048, 1024) : 1;
+    T.fall = std::max(std::max(F256, F512), std::max(F1024, 1u));
+    T.fkmax = Fk;
+    plan_hop(fa, T.hop[0], std::max(F512, 1u), 512);
+    T.cands[0] = fa.take((uint64_t)MAX_CANDS * 4);
+    T.sil_rms = fa.take(Fsil + 1);
+    T.erms = fa.take(F512 + 2);
+    T.scratch = fa.take((uint64_t)12 * T.fall);
+    T.keyspec = fa.take((uint64_t)Fk * 4097 + 8);
+    T.keymask = T.keyspec;  // the mask is applied in place
+    T.chroma = fa.take((uint64_t)Fk * 12 + 12);
+    T.chroma2 = fa.take((uint64_t)Fk * 12 + 12);
+    T.kenergy = fa.take(Fk + 1);
+    T.kweights = fa.take(Fk + 1);
+    uint32_t nseg = 0;
+    if (cfg.enable_key_segment_voting && cfg.key_segment_len_frames >= 120 && cfg.key_segment_hop_frames >= 1 && Fk >= cfg.key_segment_len_frames) {
+        const uint32_t seg_len = std::min(cfg.key_segment_len_frames, Fk);
+        const uint32_t hop = std::max(std::min(cfg.key_segment_hop_frames, seg_len), 1u);
+        nseg = (Fk - seg_len) / hop + 1;
+    }
+    T.seg_cap = nseg + 1;
+    T.seg_scores = fa.take((uint64_t)T.seg_cap * 24);
+    // onsets: each detector yields at most every other flux sample
+    const uint32_t on_cap = F512 / 2 + 8;
+    T.on_energy = ia.take(on_cap);
+    T.on_spectral = ia.take(on_cap);
+    T.on_hfc = ia.take(on_cap);
+    T.on_merged = 0;
+    T.on_final = ia.take((uint64_t)3 * on_cap);
+    // beat tracker: bpm <= 300 -> at most 5 beat frames per second
+    const double dur = (double)n / (double)std::max(T.sr, 1u);
+    T.hmm_cap = (uint32_t)std::ceil(dur * 5.0) + 8;
+    T.beat_cap = 3 * T.hmm_cap + 64;
+    T.onsets_s = fa.take((uint64_t)3 * on_cap);
+    T.hmm_em = fa.take(T.hmm_cap);
+    T.beats_tmp = fa.take((uint64_t)3 * T.beat_cap);
+    T.hmm_frames = ia.take(T.hmm_cap);
+    T.hmm_bp = ia.take(T.hmm_cap);
+    T.hmm_path = ia.take(T.hmm_cap);
+    T.beats = oa.take(T.beat_cap);
+    T.downbeats = oa.take(T.beat_cap);
+    // legacy ACF: next_pow2(2 * (max_frame + 1)), max_frame <= n / 512
+    T.lg_fft = next_pow2_u32((uint32_t)(2 * (n / 512 + 1)));
+    T.lg_work = fa.take((uint64_t)4 * T.lg_fft);
+    T.lg_tw = nullptr;
+    T.lg_pad = 0;
+}
+
+static void plan_escalation(Bump& fa, TrackDev& T) {
+    plan_hop(fa, T.hop[1], std::max(frames_of(T.n, 2048, 256), 1u), 256);
+    T.cands[1] = fa.take((uint64_t)MAX_CANDS * 4);
+    plan_hop(fa, T.hop[2], std::max(frames_of(T.n, 2048, 1024), 1u), 1024);
+    T.cands[2] = fa.take((uint64_t)MAX_CANDS * 4);
+}
+
+static int ensure_capacity(DeviceCtx& c, size_t fa_need, size_t oa_need, size_t ia_need, size_t tracks) {
+    auto grow = [&](void** p, size_t* cap, size_t need, size_t elt) -> int {
+        if (need <= *cap) return STRATUM_OK;
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+        CUDA_OK(cudaMalloc(p, need * elt));
+        *cap = need;
+        return STRATUM_OK;
+    };
+    int st;
+    if ((st = grow((void**)&c.fa, &c.fa_cap, fa_need, 4))) return st;
+    if ((st = grow((void**)&c.oa, &c.oa_cap, oa_need, 4))) return st;
+    if ((st = grow((void**)&c.ia, &c.ia_cap, ia_need, 4))) return st;
+    if (tracks > c.tr_cap) {
+        if (c.d_tracks) cudaFree(c.d_tracks);
+        if (c.d_sr_index) cudaFree(c.d_sr_index);
+        if (c.d_list) cudaFree(c.d_list);
+        c.d_tracks = nullptr;
+        c.d_sr_index = c.d_list = nullptr;
+        c.tr_cap = 0;
+        CUDA_OK(cudaMalloc(&c.d_tracks, tracks * sizeof(TrackDev)));
+        CUDA_OK(cudaMalloc(&c.d_sr_index, tracks * sizeof(int32_t)));
+        CUDA_OK(cudaMalloc(&c.d_list, tracks * sizeof(int32_t)));
+        c.tr_cap = tracks;
+    }
+    return STRATUM_OK;
+}
+
+static const char* error_message(int code) {
+    switch (code) {
+        case 1: return "Empty audio samples";                         // lib.rs:100-104
+        case 2: return "Invalid sample rate";                         // lib.rs:106-110
+        case 3: return "Audio is entirely silent after trimming";     // lib.rs:143-147
+        case 4: return "Signal too short for autocorrelation";        // period/autocorrelation.rs:131-135 via lib.rs:315
+        case 5: return "Track longer than 2^31 samples is not supported";
+        default: return "processing error";
+    }
+}
+
+static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* ia_host, float ms_per_track, StratumResult* r) {
+    memset(r, 0, sizeof *r);
+    r->status = T.status;
+    r->tempogram_multi_res_triggered = r->tempogram_multi_res_used = -1;
+    r->tempogram_percussive_triggered = r->tempogram_percussive_used = -1;
+    r->time_sig_beats_per_bar = 4;
+    if (T.status != 0) {
+        snprintf(r->error, sizeof r->error, "%s", error_message(T.err_code));
+        return;
+    }
+    r->bpm = T.bpm;
+    r->bpm_confidence = T.bpm_confidence;
+    r->key_is_minor = T.key >= 12;
+    r->key_index = (uint32_t)(T.key % 12);
+    r->key_confidence = T.key_confidence;
+    r->key_clarity = T.key_clarity;
+    r->grid_stability = T.grid_stability;
+    auto copy_f = [&](uint64_t off, uint32_t n) -> float* {
+        if (n == 0) return nullptr;
+        float* p = (float*)malloc(sizeof(float) * n);
+        memcpy(p, oa_host + off, sizeof(float) * n);
+        return p;
+    };
+    r->beats = copy_f(T.beats, T.n_beats);
+    r->n_beats = T.n_beats;
+    r->downbeats = copy_f(T.downbeats, T.n_downbeats);
+    r->n_downbeats = T.n_downbeats;
+    r->bars = copy_f(T.downbeats, T.n_downbeats);  // bars = downbeats.clone() (beat_tracking/mod.rs:316)
+    r->n_bars = T.n_downbeats;
+    r->duration_seconds = (float)T.m / (float)T.sr;
+    r->sample_rate = T.sr;
+    r->processing_time_ms = ms_per_track;
+    r->onset_method_consensus = T.onset_method_consensus;
+    // warnings / flags — lib.rs:1567-1589
+    if (T.bpm == 0.0f) r->warnings |= STRATUM_WARN_BPM_FAILED;
+    if (T.grid_stability < 0.5f) r->warnings |= STRATUM_WARN_LOW_GRID_STABILITY;
+    if (T.key_confidence < 0.3f) r->warnings |= STRATUM_WARN_LOW_KEY_CONFIDENCE;
+    if (T.key_clarity < 0.2f) {
+        r->warnings |= STRATUM_WARN_LOW_KEY_CLARITY;
+        r->flags |= STRATUM_FLAG_WEAK_TONALITY;
+    }
+    r->tempogram_multi_res_triggered = T.mr_triggered;
+    r->tempogram_multi_res_used = T.mr_used;
+    r->tempogram_percussive_triggered = T.perc_triggered;
+    r->tempogram_percussive_used = -1;
+    r->trim_start = T.trim_start;
+    r->trim_end = T.trim_end;
+    r->n_onsets = T.n_on_final;
+    if (T.n_on_final) {
+        r->onsets = (int64_t*)malloc(sizeof(int64_t) * T.n_on_final);
+        for (uint32_t i = 0; i < T.n_on_final; ++i) r->onsets[i] = ia_host[T.on_final + i];
+    }
+    r->n_hmm_beat_frames = T.n_hmm_frames;
+    if (T.n_hmm_frames) {
+        r->hmm_beat_frames = (int32_t*)malloc(sizeof(int32_t) * T.n_hmm_frames);
+        memcpy(r->hmm_beat_frames, ia_host + T.hmm_frames, sizeof(int32_t) * T.n_hmm_frames);
+    }
+    r->time_sig_beats_per_bar = T.time_sig;
+    r->beats_refined = T.beats_refined;
+}
+
+static void debug_put(const char* name, const float* d, size_t n, cudaStream_t s) {
+    std::vector<float> h(n);
+    if (n) cudaMemcpyAsync(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    std::lock_guard<std::mutex> lk(g_debug_mu);
+    g_debug_arrays[name] = std::move(h);
+}
+static void debug_put_i(const char* name, const int32_t* d, size_t n, cudaStream_t s) {
+    std::vector<int32_t> h(n);
+    if (n) cudaMemcpyAsync(h.data(), d, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    std::vector<float> f(h.begin(), h.end());
+    std::lock_guard<std::mutex> lk(g_debug_mu);
+    g_debug_arrays[name] = std::move(f);
+}
+
+// ---- one wave ----------------------------------------------------------------------------------------------------
+struct WavePlan {
+    std::vector<uint32_t> idx;  // track indices of the batch in this wave
+    uint64_t fa_base = 0, oa = 0, ia = 0;
+    uint64_t esc_each_max = 0;  // largest escalation footprint of a track in the wave
+};
+
+static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample_off, const uint64_t* lens, const uint32_t* srs, const WavePlan& wp,
+                    const StratumConfig& cfg, const DevCfg& dcfg, size_t fa_budget, StratumResult* out) {
+    const int nt = (int)wp.idx.size();
+    std::vector<TrackDev> tracks(nt);
+    std::vector<int32_t> sr_index(nt, 0);
+    Bump fa, oa, ia;
+    WaveCtx w{};
+    w.stream = c.stream;
+    w.samples = d_samples;
+    w.n_tracks = nt;
+    w.tab = c.tab;
+    w.cfg = dcfg;
+    for (int i = 0; i < nt; ++i) {
+        TrackDev& T = tracks[i];
+        memset(&T, 0, sizeof T);
+        const uint32_t gi = wp.idx[i];
+        T.off = sample_off[gi];
+        T.n = lens[gi];
+        T.sr = srs[gi];
+        T.status = 0;
+        T.mr_triggered = T.mr_used = T.perc_triggered = -1;
+        if (T.n == 0) { T.status = STRATUM_INVALID_INPUT; T.err_code = 1; }
+        else if (T.sr == 0) { T.status = STRATUM_INVALID_INPUT; T.err_code = 2; }
+        else if (T.n >= (1ull << 31)) { T.status = STRATUM_NOT_IMPLEMENTED; T.err_code = 5; }
+        if (T.status == 0) {
+            int slot = 0;
+            const int st = sr_slot(c, T.sr, cfg, &slot);
+            if (st != STRATUM_OK) return st;
+            sr_index[i] = slot;
+        } else {
+            T.n = 0;
+            T.sr = T.sr ? T.sr : 1;
+        }
+        plan_track(fa, oa, ia, T, cfg);
+        T.hop[0].tgtw = get_tw(c, T.hop[0].fft_cap);
+        T.lg_tw = get_tw(c, T.lg_fft);
+        if (!T.hop[0].tgtw || !T.lg_tw) {
+            set_error("twiddle table allocation failed");
+            return STRATUM_PROCESSING_ERROR;
+        }
+        const uint32_t Fsil = T.n >= 2048 ? frames_of(T.n, 2048, 1024) : (T.n > 0 ? 1 : 0);
+        T.Fsil = Fsil;
+        // provisional (untrimmed) frame counts; trim_kernel rewrites them
+        T.m = T.n;
+        T.trim_start = 0;
+        T.trim_end = T.n;
+        w.max_F[0] = std::max(w.max_F[0], frames_of(T.n, 2048, 512));
+        w.max_F[1] = std::max(w.max_F[1], frames_of(T.n, 2048, 256));
+        w.max_F[2] = std::max(w.max_F[2], frames_of(T.n, 2048, 1024));
+        w.max_Fk = std::max(w.max_Fk, frames_of(T.n, 8192, 512));
+        w.max_Fsil = std::max(w.max_Fsil, Fsil);
+        w.max_n = std::max<uint64_t>(w.max_n, T.n);
+        w.max_beat_cap = std::max(w.max_beat_cap, T.beat_cap);
+        w.max_seg_cap = std::max(w.max_seg_cap, T.seg_cap);
+        w.max_lg_fft = std::max(w.max_lg_fft, T.lg_fft);
+    }
+    const uint64_t fa_base_end = align_up(fa.pos, 64);
+    // escalation pool: whatever is left of the budget (at least one track's worth)
+    uint64_t esc_each = 0;
+    for (int i = 0; i < nt; ++i) {
+        Bump b;
+        TrackDev tmp = tracks[i];
+        plan_escalation(b, tmp);
+        esc_each = std::max<uint64_t>(esc_each, align_up(b.pos, 64));
+    }
+    uint64_t esc_slots = 0;
+    if (dcfg.mr_enabled && !dcfg.force_legacy) {
+        const uint64_t room = fa_budget > fa_base_end ? fa_budget - fa_base_end : 0;
+        esc_slots = esc_each ? std::min<uint64_t>(std::max<uint64_t>(room / esc_each, 1), (uint64_t)nt) : 0;
+    }
+    const uint64_t fa_total = fa_base_end + esc_slots * esc_each;
+    int st = ensure_capacity(c, fa_total + 64, oa.pos + 64, ia.pos + 64, nt);
+    if (st != STRATUM_OK) return st;
+    w.fa = c.fa;
+    w.oa = c.oa;
+    w.ia = c.ia;
+    w.tracks = c.d_tracks;
+    w.srtab = c.d_srtab;
+    w.sr_index = c.d_sr_index;
+    cudaStream_t s = c.stream;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, s);
+    CUDA_OK(cudaMemcpyAsync(c.d_tracks, tracks.data(), sizeof(TrackDev) * nt, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(c.d_sr_index, sr_index.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
+    { StageTimer t(s, "preprocess"); launch_peak_gain(w); launch_silence_trim(w); }
+    { StageTimer t(s, "onsets_energy"); launch_energy_onsets(w); }
+    { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, 0, nullptr, nt); }
+    { StageTimer t(s, "spec_features"); launch_spec_features(w, 0, nullptr, nt); }
+    { StageTimer t(s, "onsets_consensus"); launch_spectral_onsets_consensus(w); }
+    const bool want_tempogram = !dcfg.force_legacy;
+    if (want_tempogram) {
+        StageTimer t(s, "tempogram");
+        launch_tempogram(w, 0, nullptr, nt);
+        launch_escalation_gate(w);
+    }
+    { StageTimer t(s, "legacy_bpm"); launch_legacy_bpm(w); }
+    if (want_tempogram && dcfg.mr_enabled) {
+        // escalation decision needs the host: read the records back, hand out arena slots
+        CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        std::vector<int32_t> esc;
+        for (int i = 0; i < nt; ++i)
+            if (tracks[i].status == 0 && tracks[i].escalate) esc.push_back(i);
+        for (size_t p0 = 0; p0 < esc.size(); p0 += esc_slots) {
+            const size_t p1 = std::min(esc.size(), p0 + (size_t)esc_slots);
+            for (size_t p = p0; p < p1; ++p) {
+                TrackDev& T = tracks[esc[p]];
+                Bump b;
+                b.pos = fa_base_end + (p - p0) * esc_each;
+                plan_escalation(b, T);
+                T.hop[1].tgtw = get_tw(c, T.hop[1].fft_cap);
+                T.hop[2].tgtw = get_tw(c, T.hop[2].fft_cap);
+                CUDA_OK(cudaMemcpyAsync(c.d_tracks + esc[p], &T, sizeof(TrackDev), cudaMemcpyHostToDevice, s));
+            }
+            const int nl = (int)(p1 - p0);
+            CUDA_OK(cudaMemcpyAsync(c.d_list, esc.data() + p0, sizeof(int32_t) * nl, cudaMemcpyHostToDevice, s));
+            {
+                StageTimer t(s, "stft_multires");
+                launch_stft_hop(w, 1, c.d_list, nl);
+                launch_stft_hop(w, 2, c.d_list, nl);
+            }
+            {
+                StageTimer t(s, "multires_tempogram");
+                launch_spec_features(w, 1, c.d_list, nl);
+                launch_spec_features(w, 2, c.d_list, nl);
+                launch_tempogram(w, 1, c.d_list, nl);
+                launch_tempogram(w, 2, c.d_list, nl);
+                launch_multires_fusion(w, c.d_list, nl);
+            }
+            if (g_debug.load() && nt == 1) {
+                const TrackDev& T = tracks[0];
+                for (int h = 1; h < 3; ++h) {
+                    const uint32_t L = T.F[h] > 0 ? T.F[h] - 1 : 0;
+                    const std::string tag = h == 1 ? "h256." : "h1024.";
+                    debug_put((tag + "nov.full").c_str(), c.fa + T.hop[h].nov, L, s);
+                    debug_put((tag + "tg.fft.full").c_str(), c.fa + T.hop[h].tgfft, T.hop[h].fft_cap / 2 + 1, s);
+                    debug_put((tag + "tg.ac.full").c_str(), c.fa + T.hop[h].tgac, AC_CAP, s);
+                    debug_put((tag + "cands").c_str(), c.fa + T.cands[h], (size_t)MAX_CANDS * 4, s);
+                }
+            }
+        }
+    }
+    { StageTimer t(s, "final_bpm"); launch_final_bpm(w); }
+    { StageTimer t(s, "beats"); launch_beat_tracking(w); }
+    { StageTimer t(s, "stft_8192_key"); launch_stft_key(w); }
+    if (g_debug.load() && nt == 1) {
+        CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        const TrackDev& T = tracks[0];
+        const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
+        debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * 4097, s);
+    }
+    { StageTimer t(s, "key"); launch_key_path(w); }
+    CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
+    std::vector<float> oa_host(oa.pos + 1);
+    std::vector<int32_t> ia_host(ia.pos + 1);
+    CUDA_OK(cudaMemcpyAsync(oa_host.data(), c.oa, sizeof(float) * oa.pos, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(ia_host.data(), c.ia, sizeof(int32_t) * ia.pos, cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(ev1, s);
+    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaGetLastError());
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    for (int i = 0; i < nt; ++i) fill_result(tracks[i], oa_host.data(), ia_host.data(), ms / (float)nt, &out[wp.idx[i]]);
+    if (g_debug.load() && nt == 1) {
+        const TrackDev& T = tracks[0];
+        if (T.status == 0) {
+            const HopLayout& H = T.hop[0];
+            const uint32_t F = T.F[0], L = F > 0 ? F - 1 : 0;
+            const uint64_t fm = H.fmax;
+            debug_put("gain", &c.d_tracks[0].gain, 1, s);
+            debug_put("spec512_head", c.fa + H.spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
+            debug_put("onset.spectral_flux", c.fa + H.pair + 0 * fm, L, s);
+            debug_put("frame.hfc", c.fa + H.frame + 2 * fm, F, s);
+            debug_put("frame.energy", c.fa + H.frame + 1 * fm, F, s);
+            debug_put("pair.superflux", c.fa + H.pair + 1 * fm, L, s);
+            debug_put("pair.mel", c.fa + H.pair + 5 * fm, L, s);
+            debug_put_i("onset.energy", c.ia + T.on_energy, T.n_on_energy, s);
+            debug_put_i("onset.spectral", c.ia + T.on_spectral, T.n_on_spectral, s);
+            debug_put_i("onset.hfc", c.ia + T.on_hfc, T.n_on_hfc, s);
+            const char* vn[5] = {"base.nov.full", "base.nov.low", "base.nov.mid", "base.nov.high", "base.nov.mel"};
+            for (int v = 0; v < 5; ++v) debug_put(vn[v], c.fa + H.nov + (uint64_t)v * fm, L, s);
+            debug_put("base.tg.fft.full", c.fa + H.tgfft, H.fft_cap / 2 + 1, s);
+            debug_put("base.tg.ac.full", c.fa + H.tgac, AC_CAP, s);
+            debug_put("base.cands", c.fa + T.cands[0], (size_t)MAX_CANDS * 4, s);
+            float est[12] = {T.est[0].bpm, T.est[0].confidence, (float)T.est[0].agreement, (float)T.est[0].ok, (float)T.est[0].n_cands,
+                             T.legacy.bpm, T.legacy.confidence, (float)T.legacy.ok, (float)T.escalate, T.est[1].bpm, T.est[2].bpm, 0.0f};
+            {
+                std::lock_guard<std::mutex> lk(g_debug_mu);
+                g_debug_arrays["base.est"] = std::vector<float>(est, est + 12);
+            }
+            debug_put("key.hpcp_raw", c.fa + T.chroma, (size_t)T.Fk * 12, s);
+            debug_put("key.hpcp_smooth", c.fa + T.chroma2, (size_t)T.Fk * 12, s);
+            debug_put("key.energy", c.fa + T.kenergy, T.Fk, s);
+            debug_put("key.weights", c.fa + T.kweights, T.Fk, s);
+            debug_put("key.seg_scores", c.fa + T.seg_scores, (size_t)T.seg_cap * 24, s);
+            debug_put("key.mask_head", c.fa + T.keyspec, (size_t)std::min<uint32_t>(T.Fk, 64) * 4097, s);
+            debug_put_i("hmm.path", c.ia + T.hmm_path, T.hmm_T, s);
+            debug_put("hmm.em", c.fa + T.hmm_em, T.hmm_T, s);
+        }
+    }
+    return STRATUM_OK;
+}
+
+// Footprint (floats) of a track's base work areas.
+static uint64_t track_floats(uint64_t n, uint32_t sr, const StratumConfig& cfg) {
+    TrackDev T{};
+    T.n = n;
+    T.sr = sr ? sr : 1;
+    Bump fa, oa, ia;
+    plan_track(fa, oa, ia, T, cfg);
+    return align_up(fa.pos, 64) + 64;
+}
+static uint64_t esc_floats(uint64_t n) {
+    TrackDev T{};
+    T.n = n;
+    Bump b;
+    plan_escalation(b, T);
+    return align_up(b.pos, 64);
+}
+
+static int analyze_device(int device_id, const float* d_samples, const uint64_t* offsets, const uint32_t* srs, uint32_t n_tracks, const StratumConfig& cfg,
+                          StratumResult* out) {
+    int st;
+    DeviceCtx* ctx = get_ctx(device_id, &st);
+    if (!ctx) return st;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    const DevCfg dcfg = make_devcfg(cfg);
+    size_t free_b = 0, total_b = 0;
+    CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+    // budget: what is free now plus what our own arena already holds, minus head room
+    uint64_t budget_floats = (uint64_t)((double)(free_b + ctx->fa_cap * 4) * 0.90) / 4;
+    if (const char* e = getenv("STRATUM_B200_ARENA_GB")) budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(atof(e) * 1e9 / 4));
+    uint32_t wave_max = 1u << 20;
+    if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) wave_max = std::max(1, atoi(e));
+    std::vector<uint64_t> lens(n_tracks), offs(n_tracks);
+    for (uint32_t i = 0; i < n_tracks; ++i) {
+        offs[i] = offsets[i];
+        lens[i] = offsets[i + 1] - offsets[i];
+    }
+    uint32_t i = 0;
+    while (i < n_tracks) {
+        WavePlan wp;
+        uint64_t used = 0, esc_max = 0;
+        while (i < n_tracks && wp.idx.size() < wave_max) {
+            const uint64_t need = track_floats(lens[i], srs[i], cfg);
+            const uint64_t esc = esc_floats(lens[i]);
+            const uint64_t esc_new = std::max(esc_max, esc);
+            // keep room for escalating about a quarter of the wave at a time (at least one track)
+            const uint64_t esc_room = esc_new * std::max<uint64_t>(1, (wp.idx.size() + 4) / 4);
+            if (!wp.idx.empty() && used + need + esc_room > budget_floats) break;
+            used += need;
+            esc_max = esc_new;
+            wp.idx.push_back(i);
+            ++i;
+        }
+        if (used + esc_max > budget_floats && wp.idx.size() == 1) {
+            // a single track larger than the arena budget: let cudaMalloc decide
+            budget_floats = used + esc_max;
+        }
+        st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out);
+        if (st != STRATUM_OK) return st;
+    }
+    return STRATUM_OK;
+}
+
+}  // namespace sb
+
+// =================================================== C ABI ===================================================
+using namespace sb;
+
+extern "C" {
+
+void stratum_b200_config_default(StratumConfig* cfg) {
+    if (cfg) config_default(cfg);
+}
+
+int32_t stratum_b200_analyze_batch_device(const float* d_samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks,
+                                          const StratumConfig* cfg, int32_t device_id, StratumResult* out) {
+    if (!offsets || !sample_rates || !out || (!d_samples && n_tracks && offsets[n_tracks] > 0)) {
+        set_error("null argument");
+        return STRATUM_INVALID_INPUT;
+    }
+    StratumConfig def;
+    config_default(&def);
+    const StratumConfig& c = cfg ? *cfg : def;
+    int st = config_validate(c);
+    if (st != STRATUM_OK) return st;
+    if (n_tracks == 0) return STRATUM_OK;
+    return analyze_device(device_id, d_samples, offsets, sample_rates, n_tracks, c, out);
+}
+
+int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg,
+                                   const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
+    if (!offsets || !sample_rates || !out || (!samples && n_tracks && offsets[n_tracks] > 0)) {
+        set_error("null argument");
+        return STRATUM_INVALID_INPUT;
+    }
+    StratumConfig def;
+    config_default(&def);
+    const StratumConfig& c = cfg ? *cfg : def;
+    int st = config_validate(c);
+    if (st != STRATUM_OK) return st;
+    if (n_tracks == 0) return STRATUM_OK;
+    std::vector<int32_t> devs;
+    if (device_ids && n_devices) devs.assign(device_ids, device_ids + n_devices);
+    else devs.push_back(-1);
+    const uint32_t nd = (uint32_t)devs.size();
+    // contiguous shards, one host thread per device (examples/analyze_batch.rs:239-326: the only
+    // parallelism of the reference is across tracks; the gather is the result array itself)
+    std::vector<int> status(nd, STRATUM_OK);
+    std::vector<std::string> errs(nd);
+    auto work = [&](uint32_t d) {
+        const uint32_t a = (uint32_t)((uint64_t)n_tracks * d / nd), b = (uint32_t)((uint64_t)n_tracks * (d + 1) / nd);
+        if (a == b) return;
+        int stl;
+        DeviceCtx* ctx = get_ctx(devs[d], &stl);
+        if (!ctx) {
+            status[d] = stl;
+            errs[d] = g_last_error;
+            return;
+        }
+        cudaSetDevice(ctx->device);
+        // stream the shard through a device staging buffer in sub-batches that leave room for the arenas
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const uint64_t stage_budget = std::max<uint64_t>((uint64_t)((double)(free_b + ctx->stage_cap * 4 + ctx->fa_cap * 4) * 0.15) / 4, 1u << 20);
+        uint32_t i = a;
+        while (i < b) {
+            uint32_t j = i;
+            uint64_t fl = 0;
+            while (j < b && (j == i || fl + (offsets[j + 1] - offsets[j]) <= stage_budget)) {
+                fl += offsets[j + 1] - offsets[j];
+                ++j;
+            }
+            {
+                std::lock_guard<std::mutex> lk(ctx->mu);
+                if (fl + 16 > ctx->stage_cap) {
+                    if (ctx->d_stage) cudaFree(ctx->d_stage);
+                    ctx->d_stage = nullptr;
+                    ctx->stage_cap = 0;
+                    if (cudaMalloc(&ctx->d_stage, (fl + 16) * sizeof(float)) != cudaSuccess) {
+                        status[d] = STRATUM_PROCESSING_ERROR;
+                        errs[d] = "staging buffer allocation failed";
+                        return;
+                    }
+                    ctx->stage_cap = fl + 16;
+                }
+                if (fl && cudaMemcpyAsync(ctx->d_stage, samples + offsets[i], fl * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+                    status[d] = STRATUM_PROCESSING_ERROR;
+                    errs[d] = "host to device copy failed";
+                    return;
+                }
+            }
+            std::vector<uint64_t> rel(j - i + 1);
+            for (uint32_t k = i; k <= j; ++k) rel[k - i] = offsets[k] - offsets[i];
+            const int s2 = analyze_device(ctx->device, ctx->d_stage, rel.data(), sample_rates + i, j - i, c, out + i);
+            if (s2 != STRATUM_OK) {
+                status[d] = s2;
+                errs[d] = g_last_error;
+                return;
+            }
+            i = j;
+        }
+    };
+    if (nd == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < nd; ++d) th.emplace_back(work, d);
+        for (auto& t : th) t.join();
+    }
+    for (uint32_t d = 0; d < nd; ++d)
+        if (status[d] != STRATUM_OK) {
+            set_error(errs[d]);
+            return status[d];
+        }
+    return STRATUM_OK;
+}
+
+int32_t stratum_b200_analyze_audio(const float* samples, uint64_t n_samples, uint32_t sample_rate, const StratumConfig* cfg, StratumResult* out) {
+    if (!out) {
+        set_error("null argument");
+        return STRATUM_INVALID_INPUT;
+    }
+    const uint64_t offsets[2] = {0, n_samples};
+    const int st = stratum_b200_analyze_batch(samples, offsets, &sample_rate, 1, cfg, nullptr, 0, out);
+    if (st != STRATUM_OK) {
+        memset(out, 0, sizeof *out);
+        out->status = st;
+        snprintf(out->error, sizeof out->error, "%s", g_last_error.c_str());
+        return st;
+    }
+    return out->status;
+}
+
+int32_t stratum_b200_warning_strings(const StratumResult* r, char* buf, size_t cap) {  // lib.rs:1567-1589, exact strings
+    std::string all;
+    char tmp[256];
+    if (r->warnings & STRATUM_WARN_BPM_FAILED) all += "BPM detection failed: insufficient onsets or estimation error\n";
+    if (r->warnings & STRATUM_WARN_LOW_GRID_STABILITY) {
+        snprintf(tmp, sizeof tmp, "Low beat grid stability: %.2f (may indicate tempo variation)\n", r->grid_stability);
+        all += tmp;
+    }
+    if (r->warnings & STRATUM_WARN_LOW_KEY_CONFIDENCE) {
+        snprintf(tmp, sizeof tmp, "Low key detection confidence: %.2f (may indicate ambiguous or atonal music)\n", r->key_confidence);
+        all += tmp;
+    }
+    if (r->warnings & STRATUM_WARN_LOW_KEY_CLARITY) {
+        snprintf(tmp, sizeof tmp, "Low key clarity: %.2f (track may be atonal or have weak tonality)\n", r->key_clarity);
+        all += tmp;
+    }
+    if (buf && cap > 0) {
+        strncpy(buf, all.c_str(), cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return (int32_t)all.size();
+}
+
+void stratum_b200_compute_confidence(const StratumResult* r, StratumConfidence* out) {  // analysis/confidence.rs:121-297
+    char wb[1024];
+    stratum_b200_warning_strings(r, wb, sizeof wb);
+    const std::string warns = wb;
+    auto contains = [&](const char* needle) { return warns.find(needle) != std::string::npos; };
+    auto clamp01 = [](float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); };
+    float bc = 0.0f;
+    if (r->bpm > 0.0f) {
+        bc = clamp01(r->bpm_confidence);
+        if (contains("BPM")) bc = bc * 0.7f;
+    }
+    float kc = 0.0f;
+    if (r->key_confidence > 0.0f) {
+        const float base = clamp01(r->key_confidence);
+        const float ca = r->key_clarity < 0.2f ? 0.6f : (r->key_clarity < 0.5f ? 0.85f : 1.0f);
+        const float wa = (contains("key") || contains("Key") || contains("tonality")) ? 0.7f : 1.0f;
+        kc = base * ca * wa;
+    }
+    const float gs = clamp01(r->grid_stability);
+    float overall;
+    if (bc > 0.0f && kc > 0.0f) overall = clamp01(bc * 0.4f + kc * 0.3f + gs * 0.3f);
+    else if (bc > 0.0f) overall = bc * 0.6f;
+    else if (kc > 0.0f) overall = kc * 0.6f;
+    else overall = 0.0f;
+    uint32_t flags = r->flags;
+    if (bc < 0.3f) flags |= STRATUM_FLAG_MULTIMODAL_BPM;
+    if (kc < 0.2f) flags |= STRATUM_FLAG_WEAK_TONALITY;
+    if (gs < 0.3f) flags |= STRATUM_FLAG_TEMPO_VARIATION;
+    out->bpm_confidence = bc;
+    out->key_confidence = kc;
+    out->grid_stability = gs;
+    out->overall_confidence = overall;
+    out->flags = flags;
+}
+
+int32_t stratum_b200_key_name(int32_t key_is_minor, uint32_t key_index, int32_t numerical, char* buf, size_t cap) {  // analysis/result.rs:31-87
+    static const char* NOTE[12] = {"C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"};
+    std::string s;
+    if (!numerical) {
+        s = NOTE[key_index % 12];
+        if (key_is_minor) s += "m";
+    } else {
+        const int cof_major[12] = {0, 7, 2, 9, 4, 11, 6, 1, 8, 3, 10, 5};
+        const int cof_minor[12] = {9, 4, 11, 6, 1, 8, 3, 10, 5, 0, 7, 2};
+        const int* t = key_is_minor ? cof_minor : cof_major;
+        int pos = 0;
+        for (int i = 0; i < 12; ++i)
+            if (t[i] == (int)(key_index % 12)) {
+                pos = i;
+                break;
+            }
+        s = std::to_string(pos + 1) + (key_is_minor ? "B" : "A");
+    }
+    if (buf && cap > 0) {
+        strncpy(buf, s.c_str(), cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return (int32_t)s.size();
+}
+
+void stratum_b200_result_free(StratumResult* results, uint32_t n) {
+    if (!results) return;
+    for (uint32_t i = 0; i < n; ++i) {
+        free(results[i].beats);
+        free(results[i].downbeats);
+        free(results[i].bars);
+        free(results[i].onsets);
+        free(results[i].hmm_beat_frames);
+        results[i].beats = results[i].downbeats = results[i].bars = nullptr;
+        results[i].onsets = nullptr;
+        results[i].hmm_beat_frames = nullptr;
+        results[i].n_beats = results[i].n_downbeats = results[i].n_bars = results[i].n_onsets = results[i].n_hmm_beat_frames = 0;
+    }
+}
+
+int32_t stratum_b200_last_error(char* buf, size_t cap) {
+    if (buf && cap > 0) {
+        strncpy(buf, g_last_error.c_str(), cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return (int32_t)g_last_error.size();
+}
+
+uint64_t stratum_b200_launch_count(void) { return g_launches.load(); }
+
+int32_t stratum_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void stratum_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (auto& kv : g_ctx) {
+        DeviceCtx* c = kv.second;
+        if (!c) continue;
+        if (c->ready) {
+            cudaSetDevice(c->device);
+            cudaStreamSynchronize(c->stream);
+            for (void* p : c->owned) cudaFree(p);
+            cudaFree(c->fa);
+            cudaFree(c->oa);
+            cudaFree(c->ia);
+            cudaFree(c->d_tracks);
+            cudaFree(c->d_sr_index);
+            cudaFree(c->d_list);
+            cudaFree(c->d_srtab);
+            cudaFree(c->d_stage);
+            cudaStreamDestroy(c->stream);
+        }
+        delete c;
+    }
+    g_ctx.clear();
+}
+
+size_t stratum_b200_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return sizeof(StratumConfig);
+        case 1: return sizeof(StratumResult);
+        case 2: return sizeof(StratumConfidence);
+        default: return 0;
+    }
+}
+
+int64_t stratum_b200_stft(const float* samples, uint64_t n, uint32_t frame_size, uint32_t hop, float gain, float* out, uint64_t out_cap) {
+    if (frame_size != 2048 && frame_size != 8192) {
+        set_error("frame_size must be 2048 or 8192");
+        return -STRATUM_NOT_IMPLEMENTED;
+    }
+    if (hop == 0 || !samples || !out) {
+        set_error("invalid argument");
+        return -STRATUM_INVALID_INPUT;
+    }
+    if (n < frame_size) return 0;
+    int st;
+    DeviceCtx* ctx = get_ctx(-1, &st);
+    if (!ctx) return -st;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    const uint32_t frames = (uint32_t)((n - frame_size) / hop + 1);
+    const uint64_t need = (uint64_t)frames * (frame_size / 2 + 1);
+    if (need > out_cap) {
+        set_error("output buffer too small");
+        return -STRATUM_INVALID_INPUT;
+    }
+    float *d_in = nullptr, *d_out = nullptr;
+    if (cudaMalloc(&d_in, n * sizeof(float)) != cudaSuccess || cudaMalloc(&d_out, need * sizeof(float)) != cudaSuccess) {
+        cudaFree(d_in);
+        set_error("allocation failed");
+        return -STRATUM_PROCESSING_ERROR;
+    }
+    cudaMemcpyAsync(d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    launch_stft_raw(ctx->stream, d_in, n, frame_size, hop, gain, ctx->tab, d_out, frames);
+    cudaMemcpyAsync(out, d_out, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        set_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+        return -STRATUM_PROCESSING_ERROR;
+    }
+    return frames;
+}
+
+int32_t stratum_b200_synth_batch(float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sample_rate, const float* params5, int32_t device_id) {
+    int st;
+    DeviceCtx* ctx = get_ctx(device_id, &st);
+    if (!ctx) return st;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    float* d_p = nullptr;
+    CUDA_OK(cudaMalloc(&d_p, sizeof(float) * 5 * n_tracks));
+    CUDA_OK(cudaMemcpyAsync(d_p, params5, sizeof(float) * 5 * n_tracks, cudaMemcpyHostToDevice, ctx->stream));
+    launch_synth(ctx->stream, d_out, n_tracks, n_samples, sample_rate, d_p);
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_p);
+    CUDA_OK(e);
+    return STRATUM_OK;
+}
+
+int64_t stratum_b200_debug_array(const char* name, float* out, int64_t cap) {
+    std::lock_guard<std::mutex> lk(g_debug_mu);
+    auto it = g_debug_arrays.find(name);
+    if (it == g_debug_arrays.end()) return -1;
+    const int64_t n = (int64_t)it->second.size();
+    if (out && cap > 0) memcpy(out, it->second.data(), sizeof(float) * (size_t)std::min<int64_t>(n, cap));
+    return n;
+}
+
+void stratum_b200_debug_enable(int32_t on) {
+    g_debug.store(on);
+    if (!on) {
+        std::lock_guard<std::mutex> lk(g_debug_mu);
+        g_debug_arrays.clear();
+    }
+}
+
+int32_t stratum_b200_stage_times(char* names, size_t cap, double* ms, int32_t max_stages) {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    std::string all;
+    int32_t n = 0;
+    for (const std::string& s : g_stage_order) {
+        if (n >= max_stages) break;
+        all += s + "\n";
+        if (ms) ms[n] = g_stage_ms[s];
+        ++n;
+    }
+    if (names && cap > 0) {
+        strncpy(names, all.c_str(), cap - 1);
+        names[cap - 1] = 0;
+    }
+    return n;
+}
+
+void stratum_b200_stage_times_reset(void) {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    g_stage_ms.clear();
+    g_stage_order.clear();
+}
+
+void stratum_b200_stage_timing_enable(int32_t on) { g_timing.store(on); }
+
+}  // extern "C"

@@ -5,6 +5,7 @@
 // period/tempogram_fft.rs:149-151); the DAG below is our pinned restatement of the same DFT.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdint.h>
 
 namespace sb {
 

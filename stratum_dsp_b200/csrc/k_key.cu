@@ -1,0 +1,508 @@
+// Key detection kernels — the default key path of analyze_audio (reference lib.rs:961-1559):
+//   soft harmonic time mask            chroma/extractor.rs:1246-1349   (mask_kernel, in place)
+//   HPCP per frame + frame energy      chroma/extractor.rs:529-680, 1097-1150 (hpcp_kernel)
+//   5-tap median smoothing             chroma/smoothing.rs:37-94       (chroma_smooth_kernel)
+//   tonalness / energy frame weights   lib.rs:1236-1287                (key_weights_kernel)
+//   segment template scores            key/detector.rs:118-133, 984-1001 (segment_score_kernel)
+//   normalise, circle-of-fifths bonus, ranking, clarity, clarity-weighted vote
+//                                      key/detector.rs:135-313, key_clarity.rs:51-93, lib.rs:1332-1436 (key_vote_kernel)
+//
+// HBM traffic per key frame: the 4097-bin magnitude row is written once by the STFT, read + rewritten
+// in place by the mask and read once by the HPCP kernel (4 x 16 KB); everything after that is 12 floats
+// per frame.
+#include "framed.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+constexpr int KBINS = 4097;
+constexpr int RING = 32;           // mask ring: supports margin <= 15
+constexpr int HPCP_MAX_PEAKS = 512;  // local maxima in the 100..5000 Hz band (<= (hi-lo+2)/2 = 456 at 44.1 kHz)
+constexpr int HPCP_MAX_SEL = 32;     // key_hpcp_peaks_per_frame upper bound accepted by the ABI
+constexpr int HPCP_MAX_HARM = 8;     // key_hpcp_num_harmonics upper bound accepted by the ABI
+
+// ---- soft harmonic mask: one thread per (track, bin), strictly sequential f32 prefix over time ----
+// The reference builds `prefix[t+1] = prefix[t] + x[t]` per bin and takes window sums as prefix
+// differences (extractor.rs:1274-1287); the cancellation noise of that formulation is part of its
+// output, so the scan is reproduced term by term.  Adjacent threads own adjacent bins, so every
+// load and store of a frame row is coalesced.
+__global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
+    __shared__ float ringP[RING][128];
+    __shared__ float ringX[RING][128];
+    const TrackDev& T = tr[blockIdx.y];
+    const uint32_t nf = T.Fk;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T.status != 0 || nf == 0 || b >= KBINS) return;
+    const uint32_t mg = cfg.key_margin;
+    float* K = fa + T.keyspec + b;
+    const int tx = threadIdx.x;
+    const float p = fmaxf(cfg.key_mask_power, 1.0f);
+    const bool square = (p == 2.0f);
+    float P = 0.0f;
+    ringP[0][tx] = 0.0f;
+    auto emit = [&](uint32_t t, uint32_t en, float Pen) {
+        const float xt = ringX[t & (RING - 1)][tx];
+        float h_est;
+        if (mg == 0) {
+            h_est = xt;
+        } else {
+            const uint32_t st = t >= mg ? t - mg : 0;
+            const float sum = Pen - ringP[st & (RING - 1)][tx];
+            const float denom = (float)max(en - st, 1u);
+            h_est = sum / denom;
+        }
+        const float x = fmaxf(xt, 0.0f);
+        const float h = fmaxf(h_est, 0.0f);
+        const float r = fmaxf(x - h, 0.0f);
+        const float hp = square ? h * h : powf(h, p);
+        const float rp = square ? r * r : powf(r, p);
+        const float m = hp / (hp + rp + 1e-12f);
+        K[(uint64_t)t * KBINS] = x * m;
+    };
+    // frames are consumed in groups of 8 whose loads are issued together (8 independent requests in
+    // flight per thread); stores only touch rows already consumed, so the reordering is safe
+    auto step = [&](uint32_t i, float x) {
+        ringX[i & (RING - 1)][tx] = x;
+        P = P + x;
+        if (i >= mg) emit(i - mg, i + 1, P);  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
+        ringP[(i + 1) & (RING - 1)][tx] = P;
+    };
+    uint32_t i = 0;
+    for (; i + 8 <= nf; i += 8) {
+        float xs[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xs[q] = K[(uint64_t)(i + q) * KBINS];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) step(i + q, xs[q]);
+    }
+    for (; i < nf; ++i) step(i, K[(uint64_t)i * KBINS]);
+    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P);
+}
+
+// ---- HPCP: one warp per frame ---------------------------------------------------------------------
+struct HpcpSmem {
+    float mag[HPCP_MAX_PEAKS];
+    uint16_t bin[HPCP_MAX_PEAKS];
+    uint16_t sel[HPCP_MAX_SEL];
+    float val[HPCP_MAX_SEL * HPCP_MAX_HARM * 3];
+    int8_t tc[HPCP_MAX_SEL * HPCP_MAX_HARM * 3];
+};
+
+__device__ __forceinline__ float rem_euclid_f(float a, float b) {
+    float r = fmodf(a, b);
+    return r < 0.0f ? r + fabsf(b) : r;
+}
+
+__global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
+                                                   float* fa, DevCfg cfg) {
+    __shared__ HpcpSmem sm[4];
+    const int t = blockIdx.y;
+    const TrackDev& T = tr[t];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * 4 + w;
+    if (T.status != 0 || f >= T.Fk) return;
+    HpcpSmem& S = sm[w];
+    const SrTables& st = srtab[sr_index[t]];
+    const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
+    // frame energy (extractor.rs:1132-1134).  Consumed only through (E/median)^0.5 frame weights, a
+    // tolerance-level quantity, so the 4097-term sum is a warp tree instead of a serial fold.
+    float e = 0.0f;
+    for (uint32_t k = lane; k < KBINS; k += 32) {
+        const float x = row[k];
+        e = e + x * x;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    // local maxima in the band, compacted in ascending bin order (extractor.rs:582-606)
+    const uint32_t lo = st.key_bin_lo, hi = st.key_bin_hi;  // inclusive; lo > hi = empty band
+    uint32_t np = 0;
+    if (lo <= hi) {
+        for (uint32_t base = lo; base <= hi; base += 32) {
+            const uint32_t b = base + lane;
+            bool pk = false;
+            float m = 0.0f;
+            if (b <= hi) {
+                m = row[b];
+                pk = !(m <= row[b - 1] || m < row[b + 1]);
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, pk);
+            if (pk) {
+                const uint32_t pos = np + __popc(mask & ((1u << lane) - 1u));
+                if (pos < HPCP_MAX_PEAKS) {
+                    S.mag[pos] = m;
+                    S.bin[pos] = (uint16_t)b;
+                }
+            }
+            np += __popc(mask);
+        }
+        np = min(np, (uint32_t)HPCP_MAX_PEAKS);
+    }
+    __syncwarp();
+    float pc = 0.0f;  // lanes 0..11 own one pitch class each
+    if (np > 0) {
+        // top-K by (magnitude desc, bin asc); the reference's select_nth_unstable_by leaves the K
+        // survivors in unspecified order — the documented rule is "accumulate in ascending bin order".
+        const uint32_t K = min(max(cfg.hpcp_peaks, 1u), np);
+        uint32_t nsel = 0;
+        for (uint32_t base = 0; base < np; base += 32) {
+            const uint32_t i = base + lane;
+            bool keep = false;
+            if (i < np) {
+                if (np <= K) {
+                    keep = true;
+                } else {
+                    const float mi = S.mag[i];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < np; ++j) {
+                        const float mj = S.mag[j];
+                        rank += (mj > mi) || (mj == mi && j < i);
+                    }
+                    keep = rank < K;
+                }
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (keep) S.sel[nsel + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)i;
+            nsel += __popc(mask);
+        }
+        __syncwarp();
+        const float res = (float)T.sr / 8192.0f;
+        const float fmin = fmaxf(100.0f, 20.0f), fmax = fminf(5000.0f, (float)T.sr / 2.0f);
+        const float sigma = fmaxf(cfg.hpcp_sigma, 1e-6f);
+        const uint32_t hmax = min(max(cfg.hpcp_harm, 1u), (uint32_t)HPCP_MAX_HARM);
+        const float decay = clamp_rs(cfg.hpcp_decay, 0.0f, 1.0f);
+        const float pw = clamp_rs(cfg.hpcp_pow, 0.05f, 1.0f);
+        const uint32_t items = nsel * hmax;
+        for (uint32_t it = lane; it < items; it += 32) {
+            const uint32_t pi = it / hmax, h = it % hmax + 1;
+            const uint32_t idx = S.sel[pi];
+            const float f0 = (float)S.bin[idx] * res;
+            const float mg = fmaxf(S.mag[idx], 0.0f);
+            const float w0 = (pw == 0.5f) ? sqrtf(mg) : powf(mg, pw);
+            const float fh = f0 * (float)h;
+            int8_t* tcs = S.tc + it * 3;
+            float* vals = S.val + it * 3;
+            // `break` at fh > fmax and `continue` at fh < fmin both leave this (peak, h) without a contribution
+            if (!(f0 > 0.0f) || !(w0 > 0.0f) || fh > fmax || fh < fmin) {
+                tcs[0] = tcs[1] = tcs[2] = -1;
+                continue;
+            }
+            const float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f;
+            const float spc = rem_euclid_f(semitone, 12.0f);
+            const float ppc = rem_euclid_f(roundf(spc), 12.0f);
+            const int primary = as_i32(ppc);
+            float dp = 1.0f;
+            for (uint32_t q = 1; q < h; ++q) dp = dp * decay;
+            const float hw = dp / (float)h;
+            const float contrib = w0 * hw;
+#pragma unroll
+            for (int off = -1; off <= 1; ++off) {
+                const int tc = ((primary + off) % 12 + 12) % 12;
+                float dist = fabsf(spc - (float)tc);
+                dist = fminf(dist, 12.0f - dist);
+                const float wgt = expf(-dist * dist / (2.0f * sigma * sigma));
+                tcs[off + 1] = (int8_t)tc;
+                vals[off + 1] = contrib * wgt;
+            }
+        }
+        __syncwarp();
+        if (lane < 12) {
+            const uint32_t ne = items * 3;
+            for (uint32_t q = 0; q < ne; ++q)
+                if (S.tc[q] == lane) pc = pc + S.val[q];
+        }
+        // L2 normalise with the reference's sequential sum of squares (extractor.rs:668-677)
+        float ss = 0.0f;
+        for (int i = 0; i < 12; ++i) {
+            const float v = __shfl_sync(0xffffffffu, pc, i);
+            ss = ss + v * v;
+        }
+        const float norm = sqrtf(ss);
+        if (norm > 1e-10f) pc = pc / norm;
+    }
+    if (lane < 12) fa[T.chroma + (uint64_t)f * 12 + lane] = pc;
+    if (lane == 0) fa[T.kenergy + f] = e;
+}
+
+// ---- 5-tap median over time per pitch class (smoothing.rs:37-94); applied when Fk > 5 --------------
+__global__ void __launch_bounds__(256) chroma_smooth_kernel(const TrackDev* __restrict__ tr, float* fa) {
+    const TrackDev& T = tr[blockIdx.y];
+    const uint32_t nf = T.Fk;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T.status != 0 || i >= nf * 12) return;
+    const float* src = fa + T.chroma;
+    float* dst = fa + T.chroma2;
+    if (nf <= 5) {
+        dst[i] = src[i];
+        return;
+    }
+    const int t = (int)(i / 12), s = (int)(i % 12);
+    float v[5];
+    int n = 0;
+    for (int off = -2; off <= 2; ++off) {
+        const int ft = t + off;
+        if (ft >= 0 && ft < (int)nf) v[n++] = src[(uint64_t)ft * 12 + s];
+    }
+    for (int a = 1; a < n; ++a) {  // insertion sort; equal keys are indistinguishable
+        const float x = v[a];
+        int j = a;
+        while (j > 0 && v[j - 1] > x) {
+            v[j] = v[j - 1];
+            --j;
+        }
+        v[j] = x;
+    }
+    dst[i] = v[n / 2];
+}
+
+// ---- frame weights (lib.rs:1236-1287): one CTA per track -------------------------------------------
+__global__ void __launch_bounds__(256) key_weights_kernel(TrackDev* tr, float* fa, DevCfg cfg) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t bc[2];
+    __shared__ float sred[32];
+    __shared__ uint32_t sused[32];
+    TrackDev& T = tr[blockIdx.x];
+    const uint32_t nf = T.Fk;
+    if (threadIdx.x == 0) T.have_w = 0;
+    if (T.status != 0 || nf == 0 || !cfg.key_weighting) return;
+    const float* en = fa + T.kenergy;
+    const float median = fmaxf(block_select_kth(en, nf, nf / 2, hist, bc), 1e-12f);
+    const float* ch = fa + T.chroma2;
+    float* wv = fa + T.kweights;
+    const float tp = fmaxf(cfg.key_tonal_pow, 0.0f), ep = fmaxf(cfg.key_energy_pow, 0.0f);
+    const float ln12 = logf(12.0f);
+    float sw = 0.0f;
+    uint32_t used = 0;
+    for (uint32_t t = threadIdx.x; t < nf; t += blockDim.x) {
+        const float* c = ch + (uint64_t)t * 12;
+        float sum = 0.0f;
+        for (int i = 0; i < 12; ++i) sum = sum + c[i];
+        float tonal = 0.0f;
+        if (sum > 1e-12f) {
+            float ent = 0.0f;
+            for (int i = 0; i < 12; ++i) {
+                const float p = c[i] / sum;
+                if (p > 1e-12f) ent = ent - p * logf(p);
+            }
+            tonal = clamp_rs(1.0f - (ent / ln12), 0.0f, 1.0f);
+        }
+        if (tonal < cfg.key_min_tonal) tonal = 0.0f;
+        const float e = fmaxf(en[t] / median, 0.0f);
+        const float wt = (tp == 2.0f) ? tonal * tonal : powf(tonal, tp);
+        const float we = (ep == 0.5f) ? sqrtf(e) : powf(e, ep);
+        const float wgt = fmaxf(wt * we, 0.0f);
+        wv[t] = wgt;
+        sw += wgt;
+        used += wgt > 0.0f;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sw += __shfl_xor_sync(0xffffffffu, sw, o);
+        used += __shfl_xor_sync(0xffffffffu, used, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sred[threadIdx.x >> 5] = sw;
+        sused[threadIdx.x >> 5] = used;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        uint32_t u = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); ++q) {
+            s += sred[q];
+            u += sused[q];
+        }
+        T.have_w = !(s <= 1e-12f || u < 10) ? 1 : 0;
+    }
+}
+
+// Segment geometry shared by the two kernels below (lib.rs:1332-1352).
+__device__ __forceinline__ bool seg_geometry(const TrackDev& T, const DevCfg& cfg, uint32_t* seg_len, uint32_t* hop, uint32_t* nseg) {
+    const uint32_t nf = T.Fk;
+    const bool voting = cfg.key_voting && nf >= max(cfg.key_seg_len, 1u) && cfg.key_seg_len >= 120 && cfg.key_seg_hop >= 1;
+    if (!voting) {
+        *seg_len = nf;
+        *hop = 1;
+        *nseg = 0;
+        return false;
+    }
+    *seg_len = min(cfg.key_seg_len, nf);
+    *hop = max(min(cfg.key_seg_hop, *seg_len), 1u);
+    *nseg = (nf - *seg_len) / *hop + 1;
+    return true;
+}
+
+// ---- template scores: thread k of a warp folds segment s for key k in frame order -------------------
+// blockIdx.x = segment index; the extra index `nseg` is the whole-track score used when no segment
+// passes the clarity gate (lib.rs:1385-1411) or voting is off.
+__global__ void __launch_bounds__(32) segment_score_kernel(const TrackDev* __restrict__ tr, float* fa, Tables tab, DevCfg cfg) {
+    const TrackDev& T = tr[blockIdx.y];
+    if (T.status != 0 || T.Fk == 0) return;
+    uint32_t seg_len, hop, nseg;
+    seg_geometry(T, cfg, &seg_len, &hop, &nseg);
+    const uint32_t s = blockIdx.x;
+    if (s > nseg || s >= T.seg_cap) return;
+    const uint32_t start = s < nseg ? s * hop : 0;
+    const uint32_t len = s < nseg ? seg_len : T.Fk;
+    const int k = threadIdx.x;
+    if (k >= 24) return;
+    const float* tpl = (k < 12 ? tab.key_major + k * 12 : tab.key_minor + (k - 12) * 12);
+    float tp[12];
+    for (int i = 0; i < 12; ++i) tp[i] = tpl[i];
+    const float* ch = fa + T.chroma2 + (uint64_t)start * 12;
+    const float* wv = T.have_w ? fa + T.kweights + start : nullptr;
+    float acc = 0.0f;
+    for (uint32_t t = 0; t < len; ++t) {
+        const float* c = ch + (uint64_t)t * 12;
+        if (wv) {
+            const float wt = wv[t];
+            if (wt > 0.0f) {
+                float dot = 0.0f;
+                for (int i = 0; i < 12; ++i) dot = dot + c[i] * tp[i];
+                acc = acc + wt * dot;
+            }
+        } else {
+            float dot = 0.0f;
+            for (int i = 0; i < 12; ++i) dot = dot + c[i] * tp[i];
+            acc = acc + dot;
+        }
+    }
+    fa[T.seg_scores + (uint64_t)s * 24 + k] = acc;
+}
+
+// detect_key_weighted steps 1.5 - 2 on 24 raw scores: ranked keys/scores out (detector.rs:135-250).
+__device__ inline void rank_keys(const float* raw, int* keys, float* scores) {
+    float sc[24];
+    for (int k = 0; k < 24; ++k) sc[k] = raw[k];
+    float mxM = 0.0f, mxm = 0.0f;
+    for (int k = 0; k < 12; ++k) mxM = fmaxf(mxM, sc[k]);
+    for (int k = 12; k < 24; ++k) mxm = fmaxf(mxm, sc[k]);
+    if (mxM > 1e-9f && mxm > 1e-9f) {
+        for (int k = 0; k < 12; ++k) sc[k] = sc[k] / mxM;
+        for (int k = 12; k < 24; ++k) sc[k] = sc[k] / mxm;
+    }
+    const int pos_of[12] = {0, 7, 2, 9, 4, 11, 6, 1, 8, 3, 10, 5};  // position of tonic on the circle of fifths (self-inverse table)
+    int topM = 0, topm = 12;
+    for (int k = 0; k < 12; ++k)
+        if (sc[k] >= sc[topM]) topM = k;  // max_by: last maximal
+    for (int k = 12; k < 24; ++k)
+        if (sc[k] >= sc[topm]) topm = k;
+    float refined[24];
+    for (int k = 0; k < 24; ++k) {
+        refined[k] = sc[k];
+        const int ref = k < 12 ? topM : topm;
+        const float ref_score = sc[ref];
+        if (ref_score > 1e-9f) {
+            const int d = abs(pos_of[k % 12] - pos_of[ref % 12]);
+            const int dist = min(d, 12 - d);
+            if (dist <= 2) {
+                const float bonus = 0.20f * (1.0f - (float)dist * 0.5f);
+                refined[k] = refined[k] + ref_score * bonus;
+            }
+        }
+    }
+    for (int k = 0; k < 24; ++k) {  // stable insertion sort, descending
+        const float x = refined[k];
+        int j = k;
+        while (j > 0 && scores[j - 1] < x) {
+            scores[j] = scores[j - 1];
+            keys[j] = keys[j - 1];
+            --j;
+        }
+        scores[j] = x;
+        keys[j] = k;
+    }
+}
+
+__device__ inline float key_clarity(const float* sc, int n) {  // key_clarity.rs:51-93
+    if (n < 2) return 0.0f;
+    float sum = 0.0f;
+    for (int i = 0; i < n; ++i) sum = sum + sc[i];
+    const float avg = sum / (float)n;
+    float mn = sc[0], mx = sc[0];
+    for (int i = 1; i < n; ++i) {
+        if (sc[i] < mn) mn = sc[i];
+        if (sc[i] >= mx) mx = sc[i];
+    }
+    const float range = mx - mn;
+    if (range > 1e-10f) return clamp_rs((sc[0] - avg) / range, 0.0f, 1.0f);
+    return 0.0f;
+}
+
+// ---- per-track vote (lib.rs:1353-1436, 1461): one thread per track -----------------------------------
+__global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg cfg) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    TrackDev& T = tr[t];
+    T.key = 0;
+    T.key_confidence = 0.0f;
+    T.key_clarity = 0.0f;
+    if (T.status != 0 || T.Fk == 0 || T.m < 2048) return;
+    uint32_t seg_len, hop, nseg;
+    const bool voting = seg_geometry(T, cfg, &seg_len, &hop, &nseg);
+    nseg = min(nseg, T.seg_cap > 0 ? T.seg_cap - 1 : 0u);
+    const float* ss = fa + T.seg_scores;
+    int keys[24];
+    float scores[24];
+    bool voted = false;
+    int key = 0;
+    float confidence = 0.0f;
+    float fin[24];
+    if (voting) {
+        const float min_cl = clamp_rs(cfg.key_seg_min_clarity, 0.0f, 1.0f);
+        float acc[24];
+        for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
+        uint32_t used = 0;
+        for (uint32_t s = 0; s < nseg; ++s) {
+            rank_keys(ss + (uint64_t)s * 24, keys, scores);
+            const float cl = key_clarity(scores, 24);
+            if (cl >= min_cl) {
+                ++used;
+                for (int i = 0; i < 24; ++i) acc[keys[i]] = acc[keys[i]] + scores[i] * cl;
+            }
+        }
+        if (used > 0) {
+            for (int k = 0; k < 24; ++k) {
+                const float x = acc[k];
+                int j = k;
+                while (j > 0 && fin[j - 1] < x) {
+                    fin[j] = fin[j - 1];
+                    keys[j] = keys[j - 1];
+                    --j;
+                }
+                fin[j] = x;
+                keys[j] = k;
+            }
+            key = keys[0];
+            confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;
+            voted = true;
+        }
+    }
+    if (!voted) {
+        rank_keys(ss + (uint64_t)nseg * 24, keys, fin);
+        // weighted top-3 vote (detector.rs:254-275): three distinct keys, so the first-ranked key wins
+        key = keys[0];
+        confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;
+    }
+    T.key = key;
+    T.key_confidence = confidence;
+    T.key_clarity = key_clarity(fin, 24);
+}
+
+void launch_key_path(const WaveCtx& c) {
+    if (c.max_Fk > 0) {
+        if (c.cfg.key_mask) {
+            mask_kernel<<<dim3((KBINS + 127) / 128, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            count_launch("key_mask");
+        }
+        hpcp_kernel<<<dim3((c.max_Fk + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+        count_launch("key_hpcp");
+        chroma_smooth_kernel<<<dim3((c.max_Fk * 12 + 255) / 256, c.n_tracks), 256, 0, c.stream>>>(c.tracks, c.fa);
+        count_launch("key_vote");
+        key_weights_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        count_launch("key_vote");
+        segment_score_kernel<<<dim3(c.max_seg_cap, c.n_tracks), 32, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg);
+        count_launch("key_vote");
+    }
+    key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);
+    count_launch("key_vote");
+}
+
+}  // namespace sb

@@ -1,0 +1,48 @@
+// Device-side synthetic track generator (tests/synth.py): click train + triad.
+// Used by bench.py so that 1024 distinct 3-minute tracks (32.5 GB) never exist on the host.
+// Not part of the analysis path; evaluated in double like the numpy generator, rounded once to f32.
+#include "kernels.h"
+
+namespace sb {
+
+__global__ void __launch_bounds__(256) synth_kernel(float* __restrict__ out, uint64_t n_samples, uint32_t sr, const float* __restrict__ params5) {
+    const uint32_t trk = blockIdx.y;
+    const float* p = params5 + (uint64_t)trk * 5;
+    const double bpm = p[0];
+    const int tonic = (int)p[1], minor = (int)p[2];
+    const double phase = p[3], amp = p[4];
+    const double two_pi = 6.283185307179586476925286766559;
+    const double f0 = 261.6255653005986 * exp2((double)tonic / 12.0);
+    const double f1 = f0 * exp2((minor ? 3.0 : 4.0) / 12.0), f2 = f0 * exp2(7.0 / 12.0);
+    const double period = 60.0 / bpm * (double)sr;
+    const long long clen = (long long)(0.005 * (double)sr);
+    float* o = out + (uint64_t)trk * n_samples;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_samples; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double t = (double)i / (double)sr;
+        double x = amp * (sin(two_pi * f0 * t) + sin(two_pi * f1 * t) + sin(two_pi * f2 * t));
+        // latest click start s_k = rint((phase + k) * period) <= i
+        long long k = (long long)floor((double)i / period - phase) + 1;
+        for (int tries = 0; tries < 3 && k >= 0; ++tries, --k) {
+            const long long s = (long long)rint((phase + (double)k) * period);
+            if (s <= (long long)i) {
+                const long long d = (long long)i - s;
+                if (d < clen) {
+                    const double ct = (double)d / (double)sr;
+                    x += 0.8 * sin(two_pi * 1000.0 * ct) * exp(-ct / 0.001);
+                }
+                break;
+            }
+        }
+        o[i] = (float)x;
+    }
+}
+
+void launch_synth(cudaStream_t s, float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sr, const float* d_params5) {
+    if (n_tracks == 0 || n_samples == 0) return;
+    unsigned gx = (unsigned)((n_samples + 256 * 16 - 1) / (256 * 16));
+    if (gx > 4096) gx = 4096;
+    synth_kernel<<<dim3(gx, n_tracks), 256, 0, s>>>(d_out, n_samples, sr, d_params5);
+    count_launch("synth");
+}
+
+}  // namespace sb

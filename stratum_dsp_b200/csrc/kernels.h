@@ -51,7 +51,8 @@ struct SrTables {
 struct WaveCtx {
     cudaStream_t stream;
     const float* samples;  // device
-    float* fa;             // float arena
+    float* fa;             // float arena (work areas)
+    float* oa;             // float output arena (beats, downbeats) — the only float region copied back
     int32_t* ia;           // int arena
     TrackDev* tracks;      // device
     const SrTables* srtab; // device array, tracks index it through sr_index
@@ -63,6 +64,8 @@ struct WaveCtx {
     uint32_t max_F[N_HOPS], max_Fk, max_Fsil;
     uint64_t max_n;
     uint32_t max_beat_cap;
+    uint32_t max_seg_cap;
+    uint32_t max_lg_fft;
 };
 
 struct Launcher;  // counts launches + optional stage timing (engine.cu)
