@@ -222,6 +222,10 @@ int32_t stratum_b200_stage_times(char* names, size_t cap, double* ms, int32_t ma
 void stratum_b200_stage_times_reset(void);
 void stratum_b200_stage_timing_enable(int32_t on);
 
+/* Device time (CUDA events on the library's own stream, first launch to last copy, summed over the
+ * waves) of the most recent stratum_b200_analyze_batch_device call in this process. */
+double stratum_b200_last_call_device_ms(void);
+
 #ifdef __cplusplus
 }
 #endif

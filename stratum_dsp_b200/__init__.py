@@ -169,6 +169,8 @@ def lib() -> C.CDLL:
     L.stratum_b200_stage_times_reset.restype = None
     L.stratum_b200_stage_timing_enable.argtypes = [_i]
     L.stratum_b200_stage_timing_enable.restype = None
+    L.stratum_b200_last_call_device_ms.argtypes = []
+    L.stratum_b200_last_call_device_ms.restype = C.c_double
     if L.stratum_b200_sizeof(0) != C.sizeof(StratumConfig) or L.stratum_b200_sizeof(1) != C.sizeof(StratumResult) or \
             L.stratum_b200_sizeof(2) != C.sizeof(StratumConfidence):
         raise RuntimeError("ctypes mirror of include/stratum_b200.h is out of date (struct size mismatch)")
@@ -474,6 +476,10 @@ def stage_times(reset: bool = False) -> dict:
     if reset:
         lib().stratum_b200_stage_times_reset()
     return out
+
+
+def last_call_device_ms() -> float:
+    return float(lib().stratum_b200_last_call_device_ms())
 
 
 def launch_count() -> int:

@@ -47,7 +47,15 @@ static std::vector<std::string> g_stage_order;
 
 void count_launch(const char*) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct StageTimer {  // device time of a group of launches, accumulated per stage name
+// Device time of a group of launches, accumulated per stage name.  Events are only recorded here;
+// they are resolved after the wave's final stream synchronisation, so timing adds no host sync.
+struct PendingStage {
+    const char* name;
+    cudaEvent_t a, b;
+};
+static thread_local std::vector<PendingStage> g_pending;
+
+struct StageTimer {
     cudaStream_t s;
     const char* name;
     cudaEvent_t a = nullptr, b = nullptr;
@@ -61,16 +69,26 @@ struct StageTimer {  // device time of a group of launches, accumulated per stag
     ~StageTimer() {
         if (!a) return;
         cudaEventRecord(b, s);
-        cudaEventSynchronize(b);
-        float ms = 0.0f;
-        cudaEventElapsedTime(&ms, a, b);
-        cudaEventDestroy(a);
-        cudaEventDestroy(b);
-        std::lock_guard<std::mutex> lk(g_stage_mu);
-        if (!g_stage_ms.count(name)) g_stage_order.push_back(name);
-        g_stage_ms[name] += ms;
+        g_pending.push_back(PendingStage{name, a, b});
     }
 };
+
+static void resolve_stage_times() {  // call after the stream has been synchronised
+    if (g_pending.empty()) return;
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    for (PendingStage& p : g_pending) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (!g_stage_ms.count(p.name)) g_stage_order.push_back(p.name);
+            g_stage_ms[p.name] += ms;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_pending.clear();
+}
+
+static std::atomic<uint64_t> g_last_call_us{0};  // device time of the most recent batch call (all waves), microseconds
 
 // ---- debug capture (single-track calls) -----------------------------------------------------------------
 static std::atomic<int> g_debug{0};
@@ -769,7 +787,7 @@ struct WavePlan {
 };
 
 static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample_off, const uint64_t* lens, const uint32_t* srs, const WavePlan& wp,
-                    const StratumConfig& cfg, const DevCfg& dcfg, size_t fa_budget, StratumResult* out) {
+                    const StratumConfig& cfg, const DevCfg& dcfg, size_t fa_budget, StratumResult* out, double* wave_ms) {
     const int nt = (int)wp.idx.size();
     std::vector<TrackDev> tracks(nt);
     std::vector<int32_t> sr_index(nt, 0);
@@ -931,10 +949,12 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     cudaEventRecord(ev1, s);
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaGetLastError());
+    resolve_stage_times();
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    if (wave_ms) *wave_ms += ms;
     for (int i = 0; i < nt; ++i) fill_result(tracks[i], oa_host.data(), ia_host.data(), ms / (float)nt, &out[wp.idx[i]]);
     if (g_debug.load() && nt == 1) {
         const TrackDev& T = tracks[0];
@@ -1014,6 +1034,7 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
         lens[i] = offsets[i + 1] - offsets[i];
     }
     uint32_t i = 0;
+    double call_ms = 0.0;
     while (i < n_tracks) {
         WavePlan wp;
         uint64_t used = 0, esc_max = 0;
@@ -1033,9 +1054,10 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
             // a single track larger than the arena budget: let cudaMalloc decide
             budget_floats = used + esc_max;
         }
-        st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out);
+        st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out, &call_ms);
         if (st != STRATUM_OK) return st;
     }
+    g_last_call_us.store((uint64_t)(call_ms * 1000.0));
     return STRATUM_OK;
 }
 
@@ -1413,5 +1435,7 @@ void stratum_b200_stage_times_reset(void) {
 }
 
 void stratum_b200_stage_timing_enable(int32_t on) { g_timing.store(on); }
+
+double stratum_b200_last_call_device_ms(void) { return (double)g_last_call_us.load() / 1000.0; }
 
 }  // extern "C"

@@ -367,8 +367,10 @@ __global__ void __launch_bounds__(32) segment_score_kernel(const TrackDev* __res
     fa[T.seg_scores + (uint64_t)s * 24 + k] = acc;
 }
 
-// detect_key_weighted steps 1.5 - 2 on 24 raw scores: ranked keys/scores out (detector.rs:135-250).
-__device__ inline void rank_keys(const float* raw, int* keys, float* scores) {
+// detect_key_weighted steps 1.5 - 2 on 24 raw scores: ranked keys/scores out (detector.rs:135-250) and the
+// same refined scores indexed by key id (by_key).  Kept out of line: each call gets its own stack
+// frame, so the caller's accumulators never share local-memory slots with this function's temporaries.
+__device__ __noinline__ void rank_keys(const float* raw, int* keys, float* scores, float* by_key) {
     float sc[24];
     for (int k = 0; k < 24; ++k) sc[k] = raw[k];
     float mxM = 0.0f, mxm = 0.0f;
@@ -398,6 +400,7 @@ __device__ inline void rank_keys(const float* raw, int* keys, float* scores) {
             }
         }
     }
+    for (int k = 0; k < 24; ++k) by_key[k] = refined[k];
     for (int k = 0; k < 24; ++k) {  // stable insertion sort, descending
         const float x = refined[k];
         int j = k;
@@ -411,7 +414,7 @@ __device__ inline void rank_keys(const float* raw, int* keys, float* scores) {
     }
 }
 
-__device__ inline float key_clarity(const float* sc, int n) {  // key_clarity.rs:51-93
+__device__ __noinline__ float key_clarity(const float* sc, int n) {  // key_clarity.rs:51-93
     if (n < 2) return 0.0f;
     float sum = 0.0f;
     for (int i = 0; i < n; ++i) sum = sum + sc[i];
@@ -440,7 +443,7 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
     nseg = min(nseg, T.seg_cap > 0 ? T.seg_cap - 1 : 0u);
     const float* ss = fa + T.seg_scores;
     int keys[24];
-    float scores[24];
+    float scores[24], by_key[24];
     bool voted = false;
     int key = 0;
     float confidence = 0.0f;
@@ -451,11 +454,11 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
         for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
         uint32_t used = 0;
         for (uint32_t s = 0; s < nseg; ++s) {
-            rank_keys(ss + (uint64_t)s * 24, keys, scores);
+            rank_keys(ss + (uint64_t)s * 24, keys, scores, by_key);
             const float cl = key_clarity(scores, 24);
             if (cl >= min_cl) {
                 ++used;
-                for (int i = 0; i < 24; ++i) acc[keys[i]] = acc[keys[i]] + scores[i] * cl;
+                for (int k = 0; k < 24; ++k) acc[k] = acc[k] + by_key[k] * cl;  // one add per key and segment, as lib.rs:1375-1381
             }
         }
         if (used > 0) {
@@ -476,7 +479,7 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
         }
     }
     if (!voted) {
-        rank_keys(ss + (uint64_t)nseg * 24, keys, fin);
+        rank_keys(ss + (uint64_t)nseg * 24, keys, fin, by_key);
         // weighted top-3 vote (detector.rs:254-275): three distinct keys, so the first-ranked key wins
         key = keys[0];
         confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;

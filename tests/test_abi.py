@@ -1,0 +1,149 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/stratum_b200.h declares, the struct mirrors match, the pure-host entry points
+(config_default, compute_confidence, warning strings, key names) agree with the oracle, and compute
+entry points fail loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import stratum_dsp_b200 as S
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "stratum_b200.h").read_text()
+
+
+def declared_symbols():
+    return sorted(set(re.findall(r"\b(stratum_b200_[a-z0-9_]+)\s*\(", HEADER)))
+
+
+def test_header_symbols_are_exported():
+    L = S.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/stratum_b200.h but not exported"
+
+
+def test_struct_sizes_match():
+    L = S.lib()
+    assert L.stratum_b200_sizeof(0) == C.sizeof(S.StratumConfig)
+    assert L.stratum_b200_sizeof(1) == C.sizeof(S.StratumResult)
+    assert L.stratum_b200_sizeof(2) == C.sizeof(S.StratumConfidence)
+    # every config field of the header is mirrored, in order
+    body = HEADER[HEADER.index("typedef struct StratumConfig {") + len("typedef struct StratumConfig {"):HEADER.index("} StratumConfig;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        m = re.match(r"(uint32_t|int32_t|float)\s+(.*)$", decl, flags=re.S)
+        if m:
+            names += [re.sub(r"\[.*\]", "", n).strip() for n in m.group(2).split(",")]
+    assert names == [n for n, _ in S.StratumConfig._fields_]
+
+
+def test_config_default_matches_reference_defaults():
+    # src/config.rs:594-744 through the oracle's Config (same source of truth, separately typed in)
+    L = O.lib()
+    oc = L.so_config_new()
+    c = S.AnalysisConfig()
+    checked = 0
+    for name, _ in S.StratumConfig._fields_:
+        v = L.so_config_get(oc, name.encode())
+        if np.isnan(v):
+            continue
+        assert float(getattr(c, name)) == pytest.approx(v, rel=1e-7), name
+        checked += 1
+    L.so_config_free(oc)
+    assert checked >= 70
+    assert c.onset_consensus_weights == [0.25] * 4 and c.abi_version == S.ABI_VERSION
+    assert c.enable_hpss_onsets == 0 and c.enable_bpm_fusion == 0 and c.enable_key_mode_heuristic == 0
+
+
+def test_config_rejects_unknown_fields():
+    with pytest.raises(AttributeError):
+        S.AnalysisConfig(no_such_field=1)
+
+
+def test_key_names():
+    assert S.Key(False, 0).name() == "C" and S.Key(False, 6).name() == "F#" and S.Key(True, 9).name() == "Am"
+    assert S.Key(False, 0).numerical() == "1A" and S.Key(False, 7).numerical() == "2A"
+    assert S.Key(True, 9).numerical() == "1B" and S.Key(True, 4).numerical() == "2B"
+    L = O.lib()
+    for minor in (0, 1):
+        for i in range(12):
+            for num in (0, 1):
+                b = C.create_string_buffer(16)
+                L.so_key_name(minor, i, num, b, 16)
+                k = S.Key(bool(minor), i)
+                assert (k.numerical() if num else k.name()) == b.value.decode()
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_compute_confidence_matches_oracle(seed):
+    rng = np.random.default_rng(seed)
+    bpm = float(rng.choice([0.0, 90.0, 128.0]))
+    vals = [float(rng.uniform(-0.2, 1.3)) for _ in range(4)]
+    warn = int(rng.integers(0, 16))
+    flags = int(rng.integers(0, 16))
+    r = S.StratumResult()
+    r.bpm, r.bpm_confidence, r.key_confidence, r.key_clarity, r.grid_stability = bpm, *vals
+    r.warnings, r.flags = warn, flags
+    out = S.StratumConfidence()
+    S.lib().stratum_b200_compute_confidence(C.byref(r), C.byref(out))
+    exp = (C.c_float * 4)()
+    fl = C.c_uint32()
+    O.lib().so_confidence_of(bpm, *vals, warn, flags, exp, C.byref(fl))
+    assert [out.bpm_confidence, out.key_confidence, out.grid_stability, out.overall_confidence] == list(exp)
+    assert out.flags == fl.value
+
+
+def test_warning_strings_are_the_reference_strings():
+    r = S.StratumResult()
+    r.warnings = 15
+    r.grid_stability, r.key_confidence, r.key_clarity = 0.123, 0.256, 0.1
+    buf = C.create_string_buffer(1024)
+    S.lib().stratum_b200_warning_strings(C.byref(r), buf, 1024)
+    lines = buf.value.decode().strip().split("\n")
+    assert lines == [  # src/lib.rs:1567-1589
+        "BPM detection failed: insufficient onsets or estimation error",
+        "Low beat grid stability: 0.12 (may indicate tempo variation)",
+        "Low key detection confidence: 0.26 (may indicate ambiguous or atonal music)",
+        "Low key clarity: 0.10 (track may be atonal or have weak tonality)",
+    ]
+
+
+def test_no_cpu_fallback():
+    if S.device_count() > 0:
+        pytest.skip("CUDA device present")
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_audio(np.ones(4096, np.float32), 44100)
+    assert e.value.kind == "ProcessingError" and "no CPU fallback" in e.value.message
+    with pytest.raises(S.AnalysisError):
+        S.stft(np.ones(4096, np.float32), 2048, 512)
+
+
+def test_config_validation_happens_before_any_device_work():
+    # rejected switches give NotImplemented even on a box without a GPU
+    for kw in ({"enable_hpss_onsets": 1}, {"enable_bpm_fusion": 1}, {"enable_key_hpcp": 0}, {"frame_size": 1024}, {"enable_key_mode_heuristic": 1},
+               {"tempogram_band_seed_only": 0}):
+        with pytest.raises(S.AnalysisError) as e:
+            S.analyze_batch([np.ones(4096, np.float32)], 44100, S.AnalysisConfig(**kw))
+        assert e.value.kind == "NotImplemented", kw
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_batch([np.ones(4096, np.float32)], 44100, S.AnalysisConfig(min_bpm=200.0, max_bpm=100.0))
+    assert e.value.kind == "InvalidInput"
+
+
+def test_product_does_not_touch_the_oracle():
+    # the shipped package never imports, links or executes anything under oracle/
+    for p in (ROOT / "stratum_dsp_b200").rglob("*"):
+        if p.suffix in {".py", ".cu", ".cuh", ".h"} or p.name == "Makefile":
+            txt = p.read_text()
+            assert "oracle_lib" not in txt and "libstratum_oracle" not in txt and "so_common.hpp" not in txt, p
+    import subprocess
+    out = subprocess.run(["ldd", str(S.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "oracle" not in out

@@ -1,0 +1,172 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import synth
+import stratum_dsp_b200 as S
+from gpu_common import assert_parity, close
+
+pytestmark = pytest.mark.gpu
+SR = 44100
+
+
+@pytest.mark.parametrize("frame,hop", [(2048, 512), (2048, 256), (2048, 1024), (8192, 512)])
+def test_stft_bit_exact(frame, hop):
+    rng = np.random.default_rng(frame + hop)
+    x = (rng.standard_normal(3 * SR) * 0.25).astype(np.float32)
+    g, o = S.stft(x, frame, hop), O.stft(x, frame, hop)
+    assert g.shape == o.shape
+    assert np.array_equal(g, o)  # same FFT DAG (oracle/so_fft.cpp) => identical bits
+
+
+def test_stft_short_and_gain():
+    x = np.ones(1000, np.float32)
+    assert S.stft(x, 2048, 512).shape == (0, 1025)
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal(8192) * 0.1).astype(np.float32)
+    assert np.array_equal(S.stft(y, 2048, 512, gain=0.5), O.stft((y * np.float32(0.5)).astype(np.float32), 2048, 512))
+
+
+@pytest.mark.parametrize("seconds", [12.0, 30.0])
+def test_c1_click_chord(seconds):
+    x = synth.render(synth.c1_params(int(seconds * SR), SR))
+    assert_parity(S.analyze_audio(x, SR), O.analyze(x, SR, fast=True), f"C1 {seconds}s")
+
+
+@pytest.mark.parametrize("i", range(12))
+def test_c2_tracks_30s(i):
+    p = synth.c2_params(i, 30 * SR, SR)
+    x = synth.render(p)
+    assert_parity(S.analyze_audio(x, SR), O.analyze(x, SR, fast=True), f"C2[{i}] bpm={p.bpm}")
+
+
+def test_c1_full_three_minutes():
+    # BASELINE.json configs[0]: one 3-min 44.1 kHz 128 BPM click+chord track
+    x = synth.render(synth.c1_params())
+    g, o = S.analyze_audio(x, SR), O.analyze(x, SR, fast=True)
+    assert_parity(g, o, "C1 3min")
+    assert abs(g.bpm - 128.0) <= 1.0 and g.key.id == 0
+
+
+def test_reference_fixtures():
+    for name, x in [("120bpm", synth.fixture_kick(120.0, 8.0)), ("128bpm", synth.fixture_kick(128.0, 7.5)), ("cmajor", synth.fixture_cmajor_scale()),
+                    ("mixed_silence", synth.fixture_mixed_silence())]:
+        g = S.analyze_audio(x, SR)
+        assert_parity(g, O.analyze(x, SR), name)
+    # tests/integration_tests.rs assertions on the CUDA path itself
+    g = S.analyze_audio(synth.fixture_kick(120.0, 8.0), SR)
+    assert g.bpm == 0 or abs(g.bpm - 120) <= 2
+    g = S.analyze_audio(synth.fixture_mixed_silence(), SR)
+    assert 4.0 <= g.metadata.duration_seconds <= 6.0
+
+
+def test_errors_match_reference():
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_audio(np.zeros(SR, np.float32), SR)
+    assert e.value.kind == "ProcessingError" and "silent" in e.value.message  # tests/integration_tests.rs:264-274
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_audio(np.zeros(0, np.float32), SR)
+    assert e.value.kind == "InvalidInput" and "Empty" in e.value.message  # lib.rs:100-104
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_audio(np.ones(100, np.float32), 0)
+    assert e.value.kind == "InvalidInput"
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(enable_hpss_onsets=True))
+    assert e.value.kind == "NotImplemented"  # unsupported switches are rejected, never silently ignored
+
+
+def test_short_inputs():
+    rng = np.random.default_rng(5)
+    for n in (100, 2047, 2048, 4096, 8191, 8192, 12000):
+        x = (rng.standard_normal(n) * 0.2).astype(np.float32)
+        o = O.analyze(x, SR)
+        try:
+            g = S.analyze_audio(x, SR)
+        except S.AnalysisError as e:
+            assert o.status == e.code, (n, e, o.error)
+            continue
+        assert_parity(g, o, f"noise n={n}")
+
+
+def test_ragged_batch_matches_single_and_oracle():
+    # C5 shape: mixed durations and sample rates in one call; one bad track must not abort the batch
+    rng = np.random.default_rng(9)
+    tracks, srs = [], []
+    for i in range(6):
+        p = synth.c5_params(i)
+        p.n_samples = min(p.n_samples, 40 * p.sample_rate)
+        tracks.append(synth.render(p))
+        srs.append(p.sample_rate)
+    tracks.insert(3, np.zeros(30000, np.float32))  # silent -> per-track error
+    srs.insert(3, 44100)
+    tracks.append((rng.standard_normal(5000) * 0.1).astype(np.float32))
+    srs.append(48000)
+    res = S.analyze_batch(tracks, srs)
+    assert len(res) == len(tracks)
+    for i, (x, sr, g) in enumerate(zip(tracks, srs, res)):
+        o = O.analyze(x, sr, fast=True)
+        if o.status:
+            assert g.error is not None and g.error.code == o.status, i
+            continue
+        assert_parity(g, o, f"ragged[{i}] sr={sr} n={x.size}")
+        single = S.analyze_audio(x, sr)
+        assert single.bpm == g.bpm and single.key == g.key and np.array_equal(single.beat_grid.beats, g.beat_grid.beats)
+
+
+def test_waves_do_not_change_results(monkeypatch):
+    xs = [synth.render(synth.c2_params(20 + i, 15 * SR, SR)) for i in range(5)]
+    a = S.analyze_batch(xs, SR)
+    monkeypatch.setenv("STRATUM_B200_WAVE_MAX_TRACKS", "2")
+    b = S.analyze_batch(xs, SR)
+    for u, v in zip(a, b):
+        assert u.bpm == v.bpm and u.key == v.key and u.key_clarity == v.key_clarity and np.array_equal(u.beat_grid.beats, v.beat_grid.beats)
+
+
+def test_escalation_path_is_exercised():
+    # BPM 70-80 / 170-180 fall in the trap zones of lib.rs:412-413 -> multi-resolution pass
+    hit = 0
+    for bpm in (72.0, 76.0, 174.0, 178.0):
+        p = synth.TrackParams(bpm, 2, 0, 0.25, 0.1, SR, 30 * SR)
+        x = synth.render(p)
+        g, o = S.analyze_audio(x, SR), O.analyze(x, SR, fast=True)
+        assert_parity(g, o, f"trap bpm={bpm}")
+        hit += bool(g.metadata.tempogram_multi_res_triggered)
+    assert hit >= 1
+
+
+def test_stage_intermediates_single_track():
+    x = synth.render(synth.c2_params(1, 20 * SR, SR))
+    o = O.analyze(x, SR, dump=True)
+    S.debug_enable(True)
+    try:
+        S.analyze_audio(x, SR)
+        D = S.debug_array
+        assert np.array_equal(D("onset.spectral_flux"), o.farray("onset.spectral_flux"))  # FFT + sqrt + div only: exact
+        for nm in ("onset.energy", "onset.spectral", "onset.hfc"):
+            assert np.array_equal(D(nm).astype(np.int64), o.iarray(nm)), nm
+        for v in ("full", "low", "mid", "high", "mel"):  # logf differs by an ulp between libm and CUDA
+            assert np.abs(D(f"base.nov.{v}") - o.farray(f"base.nov.{v}")).max() < 2e-6, v
+        assert np.abs(D("key.hpcp_raw") - o.farray("key.hpcp_raw")).max() < 5e-6
+        assert np.array_equal(D("hmm.path").astype(np.int64), o.iarray("hmm.path"))  # Viterbi path incl. underflow behaviour
+    finally:
+        S.debug_enable(False)
+
+
+def test_device_resident_batch_and_synth():
+    torch = pytest.importorskip("torch")
+    n, nt = 20 * SR, 4
+    params = np.array([[c.bpm, c.tonic, c.minor, c.phase_frac, c.chord_amp] for c in (synth.c2_params(i) for i in range(nt))], np.float32)
+    buf = torch.empty(nt * n, dtype=torch.float32, device="cuda")
+    S.synth_batch(buf.data_ptr(), nt, n, SR, params)
+    torch.cuda.synchronize()
+    host = buf.cpu().numpy().reshape(nt, n)
+    for i in range(nt):  # device generator == numpy generator up to one f32 rounding of the last bit
+        p = synth.c2_params(i, n, SR)
+        p.phase_frac, p.chord_amp = float(params[i, 3]), float(params[i, 4])
+        assert np.abs(host[i] - synth.render(p)).max() < 1e-5
+    offsets = np.arange(nt + 1, dtype=np.uint64) * n
+    res = S.analyze_batch_device(buf.data_ptr(), offsets, [SR] * nt)
+    for i in range(nt):
+        assert_parity(res[i], O.analyze(host[i], SR, fast=True), f"device[{i}]")
+    assert S.launch_count() > 0

@@ -92,6 +92,8 @@ def compare(x, sr, label, stages=False):
         if ss is not None:
             ss = ss.reshape(-1, 24)
             print("   key.segments oracle (top key, clarity):", o.farray("key.segments"))
+            np.savez(ROOT / "gpurun_out" / f"dbg_{label.split()[0]}_{int(time.time()*1000)%100000}.npz", seg_scores=ss, oracle_segments=o.farray("key.segments"),
+                     oracle_scores=o.farray("key.scores"), oracle_order=o.farray("key.order"), gpu_clarity=g.key_clarity, oracle_clarity=o.key_clarity)
             for i, row in enumerate(ss):
                 print(f"   gpu seg_scores[{i}] top={int(row.argmax())} max={row.max():.5f} min={row.min():.5f} sum={row.sum():.5f}")
         be = D("base.est")
