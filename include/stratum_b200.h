@@ -226,6 +226,9 @@ void stratum_b200_stage_timing_enable(int32_t on);
  * waves) of the most recent stratum_b200_analyze_batch_device call in this process. */
 double stratum_b200_last_call_device_ms(void);
 
+/* Cumulative host->device / device->host bytes copied by the library in this process. */
+void stratum_b200_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
+
 #ifdef __cplusplus
 }
 #endif

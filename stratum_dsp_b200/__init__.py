@@ -171,6 +171,8 @@ def lib() -> C.CDLL:
     L.stratum_b200_stage_timing_enable.restype = None
     L.stratum_b200_last_call_device_ms.argtypes = []
     L.stratum_b200_last_call_device_ms.restype = C.c_double
+    L.stratum_b200_transfer_bytes.argtypes = [u64p, u64p]
+    L.stratum_b200_transfer_bytes.restype = None
     if L.stratum_b200_sizeof(0) != C.sizeof(StratumConfig) or L.stratum_b200_sizeof(1) != C.sizeof(StratumResult) or \
             L.stratum_b200_sizeof(2) != C.sizeof(StratumConfidence):
         raise RuntimeError("ctypes mirror of include/stratum_b200.h is out of date (struct size mismatch)")
@@ -424,6 +426,13 @@ def analyze_batch_device(d_samples_ptr: int, offsets: np.ndarray, sample_rates: 
     return _collect(res, n)
 
 
+def shard_bounds(n_tracks: int, shard: int, n_shards: int) -> tuple:
+    """Contiguous shard [a, b) of a batch for device/rank ``shard`` — the rule stratum_b200_analyze_batch uses
+    across ``device_ids`` (csrc/engine.cu) and bench.py uses across ranks: tracks are independent
+    (examples/analyze_batch.rs:260-326), so sharding by track needs no data-path collective."""
+    return (n_tracks * shard) // n_shards, (n_tracks * (shard + 1)) // n_shards
+
+
 def free_results(res) -> None:
     lib().stratum_b200_result_free(res, len(res))
 
@@ -480,6 +489,12 @@ def stage_times(reset: bool = False) -> dict:
 
 def last_call_device_ms() -> float:
     return float(lib().stratum_b200_last_call_device_ms())
+
+
+def transfer_bytes() -> tuple:
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().stratum_b200_transfer_bytes(C.byref(a), C.byref(b))
+    return int(a.value), int(b.value)
 
 
 def launch_count() -> int:

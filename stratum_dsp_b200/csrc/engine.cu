@@ -88,7 +88,8 @@ static void resolve_stage_times() {  // call after the stream has been synchroni
     g_pending.clear();
 }
 
-static std::atomic<uint64_t> g_last_call_us{0};  // device time of the most recent batch call (all waves), microseconds
+static std::atomic<uint64_t> g_last_call_us{0};
+static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // host<->device traffic of this process (results, staging)  // device time of the most recent batch call (all waves), microseconds
 
 // ---- debug capture (single-track calls) -----------------------------------------------------------------
 static std::atomic<int> g_debug{0};
@@ -142,6 +143,17 @@ static std::vector<float2> make_tw(uint32_t M) {  // TW[t] = (cos, -sin)(2 pi t 
     return tw;
 }
 
+// Per-pass compact tables for the STFT kernels: for every radix-4 pass with sub-size S = 4, 16, ..., M/4 the
+// values TW_M[(k*r) * M/(4S)] (r = 1..3, k < S) stored at [S - 4 + (r-1)*S + k] — the same floats as make_tw.
+static std::vector<float2> make_pass_tw(uint32_t M) {
+    const std::vector<float2> tw = make_tw(M);
+    std::vector<float2> t(M - 4);
+    for (uint32_t S = 4; S < M; S *= 4)
+        for (uint32_t r = 1; r <= 3; ++r)
+            for (uint32_t k = 0; k < S; ++k) t[S - 4 + (r - 1) * S + k] = tw[(uint64_t)(k * r) * (M / (4 * S))];
+    return t;
+}
+
 static std::vector<float> make_hann(uint32_t n) {  // chroma/extractor.rs:318-323, f32
     std::vector<float> w(n);
     const float pi = 3.14159265358979323846f;
@@ -186,6 +198,8 @@ static int ctx_init(DeviceCtx& c, int device) {
     CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     c.tab.tw1024 = get_tw(c, 1024);
     c.tab.tw4096 = get_tw(c, 4096);
+    c.tab.ptw1024 = dev_upload(c, make_pass_tw(1024));
+    c.tab.ptw4096 = dev_upload(c, make_pass_tw(4096));
     c.tab.rw2048 = get_tw(c, 2048);  // RW_N[k] = TW_N[k], k <= N/2
     c.tab.rw8192 = get_tw(c, 8192);
     c.tab.win2048 = dev_upload(c, make_hann(2048));
@@ -195,7 +209,7 @@ static int ctx_init(DeviceCtx& c, int device) {
     c.tab.key_major = dev_upload(c, mj);
     c.tab.key_minor = dev_upload(c, mn);
     CUDA_OK(cudaMalloc(&c.d_srtab, sizeof(SrTables) * DeviceCtx::MAX_SR));
-    if (!c.tab.tw1024 || !c.tab.tw4096 || !c.tab.rw2048 || !c.tab.rw8192 || !c.tab.win2048 || !c.tab.win8192 || !c.tab.key_major || !c.tab.key_minor) {
+    if (!c.tab.tw1024 || !c.tab.tw4096 || !c.tab.ptw1024 || !c.tab.ptw4096 || !c.tab.rw2048 || !c.tab.rw8192 || !c.tab.win2048 || !c.tab.win8192 || !c.tab.key_major || !c.tab.key_minor) {
         set_error("device table allocation failed");
         return STRATUM_PROCESSING_ERROR;
     }
@@ -946,6 +960,8 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     std::vector<int32_t> ia_host(ia.pos + 1);
     CUDA_OK(cudaMemcpyAsync(oa_host.data(), c.oa, sizeof(float) * oa.pos, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaMemcpyAsync(ia_host.data(), c.ia, sizeof(int32_t) * ia.pos, cudaMemcpyDeviceToHost, s));
+    g_d2h_bytes.fetch_add(sizeof(TrackDev) * nt * (dcfg.mr_enabled && want_tempogram ? 2 : 1) + sizeof(float) * oa.pos + sizeof(int32_t) * ia.pos);
+    g_h2d_bytes.fetch_add((sizeof(TrackDev) + sizeof(int32_t)) * nt);
     cudaEventRecord(ev1, s);
     CUDA_OK(cudaStreamSynchronize(s));
     CUDA_OK(cudaGetLastError());
@@ -1035,6 +1051,10 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     }
     uint32_t i = 0;
     double call_ms = 0.0;
+    cudaEvent_t call_a, call_b;
+    cudaEventCreate(&call_a);
+    cudaEventCreate(&call_b);
+    cudaEventRecord(call_a, ctx->stream);
     while (i < n_tracks) {
         WavePlan wp;
         uint64_t used = 0, esc_max = 0;
@@ -1057,6 +1077,12 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
         st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out, &call_ms);
         if (st != STRATUM_OK) return st;
     }
+    cudaEventRecord(call_b, ctx->stream);
+    cudaEventSynchronize(call_b);
+    float whole_ms = 0.0f;
+    if (cudaEventElapsedTime(&whole_ms, call_a, call_b) == cudaSuccess) call_ms = whole_ms;  // includes inter-wave host gaps
+    cudaEventDestroy(call_a);
+    cudaEventDestroy(call_b);
     g_last_call_us.store((uint64_t)(call_ms * 1000.0));
     return STRATUM_OK;
 }
@@ -1143,6 +1169,7 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
                     }
                     ctx->stage_cap = fl + 16;
                 }
+                g_h2d_bytes.fetch_add(fl * sizeof(float));
                 if (fl && cudaMemcpyAsync(ctx->d_stage, samples + offsets[i], fl * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
                     status[d] = STRATUM_PROCESSING_ERROR;
                     errs[d] = "host to device copy failed";
@@ -1437,5 +1464,10 @@ void stratum_b200_stage_times_reset(void) {
 void stratum_b200_stage_timing_enable(int32_t on) { g_timing.store(on); }
 
 double stratum_b200_last_call_device_ms(void) { return (double)g_last_call_us.load() / 1000.0; }
+
+void stratum_b200_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+}
 
 }  // extern "C"
