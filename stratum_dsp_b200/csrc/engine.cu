@@ -292,9 +292,11 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         for (int b = 0; b < 3; ++b)
             if (std::isfinite(w[b]) && w[b] > 0.0f && e[b] > s[b] + 1) vm |= 1u << (1 + b);
     }
-    // mel filterbank — period/novelty.rs:72-190
-    std::vector<int32_t> mel_m(n_bins * 2, -1);
-    std::vector<float> mel_w(n_bins * 2, 0.0f);
+    // mel filterbank — period/novelty.rs:72-190.  Stored per band as the entries the reference's per-bin
+    // contribution lists yield for that band in ascending-bin order: rising slope (l+1..c), then falling slope
+    // (c..r-1) — the centre bin contributes twice with weight 1, exactly as the two loops of novelty.rs:150-175 do.
+    std::vector<int32_t> mel_off(1, 0), mel_bin;
+    std::vector<float> mel_w;
     st.n_mels = 0;
     if (cfg.enable_tempogram_mel_novelty) {
         const uint32_t n_mels = std::max<uint32_t>(cfg.tempogram_mel_n_mels, 4);
@@ -325,38 +327,28 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         }
         for (size_t i = 1; i < pts.size(); ++i)
             if (pts[i] <= pts[i - 1]) pts[i] = std::min(pts[i - 1] + 1, n_bins - 1);
-        std::vector<int> fill(n_bins, 0);
-        bool overflow = false;
-        auto push = [&](uint32_t b, uint32_t m, float w) {
-            if (fill[b] >= 2) {
-                overflow = true;
-                return;
-            }
-            mel_m[b * 2 + fill[b]] = (int32_t)m;
-            mel_w[b * 2 + fill[b]] = w;
-            ++fill[b];
-        };
         for (uint32_t m = 0; m < n_mels; ++m) {
             const uint32_t l = pts[m], cc = pts[m + 1], r = pts[m + 2];
-            if (!(l < cc && cc < r)) continue;
-            for (uint32_t b = l; b <= cc; ++b) {
-                const float w = (b == l) ? 0.0f : ((float)b - (float)l) / ((float)cc - (float)l);
-                if (w > 0.0f) push(b, m, w);
+            if (l < cc && cc < r) {
+                for (uint32_t b = l; b <= cc; ++b) {
+                    const float w = (b == l) ? 0.0f : ((float)b - (float)l) / ((float)cc - (float)l);
+                    if (w > 0.0f) { mel_bin.push_back((int32_t)b); mel_w.push_back(w); }
+                }
+                for (uint32_t b = cc; b <= r; ++b) {
+                    const float w = (b == r) ? 0.0f : ((float)r - (float)b) / ((float)r - (float)cc);
+                    if (w > 0.0f) { mel_bin.push_back((int32_t)b); mel_w.push_back(w); }
+                }
             }
-            for (uint32_t b = cc; b <= r; ++b) {
-                const float w = (b == r) ? 0.0f : ((float)r - (float)b) / ((float)r - (float)cc);
-                if (w > 0.0f) push(b, m, w);
-            }
-        }
-        if (overflow) {
-            set_error("mel filterbank with more than two contributions per bin is not supported");
-            return STRATUM_NOT_IMPLEMENTED;
+            mel_off.push_back((int32_t)mel_bin.size());
         }
         st.n_mels = n_mels;
         vm |= 1u << 4;
     }
+    mel_off.resize(42, mel_off.back());
+    if (mel_bin.empty()) { mel_bin.push_back(0); mel_w.push_back(0.0f); }
     st.variant_mask = vm;
-    st.mel_m = dev_upload(c, mel_m);
+    st.mel_off = dev_upload(c, mel_off);
+    st.mel_bin = dev_upload(c, mel_bin);
     st.mel_w = dev_upload(c, mel_w);
     // HPCP band in key-STFT bins — chroma/extractor.rs:584-591 (b from 1 to n_bins-2)
     {

@@ -11,7 +11,7 @@
 
 namespace sb {
 
-// frame-region layout (q * fmax + t): 0 rowmax, 1 E, 2 H, 3..5 E_low/mid/high, 6..8 H_low/mid/high, 9.. mel[40]
+// frame-region layout (q * fmax + t): 0 rowmax, 1 E, 2 H, 3..5 E_low/mid/high, 6..8 H_low/mid/high
 constexpr int FQ_ROWMAX = 0, FQ_E = 1, FQ_H = 2, FQ_EB = 3, FQ_HB = 6, FQ_MEL = 9;
 // pair-region layout: 0 onset spectral flux, 1 SF_full, 2..4 SF_low/mid/high, 5 SF_mel
 constexpr int PQ_SFLUX = 0, PQ_SF = 1, PQ_SFB = 2, PQ_MEL = 5;
@@ -87,130 +87,182 @@ __global__ void __launch_bounds__(256) energy_onset_kernel(TrackDev* tr, float* 
     }
 }
 
-// ---- per-frame reductions over the hop-h spectrogram ------------------------------------------
-__global__ void __launch_bounds__(128) frame_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, const SrTables* srtab,
-                                                         const int32_t* sr_index, int h, float* fa) {
-    __shared__ float mel[MEL_MAX][128];
+// ---- spectrogram reductions --------------------------------------------------------------------
+// Two kernels per hop, split by what the consumer needs:
+//   seq_feat_kernel — the sums whose value decides a discrete outcome (onset spectral flux, HFC, frame
+//     energy): one lane per frame walks the bins in the reference's order; a warp transposes 33x32
+//     tiles through shared memory so global loads stay coalesced.  The row maximum it divides by is
+//     order-free and comes from the STFT epilogue.
+//   par_feat_kernel — everything behind ln(1+x) (SuperFlux full + 3 bands, mel SuperFlux) and the band
+//     energies / HFCs, which only reach the BPM through tolerance-level novelty curves: one warp walks a
+//     run of 32 consecutive frames, lanes stride the bins (coalesced), ln(1+x) is evaluated once per
+//     (frame, bin) and kept in shared memory for the next frame's max filter; reductions are warp trees.
+//     Mel bands are folded by one lane per band in ascending-bin order (the reference's order).
+constexpr int FEAT_RUN = 32;
+constexpr int HALO = 8;  // superflux radius upper bound (the ABI rejects larger values)
+
+__global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, int h, float* fa) {
+    __shared__ float tiles[4][33][33];
     const int t = list ? list[blockIdx.y] : blockIdx.y;
     const TrackDev& T = tr[t];
     const uint32_t F = T.F[h];
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x * blockDim.x >= F || T.status != 0) return;
-    const SrTables& st = srtab[sr_index[t]];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f0 = (blockIdx.x * 4 + w) * 32;
+    if (f0 >= F || T.status != 0) return;
+    float(*tile)[33] = tiles[w];
     const HopLayout& HL = T.hop[h];
-    if (f >= F) return;
-    const float* row = fa + HL.spec + (uint64_t)f * 1025;
-    for (int m = 0; m < MEL_MAX; ++m) mel[m][threadIdx.x] = 0.0f;
-    float rowmax = 0.0f, E = 0.0f, H = 0.0f;
-    float Eb[3] = {0.0f, 0.0f, 0.0f}, Hb[3] = {0.0f, 0.0f, 0.0f};
-    const uint32_t e0 = st.b0, e1 = st.b_low, e2 = st.b_mid, e3 = st.b_hi;
-    for (uint32_t k = 0; k < 1025; ++k) {
-        const float x = row[k];
-        rowmax = fmaxf(rowmax, x);
-        const float xx = __fmul_rn(x, x);
-        const float kx = __fmul_rn(__fmul_rn((float)k, x), x);
-        E = __fadd_rn(E, xx);
-        H = __fadd_rn(H, kx);
-        if (k >= e0 && k < e1) { Eb[0] = __fadd_rn(Eb[0], xx); Hb[0] = __fadd_rn(Hb[0], kx); }
-        else if (k >= e1 && k < e2) { Eb[1] = __fadd_rn(Eb[1], xx); Hb[1] = __fadd_rn(Hb[1], kx); }
-        else if (k >= e2 && k < e3) { Eb[2] = __fadd_rn(Eb[2], xx); Hb[2] = __fadd_rn(Hb[2], kx); }
-        const float v = logf(__fadd_rn(1.0f, fmaxf(x, 0.0f)));  // novelty.rs:180
-        if (v > 0.0f) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int m = st.mel_m[k * 2 + c];
-                if (m >= 0) mel[m][threadIdx.x] = __fadd_rn(mel[m][threadIdx.x], __fmul_rn(v, st.mel_w[k * 2 + c]));
-            }
-        }
-    }
+    const float* spec = fa + HL.spec;
     float* fr = fa + HL.frame;
     const uint64_t fm = HL.fmax;
-    fr[FQ_ROWMAX * fm + f] = rowmax;
-    fr[FQ_E * fm + f] = E;
-    fr[FQ_H * fm + f] = H;
-    for (int b = 0; b < 3; ++b) {
-        fr[(FQ_EB + b) * fm + f] = Eb[b];
-        fr[(FQ_HB + b) * fm + f] = Hb[b];
+    const uint32_t f = f0 + lane;
+    const bool valid = f < F, has_prev = valid && f >= 1;
+    const float maxc = valid ? fr[FQ_ROWMAX * fm + f] : 0.0f;
+    const float maxp = has_prev ? fr[FQ_ROWMAX * fm + f - 1] : 0.0f;
+    const bool nc = maxc > 1e-10f, np = maxp > 1e-10f;
+    float sflux = 0.0f, E = 0.0f, H = 0.0f;
+    auto step = [&](uint32_t k, float cur, float prev) {
+        const float xc = nc ? __fdiv_rn(cur, maxc) : 0.0f;   // spectral_flux.rs:120-157
+        const float xp = np ? __fdiv_rn(prev, maxp) : 0.0f;
+        const float d0 = fmaxf(__fsub_rn(xc, xp), 0.0f);
+        sflux = __fadd_rn(sflux, __fmul_rn(d0, d0));
+        E = __fadd_rn(E, __fmul_rn(cur, cur));
+        H = __fadd_rn(H, __fmul_rn(__fmul_rn((float)k, cur), cur));  // hfc.rs:137
+    };
+    for (uint32_t jb = 0; jb < 32; ++jb) {
+#pragma unroll 3
+        for (int r = 0; r < 33; ++r) {
+            const int64_t fr_ = (int64_t)f0 - 1 + r;
+            tile[r][lane] = (fr_ >= 0 && fr_ < (int64_t)F) ? spec[(uint64_t)fr_ * 1025 + jb * 32 + lane] : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) step(jb * 32 + j, tile[lane + 1][j], tile[lane][j]);
+        __syncwarp();
     }
-    for (uint32_t m = 0; m < st.n_mels; ++m) fr[(FQ_MEL + m) * fm + f] = mel[m][threadIdx.x];
+    if (valid) {
+        const float cur = spec[(uint64_t)f * 1025 + 1024];
+        const float prev = has_prev ? spec[(uint64_t)(f - 1) * 1025 + 1024] : 0.0f;
+        step(1024, cur, prev);
+        fr[FQ_E * fm + f] = E;
+        fr[FQ_H * fm + f] = H;
+        if (has_prev) fa[HL.pair + PQ_SFLUX * fm + f - 1] = __fadd_rn(sqrtf(sflux), 0.0f);
+    }
 }
 
-// ---- per-pair reductions (frame i -> i+1) -------------------------------------------------------
-__global__ void __launch_bounds__(128) pair_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, const SrTables* srtab,
-                                                        const int32_t* sr_index, int h, float* fa, DevCfg cfg) {
+struct ParSmem {
+    float L[2][1025 + 2 * HALO + 7];
+    float mel[2][MEL_MAX];
+};
+
+__global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, const SrTables* srtab,
+                                                       const int32_t* sr_index, int h, float* fa, DevCfg cfg) {
+    __shared__ ParSmem sm[4];
     const int t = list ? list[blockIdx.y] : blockIdx.y;
     const TrackDev& T = tr[t];
     const uint32_t F = T.F[h];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (F < 2 || i >= F - 1 || T.status != 0) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f0 = (blockIdx.x * 4 + w) * FEAT_RUN;
+    if (f0 >= F || T.status != 0) return;
+    ParSmem& S = sm[w];
     const SrTables& st = srtab[sr_index[t]];
     const HopLayout& HL = T.hop[h];
-    const float* prev = fa + HL.spec + (uint64_t)i * 1025;
-    const float* cur = prev + 1025;
-    const float* fr = fa + HL.frame;
-    const uint64_t fm = HL.fmax;
-    const float maxp = fr[FQ_ROWMAX * fm + i], maxc = fr[FQ_ROWMAX * fm + i + 1];
-    const bool np = maxp > 1e-10f, nc = maxc > 1e-10f;
-    const int K = (int)min(max(cfg.sf_k, 1u), 8u);  // superflux radius (novelty.rs:349); the ABI rejects K > 8
-    const uint32_t e0 = st.b0, e1 = st.b_low, e2 = st.b_mid, e3 = st.b_hi;
-    float sflux = 0.0f, sf = 0.0f, sfb[3] = {0.0f, 0.0f, 0.0f};
-    // sliding window of log-compressed prev bins k-8..k+8 (radius K <= 8 selected by masking)
-    float win[17];
-#pragma unroll
-    for (int j = 0; j < 17; ++j) win[j] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) win[9 + j] = logf(__fadd_rn(1.0f, fmaxf(prev[j], 0.0f)));  // shifted left once before first use
-    for (uint32_t k = 0; k < 1025; ++k) {
-        const float xc_raw = cur[k], xp_raw = prev[k];
-        // spectral_flux.rs:120-157
-        const float xc = nc ? __fdiv_rn(xc_raw, maxc) : 0.0f;
-        const float xp = np ? __fdiv_rn(xp_raw, maxp) : 0.0f;
-        const float d0 = fmaxf(__fsub_rn(xc, xp), 0.0f);
-        sflux = __fadd_rn(sflux, __fmul_rn(d0, d0));
-#pragma unroll
-        for (int j = 0; j < 16; ++j) win[j] = win[j + 1];
-        win[16] = (k + 8 < 1025) ? logf(__fadd_rn(1.0f, fmaxf(prev[k + 8], 0.0f))) : 0.0f;
-        const float Lc = logf(__fadd_rn(1.0f, fmaxf(xc_raw, 0.0f)));
-        // full band: window clipped to [0, 1025) — out-of-range slots hold 0 and logs are >= 0
-        float pm = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 17; ++j)
-            if (j >= 8 - K && j <= 8 + K) pm = fmaxf(pm, win[j]);
-        float d = fmaxf(__fsub_rn(Lc, pm), 0.0f);
-        sf = __fadd_rn(sf, __fmul_rn(d, d));
-        // band variants: window additionally clipped to the band (novelty.rs:432-441)
-        int b = -1;
-        uint32_t lo = 0, hi = 0;
-        if (k >= e0 && k < e1) { b = 0; lo = e0; hi = e1; }
-        else if (k >= e1 && k < e2) { b = 1; lo = e1; hi = e2; }
-        else if (k >= e2 && k < e3) { b = 2; lo = e2; hi = e3; }
-        if (b >= 0) {
-            float pmb = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 17; ++j) {
-                const int kb = (int)k - 8 + j;
-                if (j >= 8 - K && j <= 8 + K && kb >= (int)lo && kb < (int)hi) pmb = fmaxf(pmb, win[j]);
-            }
-            float db = fmaxf(__fsub_rn(Lc, pmb), 0.0f);
-            if (b == 0) sfb[0] = __fadd_rn(sfb[0], __fmul_rn(db, db));
-            else if (b == 1) sfb[1] = __fadd_rn(sfb[1], __fmul_rn(db, db));
-            else sfb[2] = __fadd_rn(sfb[2], __fmul_rn(db, db));
-        }
-    }
+    const float* spec = fa + HL.spec;
+    float* fr = fa + HL.frame;
     float* pr = fa + HL.pair;
-    pr[PQ_SFLUX * fm + i] = __fadd_rn(sqrtf(sflux), 0.0f);
-    pr[PQ_SF * fm + i] = sqrtf(sf);
-    for (int b = 0; b < 3; ++b) pr[(PQ_SFB + b) * fm + i] = sqrtf(sfb[b]);
-    // mel superflux (novelty.rs:576-597)
-    const int nm = (int)st.n_mels, MK = (int)max(cfg.mel_k, 1u);
-    float ms = 0.0f;
-    for (int m = 0; m < nm; ++m) {
-        float pmx = 0.0f;
-        for (int j = max(m - MK, 0); j < min(m + MK + 1, nm); ++j) pmx = fmaxf(pmx, fr[(FQ_MEL + j) * fm + i]);
-        float d = fmaxf(__fsub_rn(fr[(FQ_MEL + m) * fm + i + 1], pmx), 0.0f);
-        ms = __fadd_rn(ms, __fmul_rn(d, d));
+    const uint64_t fm = HL.fmax;
+    const int K = (int)min(max(cfg.sf_k, 1u), (uint32_t)HALO);
+    const int MK = (int)max(cfg.mel_k, 1u);
+    const int nm = (int)st.n_mels;
+    const int e0 = (int)st.b0, e1 = (int)st.b_low, e2 = (int)st.b_mid, e3 = (int)st.b_hi;
+    for (int i = lane; i < 1025 + 2 * HALO + 7; i += 32) S.L[0][i] = S.L[1][i] = 0.0f;  // halos stay zero: ln(1+x) >= 0 and the reference's running max starts at 0
+    __syncwarp();
+    int cur = 0;
+    const uint32_t f_first = f0 > 0 ? f0 - 1 : 0;
+    const uint32_t f_last = min(f0 + FEAT_RUN, F);
+    for (uint32_t f = f_first; f < f_last; ++f, cur ^= 1) {
+        float* Lc = S.L[cur] + HALO;
+        const float* Lp = S.L[cur ^ 1] + HALO;
+        const float* row = spec + (uint64_t)f * 1025;
+        const bool emit = f >= f0;           // this warp owns the outputs of frame f
+        const bool pair = emit && f >= 1;    // pair (f-1, f) -> index f-1
+        float Eb[3] = {0.0f, 0.0f, 0.0f}, Hb[3] = {0.0f, 0.0f, 0.0f};
+        for (int b = lane; b < 1025; b += 32) {
+            const float x = row[b];
+            Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
+            if (emit && b >= e0 && b < e3) {
+                const float xx = x * x, kx = (float)b * x * x;
+                const int band = b < e1 ? 0 : (b < e2 ? 1 : 2);
+                Eb[band] += xx;
+                Hb[band] += kx;
+            }
+        }
+        __syncwarp();
+        float sf = 0.0f, sfb[3] = {0.0f, 0.0f, 0.0f};
+        if (pair) {
+            for (int b = lane; b < 1025; b += 32) {
+                float pm = 0.0f;
+                for (int j = -K; j <= K; ++j) pm = fmaxf(pm, Lp[b + j]);
+                const float lc = Lc[b];
+                const float d = fmaxf(lc - pm, 0.0f);
+                sf += d * d;
+                if (b >= e0 && b < e3) {
+                    const int band = b < e1 ? 0 : (b < e2 ? 1 : 2);
+                    const int lo = band == 0 ? e0 : (band == 1 ? e1 : e2), hi = band == 0 ? e1 : (band == 1 ? e2 : e3);
+                    float pmb = pm;
+                    if (b - K < lo || b + K >= hi) {  // window clipped to the band (novelty.rs:432-441)
+                        pmb = 0.0f;
+                        for (int j = max(b - K, lo); j < min(b + K + 1, hi); ++j) pmb = fmaxf(pmb, Lp[j]);
+                    }
+                    const float db = fmaxf(lc - pmb, 0.0f);
+                    sfb[band] += db * db;
+                }
+            }
+        }
+        // mel bands: lane m folds its triangle in ascending-bin order (novelty.rs:172-189)
+        float* Mc = S.mel[cur];
+        const float* Mp = S.mel[cur ^ 1];
+        for (int m = lane; m < nm; m += 32) {
+            float acc = 0.0f;
+            const int a = st.mel_off[m], e = st.mel_off[m + 1];
+            for (int q = a; q < e; ++q) acc = __fadd_rn(acc, __fmul_rn(Lc[st.mel_bin[q]], st.mel_w[q]));
+            Mc[m] = acc;
+        }
+        __syncwarp();
+        float ms = 0.0f;
+        if (pair) {
+            for (int m = lane; m < nm; m += 32) {
+                float pmx = 0.0f;
+                for (int j = max(m - MK, 0); j < min(m + MK + 1, nm); ++j) pmx = fmaxf(pmx, Mp[j]);
+                const float d = fmaxf(Mc[m] - pmx, 0.0f);
+                ms += d * d;
+            }
+        }
+        if (emit) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sf += __shfl_xor_sync(0xffffffffu, sf, o);
+                ms += __shfl_xor_sync(0xffffffffu, ms, o);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    sfb[q] += __shfl_xor_sync(0xffffffffu, sfb[q], o);
+                    Eb[q] += __shfl_xor_sync(0xffffffffu, Eb[q], o);
+                    Hb[q] += __shfl_xor_sync(0xffffffffu, Hb[q], o);
+                }
+            }
+            if (lane == 0) {
+                for (int q = 0; q < 3; ++q) {
+                    fr[(FQ_EB + q) * fm + f] = Eb[q];
+                    fr[(FQ_HB + q) * fm + f] = Hb[q];
+                }
+                if (pair) {
+                    pr[PQ_SF * fm + f - 1] = sqrtf(sf);
+                    for (int q = 0; q < 3; ++q) pr[(PQ_SFB + q) * fm + f - 1] = sqrtf(sfb[q]);
+                    pr[PQ_MEL * fm + f - 1] = sqrtf(ms);
+                }
+            }
+        }
+        __syncwarp();
     }
-    pr[PQ_MEL * fm + i] = sqrtf(ms);
 }
 
 // ---- spectral-flux / HFC onsets: exact percentile threshold + peaks -----------------------------
@@ -320,9 +372,9 @@ void launch_energy_onsets(const WaveCtx& c) {
 void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (c.max_F[h] == 0 || n_list == 0) return;
     dim3 grid((c.max_F[h] + 127) / 128, n_list);
-    frame_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa);
+    seq_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
     count_launch("spec_features");
-    pair_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
+    par_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
     count_launch("spec_features");
 }
 

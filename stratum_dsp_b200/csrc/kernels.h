@@ -43,8 +43,9 @@ struct SrTables {
     uint32_t b0, b_low, b_mid, b_hi;  // band edges in bins of the 2048-point STFT
     uint32_t variant_mask;            // bit v set when variant v (full, low, mid, high, mel) is active
     uint32_t n_mels;
-    const int32_t* mel_m;             // [1025][2] mel index per contribution (-1 = none)
-    const float* mel_w;               // [1025][2]
+    const int32_t* mel_off;           // [n_mels + 1] entry ranges per mel band
+    const int32_t* mel_bin;           // flat entries in ascending-bin order per band (centre bin twice: rising and falling slope)
+    const float* mel_w;
     uint32_t key_bin_lo, key_bin_hi;  // HPCP peak search range in the key STFT (extractor.rs:584-591)
 };
 
