@@ -117,7 +117,8 @@ struct DeviceCtx {
     int32_t* d_sr_index = nullptr;
     int32_t* d_list = nullptr;
     size_t tr_cap = 0;
-    float* d_stage = nullptr;  // staging for host-sample batches
+    float* d_stage = nullptr;  // two staging buffers for host-sample batches (double-buffered upload)
+    cudaStream_t copy_stream = nullptr;
     size_t stage_cap = 0;
     std::mutex mu;
 };
@@ -998,7 +999,6 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             debug_put("key.seg_scores", c.fa + T.seg_scores, (size_t)T.seg_cap * 24, s);
             debug_put("key.mask_head", c.fa + T.keyspec, (size_t)std::min<uint32_t>(T.Fk, 64) * 4097, s);
             debug_put_i("hmm.path", c.ia + T.hmm_path, T.hmm_T, s);
-            debug_put("hmm.em", c.fa + T.hmm_em, T.hmm_T, s);
         }
     }
     return STRATUM_OK;
@@ -1136,47 +1136,82 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
             return;
         }
         cudaSetDevice(ctx->device);
-        // stream the shard through a device staging buffer in sub-batches that leave room for the arenas
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        const uint64_t stage_budget = std::max<uint64_t>((uint64_t)((double)(free_b + ctx->stage_cap * 4 + ctx->fa_cap * 4) * 0.15) / 4, 1u << 20);
-        uint32_t i = a;
-        while (i < b) {
+        // Stream the shard through two device staging buffers: chunk k+1 is uploaded on the copy stream
+        // while chunk k is analysed (pinned host memory makes the upload asynchronous; pageable memory
+        // still works, without the overlap).  Chunk size: STRATUM_B200_STAGE_TRACKS_MB per buffer
+        // (default 1024 MB ~ 32 three-minute tracks), always at least one track.
+        uint64_t chunk_floats = (uint64_t)1024 * 1024 * 1024 / 4;
+        if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_floats = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
+        struct Chunk {
+            uint32_t i, j;
+            uint64_t floats;
+        };
+        std::vector<Chunk> chunks;
+        uint64_t max_fl = 0;
+        for (uint32_t i = a; i < b;) {
             uint32_t j = i;
             uint64_t fl = 0;
-            while (j < b && (j == i || fl + (offsets[j + 1] - offsets[j]) <= stage_budget)) {
+            while (j < b && (j == i || fl + (offsets[j + 1] - offsets[j]) <= chunk_floats)) {
                 fl += offsets[j + 1] - offsets[j];
                 ++j;
             }
-            {
-                std::lock_guard<std::mutex> lk(ctx->mu);
-                if (fl + 16 > ctx->stage_cap) {
-                    if (ctx->d_stage) cudaFree(ctx->d_stage);
-                    ctx->d_stage = nullptr;
-                    ctx->stage_cap = 0;
-                    if (cudaMalloc(&ctx->d_stage, (fl + 16) * sizeof(float)) != cudaSuccess) {
-                        status[d] = STRATUM_PROCESSING_ERROR;
-                        errs[d] = "staging buffer allocation failed";
-                        return;
-                    }
-                    ctx->stage_cap = fl + 16;
-                }
-                g_h2d_bytes.fetch_add(fl * sizeof(float));
-                if (fl && cudaMemcpyAsync(ctx->d_stage, samples + offsets[i], fl * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            chunks.push_back(Chunk{i, j, fl});
+            max_fl = std::max(max_fl, fl);
+            i = j;
+        }
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                status[d] = STRATUM_PROCESSING_ERROR;
+                errs[d] = "copy stream creation failed";
+                return;
+            }
+            const size_t need = 2 * (max_fl + 16);
+            if (need > ctx->stage_cap) {
+                if (ctx->d_stage) cudaFree(ctx->d_stage);
+                ctx->d_stage = nullptr;
+                ctx->stage_cap = 0;
+                if (cudaMalloc(&ctx->d_stage, need * sizeof(float)) != cudaSuccess) {
                     status[d] = STRATUM_PROCESSING_ERROR;
-                    errs[d] = "host to device copy failed";
+                    errs[d] = "staging buffer allocation failed";
                     return;
                 }
+                ctx->stage_cap = need;
             }
-            std::vector<uint64_t> rel(j - i + 1);
-            for (uint32_t k = i; k <= j; ++k) rel[k - i] = offsets[k] - offsets[i];
-            const int s2 = analyze_device(ctx->device, ctx->d_stage, rel.data(), sample_rates + i, j - i, c, out + i);
+        }
+        float* bufs[2] = {ctx->d_stage, ctx->d_stage + (max_fl + 16)};
+        std::vector<cudaEvent_t> ev(chunks.size(), nullptr);
+        auto upload = [&](size_t k) -> bool {
+            const Chunk& ch = chunks[k];
+            cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+            g_h2d_bytes.fetch_add(ch.floats * sizeof(float));
+            if (ch.floats && cudaMemcpyAsync(bufs[k & 1], samples + offsets[ch.i], ch.floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
+                return false;
+            return cudaEventRecord(ev[k], ctx->copy_stream) == cudaSuccess;
+        };
+        bool ok = upload(0);
+        for (size_t k = 0; ok && k < chunks.size(); ++k) {
+            // chunk k-1 has been analysed (the call below is synchronous), so its buffer is free for chunk k+1
+            if (k + 1 < chunks.size()) ok = upload(k + 1);
+            if (!ok) break;
+            cudaStreamWaitEvent(ctx->stream, ev[k], 0);
+            const Chunk& ch = chunks[k];
+            std::vector<uint64_t> rel(ch.j - ch.i + 1);
+            for (uint32_t q = ch.i; q <= ch.j; ++q) rel[q - ch.i] = offsets[q] - offsets[ch.i];
+            const int s2 = analyze_device(ctx->device, bufs[k & 1], rel.data(), sample_rates + ch.i, ch.j - ch.i, c, out + ch.i);
             if (s2 != STRATUM_OK) {
                 status[d] = s2;
                 errs[d] = g_last_error;
-                return;
+                ok = false;
+                break;
             }
-            i = j;
+        }
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+        if (!ok && status[d] == STRATUM_OK) {
+            status[d] = STRATUM_PROCESSING_ERROR;
+            errs[d] = "host to device copy failed";
         }
     };
     if (nd == 1) {
@@ -1341,6 +1376,7 @@ void stratum_b200_shutdown(void) {
             cudaFree(c->d_list);
             cudaFree(c->d_srtab);
             cudaFree(c->d_stage);
+            if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
             cudaStreamDestroy(c->stream);
         }
         delete c;

@@ -10,6 +10,8 @@
 // path never changes the beat list; it is still computed and exposed for parity checks.
 // Tempo-variation segmentation, the Bayesian per-segment refinement, time signature, downbeats and
 // grid stability are short scalar recurrences executed by lane 0 in the reference's order.
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace sb {
@@ -211,8 +213,14 @@ __device__ inline int detect_time_signature(const float* beats, uint32_t n, floa
     return best;
 }
 
-__global__ void __launch_bounds__(128) beat_kernel(TrackDev* tr, float* fa, float* oa, int32_t* ia, int n_tracks) {
-    const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+// One warp (= one CTA) per track.  The working lists (emissions, first-pass beats, refined beats, interval
+// scratch) live in dynamic shared memory when they fit (always for tracks up to ~10 minutes), otherwise
+// in the track's arena areas; the scalar post-processing on lane 0 is dominated by access latency.
+constexpr uint32_t BEAT_SMEM_FLOATS = 24 * 1024;  // 96 KB
+
+__global__ void __launch_bounds__(32) beat_kernel(TrackDev* tr, float* fa, float* oa, int32_t* ia, int n_tracks, uint32_t smem_floats) {
+    extern __shared__ float bsm[];
+    const int t = blockIdx.x;
     const int lane = threadIdx.x & 31;
     if (t >= n_tracks) return;
     TrackDev& T = tr[t];
@@ -236,8 +244,9 @@ __global__ void __launch_bounds__(128) beat_kernel(TrackDev* tr, float* fa, floa
     float* on = fa + T.onsets_s;
     for (uint32_t i = lane; i < n_on; i += 32) on[i] = (float)on_i[i] / (float)T.sr;
     __syncwarp();
-    float* em = fa + T.hmm_em;
-    float* pos = fa + T.beats_tmp;   // beat_positions of the first pass
+    const bool in_smem = (uint64_t)3 * T.beat_cap + T.hmm_cap <= smem_floats;
+    float* em = in_smem ? bsm + 3 * T.beat_cap : fa + T.hmm_em;
+    float* pos = in_smem ? bsm : fa + T.beats_tmp;  // beat_positions of the first pass
     float* ref = pos + T.beat_cap;   // refined list; a third beat_cap-sized block holds the interval scratch
     float* beats = oa + T.beats;
     float* down = oa + T.downbeats;
@@ -391,7 +400,15 @@ __global__ void __launch_bounds__(128) beat_kernel(TrackDev* tr, float* fa, floa
 }
 
 void launch_beat_tracking(const WaveCtx& c) {
-    beat_kernel<<<(c.n_tracks + 3) / 4, 128, 0, c.stream>>>(c.tracks, c.fa, c.oa, c.ia, c.n_tracks);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(beat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BEAT_SMEM_FLOATS * sizeof(float));
+        attr = true;
+    }
+    // shared memory sized for the largest track of the wave (capped): short tracks leave room for more CTAs per SM
+    const uint64_t want = (uint64_t)3 * c.max_beat_cap + (c.max_beat_cap - 64) / 3 + 16;
+    const size_t smem = (size_t)std::min<uint64_t>(want, BEAT_SMEM_FLOATS) * sizeof(float);
+    beat_kernel<<<c.n_tracks, 32, smem, c.stream>>>(c.tracks, c.fa, c.oa, c.ia, c.n_tracks, (uint32_t)(smem / sizeof(float)));
     count_launch("beats");
 }
 

@@ -25,23 +25,28 @@ constexpr int HPCP_MAX_HARM = 8;     // key_hpcp_num_harmonics upper bound accep
 // The reference builds `prefix[t+1] = prefix[t] + x[t]` per bin and takes window sums as prefix
 // differences (extractor.rs:1274-1287); the cancellation noise of that formulation is part of its
 // output, so the scan is reproduced term by term.  Adjacent threads own adjacent bins, so every
-// load and store of a frame row is coalesced.
+// load and store of a frame row is coalesced.  Frames are consumed in groups of 16 whose loads are
+// issued together (16 independent requests in flight per thread); stores only touch rows already
+// consumed, so the mask is written in place.  MG > 0: margin known at compile time, the delayed sample
+// x[t - MG] is then a register; MG = 0: run-time margin with a shared-memory ring for the samples.
+constexpr int MASK_G = 16;
+
+template <int MG>
 __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
     __shared__ float ringP[RING][128];
-    __shared__ float ringX[RING][128];
+    __shared__ float ringX[MG > 0 ? 1 : RING][128];
     const TrackDev& T = tr[blockIdx.y];
     const uint32_t nf = T.Fk;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (T.status != 0 || nf == 0 || b >= KBINS) return;
-    const uint32_t mg = cfg.key_margin;
+    const uint32_t mg = MG > 0 ? (uint32_t)MG : cfg.key_margin;
     float* K = fa + T.keyspec + b;
     const int tx = threadIdx.x;
     const float p = fmaxf(cfg.key_mask_power, 1.0f);
     const bool square = (p == 2.0f);
     float P = 0.0f;
     ringP[0][tx] = 0.0f;
-    auto emit = [&](uint32_t t, uint32_t en, float Pen) {
-        const float xt = ringX[t & (RING - 1)][tx];
+    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt) {
         float h_est;
         if (mg == 0) {
             h_est = xt;
@@ -59,24 +64,39 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
         const float m = hp / (hp + rp + 1e-12f);
         K[(uint64_t)t * KBINS] = x * m;
     };
-    // frames are consumed in groups of 8 whose loads are issued together (8 independent requests in
-    // flight per thread); stores only touch rows already consumed, so the reordering is safe
-    auto step = [&](uint32_t i, float x) {
-        ringX[i & (RING - 1)][tx] = x;
-        P = P + x;
-        if (i >= mg) emit(i - mg, i + 1, P);  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
-        ringP[(i + 1) & (RING - 1)][tx] = P;
-    };
+    float xp[MASK_G];  // previous group (compile-time margin only)
+#pragma unroll
+    for (int q = 0; q < MASK_G; ++q) xp[q] = 0.0f;
     uint32_t i = 0;
-    for (; i + 8 <= nf; i += 8) {
-        float xs[8];
+    for (; i + MASK_G <= nf; i += MASK_G) {
+        float xs[MASK_G];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) xs[q] = K[(uint64_t)(i + q) * KBINS];
+        for (int q = 0; q < MASK_G; ++q) xs[q] = K[(uint64_t)(i + q) * KBINS];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) step(i + q, xs[q]);
+        for (int q = 0; q < MASK_G; ++q) {
+            const uint32_t ii = i + q;
+            if (MG == 0) ringX[ii & (RING - 1)][tx] = xs[q];
+            P = P + xs[q];
+            if (ii >= mg) {  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
+                float xt;
+                if (MG > 0) xt = (q >= MG) ? xs[q >= MG ? q - MG : 0] : xp[q + MASK_G - MG < MASK_G ? q + MASK_G - MG : 0];
+                else xt = ringX[(ii - mg) & (RING - 1)][tx];
+                emit(ii - mg, ii + 1, P, xt);
+            }
+            ringP[(ii + 1) & (RING - 1)][tx] = P;
+        }
+#pragma unroll
+        for (int q = 0; q < MASK_G; ++q) xp[q] = xs[q];
     }
-    for (; i < nf; ++i) step(i, K[(uint64_t)i * KBINS]);
-    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P);
+    // tail (< 16 frames) and flush: the delayed samples are re-read from rows that are still unmasked
+    // (row t is only rewritten by emit(t)), which costs at most 16 + margin scalar loads per thread
+    for (; i < nf; ++i) {
+        const float x = K[(uint64_t)i * KBINS];
+        P = P + x;
+        if (i >= mg) emit(i - mg, i + 1, P, K[(uint64_t)(i - mg) * KBINS]);
+        ringP[(i + 1) & (RING - 1)][tx] = P;
+    }
+    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P, K[(uint64_t)t * KBINS]);
 }
 
 // ---- HPCP: one warp per frame ---------------------------------------------------------------------
@@ -141,24 +161,45 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
     if (np > 0) {
         // top-K by (magnitude desc, bin asc); the reference's select_nth_unstable_by leaves the K
         // survivors in unspecified order — the documented rule is "accumulate in ascending bin order".
+        // The K-th largest magnitude is found by a bitwise search on the (positive) float bit patterns:
+        // 31 rounds of "how many peaks are >= candidate", each a register compare + one warp reduction.
         const uint32_t K = min(max(cfg.hpcp_peaks, 1u), np);
-        uint32_t nsel = 0;
+        uint32_t thr = 0, need = 0;  // keep magnitudes > thr, plus the first `need` ties in bin order
+        if (np > K) {
+            uint32_t e[HPCP_MAX_PEAKS / 32];
+#pragma unroll
+            for (int q = 0; q < HPCP_MAX_PEAKS / 32; ++q) {
+                const uint32_t i = q * 32 + lane;
+                e[q] = i < np ? __float_as_uint(S.mag[i]) : 0u;  // peaks are strictly positive, 0 never counts
+            }
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t cand = thr | (1u << bit);
+                uint32_t c = 0;
+#pragma unroll
+                for (int q = 0; q < HPCP_MAX_PEAKS / 32; ++q) c += e[q] >= cand;
+                if (__reduce_add_sync(0xffffffffu, c) >= K) thr = cand;
+            }
+            uint32_t gt = 0;
+#pragma unroll
+            for (int q = 0; q < HPCP_MAX_PEAKS / 32; ++q) gt += e[q] > thr;
+            need = K - __reduce_add_sync(0xffffffffu, gt);
+        }
+        uint32_t nsel = 0, ties_seen = 0;
         for (uint32_t base = 0; base < np; base += 32) {
             const uint32_t i = base + lane;
-            bool keep = false;
+            bool keep = false, tie = false;
             if (i < np) {
                 if (np <= K) {
                     keep = true;
                 } else {
-                    const float mi = S.mag[i];
-                    uint32_t rank = 0;
-                    for (uint32_t j = 0; j < np; ++j) {
-                        const float mj = S.mag[j];
-                        rank += (mj > mi) || (mj == mi && j < i);
-                    }
-                    keep = rank < K;
+                    const uint32_t bits = __float_as_uint(S.mag[i]);
+                    keep = bits > thr;
+                    tie = bits == thr;
                 }
             }
+            const uint32_t tmask = __ballot_sync(0xffffffffu, tie);
+            if (tie && ties_seen + __popc(tmask & ((1u << lane) - 1u)) < need) keep = true;
+            ties_seen += __popc(tmask);
             const uint32_t mask = __ballot_sync(0xffffffffu, keep);
             if (keep) S.sel[nsel + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)i;
             nsel += __popc(mask);
@@ -329,10 +370,14 @@ __device__ __forceinline__ bool seg_geometry(const TrackDev& T, const DevCfg& cf
     return true;
 }
 
-// ---- template scores: thread k of a warp folds segment s for key k in frame order -------------------
+// ---- template scores: one warp per (segment, key) ------------------------------------------------------
+// score = sum over frames (in frame order) of w_t * <c_t, T_k> (detector.rs:984-1001).  The 32 lanes
+// evaluate the 12-term dot products of 32 consecutive frames in parallel (each in the reference's term
+// order); the running sum then absorbs the 32 products strictly in frame order through shuffles, so the
+// result equals the serial fold bit for bit while the chain per frame is one add instead of ~25 ops.
 // blockIdx.x = segment index; the extra index `nseg` is the whole-track score used when no segment
-// passes the clarity gate (lib.rs:1385-1411) or voting is off.
-__global__ void __launch_bounds__(32) segment_score_kernel(const TrackDev* __restrict__ tr, float* fa, Tables tab, DevCfg cfg) {
+// passes the clarity gate (lib.rs:1385-1411) or voting is off.  blockDim = 24 warps, warp = key.
+__global__ void __launch_bounds__(768) segment_score_kernel(const TrackDev* __restrict__ tr, float* fa, Tables tab, DevCfg cfg) {
     const TrackDev& T = tr[blockIdx.y];
     if (T.status != 0 || T.Fk == 0) return;
     uint32_t seg_len, hop, nseg;
@@ -341,30 +386,40 @@ __global__ void __launch_bounds__(32) segment_score_kernel(const TrackDev* __res
     if (s > nseg || s >= T.seg_cap) return;
     const uint32_t start = s < nseg ? s * hop : 0;
     const uint32_t len = s < nseg ? seg_len : T.Fk;
-    const int k = threadIdx.x;
-    if (k >= 24) return;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* tpl = (k < 12 ? tab.key_major + k * 12 : tab.key_minor + (k - 12) * 12);
     float tp[12];
+#pragma unroll
     for (int i = 0; i < 12; ++i) tp[i] = tpl[i];
     const float* ch = fa + T.chroma2 + (uint64_t)start * 12;
     const float* wv = T.have_w ? fa + T.kweights + start : nullptr;
     float acc = 0.0f;
-    for (uint32_t t = 0; t < len; ++t) {
-        const float* c = ch + (uint64_t)t * 12;
-        if (wv) {
-            const float wt = wv[t];
-            if (wt > 0.0f) {
-                float dot = 0.0f;
-                for (int i = 0; i < 12; ++i) dot = dot + c[i] * tp[i];
-                acc = acc + wt * dot;
-            }
-        } else {
+    for (uint32_t t0 = 0; t0 < len; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        float prod = 0.0f;
+        bool use = false;
+        if (t < len) {
+            const float* c = ch + (uint64_t)t * 12;
             float dot = 0.0f;
+#pragma unroll
             for (int i = 0; i < 12; ++i) dot = dot + c[i] * tp[i];
-            acc = acc + dot;
+            if (wv) {
+                const float wt = wv[t];
+                use = wt > 0.0f;
+                prod = wt * dot;
+            } else {
+                use = true;
+                prod = dot;
+            }
+        }
+        const uint32_t um = __ballot_sync(0xffffffffu, use);
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            const float p = __shfl_sync(0xffffffffu, prod, l);
+            if ((um >> l) & 1u) acc = acc + p;
         }
     }
-    fa[T.seg_scores + (uint64_t)s * 24 + k] = acc;
+    if (lane == 0) fa[T.seg_scores + (uint64_t)s * 24 + k] = acc;
 }
 
 // detect_key_weighted steps 1.5 - 2 on 24 raw scores: ranked keys/scores out (detector.rs:135-250) and the
@@ -492,7 +547,9 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
 void launch_key_path(const WaveCtx& c) {
     if (c.max_Fk > 0) {
         if (c.cfg.key_mask) {
-            mask_kernel<<<dim3((KBINS + 127) / 128, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            const dim3 g((KBINS + 127) / 128, c.n_tracks);
+            if (c.cfg.key_margin == 12) mask_kernel<12><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // default margin (config.rs:669)
+            else mask_kernel<0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
             count_launch("key_mask");
         }
         hpcp_kernel<<<dim3((c.max_Fk + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
@@ -501,7 +558,7 @@ void launch_key_path(const WaveCtx& c) {
         count_launch("key_vote");
         key_weights_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         count_launch("key_vote");
-        segment_score_kernel<<<dim3(c.max_seg_cap, c.n_tracks), 32, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg);
+        segment_score_kernel<<<dim3(c.max_seg_cap, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg);
         count_launch("key_vote");
     }
     key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);

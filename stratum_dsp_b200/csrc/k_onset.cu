@@ -302,62 +302,98 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
 }
 
 // ---- consensus vote + caller policy ------------------------------------------------------------
-__global__ void consensus_kernel(TrackDev* tr, int32_t* ia, int n_tracks, DevCfg cfg) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA per track: the three detector lists are staged in shared memory (when they fit) so that the
+// inherently serial merge + gap clustering runs at shared-memory latency; the final list is written from
+// shared memory by the whole CTA.
+constexpr uint32_t CONS_CAP = 11264;  // ints of dynamic shared memory (44 KB): 3 inputs + output
+
+__global__ void __launch_bounds__(128) consensus_kernel(TrackDev* tr, int32_t* ia, int n_tracks, DevCfg cfg) {
+    extern __shared__ int32_t cs[];
+    __shared__ uint32_t s_nfinal;
+    const int t = blockIdx.x;
     if (t >= n_tracks) return;
     TrackDev& T = tr[t];
     if (T.status != 0) return;
-    const int32_t* L0 = ia + T.on_energy;
-    int32_t* fin = ia + T.on_final;
+    const int32_t* G0 = ia + T.on_energy;
+    int32_t* gfin = ia + T.on_final;
     const uint32_t n0 = T.n_on_energy;
-    auto copy_energy = [&]() {
-        for (uint32_t i = 0; i < n0; ++i) fin[i] = L0[i];
-        T.n_on_final = n0;
-    };
-    if (!cfg.enable_consensus || T.F[0] == 0) { copy_energy(); return; }
-    const int32_t* L1 = ia + T.on_spectral;
-    const int32_t* L2 = ia + T.on_hfc;
-    const uint32_t n1 = T.n_on_spectral, n2 = T.n_on_hfc;
-    if (n0 + n1 + n2 == 0) { T.n_on_final = 0; return; }
-    const uint32_t tol = as_u32(__fmul_rn(__fdiv_rn((float)cfg.consensus_tol_ms, 1000.0f), (float)T.sr));  // consensus.rs:149
-    // 3-way stable merge (method order 0,1,2 on equal samples) + gap clustering; two passes: first
-    // counts clusters voted by >= 2 methods, second writes the chosen set.
-    uint32_t strong = 0, clusters = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool want_strong = strong > 0;
-        uint32_t i0 = 0, i1 = 0, i2 = 0, w = 0;
-        bool open = false;
-        int64_t last = 0;
-        uint64_t sum = 0;
-        uint32_t cnt = 0, voted = 0;
-        auto close = [&]() {
-            const int32_t centre = (int32_t)(sum / cnt);
-            const uint32_t vb = __popc(voted);
-            if (pass == 0) {
-                ++clusters;
-                if (vb >= 2) ++strong;
-            } else if (!want_strong || vb >= 2) {
-                if (w == 0 || fin[w - 1] != centre) fin[w++] = centre;  // sort + dedup (lib.rs:266-271): centres ascend
-            }
-        };
-        while (i0 < n0 || i1 < n1 || i2 < n2) {
-            int method = -1;
-            int32_t s = 0x7fffffff;
-            if (i0 < n0 && L0[i0] < s) { s = L0[i0]; method = 0; }
-            if (i1 < n1 && L1[i1] < s) { s = L1[i1]; method = 1; }
-            if (i2 < n2 && L2[i2] < s) { s = L2[i2]; method = 2; }
-            if (method == 0) ++i0; else if (method == 1) ++i1; else ++i2;
-            if (open && (int64_t)s - last > (int64_t)tol) { close(); open = false; }
-            if (!open) { open = true; sum = 0; cnt = 0; voted = 0; }
-            sum += (uint64_t)s;
-            ++cnt;
-            voted |= 1u << method;
-            last = s;
-        }
-        if (open) close();
-        if (pass == 1) T.n_on_final = w;
+    if (!cfg.enable_consensus || T.F[0] == 0) {
+        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) gfin[i] = G0[i];
+        if (threadIdx.x == 0) T.n_on_final = n0;
+        return;
     }
-    if (T.n_on_final == 0) copy_energy();  // "Onset consensus produced no candidates" (lib.rs:283-285)
+    const int32_t* G1 = ia + T.on_spectral;
+    const int32_t* G2 = ia + T.on_hfc;
+    const uint32_t n1 = T.n_on_spectral, n2 = T.n_on_hfc;
+    if (n0 + n1 + n2 == 0) {
+        if (threadIdx.x == 0) T.n_on_final = 0;
+        return;
+    }
+    const uint32_t total = n0 + n1 + n2;
+    const bool staged = 2 * total <= CONS_CAP;  // inputs + (at most `total`) outputs
+    const int32_t *L0 = G0, *L1 = G1, *L2 = G2;
+    int32_t* fin = gfin;
+    if (staged) {
+        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) cs[i] = G0[i];
+        for (uint32_t i = threadIdx.x; i < n1; i += blockDim.x) cs[n0 + i] = G1[i];
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) cs[n0 + n1 + i] = G2[i];
+        L0 = cs;
+        L1 = cs + n0;
+        L2 = cs + n0 + n1;
+        fin = cs + total;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t tol = as_u32(__fmul_rn(__fdiv_rn((float)cfg.consensus_tol_ms, 1000.0f), (float)T.sr));  // consensus.rs:149
+        // 3-way stable merge (method order 0,1,2 on equal samples) + gap clustering; two passes: first
+        // counts clusters voted by >= 2 methods, second writes the chosen set.
+        uint32_t strong = 0, clusters = 0, nfinal = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool want_strong = strong > 0;
+            uint32_t i0 = 0, i1 = 0, i2 = 0, w = 0;
+            bool open = false;
+            int64_t last = 0;
+            uint64_t sum = 0;
+            uint32_t cnt = 0, voted = 0;
+            auto close = [&]() {
+                const int32_t centre = (int32_t)(sum / cnt);
+                const uint32_t vb = __popc(voted);
+                if (pass == 0) {
+                    ++clusters;
+                    if (vb >= 2) ++strong;
+                } else if (!want_strong || vb >= 2) {
+                    if (w == 0 || fin[w - 1] != centre) fin[w++] = centre;  // sort + dedup (lib.rs:266-271): centres ascend
+                }
+            };
+            while (i0 < n0 || i1 < n1 || i2 < n2) {
+                int method = -1;
+                int32_t s = 0x7fffffff;
+                if (i0 < n0 && L0[i0] < s) { s = L0[i0]; method = 0; }
+                if (i1 < n1 && L1[i1] < s) { s = L1[i1]; method = 1; }
+                if (i2 < n2 && L2[i2] < s) { s = L2[i2]; method = 2; }
+                if (method == 0) ++i0; else if (method == 1) ++i1; else ++i2;
+                if (open && (int64_t)s - last > (int64_t)tol) { close(); open = false; }
+                if (!open) { open = true; sum = 0; cnt = 0; voted = 0; }
+                sum += (uint64_t)s;
+                ++cnt;
+                voted |= 1u << method;
+                last = s;
+            }
+            if (open) close();
+            if (pass == 1) nfinal = w;
+        }
+        (void)clusters;
+        s_nfinal = nfinal;
+        T.n_on_final = nfinal;
+    }
+    __syncthreads();
+    const uint32_t nfinal = s_nfinal;
+    if (nfinal == 0) {  // "Onset consensus produced no candidates" (lib.rs:283-285)
+        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) gfin[i] = G0[i];
+        if (threadIdx.x == 0) T.n_on_final = n0;
+    } else if (staged) {
+        for (uint32_t i = threadIdx.x; i < nfinal; i += blockDim.x) gfin[i] = fin[i];
+    }
 }
 
 void launch_energy_onsets(const WaveCtx& c) {
@@ -383,7 +419,7 @@ void launch_spectral_onsets_consensus(const WaveCtx& c) {
         spectral_onset_kernel<<<dim3(c.n_tracks, 2), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg);
         count_launch("onsets");
     }
-    consensus_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.ia, c.n_tracks, c.cfg);
+    consensus_kernel<<<c.n_tracks, 128, CONS_CAP * sizeof(int32_t), c.stream>>>(c.tracks, c.ia, c.n_tracks, c.cfg);
     count_launch("onsets");
 }
 
