@@ -116,6 +116,7 @@ struct DeviceCtx {
     TrackDev* d_tracks = nullptr;
     int32_t* d_sr_index = nullptr;
     int32_t* d_list = nullptr;
+    float* d_gain = nullptr;
     size_t tr_cap = 0;
     float* d_stage = nullptr;  // two staging buffers for host-sample batches (double-buffered upload)
     cudaStream_t copy_stream = nullptr;
@@ -373,6 +374,25 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         st.key_bin_lo = lo;
         st.key_bin_hi = hi;
     }
+    {   // KWeightingFilter::new — normalization.rs:127-155 (single RBJ high-pass biquad), f32 like the reference
+        const float pi = 3.14159265358979323846f;
+        const float w0 = 2.0f * pi * 1681.9745f / (float)sr;
+        const float cw = cosf(w0), sw = sinf(w0);
+        const float alpha = sw / 2.0f * sqrtf(1.0f / 0.707f);
+        const float B0 = (1.0f + cw) / 2.0f, B1 = -(1.0f + cw), B2 = (1.0f + cw) / 2.0f;
+        const float a0 = 1.0f + alpha, A1 = -2.0f * cw, A2 = 1.0f - alpha;
+        st.kw_b0 = B0 / a0;
+        st.kw_b1 = B1 / a0;
+        st.kw_b2 = B2 / a0;
+        st.kw_a1 = A1 / a0;
+        st.kw_a2 = A2 / a0;
+        const float blk = (float)sr * 400.0f / 1000.0f;  // normalization.rs:198
+        st.lufs_block = blk > 0.0f ? (uint32_t)blk : 0u;
+    }
+    if ((st.key_bin_hi >= st.key_bin_lo ? (st.key_bin_hi - st.key_bin_lo + 2) / 2 : 0) > 512) {
+        set_error("sample rates below ~20 kHz are not supported (more than 512 HPCP peak slots per key frame)");
+        return STRATUM_NOT_IMPLEMENTED;
+    }
     c.sr_host.push_back(st);
     *slot_out = (int)c.sr_host.size() - 1;
     if (cudaMemcpy(c.d_srtab, c.sr_host.data(), sizeof(SrTables) * c.sr_host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -472,7 +492,10 @@ static int config_validate(const StratumConfig& c) {
         set_error("StratumConfig.abi_version mismatch");
         return STRATUM_INVALID_INPUT;
     }
-    if (c.enable_normalization && c.normalization != STRATUM_NORM_PEAK) return ni("normalization = RMS / Loudness");
+    if (c.enable_normalization && (c.normalization < STRATUM_NORM_PEAK || c.normalization > STRATUM_NORM_LOUDNESS)) {
+        set_error("unknown normalization method");
+        return STRATUM_INVALID_INPUT;
+    }
     if (c.enable_hpss_onsets) return ni("enable_hpss_onsets");
     if (c.enable_bpm_fusion) return ni("enable_bpm_fusion");
     if (c.enable_tempogram_percussive_fallback) return ni("enable_tempogram_percussive_fallback");
@@ -516,6 +539,7 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.silence_min_ms = 500;
     d.energy_thr_mul = powf(10.0f, -20.0f / 20.0f);
     d.target_peak = powf(10.0f, (0.0f - 1.0f) / 20.0f);
+    d.rms_target = powf(10.0f, ((-14.0f + 3.0f) - 1.0f) / 20.0f);  // normalize(.., target_lufs = -14, headroom = 1): normalization.rs:532, 345
     d.normalization = c.normalization;
     d.enable_normalization = c.enable_normalization;
     d.enable_trim = c.enable_silence_trimming;
@@ -660,6 +684,18 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.lg_work = fa.take((uint64_t)4 * T.lg_fft);
     T.lg_tw = nullptr;
     T.lg_pad = 0;
+    T.lufs_nb = T.lufs_block = 0;
+    T.lufs_z = T.lufs_s = T.lufs_e = 0;
+    if (cfg.enable_normalization && cfg.normalization == STRATUM_NORM_LOUDNESS && n > 0) {
+        const float blk = (float)T.sr * 400.0f / 1000.0f;  // normalization.rs:198
+        T.lufs_block = blk >= 1.0f ? (uint32_t)blk : 0u;
+        if (T.lufs_block) {
+            T.lufs_nb = (uint32_t)((n + T.lufs_block - 1) / T.lufs_block);
+            T.lufs_z = fa.take(2 * (uint64_t)T.lufs_nb + 2);
+            T.lufs_s = fa.take(2 * (uint64_t)T.lufs_nb + 2);
+            T.lufs_e = fa.take((uint64_t)T.lufs_nb + 1);
+        }
+    }
 }
 
 static void plan_escalation(Bump& fa, TrackDev& T) {
@@ -687,12 +723,15 @@ static int ensure_capacity(DeviceCtx& c, size_t fa_need, size_t oa_need, size_t 
         if (c.d_tracks) cudaFree(c.d_tracks);
         if (c.d_sr_index) cudaFree(c.d_sr_index);
         if (c.d_list) cudaFree(c.d_list);
+        if (c.d_gain) cudaFree(c.d_gain);
+        c.d_gain = nullptr;
         c.d_tracks = nullptr;
         c.d_sr_index = c.d_list = nullptr;
         c.tr_cap = 0;
         CUDA_OK(cudaMalloc(&c.d_tracks, tracks * sizeof(TrackDev)));
         CUDA_OK(cudaMalloc(&c.d_sr_index, tracks * sizeof(int32_t)));
         CUDA_OK(cudaMalloc(&c.d_list, tracks * sizeof(int32_t)));
+        CUDA_OK(cudaMalloc(&c.d_gain, tracks * sizeof(float)));
         c.tr_cap = tracks;
     }
     return STRATUM_OK;
@@ -848,6 +887,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         w.max_beat_cap = std::max(w.max_beat_cap, T.beat_cap);
         w.max_seg_cap = std::max(w.max_seg_cap, T.seg_cap);
         w.max_lg_fft = std::max(w.max_lg_fft, T.lg_fft);
+        w.max_lufs_nb = std::max(w.max_lufs_nb, T.lufs_nb);
     }
     const uint64_t fa_base_end = align_up(fa.pos, 64);
     // escalation pool: whatever is left of the budget (at least one track's worth)
@@ -879,7 +919,52 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     cudaEventRecord(ev0, s);
     CUDA_OK(cudaMemcpyAsync(c.d_tracks, tracks.data(), sizeof(TrackDev) * nt, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(c.d_sr_index, sr_index.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
-    { StageTimer t(s, "preprocess"); launch_peak_gain(w); launch_silence_trim(w); }
+    {
+        StageTimer t(s, "preprocess");
+        launch_peak(w);
+        const float* d_gain = nullptr;
+        if (dcfg.enable_normalization && dcfg.normalization == STRATUM_NORM_LOUDNESS) {
+            // normalize_lufs (normalization.rs:401-484): gate, mean, log10 and the dB -> linear powf are evaluated on
+            // the host (same libm as the reference's platform) from the device's block energies and peaks
+            CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
+            std::vector<std::vector<float>> en(nt);
+            for (int i = 0; i < nt; ++i) {
+                en[i].resize(tracks[i].lufs_nb);  // layout fields are host-planned, valid before the copy lands
+                if (tracks[i].lufs_nb && tracks[i].status == 0)
+                    CUDA_OK(cudaMemcpyAsync(en[i].data(), c.fa + tracks[i].lufs_e, sizeof(float) * tracks[i].lufs_nb, cudaMemcpyDeviceToHost, s));
+            }
+            CUDA_OK(cudaStreamSynchronize(s));
+            std::vector<float> gains(nt, 1.0f);
+            const float gate = powf(10.0f, (-70.0f + 0.691f) / 10.0f);
+            const float target_peak = powf(10.0f, (0.0f - 1.0f) / 20.0f);
+            for (int i = 0; i < nt; ++i) {
+                if (tracks[i].status != 0) continue;
+                const float peak = tracks[i].peak;
+                float acc = 0.0f;
+                size_t cnt = 0;
+                for (float e : en[i])
+                    if (e > gate) {
+                        acc += e;
+                        ++cnt;
+                    }
+                float g = 1.0f;
+                if (cnt == 0) {  // all blocks gated: fall back to peak normalisation (:417-424)
+                    if (peak > 1e-10f) g = fminf(target_peak / peak, 1.0f / peak);
+                } else {
+                    const float mean = acc / (float)cnt;
+                    const float lufs = -0.691f + 10.0f * log10f(mean);
+                    g = powf(10.0f, (-14.0f - lufs) / 20.0f);
+                    if (peak * g > target_peak) g = target_peak / peak;
+                }
+                gains[i] = g;
+            }
+            CUDA_OK(cudaMemcpyAsync(c.d_gain, gains.data(), sizeof(float) * nt, cudaMemcpyHostToDevice, s));
+            CUDA_OK(cudaStreamSynchronize(s));  // `gains` is a stack-owned buffer
+            d_gain = c.d_gain;
+        }
+        launch_gain(w, d_gain);
+        launch_silence_trim(w);
+    }
     { StageTimer t(s, "onsets_energy"); launch_energy_onsets(w); }
     { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, 0, nullptr, nt); }
     { StageTimer t(s, "spec_features"); launch_spec_features(w, 0, nullptr, nt); }
@@ -1374,6 +1459,7 @@ void stratum_b200_shutdown(void) {
             cudaFree(c->d_tracks);
             cudaFree(c->d_sr_index);
             cudaFree(c->d_list);
+            cudaFree(c->d_gain);
             cudaFree(c->d_srtab);
             cudaFree(c->d_stage);
             if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

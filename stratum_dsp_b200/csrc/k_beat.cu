@@ -128,12 +128,18 @@ __device__ inline bool warp_hmm(float bpm, const float* __restrict__ on, int n, 
     return true;
 }
 
-// BayesianBeatTracker::update_with_onsets (bayesian.rs:104-255): first strict maximum over cur-5..cur+5 step 0.5
+// BayesianBeatTracker::update_with_onsets (bayesian.rs:104-255): first strict maximum over cur-5..cur+5 step 0.5.
+// Warp-collective: lane i evaluates candidate i (at most 21) over the onsets in order; the winner is then
+// picked by scanning the lanes in candidate order, exactly like the reference's loop.
 __device__ inline float bayes_update(float current_bpm, const float* on, int n) {
+    const int lane = threadIdx.x & 31;
     const float lo = fmaxf(current_bpm - 5.0f, 60.0f), hi = fminf(current_bpm + 5.0f, 180.0f);
-    float best_bpm = current_bpm, best_l = 0.0f;
     const float sigma_sq = 0.05f * 0.05f;
-    for (float b = lo; b <= hi; b = b + 0.5f) {
+    float b = lo;
+    for (int q = 0; q < lane; ++q) b = b + 0.5f;  // the reference accumulates `bpm += 0.5` in f32
+    const bool valid = b <= hi;
+    float l = 0.0f;
+    if (valid && n > 0) {
         const float interval = 60.0f / b, start = on[0];
         float ll = 0.0f;
         for (int i = 0; i < n; ++i) {
@@ -143,10 +149,16 @@ __device__ inline float bayes_update(float current_bpm, const float* on, int n) 
             const float d = fabsf(o - eb);
             ll = ll + (-(d * d) / (2.0f * sigma_sq));
         }
-        const float l = n == 0 ? 0.0f : expf(ll / (float)n);
-        if (l > best_l) {
-            best_l = l;
-            best_bpm = b;
+        l = expf(ll / (float)n);
+    }
+    float best_bpm = current_bpm, best_l = 0.0f;
+    for (int q = 0; q < 32; ++q) {
+        const float lq = __shfl_sync(0xffffffffu, l, q);
+        const float bq = __shfl_sync(0xffffffffu, b, q);
+        const bool vq = __shfl_sync(0xffffffffu, (int)valid, q) != 0;
+        if (vq && lq > best_l) {
+            best_l = lq;
+            best_bpm = bq;
         }
     }
     return best_bpm;

@@ -40,19 +40,190 @@ __global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ x, 
     }
 }
 
-// normalize_peak — normalization.rs:275-295
-__global__ void gain_kernel(TrackDev* tr, int n_tracks, DevCfg cfg) {
+// normalize_peak (normalization.rs:275-295) / normalize_rms (:325-398).  Loudness gains are computed on the host
+// from the device's block energies (log10f / powf of the host libm, see engine.cu) and passed in `lufs_gain`.
+__global__ void gain_kernel(TrackDev* tr, int n_tracks, DevCfg cfg, const float* __restrict__ lufs_gain) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
     float g = 1.0f;
-    if (cfg.enable_normalization) {
-        float peak = tr[t].peak;
-        if (peak > 1e-10f) {
-            g = cfg.target_peak / peak;
-            g = fminf(g, 1.0f / peak);
+    if (cfg.enable_normalization && tr[t].status == 0) {
+        const float peak = tr[t].peak;
+        if (cfg.normalization == STRATUM_NORM_PEAK) {
+            if (peak > 1e-10f) {
+                g = cfg.target_peak / peak;
+                g = fminf(g, 1.0f / peak);
+            }
+        } else if (cfg.normalization == STRATUM_NORM_RMS) {
+            const float rms = sqrtf(tr[t].rms_sum / (float)tr[t].n);
+            if (rms > 1e-10f) {
+                g = cfg.rms_target / rms;
+                if (peak * g > 1.0f) g = 1.0f / peak;  // :362-379
+            }
+        } else if (lufs_gain) {
+            g = lufs_gain[t];
         }
     }
     tr[t].gain = g;
+}
+
+// ---- RMS: the reference folds x*x left to right in f32 over the whole track (normalization.rs:337-343) ----
+// One warp per track: 32 coalesced samples per step, every lane then adds the 32 squares in sample order
+// (shuffle broadcast), so the sum equals the serial fold bit for bit; the add chain is the critical path.
+__global__ void __launch_bounds__(32) rms_seq_kernel(const float* __restrict__ x, TrackDev* tr) {
+    TrackDev& T = tr[blockIdx.x];
+    if (T.status != 0) return;
+    const int lane = threadIdx.x;
+    const float* p = x + T.off;
+    const uint64_t n = T.n;
+    float sum = 0.0f;
+    for (uint64_t base = 0; base < n; base += 32) {
+        const float v = base + lane < n ? p[base + lane] : 0.0f;
+        const float sq = __fmul_rn(v, v);
+#pragma unroll
+        for (int l = 0; l < 32; ++l) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, sq, l));  // tail lanes add +0.0
+    }
+    if (lane == 0) T.rms_sum = sum;
+}
+
+// ---- LUFS (normalization.rs:112-259): K-weighting biquad + 400 ms block mean squares ----------------------
+// The biquad (DF-II-T) is a linear recurrence  s' = A s + B x.  It is evaluated block-parallel: the track is cut
+// into the reference's own 400 ms blocks, (1) every block is run from a zero state to get its end state z_c,
+// (2) the block start states follow from the affine scan  s_{c+1} = P s_c + z_c  (P = A^len, composed as 2x2
+// affine maps with warp shuffles), (3) every block is re-run from its true start state and its squares are
+// summed in sample order.  One lane per block; a warp transposes 32x32 sample tiles through shared memory so
+// global loads stay coalesced.
+struct Biquad {
+    float b0, b1, b2, a1, a2;
+};
+__device__ __forceinline__ float biquad_step(const Biquad& q, float s, float& x1, float& x2) {  // :161-167
+    const float out = __fadd_rn(__fmul_rn(q.b0, s), x1);
+    x1 = __fsub_rn(__fadd_rn(__fmul_rn(q.b1, s), x2), __fmul_rn(q.a1, out));
+    x2 = __fsub_rn(__fmul_rn(q.b2, s), __fmul_rn(q.a2, out));
+    return out;
+}
+
+template <bool ENERGY>
+__global__ void __launch_bounds__(128) lufs_block_kernel(const float* __restrict__ x, const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab,
+                                                         const int32_t* __restrict__ sr_index, float* fa) {
+    __shared__ float tiles[4][32][33];
+    const int t = blockIdx.y;
+    const TrackDev& T = tr[t];
+    if (T.status != 0) return;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nb = T.lufs_nb, B = T.lufs_block;
+    const uint32_t blk0 = (blockIdx.x * 4 + w) * 32;
+    if (blk0 >= nb) return;
+    const SrTables& st = srtab[sr_index[t]];
+    const Biquad q{st.kw_b0, st.kw_b1, st.kw_b2, st.kw_a1, st.kw_a2};
+    float(*tile)[33] = tiles[w];
+    const float* p = x + T.off;
+    const uint64_t n = T.n;
+    const uint32_t blk = blk0 + lane;
+    const uint64_t my_start = (uint64_t)blk * B;
+    const uint32_t my_len = blk < nb ? (uint32_t)min((uint64_t)B, n - my_start) : 0;
+    float x1 = 0.0f, x2 = 0.0f, sum = 0.0f;
+    if (ENERGY && blk < nb) {
+        x1 = fa[T.lufs_s + 2 * (uint64_t)blk];
+        x2 = fa[T.lufs_s + 2 * (uint64_t)blk + 1];
+    }
+    for (uint32_t jb = 0; jb < B; jb += 32) {
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const uint64_t idx = (uint64_t)(blk0 + r) * B + jb + lane;
+            tile[r][lane] = (blk0 + r < nb && jb + lane < B && idx < n) ? p[idx] : 0.0f;
+        }
+        __syncwarp();
+        const uint32_t lim = my_len > jb ? min(my_len - jb, 32u) : 0u;
+        for (uint32_t j = 0; j < lim; ++j) {
+            const float out = biquad_step(q, tile[lane][j], x1, x2);
+            if (ENERGY) sum = __fadd_rn(sum, __fmul_rn(out, out));  // :218
+        }
+        __syncwarp();
+    }
+    if (blk < nb) {
+        if (ENERGY) {
+            fa[T.lufs_e + blk] = __fdiv_rn(sum, (float)my_len);
+        } else {
+            fa[T.lufs_z + 2 * (uint64_t)blk] = x1;
+            fa[T.lufs_z + 2 * (uint64_t)blk + 1] = x2;
+        }
+    }
+}
+
+struct Affine {  // s -> M s + v
+    float m00, m01, m10, m11, v0, v1;
+};
+__device__ __forceinline__ Affine compose(const Affine& second, const Affine& first) {  // second o first
+    Affine r;
+    r.m00 = second.m00 * first.m00 + second.m01 * first.m10;
+    r.m01 = second.m00 * first.m01 + second.m01 * first.m11;
+    r.m10 = second.m10 * first.m00 + second.m11 * first.m10;
+    r.m11 = second.m10 * first.m01 + second.m11 * first.m11;
+    r.v0 = second.m00 * first.v0 + second.m01 * first.v1 + second.v0;
+    r.v1 = second.m10 * first.v0 + second.m11 * first.v1 + second.v1;
+    return r;
+}
+
+__global__ void __launch_bounds__(32) lufs_scan_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
+                                                       float* fa) {
+    const int t = blockIdx.x;
+    const TrackDev& T = tr[t];
+    if (T.status != 0 || T.lufs_nb == 0) return;
+    const int lane = threadIdx.x;
+    const SrTables& st = srtab[sr_index[t]];
+    const Biquad q{st.kw_b0, st.kw_b1, st.kw_b2, st.kw_a1, st.kw_a2};
+    const uint32_t nb = T.lufs_nb, B = T.lufs_block;
+    // P = A^B: lanes 0 and 1 run the homogeneous recurrence from the two basis states
+    float h1 = lane == 0 ? 1.0f : 0.0f, h2 = lane == 1 ? 1.0f : 0.0f;
+    if (lane < 2)
+        for (uint32_t i = 0; i < B; ++i) biquad_step(q, 0.0f, h1, h2);
+    Affine P;
+    P.m00 = __shfl_sync(0xffffffffu, h1, 0);
+    P.m10 = __shfl_sync(0xffffffffu, h2, 0);
+    P.m01 = __shfl_sync(0xffffffffu, h1, 1);
+    P.m11 = __shfl_sync(0xffffffffu, h2, 1);
+    P.v0 = P.v1 = 0.0f;
+    // every full block c maps its start state to the next one by (P, z_c); lane l owns blocks [a, b)
+    const uint32_t n_maps = nb - 1;  // the last block's end state is never needed
+    const uint32_t per = (n_maps + 31) / 32;
+    const uint32_t a = min(lane * per, n_maps), b = min(a + per, n_maps);
+    const float* z = fa + T.lufs_z;
+    Affine loc{1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f};
+    for (uint32_t c = a; c < b; ++c) {
+        Affine m = P;
+        m.v0 = z[2 * (uint64_t)c];
+        m.v1 = z[2 * (uint64_t)c + 1];
+        loc = compose(m, loc);
+    }
+    // inclusive warp scan of the per-lane composites (Hillis-Steele over affine composition)
+    Affine inc = loc;
+    for (int o = 1; o < 32; o <<= 1) {
+        Affine up;
+        up.m00 = __shfl_up_sync(0xffffffffu, inc.m00, o);
+        up.m01 = __shfl_up_sync(0xffffffffu, inc.m01, o);
+        up.m10 = __shfl_up_sync(0xffffffffu, inc.m10, o);
+        up.m11 = __shfl_up_sync(0xffffffffu, inc.m11, o);
+        up.v0 = __shfl_up_sync(0xffffffffu, inc.v0, o);
+        up.v1 = __shfl_up_sync(0xffffffffu, inc.v1, o);
+        if (lane >= o) inc = compose(inc, up);
+    }
+    // state entering this lane's first block = exclusive prefix applied to the zero state
+    float s0 = __shfl_up_sync(0xffffffffu, inc.v0, 1), s1 = __shfl_up_sync(0xffffffffu, inc.v1, 1);
+    if (lane == 0) s0 = s1 = 0.0f;
+    float* sout = fa + T.lufs_s;
+    for (uint32_t c = a; c < b; ++c) {
+        sout[2 * (uint64_t)c] = s0;
+        sout[2 * (uint64_t)c + 1] = s1;
+        const float n0 = P.m00 * s0 + P.m01 * s1 + z[2 * (uint64_t)c];
+        const float n1 = P.m10 * s0 + P.m11 * s1 + z[2 * (uint64_t)c + 1];
+        s0 = n0;
+        s1 = n1;
+    }
+    // lane 31's range always ends at n_maps, so after its loop it holds the state entering the last block
+    if (lane == 31) {
+        sout[2 * (uint64_t)n_maps] = s0;
+        sout[2 * (uint64_t)n_maps + 1] = s1;
+    }
 }
 
 __global__ void __launch_bounds__(128) silence_rms_kernel(const float* __restrict__ x, TrackDev* tr, float* fa) {
@@ -118,7 +289,7 @@ __global__ void trim_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg 
     }
 }
 
-void launch_peak_gain(const WaveCtx& c) {
+void launch_peak(const WaveCtx& c) {
     if (c.cfg.enable_normalization) {
         uint64_t per = (c.max_n + 255) / 256;
         unsigned gx = (unsigned)((per + 63) / 64);  // ~64 float4-less iterations per thread
@@ -126,8 +297,23 @@ void launch_peak_gain(const WaveCtx& c) {
         if (gx > 2048) gx = 2048;
         peak_kernel<<<dim3(gx, c.n_tracks), 256, 0, c.stream>>>(c.samples, c.tracks);
         count_launch("preprocess");
+        if (c.cfg.normalization == STRATUM_NORM_RMS) {
+            rms_seq_kernel<<<c.n_tracks, 32, 0, c.stream>>>(c.samples, c.tracks);
+            count_launch("preprocess");
+        } else if (c.cfg.normalization == STRATUM_NORM_LOUDNESS && c.max_lufs_nb > 0) {
+            const dim3 g((c.max_lufs_nb + 127) / 128, c.n_tracks);
+            lufs_block_kernel<false><<<g, 128, 0, c.stream>>>(c.samples, c.tracks, c.srtab, c.sr_index, c.fa);
+            lufs_scan_kernel<<<c.n_tracks, 32, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa);
+            lufs_block_kernel<true><<<g, 128, 0, c.stream>>>(c.samples, c.tracks, c.srtab, c.sr_index, c.fa);
+            count_launch("preprocess");
+            count_launch("preprocess");
+            count_launch("preprocess");
+        }
     }
-    gain_kernel<<<(c.n_tracks + 127) / 128, 128, 0, c.stream>>>(c.tracks, c.n_tracks, c.cfg);
+}
+
+void launch_gain(const WaveCtx& c, const float* d_lufs_gain) {
+    gain_kernel<<<(c.n_tracks + 127) / 128, 128, 0, c.stream>>>(c.tracks, c.n_tracks, c.cfg, d_lufs_gain);
     count_launch("preprocess");
 }
 

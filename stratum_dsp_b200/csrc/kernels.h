@@ -11,6 +11,7 @@ struct DevCfg {
     uint32_t silence_min_ms;      // 500, lib.rs:134
     float energy_thr_mul;         // 10^(-20/20), energy_flux.rs:160
     float target_peak;            // 10^(-1/20), normalization.rs:290
+    float rms_target;             // 10^((target_lufs + 3 - headroom)/20), normalization.rs:345 via :532
     int32_t normalization, enable_normalization, enable_trim, enable_consensus;
     float onset_pct;
     uint32_t consensus_tol_ms;
@@ -47,6 +48,8 @@ struct SrTables {
     const int32_t* mel_bin;           // flat entries in ascending-bin order per band (centre bin twice: rising and falling slope)
     const float* mel_w;
     uint32_t key_bin_lo, key_bin_hi;  // HPCP peak search range in the key STFT (extractor.rs:584-591)
+    float kw_b0, kw_b1, kw_b2, kw_a1, kw_a2;  // K-weighting biquad (normalization.rs:127-155)
+    uint32_t lufs_block;              // (sr * 0.4) as usize, normalization.rs:198
 };
 
 struct WaveCtx {
@@ -67,13 +70,15 @@ struct WaveCtx {
     uint32_t max_beat_cap;
     uint32_t max_seg_cap;
     uint32_t max_lg_fft;
+    uint32_t max_lufs_nb;
 };
 
 struct Launcher;  // counts launches + optional stage timing (engine.cu)
 void count_launch(const char* stage);
 
 // k_preprocess.cu
-void launch_peak_gain(const WaveCtx& c);
+void launch_peak(const WaveCtx& c);
+void launch_gain(const WaveCtx& c, const float* d_lufs_gain);
 void launch_silence_trim(const WaveCtx& c);
 // k_stft.cu
 void launch_stft_hop(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);

@@ -76,6 +76,30 @@ def test_errors_match_reference():
     assert e.value.kind == "NotImplemented"  # unsupported switches are rejected, never silently ignored
 
 
+@pytest.mark.parametrize("method", [S.NORM_RMS, S.NORM_LOUDNESS])
+def test_rms_and_lufs_normalisation(method):
+    # a5: normalize_rms (normalization.rs:325-398) and normalize_lufs (:401-484, K-weighting biquad evaluated as a
+    # block-parallel affine scan).  Quiet and loud renderings so that both the gain and the clip limiter are hit.
+    for i, scale in enumerate((0.05, 0.6, 1.4)):
+        p = synth.c2_params(40 + i, 25 * SR, SR)
+        x = (synth.render(p) * np.float32(scale)).astype(np.float32)
+        g = S.analyze_audio(x, SR, S.AnalysisConfig(normalization=method))
+        o = O.analyze(x, SR, {"normalization": method}, fast=True)
+        assert_parity(g, o, f"norm={method} scale={scale}")
+    # 48 kHz, ragged length (last LUFS block partial)
+    p = synth.c2_params(44, 11 * 48000 + 1234, 48000)
+    p.sample_rate = 48000
+    x = synth.render(p)
+    assert_parity(S.analyze_audio(x, 48000, S.AnalysisConfig(normalization=method)), O.analyze(x, 48000, {"normalization": method}), "48k")
+
+
+def test_lufs_all_gated_falls_back_to_peak():
+    x = (synth.render(synth.c2_params(45, 12 * SR, SR)) * np.float32(1e-5)).astype(np.float32)  # every 400 ms block below -70 LUFS
+    cfg = S.AnalysisConfig(normalization=S.NORM_LOUDNESS, enable_silence_trimming=False)
+    o = O.analyze(x, SR, {"normalization": 2, "enable_silence_trimming": 0})
+    assert_parity(S.analyze_audio(x, SR, cfg), o, "gated")
+
+
 def test_short_inputs():
     rng = np.random.default_rng(5)
     for n in (100, 2047, 2048, 4096, 8191, 8192, 12000):
