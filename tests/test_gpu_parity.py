@@ -194,3 +194,14 @@ def test_device_resident_batch_and_synth():
     for i in range(nt):
         assert_parity(res[i], O.analyze(host[i], SR, fast=True), f"device[{i}]")
     assert S.launch_count() > 0
+
+
+def test_multi_device_sharding_matches_single_device():
+    # stratum_b200_analyze_batch(device_ids=...) shards contiguous track ranges over devices, one host thread each
+    if S.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    xs = [synth.render(synth.c2_params(60 + i, 15 * SR, SR)) for i in range(7)]
+    one = S.analyze_batch(xs, SR, devices=[0])
+    two = S.analyze_batch(xs, SR, devices=[0, 1])
+    for u, v in zip(one, two):
+        assert u.bpm == v.bpm and u.key == v.key and u.key_clarity == v.key_clarity and np.array_equal(u.beat_grid.beats, v.beat_grid.beats)
