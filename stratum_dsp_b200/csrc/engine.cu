@@ -1002,9 +1002,12 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
                 launch_stft_hop(w, 2, c.d_list, nl);
             }
             {
-                StageTimer t(s, "multires_tempogram");
+                StageTimer t(s, "multires_features");
                 launch_spec_features(w, 1, c.d_list, nl);
                 launch_spec_features(w, 2, c.d_list, nl);
+            }
+            {
+                StageTimer t(s, "multires_tempogram");
                 launch_tempogram(w, 1, c.d_list, nl);
                 launch_tempogram(w, 2, c.d_list, nl);
                 launch_multires_fusion(w, c.d_list, nl);
@@ -1032,7 +1035,9 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
         debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * 4097, s);
     }
-    { StageTimer t(s, "key"); launch_key_path(w); }
+    { StageTimer t(s, "key_mask"); launch_key_mask(w); }
+    { StageTimer t(s, "key_hpcp"); launch_key_hpcp(w); }
+    { StageTimer t(s, "key_vote"); launch_key_vote(w); }
     CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
     std::vector<float> oa_host(oa.pos + 1);
     std::vector<int32_t> ia_host(ia.pos + 1);

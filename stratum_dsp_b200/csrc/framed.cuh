@@ -15,7 +15,7 @@ __device__ __forceinline__ void framed_rms_warp(const float* __restrict__ x, uin
     const uint32_t f = f0 + lane;
     float sum = 0.0f;
     for (uint32_t jb = 0; jb < FRAME; jb += 32) {
-#pragma unroll 16
+#pragma unroll 4
         for (int r = 0; r < 32; ++r) {
             uint64_t idx = (uint64_t)(f0 + r) * hop + jb + lane;
             tile[r][lane] = (f0 + r < nf && idx < limit) ? __fmul_rn(x[idx], g) : 0.0f;

@@ -412,10 +412,12 @@ __global__ void __launch_bounds__(32) beat_kernel(TrackDev* tr, float* fa, float
 }
 
 void launch_beat_tracking(const WaveCtx& c) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr_dev[64] = {};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_dev[dev & 63]) {
         cudaFuncSetAttribute(beat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BEAT_SMEM_FLOATS * sizeof(float));
-        attr = true;
+        attr_dev[dev & 63] = true;
     }
     // shared memory sized for the largest track of the wave (capped): short tracks leave room for more CTAs per SM
     const uint64_t want = (uint64_t)3 * c.max_beat_cap + (c.max_beat_cap - 64) / 3 + 16;

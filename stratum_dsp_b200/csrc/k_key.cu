@@ -544,16 +544,24 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
     T.key_clarity = key_clarity(fin, 24);
 }
 
-void launch_key_path(const WaveCtx& c) {
+void launch_key_mask(const WaveCtx& c) {
+    if (c.max_Fk > 0 && c.cfg.key_mask) {
+        const dim3 g((KBINS + 127) / 128, c.n_tracks);
+        if (c.cfg.key_margin == 12) mask_kernel<12><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // default margin (config.rs:669)
+        else mask_kernel<0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        count_launch("key_mask");
+    }
+}
+
+void launch_key_hpcp(const WaveCtx& c) {
     if (c.max_Fk > 0) {
-        if (c.cfg.key_mask) {
-            const dim3 g((KBINS + 127) / 128, c.n_tracks);
-            if (c.cfg.key_margin == 12) mask_kernel<12><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // default margin (config.rs:669)
-            else mask_kernel<0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-            count_launch("key_mask");
-        }
         hpcp_kernel<<<dim3((c.max_Fk + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
         count_launch("key_hpcp");
+    }
+}
+
+void launch_key_vote(const WaveCtx& c) {
+    if (c.max_Fk > 0) {
         chroma_smooth_kernel<<<dim3((c.max_Fk * 12 + 255) / 256, c.n_tracks), 256, 0, c.stream>>>(c.tracks, c.fa);
         count_launch("key_vote");
         key_weights_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg);

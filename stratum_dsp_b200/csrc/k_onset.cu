@@ -198,42 +198,7 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
         }
         __syncwarp();
         float sf = 0.0f, sfb[3] = {0.0f, 0.0f, 0.0f};
-        if (pair && K == 4) {
-            // default radius: lane l owns the contiguous bins [33 l, 33 l + 33) and slides a 9-tap register window over
-            // the previous frame's logs (one shared load per bin instead of nine; stride-33 lanes hit distinct banks)
-            const int c0 = 33 * lane, c1 = min(c0 + 33, 1025);
-            float win[9];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) win[j + 1] = Lp[c0 - 4 + j];  // shifted once before the first use
-#pragma unroll 3
-            for (int i = 0; i < 33; ++i) {
-                const int b = c0 + i;
-                if (b < c1) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) win[j] = win[j + 1];
-                    win[8] = Lp[b + 4];
-                    float pm = fmaxf(fmaxf(fmaxf(win[0], win[1]), fmaxf(win[2], win[3])), fmaxf(fmaxf(win[4], win[5]), fmaxf(win[6], win[7])));
-                    pm = fmaxf(fmaxf(pm, win[8]), 0.0f);
-                    const float lc = Lc[b];
-                    const float d = fmaxf(lc - pm, 0.0f);
-                    sf += d * d;
-                    if (b >= e0 && b < e3) {
-                        const int band = b < e1 ? 0 : (b < e2 ? 1 : 2);
-                        const int lo = band == 0 ? e0 : (band == 1 ? e1 : e2), hi = band == 0 ? e1 : (band == 1 ? e2 : e3);
-                        float pmb = pm;
-                        if (b - 4 < lo || b + 4 >= hi) {  // window clipped to the band (novelty.rs:432-441)
-                            pmb = 0.0f;
-                            for (int j = max(b - 4, lo); j < min(b + 5, hi); ++j) pmb = fmaxf(pmb, Lp[j]);
-                        }
-                        const float db = fmaxf(lc - pmb, 0.0f);
-                        const float dd = db * db;
-                        sfb[0] += band == 0 ? dd : 0.0f;
-                        sfb[1] += band == 1 ? dd : 0.0f;
-                        sfb[2] += band == 2 ? dd : 0.0f;
-                    }
-                }
-            }
-        } else if (pair) {
+        if (pair) {
             for (int b = lane; b < 1025; b += 32) {
                 float pm = 0.0f;
                 for (int j = -K; j <= K; ++j) pm = fmaxf(pm, Lp[b + j]);

@@ -99,7 +99,9 @@ void launch_legacy_bpm(const WaveCtx& c);
 // k_beat.cu
 void launch_beat_tracking(const WaveCtx& c);
 // k_key.cu
-void launch_key_path(const WaveCtx& c);
+void launch_key_mask(const WaveCtx& c);
+void launch_key_hpcp(const WaveCtx& c);
+void launch_key_vote(const WaveCtx& c);
 // k_synth.cu
 void launch_synth(cudaStream_t s, float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sr, const float* d_params5);
 
