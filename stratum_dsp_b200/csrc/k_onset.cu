@@ -302,14 +302,28 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
 }
 
 // ---- consensus vote + caller policy ------------------------------------------------------------
-// One CTA per track: the three detector lists are staged in shared memory (when they fit) so that the
-// inherently serial merge + gap clustering runs at shared-memory latency; the final list is written from
-// shared memory by the whole CTA.
-constexpr uint32_t CONS_CAP = 11264;  // ints of dynamic shared memory (44 KB): 3 inputs + output
+// One CTA per track.  Fast path (lists fit in shared memory): parallel 3-way merge by rank (binary searches,
+// method order 0,1,2 on equal samples like the reference's stable sort), gap flags, block scan -> cluster ids,
+// one thread per cluster for the integer mean / vote mask, block scan -> compaction.  Clusters are separated by
+// more than `tol` samples, so their centres are strictly increasing and the reference's sort + dedup
+// (lib.rs:266-271) is the identity.  Slow path (very long tracks): the same logic run serially by thread 0.
+constexpr uint32_t CONS_MAX = 12288;  // onsets (all three lists) handled by the fast path (a 3-minute track has ~5 000)
+constexpr uint32_t CONS_SMEM = (CONS_MAX + 2) * 4 + CONS_MAX * (4 + 4) + CONS_MAX + 64;  // in/starts, merged, centres, methods
 
-__global__ void __launch_bounds__(128) consensus_kernel(TrackDev* tr, int32_t* ia, int n_tracks, DevCfg cfg) {
+__device__ __forceinline__ uint32_t count_less(const int32_t* a, uint32_t n, int32_t s, bool or_equal) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const bool before = or_equal ? a[mid] <= s : a[mid] < s;
+        if (before) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* ia, int n_tracks, DevCfg cfg) {
     extern __shared__ int32_t cs[];
-    __shared__ uint32_t s_nfinal;
+    __shared__ uint32_t sc[34];
+    __shared__ uint32_t s_nfinal, s_strong;
     const int t = blockIdx.x;
     if (t >= n_tracks) return;
     TrackDev& T = tr[t];
@@ -325,29 +339,81 @@ __global__ void __launch_bounds__(128) consensus_kernel(TrackDev* tr, int32_t* i
     const int32_t* G1 = ia + T.on_spectral;
     const int32_t* G2 = ia + T.on_hfc;
     const uint32_t n1 = T.n_on_spectral, n2 = T.n_on_hfc;
-    if (n0 + n1 + n2 == 0) {
+    const uint32_t total = n0 + n1 + n2;
+    if (total == 0) {
         if (threadIdx.x == 0) T.n_on_final = 0;
         return;
     }
-    const uint32_t total = n0 + n1 + n2;
-    const bool staged = 2 * total <= CONS_CAP;  // inputs + (at most `total`) outputs
-    const int32_t *L0 = G0, *L1 = G1, *L2 = G2;
-    int32_t* fin = gfin;
-    if (staged) {
-        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) cs[i] = G0[i];
-        for (uint32_t i = threadIdx.x; i < n1; i += blockDim.x) cs[n0 + i] = G1[i];
-        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) cs[n0 + n1 + i] = G2[i];
-        L0 = cs;
-        L1 = cs + n0;
-        L2 = cs + n0 + n1;
-        fin = cs + total;
+    const uint32_t tol = as_u32(__fmul_rn(__fdiv_rn((float)cfg.consensus_tol_ms, 1000.0f), (float)T.sr));  // consensus.rs:149
+    if (total <= CONS_MAX) {
+        int32_t* in = cs;                            // [total] the three lists back to back; dead after the merge ...
+        int32_t* starts = cs;                        // ... and reused as [clusters + 1] first merged index of each cluster
+        int32_t* merged = cs + CONS_MAX + 2;         // [total]
+        int32_t* centre = cs + 2 * CONS_MAX + 2;     // [clusters] centre; bit 31 marks "voted by >= 2 methods"
+        uint8_t* meth = reinterpret_cast<uint8_t*>(cs + 3 * CONS_MAX + 2);  // [total]
+        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) in[i] = G0[i];
+        for (uint32_t i = threadIdx.x; i < n1; i += blockDim.x) in[n0 + i] = G1[i];
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) in[n0 + n1 + i] = G2[i];
+        if (threadIdx.x == 0) s_strong = 0;
+        __syncthreads();
+        const int32_t *L0 = in, *L1 = in + n0, *L2 = in + n0 + n1;
+        for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+            uint32_t m, i;
+            if (e < n0) { m = 0; i = e; } else if (e < n0 + n1) { m = 1; i = e - n0; } else { m = 2; i = e - n0 - n1; }
+            const int32_t s = in[e];
+            uint32_t r = i;
+            if (m != 0) r += count_less(L0, n0, s, true);          // lower method ids come first on ties
+            else { r += count_less(L1, n1, s, false); r += count_less(L2, n2, s, false); }
+            if (m == 1) r += count_less(L2, n2, s, false);
+            if (m == 2) r += count_less(L1, n1, s, true);
+            merged[r] = s;
+            meth[r] = (uint8_t)m;
+        }
+        __syncthreads();
+        // cluster starts: gap to the previous onset > tol (equivalent to the reference's greedy clustering on a sorted list)
+        const uint32_t per = (total + blockDim.x - 1) / blockDim.x;
+        const uint32_t a = min(threadIdx.x * per, total), b = min(a + per, total);
+        uint32_t cnt = 0;
+        for (uint32_t r = a; r < b; ++r) cnt += (r == 0) || ((int64_t)merged[r] - (int64_t)merged[r - 1] > (int64_t)tol);
+        uint32_t n_clusters;
+        uint32_t pos = block_exclusive_scan(cnt, &n_clusters, sc);
+        for (uint32_t r = a; r < b; ++r)
+            if ((r == 0) || ((int64_t)merged[r] - (int64_t)merged[r - 1] > (int64_t)tol)) starts[pos++] = (int32_t)r;
+        if (threadIdx.x == 0) starts[n_clusters] = (int32_t)total;
+        __syncthreads();
+        // integer mean + distinct-method count per cluster (consensus.rs:236-262)
+        bool any_strong = false;
+        for (uint32_t c = threadIdx.x; c < n_clusters; c += blockDim.x) {
+            uint64_t sum = 0;
+            uint32_t voted = 0;
+            const int32_t s0 = starts[c], s1 = starts[c + 1];
+            for (int32_t r = s0; r < s1; ++r) {
+                sum += (uint64_t)merged[r];
+                voted |= 1u << meth[r];
+            }
+            const bool strong = __popc(voted) >= 2;
+            any_strong |= strong;
+            centre[c] = (int32_t)(sum / (uint64_t)(s1 - s0)) | (strong ? (int32_t)0x80000000 : 0);  // samples < 2^31: bit 31 is free
+        }
+        if (any_strong) s_strong = 1;  // benign race: every writer stores 1
+        __syncthreads();
+        const bool want_strong = s_strong != 0;  // lib.rs:258-271: clusters voted by >= 2 methods, else all of them
+        const uint32_t perc = (n_clusters + blockDim.x - 1) / blockDim.x;
+        const uint32_t ca = min(threadIdx.x * perc, n_clusters), cb = min(ca + perc, n_clusters);
+        uint32_t keep = 0;
+        for (uint32_t c = ca; c < cb; ++c) keep += !want_strong || (centre[c] < 0);
+        uint32_t nfinal;
+        uint32_t w = block_exclusive_scan(keep, &nfinal, sc);
+        for (uint32_t c = ca; c < cb; ++c)
+            if (!want_strong || (centre[c] < 0)) gfin[w++] = centre[c] & 0x7fffffff;
+        if (threadIdx.x == 0) T.n_on_final = nfinal;
+        return;
     }
-    __syncthreads();
+    // ---- slow path ----
     if (threadIdx.x == 0) {
-        const uint32_t tol = as_u32(__fmul_rn(__fdiv_rn((float)cfg.consensus_tol_ms, 1000.0f), (float)T.sr));  // consensus.rs:149
-        // 3-way stable merge (method order 0,1,2 on equal samples) + gap clustering; two passes: first
-        // counts clusters voted by >= 2 methods, second writes the chosen set.
-        uint32_t strong = 0, clusters = 0, nfinal = 0;
+        const int32_t *L0 = G0, *L1 = G1, *L2 = G2;
+        int32_t* fin = gfin;
+        uint32_t strong = 0, nfinal = 0;
         for (int pass = 0; pass < 2; ++pass) {
             const bool want_strong = strong > 0;
             uint32_t i0 = 0, i1 = 0, i2 = 0, w = 0;
@@ -356,13 +422,12 @@ __global__ void __launch_bounds__(128) consensus_kernel(TrackDev* tr, int32_t* i
             uint64_t sum = 0;
             uint32_t cnt = 0, voted = 0;
             auto close = [&]() {
-                const int32_t centre = (int32_t)(sum / cnt);
+                const int32_t c = (int32_t)(sum / cnt);
                 const uint32_t vb = __popc(voted);
                 if (pass == 0) {
-                    ++clusters;
                     if (vb >= 2) ++strong;
                 } else if (!want_strong || vb >= 2) {
-                    if (w == 0 || fin[w - 1] != centre) fin[w++] = centre;  // sort + dedup (lib.rs:266-271): centres ascend
+                    if (w == 0 || fin[w - 1] != c) fin[w++] = c;
                 }
             };
             while (i0 < n0 || i1 < n1 || i2 < n2) {
@@ -382,17 +447,7 @@ __global__ void __launch_bounds__(128) consensus_kernel(TrackDev* tr, int32_t* i
             if (open) close();
             if (pass == 1) nfinal = w;
         }
-        (void)clusters;
-        s_nfinal = nfinal;
         T.n_on_final = nfinal;
-    }
-    __syncthreads();
-    const uint32_t nfinal = s_nfinal;
-    if (nfinal == 0) {  // "Onset consensus produced no candidates" (lib.rs:283-285)
-        for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) gfin[i] = G0[i];
-        if (threadIdx.x == 0) T.n_on_final = n0;
-    } else if (staged) {
-        for (uint32_t i = threadIdx.x; i < nfinal; i += blockDim.x) gfin[i] = fin[i];
     }
 }
 
@@ -419,7 +474,16 @@ void launch_spectral_onsets_consensus(const WaveCtx& c) {
         spectral_onset_kernel<<<dim3(c.n_tracks, 2), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg);
         count_launch("onsets");
     }
-    consensus_kernel<<<c.n_tracks, 128, CONS_CAP * sizeof(int32_t), c.stream>>>(c.tracks, c.ia, c.n_tracks, c.cfg);
+    {
+        static bool attr_dev[64] = {};  // function attributes are per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_dev[dev & 63]) {
+            cudaFuncSetAttribute(consensus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONS_SMEM);
+            attr_dev[dev & 63] = true;
+        }
+    }
+    consensus_kernel<<<c.n_tracks, 256, CONS_SMEM, c.stream>>>(c.tracks, c.ia, c.n_tracks, c.cfg);
     count_launch("onsets");
 }
 

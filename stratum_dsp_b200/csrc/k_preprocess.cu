@@ -236,43 +236,50 @@ __global__ void __launch_bounds__(128) silence_rms_kernel(const float* __restric
     framed_rms_warp<2048>(x + T.off, T.n, T.gain, 1024, f0, nf, tiles[threadIdx.x >> 5], fa + T.sil_rms);
 }
 
-// detect_and_trim region logic — silence.rs:171-256.  One thread per track.
-__global__ void trim_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg cfg) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+// detect_and_trim region logic — silence.rs:171-256.  One CTA per track.
+// Only two of the reference's silence regions can move the trim points: the run that starts at frame 0 (always
+// kept: `sil_start == 0`) and the run that reaches the end of the track (kept when it is long enough or starts at
+// 0).  They are determined by the first and the last non-silent frame, two order-free index reductions.
+__global__ void __launch_bounds__(256) trim_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg cfg) {
+    __shared__ uint32_t s_first, s_last;
+    const int t = blockIdx.x;
     if (t >= n_tracks) return;
     TrackDev& T = tr[t];
     const uint64_t n = T.n;
-    uint64_t ts = 0, te = n;
+    const uint32_t nf = T.Fsil;
+    const uint32_t hop = 1024;
+    if (threadIdx.x == 0) {
+        s_first = 0xffffffffu;  // first non-silent frame
+        s_last = 0u;            // last non-silent frame + 1
+    }
+    __syncthreads();
     if (cfg.enable_trim) {
         const float* rms = fa + T.sil_rms;
-        const uint32_t nf = T.Fsil;
-        const uint32_t hop = 1024;
-        uint32_t min_samples = as_u32(__fmul_rn(__fdiv_rn((float)cfg.silence_min_ms, 1000.0f), (float)T.sr));
-        uint32_t min_frames = (min_samples + hop - 1) / hop;
-        bool in_sil = false, have_first = false;
-        uint32_t sil_start = 0;
-        uint64_t first_a = 0, first_b = 0, last_a = 0, last_b = 0;
-        for (uint32_t f = 0; f < nf; ++f) {
-            bool s = rms[f] <= cfg.silence_thr_linear;
-            if (s && !in_sil) {
-                in_sil = true;
-                sil_start = f;
-            } else if (!s && in_sil) {
-                in_sil = false;
-                if (f - sil_start >= min_frames || sil_start == 0) {
-                    uint64_t a = (uint64_t)sil_start * hop, b = (uint64_t)f * hop;
-                    if (!have_first) { first_a = a; first_b = b; have_first = true; }
-                    last_a = a; last_b = b;
-                }
+        uint32_t lf = 0xffffffffu, ll = 0u;
+        for (uint32_t f = threadIdx.x; f < nf; f += blockDim.x)
+            if (!(rms[f] <= cfg.silence_thr_linear)) {
+                lf = min(lf, f);
+                ll = max(ll, f + 1);
             }
+        for (int o = 16; o > 0; o >>= 1) {
+            lf = min(lf, __shfl_xor_sync(0xffffffffu, lf, o));
+            ll = max(ll, __shfl_xor_sync(0xffffffffu, ll, o));
         }
-        if (in_sil && (nf - sil_start >= min_frames || sil_start == 0)) {
-            uint64_t a = (uint64_t)sil_start * hop, b = n;
-            if (!have_first) { first_a = a; first_b = b; have_first = true; }
-            last_a = a; last_b = b;
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&s_first, lf);
+            atomicMax(&s_last, ll);
         }
-        if (have_first && first_a == 0) ts = first_b;
-        if (have_first && last_b == n) te = last_a;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    uint64_t ts = 0, te = n;
+    if (cfg.enable_trim && nf > 0) {
+        const uint32_t min_samples = as_u32(__fmul_rn(__fdiv_rn((float)cfg.silence_min_ms, 1000.0f), (float)T.sr));
+        const uint32_t min_frames = (min_samples + hop - 1) / hop;
+        const uint32_t lead_end = s_first == 0xffffffffu ? nf : s_first;  // frames [0, lead_end) are silent
+        const uint32_t trail_start = s_last;                               // frames [trail_start, nf) are silent
+        if (lead_end > 0) ts = lead_end < nf ? (uint64_t)lead_end * hop : n;
+        if (trail_start < nf && (nf - trail_start >= min_frames || trail_start == 0)) te = (uint64_t)trail_start * hop;
         if (ts > te) ts = te;  // trim_start.min(trim_end); trim_end.max(trim_start)
         if (!(ts < te && te <= n)) { ts = 0; te = 0; }
     }
@@ -322,7 +329,7 @@ void launch_silence_trim(const WaveCtx& c) {
         silence_rms_kernel<<<dim3((c.max_Fsil + 127) / 128, c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
         count_launch("preprocess");
     }
-    trim_kernel<<<(c.n_tracks + 127) / 128, 128, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);
+    trim_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);
     count_launch("preprocess");
 }
 

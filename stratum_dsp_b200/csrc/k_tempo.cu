@@ -118,10 +118,15 @@ __global__ void __launch_bounds__(512) tgfft_kernel(const TrackDev* tr, const in
     const float* nov = fa + HL.nov + (uint64_t)v * HL.fmax;
     const uint32_t N = next_pow2_u32(n);
     float* power = fa + HL.tgfft + (uint64_t)v * (HL.fft_cap / 2 + 1);
-    if (threadIdx.x == 0) {  // mean with the reference's left-to-right f32 sum (tempogram_fft.rs:126)
+    if (threadIdx.x < 32) {  // mean with the reference's left-to-right f32 sum (tempogram_fft.rs:126): coalesced loads, adds in order
+        const int lane = threadIdx.x;
         float s = 0.0f;
-        for (uint32_t i = 0; i < n; ++i) s = __fadd_rn(s, nov[i]);
-        smean = __fdiv_rn(s, (float)n);
+        for (uint32_t base = 0; base < n; base += 32) {
+            const float v = base + lane < n ? nov[base + lane] : 0.0f;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) s = __fadd_rn(s, __shfl_sync(0xffffffffu, v, l));  // tail lanes add +0.0 to a non-negative sum
+        }
+        if (lane == 0) smean = __fdiv_rn(s, (float)n);
     }
     __syncthreads();
     const float mean = smean;
@@ -177,8 +182,14 @@ __device__ __forceinline__ int ac_count(const DevCfg& cfg) {
 }
 
 // ---- autocorrelation tempogram: one thread per BPM hypothesis, sequential f32 sum -----------------
+// 201 independent add chains of n terms each (tempogram_autocorr.rs:141-150): the chain latency is the
+// floor, so the novelty curve is staged in shared memory (when it fits) and the loop is unrolled to
+// keep the loads ahead of the adds.
+constexpr uint32_t TGAC_SMEM_FLOATS = 40 * 1024;  // 160 KB: covers hop-256 curves of 6-minute tracks
+
 __global__ void __launch_bounds__(256) tgac_kernel(const TrackDev* tr, const int32_t* __restrict__ list, const SrTables* srtab, const int32_t* sr_index, int h,
-                                                   float* fa, DevCfg cfg) {
+                                                   float* fa, DevCfg cfg, uint32_t smem_floats) {
+    extern __shared__ float snov[];
     const int t = list ? list[blockIdx.y] : blockIdx.y;
     const int v = blockIdx.x;
     const TrackDev& T = tr[t];
@@ -186,7 +197,13 @@ __global__ void __launch_bounds__(256) tgac_kernel(const TrackDev* tr, const int
     if (!variant_on(srtab[sr_index[t]], v)) return;
     const uint32_t n = T.F[h] - 1;
     const HopLayout& HL = T.hop[h];
-    const float* nov = fa + HL.nov + (uint64_t)v * HL.fmax;
+    const float* gnov = fa + HL.nov + (uint64_t)v * HL.fmax;
+    const float* nov = gnov;
+    if (n <= smem_floats) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) snov[i] = gnov[i];
+        nov = snov;
+    }
+    __syncthreads();
     float* ac = fa + HL.tgac + (uint64_t)v * AC_CAP;
     const int nb = ac_count(cfg);
     const float frame_rate = __fdiv_rn((float)T.sr, (float)HL.hop);
@@ -198,7 +215,16 @@ __global__ void __launch_bounds__(256) tgac_kernel(const TrackDev* tr, const int
         uint32_t cnt = 0;
         if (lag < n) {
             cnt = n - lag;
-            for (uint32_t i = 0; i < cnt; ++i) sum = __fadd_rn(sum, __fmul_rn(nov[i], nov[i + lag]));
+            const float* q = nov + lag;
+            uint32_t i = 0;
+            for (; i + 8 <= cnt; i += 8) {
+                float pr[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pr[u] = __fmul_rn(nov[i + u], q[i + u]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sum = __fadd_rn(sum, pr[u]);
+            }
+            for (; i < cnt; ++i) sum = __fadd_rn(sum, __fmul_rn(nov[i], q[i]));
         }
         ac[b] = cnt > 0 ? __fdiv_rn(sum, (float)cnt) : 0.0f;
     }
@@ -821,7 +847,18 @@ void launch_tempogram(const WaveCtx& c, int h, const int32_t* d_list, int n_list
     count_launch("tempogram");
     tgfft_kernel<<<g5, 512, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa);
     count_launch("tempogram");
-    tgac_kernel<<<g5, 256, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
+    {
+        static bool attr_dev[64] = {};  // function attributes are per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_dev[dev & 63]) {
+            cudaFuncSetAttribute(tgac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TGAC_SMEM_FLOATS * sizeof(float));
+            attr_dev[dev & 63] = true;
+        }
+        const uint32_t want = c.max_F[h];  // novelty length upper bound of the wave
+        const uint32_t smem_floats = want <= TGAC_SMEM_FLOATS ? want : 0;  // curves that do not fit stay in global memory
+        tgac_kernel<<<g5, 256, smem_floats * sizeof(float), c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg, smem_floats);
+    }
     count_launch("tempogram");
     const uint32_t top_n = (h == 0) ? c.cfg.base_top_n : c.cfg.mr_aux_k;
     score_kernel<<<n_list, 256, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg, top_n);
