@@ -101,6 +101,7 @@ struct DeviceCtx {
     int device = -1;
     bool ready = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t key_stream = nullptr;  // the key path of a wave runs beside the tempo path
     Tables tab{};
     std::vector<void*> owned;                 // table allocations
     std::map<uint32_t, float2*> tw_tables;    // size -> TW table (Stockham twiddles, oracle/so_fft.cpp)
@@ -198,6 +199,7 @@ static int ctx_init(DeviceCtx& c, int device) {
     CUDA_OK(cudaSetDevice(device));
     c.device = device;
     CUDA_OK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&c.key_stream, cudaStreamNonBlocking));
     c.tab.tw1024 = get_tw(c, 1024);
     c.tab.tw4096 = get_tw(c, 4096);
     c.tab.ptw1024 = dev_upload(c, make_pass_tw(1024));
@@ -965,6 +967,36 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         launch_gain(w, d_gain);
         launch_silence_trim(w);
     }
+    // The key path (8192-point STFT -> harmonic mask -> HPCP -> vote) only needs the trimmed, normalised samples, so it
+    // can run on its own stream beside the onset / tempo / beat path.  Measured on B200 (256 x 3-min tracks): 925
+    // tracks/s with the two paths overlapped vs 970 one after the other — both are bound by the same SM resources
+    // (issue slots, L1/shared pipe), so overlap only adds cache pressure.  Off unless STRATUM_B200_DUAL_STREAM is set.
+    static const bool dual_stream = getenv("STRATUM_B200_DUAL_STREAM") != nullptr;
+    const bool split = dual_stream && !(g_debug.load() && nt == 1);
+    cudaEvent_t ev_pre = nullptr, ev_key = nullptr;
+    auto run_key_path = [&](cudaStream_t ks) {
+        WaveCtx wk = w;
+        wk.stream = ks;
+        { StageTimer t(ks, "stft_8192_key"); launch_stft_key(wk); }
+        if (g_debug.load() && nt == 1) {
+            cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, ks);
+            cudaStreamSynchronize(ks);
+            const TrackDev& T = tracks[0];
+            const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
+            debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * 4097, ks);
+        }
+        { StageTimer t(ks, "key_mask"); launch_key_mask(wk); }
+        { StageTimer t(ks, "key_hpcp"); launch_key_hpcp(wk); }
+        { StageTimer t(ks, "key_vote"); launch_key_vote(wk); }
+    };
+    if (split) {
+        cudaEventCreateWithFlags(&ev_pre, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_key, cudaEventDisableTiming);
+        cudaEventRecord(ev_pre, s);
+        cudaStreamWaitEvent(c.key_stream, ev_pre, 0);
+        run_key_path(c.key_stream);
+        cudaEventRecord(ev_key, c.key_stream);
+    }
     { StageTimer t(s, "onsets_energy"); launch_energy_onsets(w); }
     { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, 0, nullptr, nt); }
     { StageTimer t(s, "spec_features"); launch_spec_features(w, 0, nullptr, nt); }
@@ -992,7 +1024,10 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
                 plan_escalation(b, T);
                 T.hop[1].tgtw = get_tw(c, T.hop[1].fft_cap);
                 T.hop[2].tgtw = get_tw(c, T.hop[2].fft_cap);
-                CUDA_OK(cudaMemcpyAsync(c.d_tracks + esc[p], &T, sizeof(TrackDev), cudaMemcpyHostToDevice, s));
+                // only the escalation layouts are rewritten: the key path may be updating other fields of the record concurrently
+                char* drec = reinterpret_cast<char*>(c.d_tracks + esc[p]);
+                CUDA_OK(cudaMemcpyAsync(drec + offsetof(TrackDev, hop) + sizeof(HopLayout), &T.hop[1], 2 * sizeof(HopLayout), cudaMemcpyHostToDevice, s));
+                CUDA_OK(cudaMemcpyAsync(drec + offsetof(TrackDev, cands) + sizeof(uint64_t), &T.cands[1], 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
             }
             const int nl = (int)(p1 - p0);
             CUDA_OK(cudaMemcpyAsync(c.d_list, esc.data() + p0, sizeof(int32_t) * nl, cudaMemcpyHostToDevice, s));
@@ -1027,17 +1062,11 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     }
     { StageTimer t(s, "final_bpm"); launch_final_bpm(w); }
     { StageTimer t(s, "beats"); launch_beat_tracking(w); }
-    { StageTimer t(s, "stft_8192_key"); launch_stft_key(w); }
-    if (g_debug.load() && nt == 1) {
-        CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, s));
-        CUDA_OK(cudaStreamSynchronize(s));
-        const TrackDev& T = tracks[0];
-        const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
-        debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * 4097, s);
+    if (split) {
+        cudaStreamWaitEvent(s, ev_key, 0);
+    } else {
+        run_key_path(s);
     }
-    { StageTimer t(s, "key_mask"); launch_key_mask(w); }
-    { StageTimer t(s, "key_hpcp"); launch_key_hpcp(w); }
-    { StageTimer t(s, "key_vote"); launch_key_vote(w); }
     CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
     std::vector<float> oa_host(oa.pos + 1);
     std::vector<int32_t> ia_host(ia.pos + 1);
@@ -1053,6 +1082,8 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    if (ev_pre) cudaEventDestroy(ev_pre);
+    if (ev_key) cudaEventDestroy(ev_key);
     if (wave_ms) *wave_ms += ms;
     for (int i = 0; i < nt; ++i) fill_result(tracks[i], oa_host.data(), ia_host.data(), ms / (float)nt, &out[wp.idx[i]]);
     if (g_debug.load() && nt == 1) {
@@ -1469,6 +1500,7 @@ void stratum_b200_shutdown(void) {
             cudaFree(c->d_stage);
             if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
             cudaStreamDestroy(c->stream);
+            if (c->key_stream) cudaStreamDestroy(c->key_stream);
         }
         delete c;
     }
