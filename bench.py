@@ -250,7 +250,31 @@ def main():
         e_ms = (time.perf_counter() - te0) * 1000.0 / e_steps
         h1, d1 = S.transfer_bytes()
         e2e = {"tracks_per_step": ne, "ms_per_step": e_ms, "h2d": (h1 - h0) // e_steps, "d2h": (d1 - d0) // e_steps}
-        del host
+        # informational: the decoder-side entry (16-bit PCM uploaded as is, converted on the device): half the H2D bytes
+        pcm = torch.empty(ne * N_SAMPLES, dtype=torch.int16, pin_memory=True)
+        pcm.copy_((buf[: ne * N_SAMPLES] * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+        torch.cuda.synchronize()
+        pnp = pcm.numpy()
+        ptracks = [pnp[i * N_SAMPLES:(i + 1) * N_SAMPLES] for i in range(ne)]
+        import ctypes as _C
+        chans = np.ones(ne, np.uint32)
+        srs_e = np.full(ne, SR, np.uint32)
+
+        def pcm_step():
+            res = (S.StratumResult * ne)()
+            st = S.lib().stratum_b200_analyze_batch_pcm16(pnp.ctypes.data, eoff.ctypes.data_as(_C.POINTER(_C.c_uint64)), srs_e.ctypes.data_as(_C.POINTER(_C.c_uint32)),
+                                                          chans.ctypes.data_as(_C.POINTER(_C.c_uint32)), ne, None, (_C.c_int32 * 1)(local_rank), 1, res)
+            assert st == 0, S.last_error()
+            S.free_results(res)
+
+        pcm_step()
+        barrier()
+        tp0 = time.perf_counter()
+        for _ in range(e_steps):
+            pcm_step()
+        barrier()
+        e2e["pcm16_ms_per_step"] = (time.perf_counter() - tp0) * 1000.0 / e_steps
+        del host, pcm, ptracks
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only) ----
     cpu = None
@@ -269,10 +293,11 @@ def main():
     ms_step = dev_ms / args.steps
     wall_step = wall_ms / args.steps
     e_ms_step = e2e["ms_per_step"] if e2e else 0.0
+    p_ms_step = e2e["pcm16_ms_per_step"] if e2e else 0.0
     if dist:
-        t = torch.tensor([ms_step, wall_step, e_ms_step], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_step, wall_step, e_ms_step, p_ms_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, wall_step, e_ms_step = (float(v) for v in t.tolist())
+        ms_step, wall_step, e_ms_step, p_ms_step = (float(v) for v in t.tolist())
         c = torch.tensor([ok, bpm_hit, launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         ok, bpm_hit, launches = (int(v) for v in c.tolist())
@@ -312,7 +337,9 @@ def main():
             "cpu_baseline": cpu,
             "e2e": ({"value": e2e["tracks_per_step"] * world / (e_ms_step / 1000.0), "unit": "tracks/s", "h2d_bytes_per_step": int(e2e["h2d"]),
                      "d2h_bytes_per_step": int(e2e["d2h"]), "tracks_per_step": e2e["tracks_per_step"], "ms_per_step": e_ms_step,
-                     "note": "stratum_b200_analyze_batch on pinned host samples: H2D of the samples and D2H of the results inside the timed region"}
+                     "pcm16_value": e2e["tracks_per_step"] * world / (p_ms_step / 1000.0),
+                     "note": "stratum_b200_analyze_batch on pinned host f32 samples: H2D of the samples and D2H of the results inside the timed region; "
+                             "pcm16_value = same through stratum_b200_analyze_batch_pcm16 (int16 upload, conversion on the device)"}
                     if e2e else None),
         }
         print(json.dumps(line), flush=True)

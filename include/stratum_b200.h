@@ -167,6 +167,14 @@ void stratum_b200_config_default(StratumConfig* cfg);
 int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks,
                                    const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out);
 
+/* Decoder-side entry: track i is INTERLEAVED 16-bit PCM with channels[i] channels,
+ * pcm[offsets[i] .. offsets[i+1]) (offsets in int16 elements; a multiple of channels[i] per track).  The PCM is
+ * uploaded as is — half the PCIe bytes of f32 — and converted on the device exactly like the reference's decoder
+ * loop (examples/analyze_batch.rs:96-113): mono `s as f32 / 32768.0`; multi-channel the left-to-right f32 sum of the
+ * per-channel values divided by the channel count.  Everything else as stratum_b200_analyze_batch. */
+int32_t stratum_b200_analyze_batch_pcm16(const int16_t* pcm, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels,
+                                         uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out);
+
 /* Same, with `samples` already resident in the memory of device `device_id` (single device). */
 int32_t stratum_b200_analyze_batch_device(const float* d_samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks,
                                           const StratumConfig* cfg, int32_t device_id, StratumResult* out);

@@ -133,6 +133,8 @@ def lib() -> C.CDLL:
     L.stratum_b200_config_default.restype = None
     L.stratum_b200_analyze_batch.argtypes = [C.c_void_p, u64p, u32p, _u, cfgp, i32p, _u, resp]
     L.stratum_b200_analyze_batch.restype = _i
+    L.stratum_b200_analyze_batch_pcm16.argtypes = [C.c_void_p, u64p, u32p, u32p, _u, cfgp, i32p, _u, resp]
+    L.stratum_b200_analyze_batch_pcm16.restype = _i
     L.stratum_b200_analyze_batch_device.argtypes = [C.c_void_p, u64p, u32p, _u, cfgp, _i, resp]
     L.stratum_b200_analyze_batch_device.restype = _i
     L.stratum_b200_analyze_audio.argtypes = [C.c_void_p, C.c_uint64, _u, cfgp, resp]
@@ -403,6 +405,31 @@ def analyze_batch_packed(samples: np.ndarray, offsets: np.ndarray, sample_rates:
     dev = (C.c_int32 * len(devices))(*devices) if devices else None
     st = lib().stratum_b200_analyze_batch(samples.ctypes.data if samples.size else None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
                                           srs.ctypes.data_as(C.POINTER(_u)), n, _cfg_ptr(config), dev, len(devices) if devices else 0, res)
+    if st != OK:
+        _raise(st)
+    return _collect(res, n)
+
+
+def analyze_batch_pcm16(tracks: Sequence, sample_rates: int | Iterable[int], config: AnalysisConfig | None = None,
+                        devices: Sequence[int] | None = None) -> list:
+    """Decoder-side batch entry: ``tracks`` are int16 PCM arrays, shape (frames,) for mono or
+    (frames, channels) interleaved.  The PCM is uploaded as is (half the PCIe bytes of f32) and converted on the device
+    with the reference decoder's arithmetic (examples/analyze_batch.rs:96-113)."""
+    arrs = [np.ascontiguousarray(t, dtype=np.int16) for t in tracks]
+    n = len(arrs)
+    if n == 0:
+        return []
+    chans = np.array([a.shape[1] if a.ndim == 2 else 1 for a in arrs], dtype=np.uint32)
+    flat = [a.reshape(-1) for a in arrs]
+    srs = np.ascontiguousarray([int(sample_rates)] * n if isinstance(sample_rates, (int, np.integer)) else [int(s) for s in sample_rates], dtype=np.uint32)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([a.size for a in flat], dtype=np.uint64)
+    cat = np.concatenate(flat) if n > 1 else flat[0]
+    res = (StratumResult * n)()
+    dev = (C.c_int32 * len(devices))(*devices) if devices else None
+    st = lib().stratum_b200_analyze_batch_pcm16(cat.ctypes.data if cat.size else None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                srs.ctypes.data_as(C.POINTER(_u)), chans.ctypes.data_as(C.POINTER(_u)), n, _cfg_ptr(config), dev,
+                                                len(devices) if devices else 0, res)
     if st != OK:
         _raise(st)
     return _collect(res, n)

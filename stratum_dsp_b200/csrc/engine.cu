@@ -121,7 +121,9 @@ struct DeviceCtx {
     size_t tr_cap = 0;
     float* d_stage = nullptr;  // two staging buffers for host-sample batches (double-buffered upload)
     cudaStream_t copy_stream = nullptr;
-    size_t stage_cap = 0;
+    size_t stage_cap = 0;  // bytes
+    float* d_conv = nullptr;  // mono f32 buffer the PCM16 chunks are converted into
+    size_t conv_cap = 0;   // bytes
     std::mutex mu;
 };
 
@@ -1226,9 +1228,14 @@ int32_t stratum_b200_analyze_batch_device(const float* d_samples, const uint64_t
     return analyze_device(device_id, d_samples, offsets, sample_rates, n_tracks, c, out);
 }
 
-int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg,
-                                   const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
-    if (!offsets || !sample_rates || !out || (!samples && n_tracks && offsets[n_tracks] > 0)) {
+// Host-buffer batches (f32 samples, or interleaved PCM16 converted on the device): contiguous shards, one host
+// thread per device (examples/analyze_batch.rs:239-326: the only parallelism of the reference is across tracks; the
+// gather is the result array itself).  Each shard is streamed through two device staging buffers: chunk k+1 is
+// uploaded on the copy stream while chunk k is analysed (pinned host memory makes the upload asynchronous; pageable
+// memory still works, without the overlap).
+static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels,
+                                  uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
+    if (!offsets || !sample_rates || !out || (!src && n_tracks && offsets[n_tracks] > 0) || (pcm16 && !channels)) {
         set_error("null argument");
         return STRATUM_INVALID_INPUT;
     }
@@ -1238,12 +1245,17 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
     int st = config_validate(c);
     if (st != STRATUM_OK) return st;
     if (n_tracks == 0) return STRATUM_OK;
+    if (pcm16)
+        for (uint32_t i = 0; i < n_tracks; ++i)
+            if (channels[i] == 0 || channels[i] > 64 || (offsets[i + 1] - offsets[i]) % channels[i] != 0) {
+                set_error("PCM16 track length is not a multiple of its channel count (or channels outside 1..64)");
+                return STRATUM_INVALID_INPUT;
+            }
+    const size_t elt = pcm16 ? sizeof(int16_t) : sizeof(float);
     std::vector<int32_t> devs;
     if (device_ids && n_devices) devs.assign(device_ids, device_ids + n_devices);
     else devs.push_back(-1);
     const uint32_t nd = (uint32_t)devs.size();
-    // contiguous shards, one host thread per device (examples/analyze_batch.rs:239-326: the only
-    // parallelism of the reference is across tracks; the gather is the result array itself)
     std::vector<int> status(nd, STRATUM_OK);
     std::vector<std::string> errs(nd);
     auto work = [&](uint32_t d) {
@@ -1257,29 +1269,30 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
             return;
         }
         cudaSetDevice(ctx->device);
-        // Stream the shard through two device staging buffers: chunk k+1 is uploaded on the copy stream
-        // while chunk k is analysed (pinned host memory makes the upload asynchronous; pageable memory
-        // still works, without the overlap).  Chunk size: STRATUM_B200_STAGE_TRACKS_MB per buffer
-        // (default 1024 MB ~ 32 three-minute tracks), always at least one track.
-        uint64_t chunk_floats = (uint64_t)1024 * 1024 * 1024 / 4;
-        if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_floats = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
+        // chunk size: STRATUM_B200_STAGE_MB of mono f32 per chunk (default 1024 MB ~ 32 three-minute tracks), at least one track
+        uint64_t chunk_frames = (uint64_t)1024 * 1024 * 1024 / 4;
+        if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_frames = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
         struct Chunk {
             uint32_t i, j;
-            uint64_t floats;
+            uint64_t elems, frames;
         };
+        auto frames_of_track = [&](uint32_t q) { return (offsets[q + 1] - offsets[q]) / (pcm16 ? channels[q] : 1u); };
         std::vector<Chunk> chunks;
-        uint64_t max_fl = 0;
+        uint64_t max_el = 0, max_fr = 0;
         for (uint32_t i = a; i < b;) {
             uint32_t j = i;
-            uint64_t fl = 0;
-            while (j < b && (j == i || fl + (offsets[j + 1] - offsets[j]) <= chunk_floats)) {
-                fl += offsets[j + 1] - offsets[j];
+            uint64_t fr = 0;
+            while (j < b && (j == i || fr + frames_of_track(j) <= chunk_frames)) {
+                fr += frames_of_track(j);
                 ++j;
             }
-            chunks.push_back(Chunk{i, j, fl});
-            max_fl = std::max(max_fl, fl);
+            const uint64_t el = offsets[j] - offsets[i];
+            chunks.push_back(Chunk{i, j, el, fr});
+            max_el = std::max(max_el, el);
+            max_fr = std::max(max_fr, fr);
             i = j;
         }
+        const size_t buf_bytes = (size_t)align_up(max_el * elt + 64, 256);
         {
             std::lock_guard<std::mutex> lk(ctx->mu);
             if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1287,26 +1300,31 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
                 errs[d] = "copy stream creation failed";
                 return;
             }
-            const size_t need = 2 * (max_fl + 16);
-            if (need > ctx->stage_cap) {
-                if (ctx->d_stage) cudaFree(ctx->d_stage);
-                ctx->d_stage = nullptr;
-                ctx->stage_cap = 0;
-                if (cudaMalloc(&ctx->d_stage, need * sizeof(float)) != cudaSuccess) {
-                    status[d] = STRATUM_PROCESSING_ERROR;
-                    errs[d] = "staging buffer allocation failed";
-                    return;
-                }
-                ctx->stage_cap = need;
+            auto grow = [&](void** p, size_t* cap, size_t need) {
+                if (need <= *cap) return true;
+                if (*p) cudaFree(*p);
+                *p = nullptr;
+                *cap = 0;
+                if (cudaMalloc(p, need) != cudaSuccess) return false;
+                *cap = need;
+                return true;
+            };
+            bool okm = grow((void**)&ctx->d_stage, &ctx->stage_cap, 2 * buf_bytes);
+            if (okm && pcm16) okm = grow((void**)&ctx->d_conv, &ctx->conv_cap, (max_fr + 16) * sizeof(float));
+            if (!okm) {
+                status[d] = STRATUM_PROCESSING_ERROR;
+                errs[d] = "staging buffer allocation failed";
+                return;
             }
         }
-        float* bufs[2] = {ctx->d_stage, ctx->d_stage + (max_fl + 16)};
+        char* bufs[2] = {reinterpret_cast<char*>(ctx->d_stage), reinterpret_cast<char*>(ctx->d_stage) + buf_bytes};
         std::vector<cudaEvent_t> ev(chunks.size(), nullptr);
         auto upload = [&](size_t k) -> bool {
             const Chunk& ch = chunks[k];
             cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
-            g_h2d_bytes.fetch_add(ch.floats * sizeof(float));
-            if (ch.floats && cudaMemcpyAsync(bufs[k & 1], samples + offsets[ch.i], ch.floats * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
+            g_h2d_bytes.fetch_add(ch.elems * elt);
+            if (ch.elems && cudaMemcpyAsync(bufs[k & 1], static_cast<const char*>(src) + offsets[ch.i] * elt, ch.elems * elt, cudaMemcpyHostToDevice,
+                                            ctx->copy_stream) != cudaSuccess)
                 return false;
             return cudaEventRecord(ev[k], ctx->copy_stream) == cudaSuccess;
         };
@@ -1317,9 +1335,37 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
             if (!ok) break;
             cudaStreamWaitEvent(ctx->stream, ev[k], 0);
             const Chunk& ch = chunks[k];
-            std::vector<uint64_t> rel(ch.j - ch.i + 1);
-            for (uint32_t q = ch.i; q <= ch.j; ++q) rel[q - ch.i] = offsets[q] - offsets[ch.i];
-            const int s2 = analyze_device(ctx->device, bufs[k & 1], rel.data(), sample_rates + ch.i, ch.j - ch.i, c, out + ch.i);
+            const uint32_t cn = ch.j - ch.i;
+            std::vector<uint64_t> rel(cn + 1, 0);  // per-track offsets in mono frames inside the chunk
+            for (uint32_t q = 0; q < cn; ++q) rel[q + 1] = rel[q] + frames_of_track(ch.i + q);
+            const float* d_mono = reinterpret_cast<const float*>(bufs[k & 1]);
+            if (pcm16) {
+                // decoder arithmetic on the device: interleaved int16 -> mono f32 (examples/analyze_batch.rs:96-113)
+                std::vector<uint64_t> poff(cn + 1);
+                for (uint32_t q = 0; q <= cn; ++q) poff[q] = offsets[ch.i + q] - offsets[ch.i];
+                uint64_t *d_poff = nullptr, *d_ooff = nullptr;
+                uint32_t* d_ch = nullptr;
+                uint64_t max_frames = 0;
+                for (uint32_t q = 0; q < cn; ++q) max_frames = std::max(max_frames, rel[q + 1] - rel[q]);
+                bool okc = cudaMalloc(&d_poff, (cn + 1) * 8) == cudaSuccess && cudaMalloc(&d_ooff, (cn + 1) * 8) == cudaSuccess &&
+                           cudaMalloc(&d_ch, cn * 4) == cudaSuccess;
+                if (okc) {
+                    cudaMemcpyAsync(d_poff, poff.data(), (cn + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+                    cudaMemcpyAsync(d_ooff, rel.data(), (cn + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+                    cudaMemcpyAsync(d_ch, channels + ch.i, cn * 4, cudaMemcpyHostToDevice, ctx->stream);
+                    launch_pcm16_to_mono(ctx->stream, reinterpret_cast<const int16_t*>(bufs[k & 1]), ctx->d_conv, d_poff, d_ooff, d_ch, cn, max_frames);
+                    okc = cudaStreamSynchronize(ctx->stream) == cudaSuccess;  // the offset vectors are stack-owned
+                }
+                cudaFree(d_poff);
+                cudaFree(d_ooff);
+                cudaFree(d_ch);
+                if (!okc) {
+                    ok = false;
+                    break;
+                }
+                d_mono = ctx->d_conv;
+            }
+            const int s2 = analyze_device(ctx->device, d_mono, rel.data(), sample_rates + ch.i, cn, c, out + ch.i);
             if (s2 != STRATUM_OK) {
                 status[d] = s2;
                 errs[d] = g_last_error;
@@ -1348,6 +1394,16 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
             return status[d];
         }
     return STRATUM_OK;
+}
+
+int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg,
+                                   const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
+    return analyze_host_batch(samples, false, offsets, sample_rates, nullptr, n_tracks, cfg, device_ids, n_devices, out);
+}
+
+int32_t stratum_b200_analyze_batch_pcm16(const int16_t* pcm, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels, uint32_t n_tracks,
+                                         const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
+    return analyze_host_batch(pcm, true, offsets, sample_rates, channels, n_tracks, cfg, device_ids, n_devices, out);
 }
 
 int32_t stratum_b200_analyze_audio(const float* samples, uint64_t n_samples, uint32_t sample_rate, const StratumConfig* cfg, StratumResult* out) {
@@ -1498,6 +1554,7 @@ void stratum_b200_shutdown(void) {
             cudaFree(c->d_gain);
             cudaFree(c->d_srtab);
             cudaFree(c->d_stage);
+            cudaFree(c->d_conv);
             if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
             cudaStreamDestroy(c->stream);
             if (c->key_stream) cudaStreamDestroy(c->key_stream);

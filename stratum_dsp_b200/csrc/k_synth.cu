@@ -37,6 +37,35 @@ __global__ void __launch_bounds__(256) synth_kernel(float* __restrict__ out, uin
     }
 }
 
+// Interleaved PCM16 -> mono f32, the reference's decoder arithmetic (examples/analyze_batch.rs:96-113):
+// `s as f32 / 32768.0` per channel, summed left to right in f32 from 0.0, divided by the channel count.
+__global__ void __launch_bounds__(256) pcm16_to_mono_kernel(const int16_t* __restrict__ pcm, float* __restrict__ out, const uint64_t* __restrict__ pcm_off,
+                                                            const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ channels) {
+    const uint32_t trk = blockIdx.y;
+    const uint32_t C = channels[trk];
+    const uint64_t frames = out_off[trk + 1] - out_off[trk];
+    const int16_t* p = pcm + pcm_off[trk];
+    float* o = out + out_off[trk];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < frames; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (C == 1) {
+            o[i] = __fdiv_rn((float)p[i], 32768.0f);
+        } else {
+            float acc = 0.0f;
+            for (uint32_t ch = 0; ch < C; ++ch) acc = __fadd_rn(acc, __fdiv_rn((float)p[i * C + ch], 32768.0f));
+            o[i] = __fdiv_rn(acc, (float)C);
+        }
+    }
+}
+
+void launch_pcm16_to_mono(cudaStream_t s, const int16_t* d_pcm, float* d_out, const uint64_t* d_pcm_off, const uint64_t* d_out_off, const uint32_t* d_channels,
+                          uint32_t n_tracks, uint64_t max_frames) {
+    if (n_tracks == 0 || max_frames == 0) return;
+    unsigned gx = (unsigned)((max_frames + 256 * 8 - 1) / (256 * 8));
+    if (gx > 8192) gx = 8192;
+    pcm16_to_mono_kernel<<<dim3(gx, n_tracks), 256, 0, s>>>(d_pcm, d_out, d_pcm_off, d_out_off, d_channels);
+    count_launch("pcm16");
+}
+
 void launch_synth(cudaStream_t s, float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sr, const float* d_params5) {
     if (n_tracks == 0 || n_samples == 0) return;
     unsigned gx = (unsigned)((n_samples + 256 * 16 - 1) / (256 * 16));

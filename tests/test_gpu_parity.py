@@ -205,3 +205,53 @@ def test_multi_device_sharding_matches_single_device():
     two = S.analyze_batch(xs, SR, devices=[0, 1])
     for u, v in zip(one, two):
         assert u.bpm == v.bpm and u.key == v.key and u.key_clarity == v.key_clarity and np.array_equal(u.beat_grid.beats, v.beat_grid.beats)
+
+
+def _to_pcm16(x):
+    return np.clip(np.round(x.astype(np.float64) * 32767.0), -32768, 32767).astype(np.int16)
+
+
+def test_pcm16_ingestion_matches_reference_decoder_arithmetic():
+    # int16 PCM uploaded as is, converted + mixed down on the device like examples/analyze_batch.rs:96-113
+    mono = _to_pcm16(synth.render(synth.c2_params(70, 14 * SR, SR)))
+    left = _to_pcm16(synth.render(synth.c2_params(71, 12 * SR, SR)) * 0.7)
+    right = _to_pcm16(synth.render(synth.c2_params(72, 12 * SR, SR)) * 0.7)
+    stereo = np.stack([left, right], axis=1)
+    res = S.analyze_batch_pcm16([mono, stereo, np.zeros(20000, np.int16)], [SR, 48000, SR])
+    f_mono = mono.astype(np.float32) / np.float32(32768.0)
+    f_st = ((np.float32(0.0) + left.astype(np.float32) / np.float32(32768.0)) + right.astype(np.float32) / np.float32(32768.0)) / np.float32(2.0)
+    assert_parity(res[0], O.analyze(f_mono, SR), "pcm16 mono")
+    assert_parity(res[1], O.analyze(f_st.astype(np.float32), 48000), "pcm16 stereo")
+    assert res[2].error is not None and "silent" in res[2].error.message
+    same = S.analyze_audio(f_mono, SR)
+    assert same.bpm == res[0].bpm and np.array_equal(same.onsets, res[0].onsets) and same.key_clarity == res[0].key_clarity
+
+
+def test_analyze_batch_cli_jsonl(tmp_path):
+    import json
+    import subprocess
+    import sys
+    import wave
+
+    paths = []
+    for i in range(3):
+        x = _to_pcm16(synth.render(synth.c2_params(80 + i, 10 * SR, SR)))
+        p = tmp_path / f"t{i}.wav"
+        with wave.open(str(p), "wb") as w:
+            w.setnchannels(1)
+            w.setsampwidth(2)
+            w.setframerate(SR)
+            w.writeframes(x.tobytes())
+        paths.append(str(p))
+    paths.append(str(tmp_path / "missing.wav"))
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "examples" / "analyze_batch.py"), "--json", *paths], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [json.loads(l) for l in out.stdout.strip().splitlines()]
+    assert len(lines) == 4
+    for l in lines[:3]:  # examples/analyze_batch.rs:331-343 keys
+        assert set(l) == {"file", "bpm", "bpm_confidence", "key", "key_confidence", "processing_time_ms", "tempogram_multi_res_triggered",
+                          "tempogram_multi_res_used", "tempogram_percussive_triggered", "tempogram_percussive_used"}
+        assert l["bpm"] > 0
+    assert set(lines[3]) == {"file", "error"}
+    assert "Done: ok=3/4" in out.stderr
