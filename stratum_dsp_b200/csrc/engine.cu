@@ -124,6 +124,8 @@ struct DeviceCtx {
     size_t stage_cap = 0;  // bytes
     float* d_conv = nullptr;  // mono f32 buffer the PCM16 chunks are converted into
     size_t conv_cap = 0;   // bytes
+    char* d_meta = nullptr;   // per-chunk offset / channel tables of the PCM16 path
+    size_t meta_cap = 0;
     std::mutex mu;
 };
 
@@ -1269,8 +1271,9 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             return;
         }
         cudaSetDevice(ctx->device);
-        // chunk size: STRATUM_B200_STAGE_MB of mono f32 per chunk (default 1024 MB ~ 32 three-minute tracks), at least one track
-        uint64_t chunk_frames = (uint64_t)1024 * 1024 * 1024 / 4;
+        // chunk size: STRATUM_B200_STAGE_MB of mono f32 per chunk (default 2048 MB ~ 64 three-minute tracks: measured 732 vs 679
+        // tracks/s end to end against 1024 MB), at least one track
+        uint64_t chunk_frames = (uint64_t)2048 * 1024 * 1024 / 4;
         if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_frames = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
         struct Chunk {
             uint32_t i, j;
@@ -1343,12 +1346,21 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 // decoder arithmetic on the device: interleaved int16 -> mono f32 (examples/analyze_batch.rs:96-113)
                 std::vector<uint64_t> poff(cn + 1);
                 for (uint32_t q = 0; q <= cn; ++q) poff[q] = offsets[ch.i + q] - offsets[ch.i];
-                uint64_t *d_poff = nullptr, *d_ooff = nullptr;
-                uint32_t* d_ch = nullptr;
                 uint64_t max_frames = 0;
                 for (uint32_t q = 0; q < cn; ++q) max_frames = std::max(max_frames, rel[q + 1] - rel[q]);
-                bool okc = cudaMalloc(&d_poff, (cn + 1) * 8) == cudaSuccess && cudaMalloc(&d_ooff, (cn + 1) * 8) == cudaSuccess &&
-                           cudaMalloc(&d_ch, cn * 4) == cudaSuccess;
+                // small per-chunk tables live in a context buffer: no cudaMalloc / cudaFree (device-wide syncs) between chunks
+                const size_t meta_need = (size_t)(cn + 1) * 16 + (size_t)cn * 4 + 64;
+                bool okc = true;
+                if (meta_need > ctx->meta_cap) {
+                    if (ctx->d_meta) cudaFree(ctx->d_meta);
+                    ctx->d_meta = nullptr;
+                    ctx->meta_cap = 0;
+                    okc = cudaMalloc(&ctx->d_meta, 2 * meta_need) == cudaSuccess;
+                    if (okc) ctx->meta_cap = 2 * meta_need;
+                }
+                uint64_t* d_poff = reinterpret_cast<uint64_t*>(ctx->d_meta);
+                uint64_t* d_ooff = d_poff + (cn + 1);
+                uint32_t* d_ch = reinterpret_cast<uint32_t*>(d_ooff + (cn + 1));
                 if (okc) {
                     cudaMemcpyAsync(d_poff, poff.data(), (cn + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
                     cudaMemcpyAsync(d_ooff, rel.data(), (cn + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -1356,9 +1368,6 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                     launch_pcm16_to_mono(ctx->stream, reinterpret_cast<const int16_t*>(bufs[k & 1]), ctx->d_conv, d_poff, d_ooff, d_ch, cn, max_frames);
                     okc = cudaStreamSynchronize(ctx->stream) == cudaSuccess;  // the offset vectors are stack-owned
                 }
-                cudaFree(d_poff);
-                cudaFree(d_ooff);
-                cudaFree(d_ch);
                 if (!okc) {
                     ok = false;
                     break;
@@ -1555,6 +1564,7 @@ void stratum_b200_shutdown(void) {
             cudaFree(c->d_srtab);
             cudaFree(c->d_stage);
             cudaFree(c->d_conv);
+            cudaFree(c->d_meta);
             if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
             cudaStreamDestroy(c->stream);
             if (c->key_stream) cudaStreamDestroy(c->key_stream);
