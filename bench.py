@@ -137,7 +137,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "tracks_per_sec_3min_44k1", "value": val, "unit": "tracks/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: synthetic 3-min 44.1 kHz mono tracks, BPM 70-180, random keys (SURVEY §8d); analyze_audio defaults",
+        "config": {"workload": "C2: batch of synthetic 3-min 44.1 kHz mono tracks, BPM 70-180, random keys (BASELINE.json configs[1]); analyze_audio defaults",
                    "tracks_per_step": n, "note": "CPU oracle port of stratum-dsp 1.0.0 (Rust toolchain absent), std::thread pool over tracks"},
         "cpu_baseline": {"value": val, "unit": "tracks/s", "cores": jobs, "kind": "port", "sample": f"{n} C2 tracks per step, {args.steps} steps"},
         "e2e": {"value": val, "unit": "tracks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -192,9 +192,12 @@ def main():
     offsets = np.arange(nt + 1, dtype=np.uint64) * np.uint64(N_SAMPLES)
     srs = np.full(nt, SR, np.uint32)
 
+    waves = [1]
+
     def step():
         res = S.analyze_batch_device(buf.data_ptr(), offsets, srs, None, local_rank, convert=False)
         ms = S.last_call_device_ms()
+        waves[0] = max(1, S.last_call_waves())
         return res, ms
 
     for _ in range(args.warmup):
@@ -252,7 +255,9 @@ def main():
         e2e = {"tracks_per_step": ne, "ms_per_step": e_ms, "h2d": (h1 - h0) // e_steps, "d2h": (d1 - d0) // e_steps}
         # informational: the decoder-side entry (16-bit PCM uploaded as is, converted on the device): half the H2D bytes
         pcm = torch.empty(ne * N_SAMPLES, dtype=torch.int16, pin_memory=True)
-        pcm.copy_((buf[: ne * N_SAMPLES] * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+        for i in range(0, ne, 8):  # converted in slices: the analysis arenas own most of the device memory
+            a, b = i * N_SAMPLES, min(i + 8, ne) * N_SAMPLES
+            pcm[a:b].copy_((buf[a:b] * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
         torch.cuda.synchronize()
         pnp = pcm.numpy()
         ptracks = [pnp[i * N_SAMPLES:(i + 1) * N_SAMPLES] for i in range(ne)]
@@ -310,16 +315,20 @@ def main():
         roof = None
         if dom:
             k_ms = stages[dom] / args.steps  # per step (all waves of the step)
-            ach = nt * ALGO_BYTES_PER_TRACK / (k_ms / 1000.0) / 1e9
+            launches_per_step = waves[0]     # one launch of the kernel per wave
+            ach = nt * ALGO_BYTES_PER_TRACK / (k_ms / 1000.0) / 1e9  # = per-launch bytes / per-launch time
             traffic = None
             tp = ROOT / "profiles" / "roofline_traffic.json"
-            if tp.exists():
+            if tp.exists():  # DRAM bytes per track of this kernel from the committed `ncu --set full` capture -> bytes per launch
                 try:
-                    traffic = json.loads(tp.read_text()).get(dom)
+                    per_track = json.loads(tp.read_text()).get(dom, {}).get("dram_bytes_per_track")
+                    traffic = per_track * nt / launches_per_step if per_track else None
                 except Exception:
                     traffic = None
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_track": ALGO_BYTES_PER_TRACK, "kernel_ms_per_step": k_ms,
+                    "launches_per_step": launches_per_step, "algorithmic_bytes_per_launch": nt * ALGO_BYTES_PER_TRACK / launches_per_step,
+                    "kernel_ms_per_launch": k_ms / launches_per_step,
                     "share_of_step": k_ms / ms_step,
                     "note": "path is FP32/shared-memory bound (SURVEY §8d: ~315 flop/B); the HBM fraction is reported as the contract asks",
                     "fp32_tflops_key_stft": (nt * FLOPS_KEY_STFT / (stages["stft_8192_key"] / args.steps / 1000.0) / 1e12) if "stft_8192_key" in stages else None}

@@ -234,6 +234,9 @@ void stratum_b200_stage_timing_enable(int32_t on);
  * waves) of the most recent stratum_b200_analyze_batch_device call in this process. */
 double stratum_b200_last_call_device_ms(void);
 
+/* Number of waves (arena-sized sub-batches = launches of every stage kernel) the most recent batch call was cut into. */
+uint32_t stratum_b200_last_call_waves(void);
+
 /* Cumulative host->device / device->host bytes copied by the library in this process. */
 void stratum_b200_transfer_bytes(uint64_t* h2d, uint64_t* d2h);
 

@@ -173,6 +173,8 @@ def lib() -> C.CDLL:
     L.stratum_b200_stage_timing_enable.restype = None
     L.stratum_b200_last_call_device_ms.argtypes = []
     L.stratum_b200_last_call_device_ms.restype = C.c_double
+    L.stratum_b200_last_call_waves.argtypes = []
+    L.stratum_b200_last_call_waves.restype = _u
     L.stratum_b200_transfer_bytes.argtypes = [u64p, u64p]
     L.stratum_b200_transfer_bytes.restype = None
     if L.stratum_b200_sizeof(0) != C.sizeof(StratumConfig) or L.stratum_b200_sizeof(1) != C.sizeof(StratumResult) or \
@@ -516,6 +518,10 @@ def stage_times(reset: bool = False) -> dict:
 
 def last_call_device_ms() -> float:
     return float(lib().stratum_b200_last_call_device_ms())
+
+
+def last_call_waves() -> int:
+    return int(lib().stratum_b200_last_call_waves())
 
 
 def transfer_bytes() -> tuple:

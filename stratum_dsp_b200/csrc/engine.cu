@@ -89,6 +89,7 @@ static void resolve_stage_times() {  // call after the stream has been synchroni
 }
 
 static std::atomic<uint64_t> g_last_call_us{0};
+static std::atomic<uint32_t> g_last_call_waves{0};
 static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // host<->device traffic of this process (results, staging)  // device time of the most recent batch call (all waves), microseconds
 
 // ---- debug capture (single-track calls) -----------------------------------------------------------------
@@ -1158,7 +1159,11 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     // budget: what is free now plus what our own arena already holds, minus head room
     uint64_t budget_floats = (uint64_t)((double)(free_b + ctx->fa_cap * 4) * 0.90) / 4;
-    if (const char* e = getenv("STRATUM_B200_ARENA_GB")) budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(atof(e) * 1e9 / 4));
+    // waves of a few hundred tracks already fill the GPU; a larger arena buys nothing and starves the caller (and our
+    // own staging buffers) of memory, so the default is capped at 100 GB
+    double cap_gb = 100.0;
+    if (const char* e = getenv("STRATUM_B200_ARENA_GB")) cap_gb = atof(e);
+    budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(cap_gb * 1e9 / 4));
     uint32_t wave_max = 1u << 20;
     if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) wave_max = std::max(1, atoi(e));
     std::vector<uint64_t> lens(n_tracks), offs(n_tracks);
@@ -1166,7 +1171,7 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
         offs[i] = offsets[i];
         lens[i] = offsets[i + 1] - offsets[i];
     }
-    uint32_t i = 0;
+    uint32_t i = 0, n_waves = 0;
     double call_ms = 0.0;
     cudaEvent_t call_a, call_b;
     cudaEventCreate(&call_a);
@@ -1193,6 +1198,7 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
         }
         st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out, &call_ms);
         if (st != STRATUM_OK) return st;
+        ++n_waves;
     }
     cudaEventRecord(call_b, ctx->stream);
     cudaEventSynchronize(call_b);
@@ -1201,6 +1207,7 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     cudaEventDestroy(call_a);
     cudaEventDestroy(call_b);
     g_last_call_us.store((uint64_t)(call_ms * 1000.0));
+    g_last_call_waves.store(n_waves);
     return STRATUM_OK;
 }
 
@@ -1682,6 +1689,8 @@ void stratum_b200_stage_times_reset(void) {
 void stratum_b200_stage_timing_enable(int32_t on) { g_timing.store(on); }
 
 double stratum_b200_last_call_device_ms(void) { return (double)g_last_call_us.load() / 1000.0; }
+
+uint32_t stratum_b200_last_call_waves(void) { return g_last_call_waves.load(); }
 
 void stratum_b200_transfer_bytes(uint64_t* h2d, uint64_t* d2h) {
     if (h2d) *h2d = g_h2d_bytes.load();

@@ -377,13 +377,16 @@ __device__ __forceinline__ bool seg_geometry(const TrackDev& T, const DevCfg& cf
 // result equals the serial fold bit for bit while the chain per frame is one add instead of ~25 ops.
 // blockIdx.x = segment index; the extra index `nseg` is the whole-track score used when no segment
 // passes the clarity gate (lib.rs:1385-1411) or voting is off.  blockDim = 24 warps, warp = key.
-__global__ void __launch_bounds__(768) segment_score_kernel(const TrackDev* __restrict__ tr, float* fa, Tables tab, DevCfg cfg) {
+// The whole-track row of a track that votes by segments is only needed when no segment passes the clarity gate, so the
+// first launch skips it and a second launch (fallback_only) computes it for the tracks key_vote_kernel flagged.
+__global__ void __launch_bounds__(768) segment_score_kernel(const TrackDev* __restrict__ tr, float* fa, Tables tab, DevCfg cfg, int fallback_only) {
     const TrackDev& T = tr[blockIdx.y];
     if (T.status != 0 || T.Fk == 0) return;
     uint32_t seg_len, hop, nseg;
-    seg_geometry(T, cfg, &seg_len, &hop, &nseg);
-    const uint32_t s = blockIdx.x;
+    const bool voting = seg_geometry(T, cfg, &seg_len, &hop, &nseg);
+    const uint32_t s = fallback_only ? nseg : blockIdx.x;
     if (s > nseg || s >= T.seg_cap) return;
+    if (fallback_only ? !T.key_fallback : (voting && s == nseg)) return;
     const uint32_t start = s < nseg ? s * hop : 0;
     const uint32_t len = s < nseg ? seg_len : T.Fk;
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -485,13 +488,18 @@ __device__ __noinline__ float key_clarity(const float* sc, int n) {  // key_clar
 }
 
 // ---- per-track vote (lib.rs:1353-1436, 1461): one thread per track -----------------------------------
-__global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg cfg) {
+__global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg cfg, int fallback_only) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
     TrackDev& T = tr[t];
-    T.key = 0;
-    T.key_confidence = 0.0f;
-    T.key_clarity = 0.0f;
+    if (fallback_only) {
+        if (!T.key_fallback) return;
+    } else {
+        T.key = 0;
+        T.key_confidence = 0.0f;
+        T.key_clarity = 0.0f;
+        T.key_fallback = 0;
+    }
     if (T.status != 0 || T.Fk == 0 || T.m < 2048) return;
     uint32_t seg_len, hop, nseg;
     const bool voting = seg_geometry(T, cfg, &seg_len, &hop, &nseg);
@@ -503,7 +511,7 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
     int key = 0;
     float confidence = 0.0f;
     float fin[24];
-    if (voting) {
+    if (voting && !fallback_only) {
         const float min_cl = clamp_rs(cfg.key_seg_min_clarity, 0.0f, 1.0f);
         float acc[24];
         for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
@@ -532,6 +540,10 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
             confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;
             voted = true;
         }
+    }
+    if (!voted && voting && !fallback_only) {
+        T.key_fallback = 1;  // no segment passed the clarity gate (lib.rs:1385-1411): the whole-track row is computed on demand
+        return;
     }
     if (!voted) {
         rank_keys(ss + (uint64_t)nseg * 24, keys, fin, by_key);
@@ -566,11 +578,17 @@ void launch_key_vote(const WaveCtx& c) {
         count_launch("key_vote");
         key_weights_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         count_launch("key_vote");
-        segment_score_kernel<<<dim3(c.max_seg_cap, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg);
+        segment_score_kernel<<<dim3(c.max_seg_cap, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg, 0);
         count_launch("key_vote");
     }
-    key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);
+    key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg, 0);
     count_launch("key_vote");
+    if (c.max_Fk > 0 && c.cfg.key_voting) {  // rare path: tracks whose segments were all rejected
+        segment_score_kernel<<<dim3(1, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg, 1);
+        count_launch("key_vote");
+        key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg, 1);
+        count_launch("key_vote");
+    }
 }
 
 }  // namespace sb

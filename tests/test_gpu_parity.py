@@ -100,6 +100,19 @@ def test_lufs_all_gated_falls_back_to_peak():
     assert_parity(S.analyze_audio(x, SR, cfg), o, "gated")
 
 
+def test_key_segment_fallback_to_whole_track():
+    # lib.rs:1385-1411: when no segment reaches key_segment_min_clarity the whole-track detection is used
+    x = synth.render(synth.c2_params(90, 30 * SR, SR))
+    g = S.analyze_audio(x, SR, S.AnalysisConfig(key_segment_min_clarity=0.99))
+    o = O.analyze(x, SR, {"key_segment_min_clarity": 0.99}, fast=True)
+    assert_parity(g, o, "all segments rejected")
+    batch = S.analyze_batch([x, synth.render(synth.c2_params(91, 30 * SR, SR))], SR, S.AnalysisConfig(key_segment_min_clarity=0.99))
+    assert batch[0].key == g.key and batch[0].key_clarity == g.key_clarity
+    # voting disabled: whole-track detection directly
+    g2 = S.analyze_audio(x, SR, S.AnalysisConfig(enable_key_segment_voting=False))
+    assert_parity(g2, O.analyze(x, SR, {"enable_key_segment_voting": 0}, fast=True), "voting off")
+
+
 def test_short_inputs():
     rng = np.random.default_rng(5)
     for n in (100, 2047, 2048, 4096, 8191, 8192, 12000):
