@@ -65,7 +65,7 @@ typedef struct StratumConfig {
     float onset_threshold_percentile;
     uint32_t onset_consensus_tolerance_ms;
     float onset_consensus_weights[4];
-    int32_t enable_hpss_onsets;            /* must be 0 */
+    int32_t enable_hpss_onsets;
     int32_t force_legacy_bpm;
     int32_t enable_bpm_fusion;             /* must be 0 */
     int32_t enable_legacy_bpm_guardrails;
@@ -76,7 +76,7 @@ typedef struct StratumConfig {
     float tempogram_multi_res_double_time_512_factor;
     float tempogram_multi_res_margin_threshold;
     int32_t tempogram_multi_res_use_human_prior;
-    int32_t enable_tempogram_percussive_fallback; /* must be 0 */
+    int32_t enable_tempogram_percussive_fallback;
     int32_t enable_tempogram_band_fusion;
     float tempogram_band_low_max_hz, tempogram_band_mid_max_hz, tempogram_band_high_max_hz;
     float tempogram_band_w_full, tempogram_band_w_low, tempogram_band_w_mid, tempogram_band_w_high;
@@ -115,6 +115,7 @@ typedef struct StratumConfig {
         enable_key_ensemble, enable_key_median, enable_key_tuning_compensation, enable_key_edge_trim, enable_key_mode_heuristic,
         enable_key_hpcp_whitening, enable_key_hpcp_bass_blend, enable_key_minor_harmonic_bonus;
     float chroma_sharpening_power; /* must be <= 1.0 */
+    uint32_t hpss_margin;          /* median half-width of the HPSS filters (config.rs:43, default 10; at most 10 here) */
 } StratumConfig;
 
 /* AnalysisResult + AnalysisMetadata (src/analysis/result.rs:183-263; built at src/lib.rs:1592-1619). */

@@ -54,13 +54,25 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
         std::vector<float> sflux, hflux;
         if (detect_spectral_flux_onsets(S, c.onset_threshold_percentile, sf, dump ? &sflux : nullptr)) sf.clear();
         if (detect_hfc_onsets(S, sr, c.onset_threshold_percentile, hf, dump ? &hflux : nullptr)) hf.clear();
-        std::vector<size_t> lists[4] = {energy_onsets, to_samples(sf), to_samples(hf), {}};
+        std::vector<size_t> hp;  // lib.rs:222-235: HPSS onsets as the fourth detector
+        std::vector<float> pflux;
+        if (c.enable_hpss_onsets) {
+            Spec Hh, Pp;
+            if (hpss_decompose(S, c.hpss_margin, Hh, Pp) || detect_hpss_onsets(Pp, c.onset_threshold_percentile, hp, dump ? &pflux : nullptr)) hp.clear();
+            if (dump) {
+                dump->f["hpss.flux"] = pflux;
+                const size_t head = std::min<size_t>(Pp.frames, 64) * Pp.bins;
+                dump->f["hpss.perc_head"] = std::vector<float>(Pp.d.begin(), Pp.d.begin() + head);
+            }
+        }
+        std::vector<size_t> lists[4] = {energy_onsets, to_samples(sf), to_samples(hf), to_samples(hp)};
         if (dump) {
             dump->f["onset.spectral_flux"] = sflux;
             dump->f["onset.hfc_flux"] = hflux;
             dump->i["onset.energy"] = std::vector<int64_t>(energy_onsets.begin(), energy_onsets.end());
             dump->i["onset.spectral"] = std::vector<int64_t>(lists[1].begin(), lists[1].end());
             dump->i["onset.hfc"] = std::vector<int64_t>(lists[2].begin(), lists[2].end());
+            dump->i["onset.hpss"] = std::vector<int64_t>(lists[3].begin(), lists[3].end());
         }
         std::vector<OnsetCand> cands;
         if (!vote_onsets(lists, c.onset_consensus_weights, c.onset_consensus_tolerance_ms, sr, cands)) {
@@ -132,7 +144,32 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
                     }
                 }
                 r.multi_res_used = used ? 1 : 0;
-                r.percussive_triggered = (ambiguous && trap_low) ? 1 : 0;  // lib.rs:587-588 (fallback itself off by default)
+                const bool percussive_needed = ambiguous && trap_low;  // lib.rs:587-588
+                r.percussive_triggered = percussive_needed ? 1 : 0;
+                if (c.enable_tempogram_percussive_fallback && percussive_needed) {  // lib.rs:590-683
+                    r.percussive_used = 0;
+                    Spec Hh, Pp;
+                    BpmEstimate pe;
+                    std::vector<TempoCand> pc;
+                    if (!hpss_decompose(S, c.hpss_margin, Hh, Pp) && !estimate_bpm_tempogram(Pp, sr, (uint32_t)c.hop_size, c, base_top_n, pe, pc, dump, "perc.")) {
+                        if (dump) dump->f["perc.est"] = {pe.bpm, pe.confidence, (float)pe.method_agreement};
+                        const float rel = tg.bpm > 1e-6f ? fmax_rs(pe.bpm / tg.bpm, tg.bpm / pe.bpm) : 1.0f;
+                        const bool family_related = fabsf(rel - 2.0f) < 0.05f || fabsf(rel - 1.5f) < 0.05f || fabsf(rel - (4.0f / 3.0f)) < 0.05f ||
+                                                    fabsf(rel - (3.0f / 2.0f)) < 0.05f || fabsf(rel - (2.0f / 3.0f)) < 0.05f || fabsf(rel - (3.0f / 4.0f)) < 0.05f;
+                        const bool forbid_promote_high = tg.bpm <= 180.0f && pe.bpm > 180.0f;
+                        const bool base_low_trap = trap_low || base.bpm < 95.0f;
+                        const bool percussive_in_common = pe.bpm >= 70.0f && pe.bpm <= 180.0f;
+                        const bool p_better = !forbid_promote_high && family_related && percussive_in_common &&
+                                              (pe.confidence >= tg.confidence + 0.04f || (base_low_trap && pe.confidence >= tg.confidence * 0.85f) ||
+                                               (pe.method_agreement > tg.method_agreement && pe.confidence >= tg.confidence * 0.92f));
+                        if (p_better) {
+                            tg = pe;
+                            r.percussive_used = 1;
+                        }
+                    }
+                } else if (c.enable_tempogram_percussive_fallback) {
+                    r.percussive_used = 0;
+                }
             }
         }
     }

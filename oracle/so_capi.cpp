@@ -17,7 +17,7 @@ struct SoHandle {
 
 #define SO_FIELDS(X)                                                                                                                     \
     X(min_amplitude_db) X(normalization) X(enable_normalization) X(enable_silence_trimming) X(enable_onset_consensus)                     \
-    X(onset_threshold_percentile) X(onset_consensus_tolerance_ms) X(force_legacy_bpm) X(enable_bpm_fusion) X(enable_legacy_bpm_guardrails) \
+    X(onset_threshold_percentile) X(onset_consensus_tolerance_ms) X(enable_hpss_onsets) X(hpss_margin) X(enable_tempogram_percussive_fallback) X(force_legacy_bpm) X(enable_bpm_fusion) X(enable_legacy_bpm_guardrails) \
     X(enable_tempogram_multi_resolution) X(tempogram_multi_res_top_k) X(tempogram_multi_res_w512) X(tempogram_multi_res_w256)             \
     X(tempogram_multi_res_w1024) X(tempogram_multi_res_structural_discount) X(tempogram_multi_res_double_time_512_factor)                 \
     X(tempogram_multi_res_margin_threshold) X(tempogram_multi_res_use_human_prior) X(enable_tempogram_band_fusion)                        \
@@ -264,6 +264,29 @@ int so_beat_grid(float bpm, float conf, const float* onsets, int n, uint32_t sr,
     *n_down = (int)r.downbeats.size();
     *bpb = r.time_sig_beats_per_bar;
     return 0;
+}
+
+int so_hpss_decompose(const float* spec, uint64_t frames, uint64_t bins, uint64_t margin, float* h_out, float* p_out) {
+    Spec S, H, P;
+    S.frames = frames;
+    S.bins = bins;
+    S.d.assign(spec, spec + frames * bins);
+    Error e = hpss_decompose(S, margin, H, P);
+    if (e) return e.kind;
+    memcpy(h_out, H.d.data(), H.d.size() * sizeof(float));
+    memcpy(p_out, P.d.data(), P.d.size() * sizeof(float));
+    return 0;
+}
+int so_hpss_onsets(const float* perc, uint64_t frames, uint64_t bins, float pct, int64_t* out, int cap) {
+    Spec P;
+    P.frames = frames;
+    P.bins = bins;
+    P.d.assign(perc, perc + frames * bins);
+    std::vector<size_t> on;
+    Error e = detect_hpss_onsets(P, pct, on, nullptr);
+    if (e) return -e.kind;
+    for (int i = 0; i < std::min<int>(cap, (int)on.size()); ++i) out[i] = (int64_t)on[i];
+    return (int)on.size();
 }
 
 // ---- batch timing (CPU baseline; mirrors examples/analyze_batch.rs:239-326 with a std::thread pool) ----

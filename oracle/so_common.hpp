@@ -82,6 +82,9 @@ struct Config {
     float onset_threshold_percentile = 0.80f;
     uint32_t onset_consensus_tolerance_ms = 50;
     float onset_consensus_weights[4] = {0.25f, 0.25f, 0.25f, 0.25f};
+    bool enable_hpss_onsets = false;
+    size_t hpss_margin = 10;
+    bool enable_tempogram_percussive_fallback = false;
     bool force_legacy_bpm = false;
     bool enable_bpm_fusion = false;
     bool enable_legacy_bpm_guardrails = true;
@@ -234,6 +237,8 @@ struct OnsetCand {
     float confidence;
     uint32_t voted_by;
 };
+Error hpss_decompose(const Spec& S, size_t margin, Spec& harmonic, Spec& percussive);
+Error detect_hpss_onsets(const Spec& P, float pct, std::vector<size_t>& out, std::vector<float>* flux_out = nullptr);
 Error vote_onsets(const std::vector<size_t> lists[4], const float weights[4], uint32_t tol_ms, uint32_t sr, std::vector<OnsetCand>& out);
 
 // ---- period ---------------------------------------------------------------------

@@ -487,6 +487,7 @@ static void config_default(StratumConfig* c) {  // src/config.rs:594-744
     c->key_hpcp_harmonic_decay = 0.60f;
     c->key_hpcp_mag_power = 0.50f;
     c->chroma_sharpening_power = 1.0f;
+    c->hpss_margin = 10;
 }
 
 // Rejects configurations whose branch is not built instead of silently ignoring them.
@@ -503,9 +504,8 @@ static int config_validate(const StratumConfig& c) {
         set_error("unknown normalization method");
         return STRATUM_INVALID_INPUT;
     }
-    if (c.enable_hpss_onsets) return ni("enable_hpss_onsets");
+    if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
     if (c.enable_bpm_fusion) return ni("enable_bpm_fusion");
-    if (c.enable_tempogram_percussive_fallback) return ni("enable_tempogram_percussive_fallback");
     if (c.emit_tempogram_candidates) return ni("emit_tempogram_candidates");
     if (!c.tempogram_band_seed_only) return ni("tempogram_band_seed_only = false");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
@@ -554,6 +554,9 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.onset_pct = c.onset_threshold_percentile;
     d.consensus_tol_ms = c.onset_consensus_tolerance_ms;
     for (int i = 0; i < 4; ++i) d.cons_w[i] = c.onset_consensus_weights[i];
+    d.hpss_onsets = c.enable_hpss_onsets;
+    d.perc_fallback = c.enable_tempogram_percussive_fallback && c.enable_tempogram_multi_resolution && !c.force_legacy_bpm;
+    d.hpss_margin = c.hpss_margin;
     d.sf_k = c.tempogram_superflux_max_filter_bins;
     d.mel_k = c.tempogram_mel_max_filter_bins;
     d.nov_ws = c.tempogram_novelty_w_spectral;
@@ -625,11 +628,11 @@ struct Bump {
     }
 };
 
-static void plan_hop(Bump& fa, HopLayout& H, uint32_t fcap, uint32_t hop) {
+static void plan_hop(Bump& fa, HopLayout& H, uint32_t fcap, uint32_t hop, bool with_spec = true) {
     H.fmax = fcap;
     H.hop = hop;
     H.fft_cap = std::max<uint32_t>(next_pow2_u32(fcap > 1 ? fcap - 1 : 1), 4);
-    H.spec = fa.take((uint64_t)fcap * 1025);
+    H.spec = with_spec ? fa.take((uint64_t)fcap * 1025) : 0;
     H.frame = fa.take((uint64_t)FRAME_Q * fcap);
     H.pair = fa.take((uint64_t)PAIR_Q * fcap);
     H.nov = fa.take((uint64_t)MAX_VARIANTS * fcap);
@@ -673,7 +676,18 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.on_spectral = ia.take(on_cap);
     T.on_hfc = ia.take(on_cap);
     T.on_merged = 0;
-    T.on_final = ia.take((uint64_t)3 * on_cap);
+    T.on_hpss = 0;
+    const bool hpss = cfg.enable_hpss_onsets || cfg.enable_tempogram_percussive_fallback;
+    if (hpss) {  // HPSS work areas (onset/hpss.rs): two ping-pong pairs of F x 1025 and the feature slot of the percussive part
+        T.on_hpss = ia.take(on_cap);
+        for (int q = 0; q < 2; ++q) {
+            T.hpss_h[q] = fa.take((uint64_t)std::max(F512, 1u) * 1025);
+            T.hpss_p[q] = fa.take((uint64_t)std::max(F512, 1u) * 1025);
+        }
+        plan_hop(fa, T.hop[SLOT_PERC], std::max(F512, 1u), 512, false);
+        T.cands[SLOT_PERC] = fa.take((uint64_t)MAX_CANDS * 4);
+    }
+    T.on_final = ia.take((uint64_t)(hpss ? 4 : 3) * on_cap);
     // beat tracker: bpm <= 300 -> at most 5 beat frames per second
     const double dur = (double)n / (double)std::max(T.sr, 1u);
     T.hmm_cap = (uint32_t)std::ceil(dur * 5.0) + 8;
@@ -799,7 +813,7 @@ static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* 
     r->tempogram_multi_res_triggered = T.mr_triggered;
     r->tempogram_multi_res_used = T.mr_used;
     r->tempogram_percussive_triggered = T.perc_triggered;
-    r->tempogram_percussive_used = -1;
+    r->tempogram_percussive_used = T.perc_used;
     r->trim_start = T.trim_start;
     r->trim_end = T.trim_end;
     r->n_onsets = T.n_on_final;
@@ -859,7 +873,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         T.n = lens[gi];
         T.sr = srs[gi];
         T.status = 0;
-        T.mr_triggered = T.mr_used = T.perc_triggered = -1;
+        T.mr_triggered = T.mr_used = T.perc_triggered = T.perc_used = -1;
         if (T.n == 0) { T.status = STRATUM_INVALID_INPUT; T.err_code = 1; }
         else if (T.sr == 0) { T.status = STRATUM_INVALID_INPUT; T.err_code = 2; }
         else if (T.n >= (1ull << 31)) { T.status = STRATUM_NOT_IMPLEMENTED; T.err_code = 5; }
@@ -874,6 +888,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         }
         plan_track(fa, oa, ia, T, cfg);
         T.hop[0].tgtw = get_tw(c, T.hop[0].fft_cap);
+        if (dcfg.hpss_onsets || dcfg.perc_fallback) T.hop[SLOT_PERC].tgtw = get_tw(c, T.hop[SLOT_PERC].fft_cap);
         T.lg_tw = get_tw(c, T.lg_fft);
         if (!T.hop[0].tgtw || !T.lg_tw) {
             set_error("twiddle table allocation failed");
@@ -888,6 +903,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         w.max_F[0] = std::max(w.max_F[0], frames_of(T.n, 2048, 512));
         w.max_F[1] = std::max(w.max_F[1], frames_of(T.n, 2048, 256));
         w.max_F[2] = std::max(w.max_F[2], frames_of(T.n, 2048, 1024));
+        w.max_F[SLOT_PERC] = w.max_F[0];
         w.max_Fk = std::max(w.max_Fk, frames_of(T.n, 8192, 512));
         w.max_Fsil = std::max(w.max_Fsil, Fsil);
         w.max_n = std::max<uint64_t>(w.max_n, T.n);
@@ -1005,6 +1021,12 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     { StageTimer t(s, "onsets_energy"); launch_energy_onsets(w); }
     { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, 0, nullptr, nt); }
     { StageTimer t(s, "spec_features"); launch_spec_features(w, 0, nullptr, nt); }
+    if (dcfg.hpss_onsets) {  // lib.rs:222-235: onsets of the percussive component as the fourth detector
+        StageTimer t(s, "hpss");
+        launch_hpss(w, nullptr, nt);
+        launch_seq_features(w, SLOT_PERC, nullptr, nt);
+        launch_hpss_onsets(w);
+    }
     { StageTimer t(s, "onsets_consensus"); launch_spectral_onsets_consensus(w); }
     const bool want_tempogram = !dcfg.force_legacy;
     if (want_tempogram) {
@@ -1065,6 +1087,23 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             }
         }
     }
+    if (want_tempogram && dcfg.mr_enabled && dcfg.perc_fallback) {
+        // percussive tempogram fallback (lib.rs:587-683) for the tracks the gate put in the low-tempo trap; `tracks` was
+        // read back after the gate, so perc_triggered is valid on the host
+        std::vector<int32_t> pl;
+        for (int i = 0; i < nt; ++i)
+            if (tracks[i].status == 0 && tracks[i].perc_triggered == 1) pl.push_back(i);
+        if (!pl.empty()) {
+            StageTimer t(s, "percussive_fallback");
+            const int nl = (int)pl.size();
+            CUDA_OK(cudaMemcpyAsync(c.d_list, pl.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, s));
+            if (!dcfg.hpss_onsets) launch_hpss(w, c.d_list, nl);
+            launch_spec_features(w, SLOT_PERC, c.d_list, nl);
+            launch_tempogram(w, SLOT_PERC, c.d_list, nl);
+            launch_perc_accept(w, c.d_list, nl);
+            CUDA_OK(cudaStreamSynchronize(s));  // `pl` is a stack-owned buffer
+        }
+    }
     { StageTimer t(s, "final_bpm"); launch_final_bpm(w); }
     { StageTimer t(s, "beats"); launch_beat_tracking(w); }
     if (split) {
@@ -1107,6 +1146,13 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             debug_put_i("onset.energy", c.ia + T.on_energy, T.n_on_energy, s);
             debug_put_i("onset.spectral", c.ia + T.on_spectral, T.n_on_spectral, s);
             debug_put_i("onset.hfc", c.ia + T.on_hfc, T.n_on_hfc, s);
+            if (dcfg.hpss_onsets) debug_put_i("onset.hpss", c.ia + T.on_hpss, T.n_on_hpss, s);
+            if (T.hpss_ready) {
+                debug_put("hpss.perc_head", c.fa + T.hop[SLOT_PERC].spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
+                float pe[4] = {T.est[SLOT_PERC].bpm, T.est[SLOT_PERC].confidence, (float)T.est[SLOT_PERC].agreement, (float)T.est[SLOT_PERC].ok};
+                std::lock_guard<std::mutex> lk(g_debug_mu);
+                g_debug_arrays["perc.est"] = std::vector<float>(pe, pe + 4);
+            }
             const char* vn[5] = {"base.nov.full", "base.nov.low", "base.nov.mid", "base.nov.high", "base.nov.mel"};
             for (int v = 0; v < 5; ++v) debug_put(vn[v], c.fa + H.nov + (uint64_t)v * fm, L, s);
             debug_put("base.tg.fft.full", c.fa + H.tgfft, H.fft_cap / 2 + 1, s);

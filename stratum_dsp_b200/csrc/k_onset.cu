@@ -266,15 +266,15 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
 }
 
 // ---- spectral-flux / HFC onsets: exact percentile threshold + peaks -----------------------------
-__global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float* fa, int32_t* ia, DevCfg cfg) {
+__global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float* fa, int32_t* ia, DevCfg cfg, int which0) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t bc[2];
     __shared__ uint32_t sc[34];
     TrackDev& T = tr[blockIdx.x];
-    const int which = blockIdx.y;  // 0 spectral flux, 1 HFC
+    const int which = blockIdx.y + which0;  // 0 spectral flux, 1 HFC, 2 HPSS (energy flux of the percussive component, hpss.rs:300-317)
     if (T.status != 0) return;
     if (threadIdx.x == 0) {
-        if (which == 0) T.n_on_spectral = 0; else T.n_on_hfc = 0;
+        if (which == 0) T.n_on_spectral = 0; else if (which == 1) T.n_on_hfc = 0; else T.n_on_hpss = 0;
     }
     const uint32_t F = T.F[0];
     if (F < 2) return;
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
     if (which == 0) {
         flux = fa + HL.pair + PQ_SFLUX * fm;
     } else {
-        float* hf = fa + T.scratch + fm;  // HFC flux (hfc.rs:151-154)
-        const float* H = fa + HL.frame + FQ_H * fm;
+        float* hf = fa + T.scratch + (which == 1 ? fm : 2 * fm);  // HFC flux (hfc.rs:151-154) / percussive energy flux
+        const float* H = which == 1 ? fa + HL.frame + FQ_H * fm : fa + T.hop[SLOT_PERC].frame + FQ_E * T.hop[SLOT_PERC].fmax;
         for (uint32_t i = threadIdx.x; i < L; i += blockDim.x) hf[i] = __fadd_rn(fmaxf(__fsub_rn(H[i + 1], H[i]), 0.0f), 0.0f);
         __syncthreads();
         flux = hf;
@@ -294,10 +294,10 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
     uint32_t idx = as_u32(__fmul_rn((float)L, cfg.onset_pct));  // spectral_flux.rs:168
     idx = min(idx, L - 1);
     const float thr = block_select_kth(flux, L, idx, hist, bc);
-    int32_t* out = ia + (which == 0 ? T.on_spectral : T.on_hfc);
+    int32_t* out = ia + (which == 0 ? T.on_spectral : (which == 1 ? T.on_hfc : T.on_hpss));
     uint32_t total = compact_peaks(flux, L, thr, 512, T.m, out, sc);  // frame i+1 -> sample (i+1)*hop, kept if < m (lib.rs:181-190)
     if (threadIdx.x == 0) {
-        if (which == 0) T.n_on_spectral = total; else T.n_on_hfc = total;
+        if (which == 0) T.n_on_spectral = total; else if (which == 1) T.n_on_hfc = total; else T.n_on_hpss = total;
     }
 }
 
@@ -338,8 +338,9 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
     }
     const int32_t* G1 = ia + T.on_spectral;
     const int32_t* G2 = ia + T.on_hfc;
-    const uint32_t n1 = T.n_on_spectral, n2 = T.n_on_hfc;
-    const uint32_t total = n0 + n1 + n2;
+    const int32_t* G3 = ia + T.on_hpss;
+    const uint32_t n1 = T.n_on_spectral, n2 = T.n_on_hfc, n3 = cfg.hpss_onsets ? T.n_on_hpss : 0;
+    const uint32_t total = n0 + n1 + n2 + n3;
     if (total == 0) {
         if (threadIdx.x == 0) T.n_on_final = 0;
         return;
@@ -354,18 +355,21 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
         for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) in[i] = G0[i];
         for (uint32_t i = threadIdx.x; i < n1; i += blockDim.x) in[n0 + i] = G1[i];
         for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) in[n0 + n1 + i] = G2[i];
+        for (uint32_t i = threadIdx.x; i < n3; i += blockDim.x) in[n0 + n1 + n2 + i] = G3[i];
         if (threadIdx.x == 0) s_strong = 0;
         __syncthreads();
-        const int32_t *L0 = in, *L1 = in + n0, *L2 = in + n0 + n1;
+        const int32_t* L[4] = {in, in + n0, in + n0 + n1, in + n0 + n1 + n2};
+        const uint32_t nl[4] = {n0, n1, n2, n3};
         for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
-            uint32_t m, i;
-            if (e < n0) { m = 0; i = e; } else if (e < n0 + n1) { m = 1; i = e - n0; } else { m = 2; i = e - n0 - n1; }
+            uint32_t m = 0, i = e;
+            while (i >= nl[m]) {
+                i -= nl[m];
+                ++m;
+            }
             const int32_t s = in[e];
             uint32_t r = i;
-            if (m != 0) r += count_less(L0, n0, s, true);          // lower method ids come first on ties
-            else { r += count_less(L1, n1, s, false); r += count_less(L2, n2, s, false); }
-            if (m == 1) r += count_less(L2, n2, s, false);
-            if (m == 2) r += count_less(L1, n1, s, true);
+            for (uint32_t q = 0; q < 4; ++q)
+                if (q != m) r += count_less(L[q], nl[q], s, q < m);  // lower method ids come first on ties
             merged[r] = s;
             meth[r] = (uint8_t)m;
         }
@@ -411,12 +415,12 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
     }
     // ---- slow path ----
     if (threadIdx.x == 0) {
-        const int32_t *L0 = G0, *L1 = G1, *L2 = G2;
+        const int32_t *L0 = G0, *L1 = G1, *L2 = G2, *L3 = G3;
         int32_t* fin = gfin;
         uint32_t strong = 0, nfinal = 0;
         for (int pass = 0; pass < 2; ++pass) {
             const bool want_strong = strong > 0;
-            uint32_t i0 = 0, i1 = 0, i2 = 0, w = 0;
+            uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0, w = 0;
             bool open = false;
             int64_t last = 0;
             uint64_t sum = 0;
@@ -430,13 +434,14 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
                     if (w == 0 || fin[w - 1] != c) fin[w++] = c;
                 }
             };
-            while (i0 < n0 || i1 < n1 || i2 < n2) {
+            while (i0 < n0 || i1 < n1 || i2 < n2 || i3 < n3) {
                 int method = -1;
                 int32_t s = 0x7fffffff;
                 if (i0 < n0 && L0[i0] < s) { s = L0[i0]; method = 0; }
                 if (i1 < n1 && L1[i1] < s) { s = L1[i1]; method = 1; }
                 if (i2 < n2 && L2[i2] < s) { s = L2[i2]; method = 2; }
-                if (method == 0) ++i0; else if (method == 1) ++i1; else ++i2;
+                if (i3 < n3 && L3[i3] < s) { s = L3[i3]; method = 3; }
+                if (method == 0) ++i0; else if (method == 1) ++i1; else if (method == 2) ++i2; else ++i3;
                 if (open && (int64_t)s - last > (int64_t)tol) { close(); open = false; }
                 if (!open) { open = true; sum = 0; cnt = 0; voted = 0; }
                 sum += (uint64_t)s;
@@ -460,6 +465,20 @@ void launch_energy_onsets(const WaveCtx& c) {
     count_launch("onsets");
 }
 
+// Percussive-component onsets (lib.rs:222-235): frame energies come from seq_feat_kernel on the percussive slot.
+void launch_hpss_onsets(const WaveCtx& c) {
+    if (c.max_F[0] == 0) return;
+    spectral_onset_kernel<<<dim3(c.n_tracks, 1), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg, 2);
+    count_launch("hpss");
+}
+
+void launch_seq_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
+    if (c.max_F[h] == 0 || n_list == 0) return;
+    dim3 grid((c.max_F[h] + 127) / 128, n_list);
+    seq_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
+    count_launch("spec_features");
+}
+
 void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (c.max_F[h] == 0 || n_list == 0) return;
     dim3 grid((c.max_F[h] + 127) / 128, n_list);
@@ -471,7 +490,7 @@ void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_
 
 void launch_spectral_onsets_consensus(const WaveCtx& c) {
     if (c.cfg.enable_consensus && c.max_F[0] > 0) {
-        spectral_onset_kernel<<<dim3(c.n_tracks, 2), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg);
+        spectral_onset_kernel<<<dim3(c.n_tracks, 2), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg, 0);
         count_launch("onsets");
     }
     {

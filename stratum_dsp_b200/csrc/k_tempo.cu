@@ -527,6 +527,8 @@ __global__ void escalation_gate_kernel(TrackDev* tr, const float* fa, int n_trac
     T.mr_triggered = -1;
     T.mr_used = -1;
     T.perc_triggered = -1;
+    T.perc_used = -1;
+    T.chosen_agree = T.est[0].ok ? T.est[0].agreement : 0;
     T.trap_low = T.trap_high = 0;
     if (T.status != 0 || !T.est[0].ok || !cfg.mr_enabled || cfg.force_legacy) return;
     const TempoEstDev& b = T.est[0];
@@ -546,6 +548,7 @@ __global__ void escalation_gate_kernel(TrackDev* tr, const float* fa, int n_trac
     T.mr_triggered = ambiguous ? 1 : 0;
     T.mr_used = 0;
     T.perc_triggered = (ambiguous && trap_low) ? 1 : 0;
+    if (cfg.perc_fallback) T.perc_used = 0;  // lib.rs:587-683: Some(false) unless the fallback is evaluated and accepted
     T.trap_low = trap_low;
     T.trap_high = trap_high;
 }
@@ -816,6 +819,7 @@ __global__ void __launch_bounds__(128) multires_fusion_kernel(TrackDev* tr, cons
             T.mr_used = 1;
             T.bpm = bb;
             T.bpm_confidence = conf;
+            T.chosen_agree = agree;
         }
     }
 }
@@ -830,7 +834,8 @@ __global__ void final_bpm_kernel(TrackDev* tr, int n_tracks, DevCfg cfg) {
     if (cfg.force_legacy) {
         if (T.legacy.ok) { bpm = T.legacy.bpm; conf = T.legacy.confidence; }
     } else if (T.est[0].ok) {
-        if (T.mr_used == 1) { bpm = T.bpm; conf = T.bpm_confidence; }
+        if (T.perc_used == 1) { bpm = T.perc_bpm; conf = T.perc_conf; }
+        else if (T.mr_used == 1) { bpm = T.bpm; conf = T.bpm_confidence; }
         else { bpm = T.est[0].bpm; conf = T.est[0].confidence; }
     } else if (T.legacy.ok) {
         bpm = T.legacy.bpm;
@@ -838,6 +843,41 @@ __global__ void final_bpm_kernel(TrackDev* tr, int n_tracks, DevCfg cfg) {
     }
     T.bpm = bpm;
     T.bpm_confidence = conf;
+}
+
+// ---- percussive tempogram fallback: acceptance rule of lib.rs:621-662, one thread per listed track ------------
+__global__ void perc_accept_kernel(TrackDev* tr, const int32_t* __restrict__ list, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrackDev& T = tr[list[i]];
+    if (T.status != 0 || !T.est[0].ok) return;
+    T.perc_used = 0;
+    const TempoEstDev& pe = T.est[SLOT_PERC];
+    if (!pe.ok) return;  // "Percussive tempogram fallback failed"
+    const TempoEstDev& base = T.est[0];
+    const float cb = T.mr_used == 1 ? T.bpm : base.bpm;  // chosen_est after the multi-resolution decision
+    const float cc = T.mr_used == 1 ? T.bpm_confidence : base.confidence;
+    const uint32_t ca = T.chosen_agree;
+    const float rel = cb > 1e-6f ? fmaxf(__fdiv_rn(pe.bpm, cb), __fdiv_rn(cb, pe.bpm)) : 1.0f;
+    const bool family_related = fabsf(__fsub_rn(rel, 2.0f)) < 0.05f || fabsf(__fsub_rn(rel, 1.5f)) < 0.05f || fabsf(__fsub_rn(rel, 4.0f / 3.0f)) < 0.05f ||
+                                fabsf(__fsub_rn(rel, 3.0f / 2.0f)) < 0.05f || fabsf(__fsub_rn(rel, 2.0f / 3.0f)) < 0.05f || fabsf(__fsub_rn(rel, 3.0f / 4.0f)) < 0.05f;
+    const bool forbid_promote_high = cb <= 180.0f && pe.bpm > 180.0f;
+    const bool base_low_trap = T.trap_low || base.bpm < 95.0f;
+    const bool percussive_in_common = pe.bpm >= 70.0f && pe.bpm <= 180.0f;
+    const bool p_better = !forbid_promote_high && family_related && percussive_in_common &&
+                          (pe.confidence >= __fadd_rn(cc, 0.04f) || (base_low_trap && pe.confidence >= __fmul_rn(cc, 0.85f)) ||
+                           (pe.agreement > ca && pe.confidence >= __fmul_rn(cc, 0.92f)));
+    if (p_better) {
+        T.perc_used = 1;
+        T.perc_bpm = pe.bpm;
+        T.perc_conf = pe.confidence;
+    }
+}
+
+void launch_perc_accept(const WaveCtx& c, const int32_t* d_list, int n_list) {
+    if (n_list == 0) return;
+    perc_accept_kernel<<<(n_list + 127) / 128, 128, 0, c.stream>>>(c.tracks, d_list, n_list);
+    count_launch("hpss");
 }
 
 void launch_tempogram(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
@@ -860,7 +900,7 @@ void launch_tempogram(const WaveCtx& c, int h, const int32_t* d_list, int n_list
         tgac_kernel<<<g5, 256, smem_floats * sizeof(float), c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg, smem_floats);
     }
     count_launch("tempogram");
-    const uint32_t top_n = (h == 0) ? c.cfg.base_top_n : c.cfg.mr_aux_k;
+    const uint32_t top_n = (h == 0 || h == SLOT_PERC) ? c.cfg.base_top_n : c.cfg.mr_aux_k;
     score_kernel<<<n_list, 256, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg, top_n);
     count_launch("tempogram");
 }

@@ -16,6 +16,8 @@ struct DevCfg {
     float onset_pct;
     uint32_t consensus_tol_ms;
     float cons_w[4];
+    int32_t hpss_onsets, perc_fallback;
+    uint32_t hpss_margin;
     uint32_t sf_k, mel_k;
     float nov_ws, nov_we, nov_wh;
     uint32_t nov_lmw, nov_smw;
@@ -65,7 +67,7 @@ struct WaveCtx {
     Tables tab;
     DevCfg cfg;
     // maxima over the wave (grid sizing upper bounds)
-    uint32_t max_F[N_HOPS], max_Fk, max_Fsil;
+    uint32_t max_F[N_SLOTS], max_Fk, max_Fsil;
     uint64_t max_n;
     uint32_t max_beat_cap;
     uint32_t max_seg_cap;
@@ -96,6 +98,11 @@ void launch_multires_fusion(const WaveCtx& c, const int32_t* d_list, int n_list)
 void launch_final_bpm(const WaveCtx& c);
 // k_legacy.cu
 void launch_legacy_bpm(const WaveCtx& c);
+// k_hpss.cu
+void launch_hpss(const WaveCtx& c, const int32_t* d_list, int n_list);
+void launch_hpss_onsets(const WaveCtx& c);
+void launch_seq_features(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);
+void launch_perc_accept(const WaveCtx& c, const int32_t* d_list, int n_list);
 // k_beat.cu
 void launch_beat_tracking(const WaveCtx& c);
 // k_key.cu

@@ -62,6 +62,8 @@ def _load(fast: bool = False) -> C.CDLL:
     lib.so_key_name.argtypes = [C.c_int, C.c_uint32, C.c_int, cp, C.c_int]
     lib.so_hmm.argtypes = [C.c_float, f32p, C.c_int, C.POINTER(C.c_int32), f32p, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     lib.so_beat_grid.argtypes = [C.c_float, C.c_float, f32p, C.c_int, C.c_uint32, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.so_hpss_decompose.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint64, f32p, f32p]
+    lib.so_hpss_onsets.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_float, i64p, C.c_int]
     lib.so_batch_timed.argtypes = [f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, f32p, C.POINTER(C.c_int),
                                    C.POINTER(C.c_double)]
     lib.so_batch_timed.restype = C.c_double

@@ -72,7 +72,7 @@ def test_errors_match_reference():
         S.analyze_audio(np.ones(100, np.float32), 0)
     assert e.value.kind == "InvalidInput"
     with pytest.raises(S.AnalysisError) as e:
-        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(enable_hpss_onsets=True))
+        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(enable_bpm_fusion=True))
     assert e.value.kind == "NotImplemented"  # unsupported switches are rejected, never silently ignored
 
 
@@ -268,3 +268,34 @@ def test_analyze_batch_cli_jsonl(tmp_path):
         assert l["bpm"] > 0
     assert set(lines[3]) == {"file", "error"}
     assert "Done: ok=3/4" in out.stderr
+
+
+def test_hpss_onsets_fourth_detector():
+    # enable_hpss_onsets (lib.rs:222-235) — iterative median filtering on the device, 4-way consensus
+    x = synth.render(synth.c2_params(95, 7 * SR, SR))
+    cfg = {"enable_hpss_onsets": 1}
+    o = O.analyze(x, SR, cfg, dump=True, fast=True)
+    S.debug_enable(True)
+    try:
+        g = S.analyze_audio(x, SR, S.AnalysisConfig(**cfg))
+        assert np.array_equal(S.debug_array("onset.hpss").astype(np.int64), o.iarray("onset.hpss"))
+        ph = o.farray("hpss.perc_head")
+        assert np.array_equal(S.debug_array("hpss.perc_head")[: ph.size], ph)  # medians, divisions, products: exact
+    finally:
+        S.debug_enable(False)
+    assert_parity(g, o, "hpss onsets")
+    batch = S.analyze_batch([x, synth.render(synth.c2_params(96, 6 * SR, SR))], SR, S.AnalysisConfig(**cfg))
+    assert np.array_equal(batch[0].onsets, g.onsets) and batch[0].bpm == g.bpm
+
+
+def test_percussive_tempogram_fallback():
+    # lib.rs:587-683: HPSS + tempogram on the percussive component for low-tempo-trap tracks
+    cfg = {"enable_tempogram_percussive_fallback": 1}
+    for bpm in (74.0, 128.0):
+        x = synth.render(synth.TrackParams(bpm, 2, 0, 0.25, 0.1, SR, 8 * SR))
+        o = O.analyze(x, SR, cfg, fast=True)
+        g = S.analyze_audio(x, SR, S.AnalysisConfig(**cfg))
+        assert_parity(g, o, f"perc fallback bpm={bpm}")
+        opt = lambda v: None if v < 0 else bool(v)
+        assert g.metadata.tempogram_percussive_triggered == opt(o.percussive_triggered)
+        assert g.metadata.tempogram_percussive_used == opt(o.percussive_used)

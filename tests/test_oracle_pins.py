@@ -182,3 +182,27 @@ def test_oracle_is_deterministic_and_build_independent():
     x = synth.render(p)
     a, b = O.analyze(x, 44100), O.analyze(x, 44100, fast=True)
     assert a.bpm == b.bpm and a.key == b.key and a.key_clarity == b.key_clarity and np.array_equal(a.beats, b.beats)
+
+
+def test_hpss_known_answers():
+    # onset/hpss.rs:379-420: constant spectrogram -> harmonic + percussive reconstruct the input; empty input is an error
+    L = O.lib()
+    spec = np.full((10, 64), 0.5, np.float32)
+    h, p = np.zeros_like(spec), np.zeros_like(spec)
+    assert L.so_hpss_decompose(O.f32ptr(spec), 10, 64, 5, O.f32ptr(h), O.f32ptr(p)) == 0
+    assert np.abs(h + p - spec).max() < 0.1 and np.allclose(h, 0.25) and np.allclose(p, 0.25)
+    assert L.so_hpss_decompose(O.f32ptr(spec), 0, 64, 5, O.f32ptr(h), O.f32ptr(p)) == 1
+    # a percussive burst (one bright frame) ends up in the percussive part and is picked as an onset at that frame
+    spec = np.full((40, 64), 0.01, np.float32)
+    spec[20] = 1.0
+    h, p = np.zeros_like(spec), np.zeros_like(spec)
+    assert L.so_hpss_decompose(O.f32ptr(spec), 40, 64, 10, O.f32ptr(h), O.f32ptr(p)) == 0
+    assert p[20].sum() > 10 * h[20].sum()
+    on = np.zeros(8, np.int64)
+    n = L.so_hpss_onsets(O.f32ptr(p), 40, 64, 0.8, O.i64ptr(on), 8)
+    assert n >= 1 and 20 in on[:n]
+    # a steady tone (one bright bin) stays harmonic
+    spec = np.full((40, 64), 0.01, np.float32)
+    spec[:, 30] = 1.0
+    assert L.so_hpss_decompose(O.f32ptr(spec), 40, 64, 10, O.f32ptr(h), O.f32ptr(p)) == 0
+    assert h[:, 30].sum() > 10 * p[:, 30].sum()
