@@ -114,8 +114,10 @@ typedef struct StratumConfig {
     int32_t enable_key_hpss_harmonic, enable_key_log_frequency, enable_key_beat_synchronous, enable_key_multi_scale,
         enable_key_ensemble, enable_key_median, enable_key_tuning_compensation, enable_key_edge_trim, enable_key_mode_heuristic,
         enable_key_hpcp_whitening, enable_key_hpcp_bass_blend, enable_key_minor_harmonic_bonus;
-    float chroma_sharpening_power; /* must be <= 1.0 */
+    float chroma_sharpening_power; /* > 1 sharpens the chroma vectors (chroma/normalization.rs:41-65) */
     uint32_t hpss_margin;          /* median half-width of the HPSS filters (config.rs:43, default 10; at most 10 here) */
+    int32_t soft_chroma_mapping;   /* chroma folding (enable_key_hpcp = 0): Gaussian soft mapping (config.rs:244, default 1) */
+    int32_t enable_key_spectrogram_time_smoothing; /* used when the harmonic mask is off (config.rs:261, default 1) */
 } StratumConfig;
 
 /* AnalysisResult + AnalysisMetadata (src/analysis/result.rs:183-263; built at src/lib.rs:1592-1619). */

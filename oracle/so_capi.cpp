@@ -28,7 +28,7 @@ struct SoHandle {
     X(tempogram_mel_n_mels) X(tempogram_mel_fmin_hz) X(tempogram_mel_fmax_hz) X(tempogram_mel_max_filter_bins) X(tempogram_mel_weight)    \
     X(tempogram_superflux_max_filter_bins) X(tempogram_candidates_top_n) X(legacy_bpm_preferred_min) X(legacy_bpm_preferred_max)          \
     X(legacy_bpm_soft_min) X(legacy_bpm_soft_max) X(legacy_bpm_conf_mul_preferred) X(legacy_bpm_conf_mul_soft)                            \
-    X(legacy_bpm_conf_mul_extreme) X(min_bpm) X(max_bpm) X(bpm_resolution) X(frame_size) X(hop_size) X(soft_mapping_sigma)                \
+    X(legacy_bpm_conf_mul_extreme) X(min_bpm) X(max_bpm) X(bpm_resolution) X(frame_size) X(hop_size) X(soft_chroma_mapping) X(soft_mapping_sigma) X(chroma_sharpening_power) X(enable_key_spectrogram_time_smoothing)                \
     X(key_spectrogram_smooth_margin) X(enable_key_frame_weighting) X(key_min_tonalness) X(key_tonalness_power) X(key_energy_power)        \
     X(enable_key_harmonic_mask) X(key_harmonic_mask_power) X(enable_key_stft_override) X(key_stft_frame_size) X(key_stft_hop_size)        \
     X(enable_key_segment_voting) X(key_segment_len_frames) X(key_segment_hop_frames) X(key_segment_min_clarity) X(enable_key_hpcp)        \

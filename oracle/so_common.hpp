@@ -133,7 +133,10 @@ struct Config {
     float bpm_resolution = 1.0f;
     size_t frame_size = 2048;
     size_t hop_size = 512;
+    bool soft_chroma_mapping = true;
     float soft_mapping_sigma = 0.5f;
+    float chroma_sharpening_power = 1.0f;
+    bool enable_key_spectrogram_time_smoothing = true;
     size_t key_spectrogram_smooth_margin = 12;
     bool enable_key_frame_weighting = true;
     float key_min_tonalness = 0.0f;
@@ -271,6 +274,8 @@ Error generate_beat_grid(float bpm, float bpm_conf, const std::vector<float>& on
 
 // ---- key ---------------------------------------------------------------------------
 Spec harmonic_spectrogram_time_mask(const Spec& K, size_t margin, float power);
+Spec smooth_spectrogram_time(const Spec& K, size_t margin);
+void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, float sigma, std::vector<float>& chroma, std::vector<float>& energy);
 void extract_hpcp(const Spec& K, uint32_t sr, size_t fft_size, const Config& c, std::vector<float>& chroma /*frames*12*/, std::vector<float>& energy);
 void smooth_chroma(std::vector<float>& chroma, size_t frames, size_t window);
 struct KeyScores {

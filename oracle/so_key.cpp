@@ -47,6 +47,28 @@ Spec harmonic_spectrogram_time_mask(const Spec& K, size_t margin, float power) {
     return out;
 }
 
+// smooth_spectrogram_time — extractor.rs:1246-1290 (same sequential prefix as the mask above)
+Spec smooth_spectrogram_time(const Spec& K, size_t margin) {
+    if (K.frames == 0 || margin == 0) return K;
+    Spec out;
+    out.frames = K.frames;
+    out.bins = K.bins;
+    out.d.assign(K.d.size(), 0.0f);
+    const size_t nf = K.frames, nb = K.bins;
+    std::vector<float> prefix(nf + 1);
+    for (size_t b = 0; b < nb; ++b) {
+        prefix[0] = 0.0f;
+        for (size_t t = 0; t < nf; ++t) prefix[t + 1] = prefix[t] + K.d[t * nb + b];
+        for (size_t t = 0; t < nf; ++t) {
+            size_t st = t >= margin ? t - margin : 0, en = std::min(t + margin + 1, nf);
+            float sum = prefix[en] - prefix[st];
+            float denom = (float)std::max<size_t>(en - st, 1);
+            out.d[t * nb + b] = sum / denom;
+        }
+    }
+    return out;
+}
+
 // rem_euclid for f32 (Rust): r = fmod(a,b); if r < 0 { r += |b| }
 static float rem_euclid(float a, float b) {
     float r = fmodf(a, b);
@@ -117,6 +139,55 @@ static void frame_to_hpcp(const float* mag, size_t nb, uint32_t sr, size_t fft_s
     float norm = sqrtf(ss);
     if (norm > EPSILON)
         for (int i = 0; i < 12; ++i) pc[i] /= norm;
+}
+
+// frame_to_chroma_tuned ("chroma folding") — extractor.rs:393-487, tuning offset 0
+static void frame_to_chroma(const float* mag, size_t nb, uint32_t sr, size_t fft_size, bool soft, float sigma_in, float pc[12]) {
+    for (int i = 0; i < 12; ++i) pc[i] = 0.0f;
+    float res = (float)sr / (float)fft_size;
+    for (size_t b = 0; b < nb; ++b) {
+        float freq = (float)b * res;
+        if (freq < 100.0f) continue;
+        if (freq > fmin_rs(5000.0f, (float)sr / 2.0f)) break;
+        if (freq >= (float)sr / 2.0f) break;
+        float semitone = 12.0f * log2f(freq / 440.0f) + 57.0f - 0.0f;
+        float contrib = powf(fmax_rs(mag[b], 0.0f), 0.6f);
+        if (soft) {
+            float spc = rem_euclid(semitone, 12.0f);
+            float ppc = rem_euclid(roundf(spc), 12.0f);
+            int primary = as_i32(ppc);
+            for (int off = -1; off <= 1; ++off) {
+                int tc = ((primary + off) % 12 + 12) % 12;
+                float dist = fabsf(spc - (float)tc);
+                dist = fmin_rs(dist, 12.0f - dist);
+                float sigma = fmax_rs(sigma_in, 1e-6f);
+                float w = expf(-dist * dist / (2.0f * sigma * sigma));
+                pc[tc] += contrib * w;
+            }
+        } else {
+            int cls = as_i32(roundf(semitone)) % 12;
+            if (cls < 0) cls += 12;
+            pc[cls] += contrib;
+        }
+    }
+    float ss = 0.0f;
+    for (int i = 0; i < 12; ++i) ss += pc[i] * pc[i];
+    float norm = sqrtf(ss);
+    if (norm > EPSILON)
+        for (int i = 0; i < 12; ++i) pc[i] /= norm;
+}
+
+// extract_chroma_from_spectrogram_with_options_and_energy — extractor.rs:1028-1091
+void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, float sigma, std::vector<float>& chroma, std::vector<float>& energy) {
+    chroma.assign(K.frames * 12, 0.0f);
+    energy.assign(K.frames, 0.0f);
+    for (size_t t = 0; t < K.frames; ++t) {
+        const float* r = K.row(t);
+        float e = 0.0f;
+        for (size_t b = 0; b < K.bins; ++b) e += r[b] * r[b];
+        energy[t] = e;
+        frame_to_chroma(r, K.bins, sr, fft_size, soft, sigma, &chroma[t * 12]);
+    }
 }
 
 // extract_hpcp_from_spectrogram_with_options_and_energy_tuned — extractor.rs:1097-1150
@@ -294,13 +365,33 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
     const Spec& K = c.enable_key_stft_override ? Kown : S_base;
     Spec masked;
     const Spec* forkey = &K;
-    if (!K.empty() && c.enable_key_harmonic_mask) {
+    if (!K.empty() && c.enable_key_harmonic_mask) {  // lib.rs:1011-1060
         masked = harmonic_spectrogram_time_mask(K, c.key_spectrogram_smooth_margin, c.key_harmonic_mask_power);
+        forkey = &masked;
+    } else if (!K.empty() && c.enable_key_spectrogram_time_smoothing) {
+        masked = smooth_spectrogram_time(K, c.key_spectrogram_smooth_margin);
         forkey = &masked;
     }
     std::vector<float> chroma, energy;
-    extract_hpcp(*forkey, sr, kfft, c, chroma, energy);
+    if (c.enable_key_hpcp)
+        extract_hpcp(*forkey, sr, kfft, c, chroma, energy);
+    else  // lib.rs:1188-1196 (tuning compensation off)
+        extract_chroma(*forkey, sr, kfft, c.soft_chroma_mapping, c.soft_mapping_sigma, chroma, energy);
     size_t nf = forkey->frames;
+    if (c.chroma_sharpening_power > 1.0f)  // lib.rs:1200-1208, chroma/normalization.rs:41-65
+        for (size_t t = 0; t < nf; ++t) {
+            float* ch = &chroma[t * 12];
+            float ss = 0.0f;
+            for (int i = 0; i < 12; ++i) {
+                ch[i] = powf(ch[i], c.chroma_sharpening_power);
+                ss += ch[i] * ch[i];
+            }
+            float norm = sqrtf(ss);
+            if (norm > EPSILON)
+                for (int i = 0; i < 12; ++i) ch[i] /= norm;
+            else
+                for (int i = 0; i < 12; ++i) ch[i] = 1.0f / sqrtf(12.0f);
+        }
     if (dump) {
         dump->f["key.hpcp_raw"] = chroma;
         dump->f["key.energy"] = energy;

@@ -85,7 +85,8 @@ class StratumConfig(C.Structure):
         ("enable_key_multi_scale", _i), ("enable_key_ensemble", _i), ("enable_key_median", _i),
         ("enable_key_tuning_compensation", _i), ("enable_key_edge_trim", _i), ("enable_key_mode_heuristic", _i),
         ("enable_key_hpcp_whitening", _i), ("enable_key_hpcp_bass_blend", _i), ("enable_key_minor_harmonic_bonus", _i),
-        ("chroma_sharpening_power", _f), ("hpss_margin", _u),
+        ("chroma_sharpening_power", _f), ("hpss_margin", _u), ("soft_chroma_mapping", _i),
+        ("enable_key_spectrogram_time_smoothing", _i),
     ]
 
 

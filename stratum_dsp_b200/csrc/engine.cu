@@ -107,6 +107,7 @@ struct DeviceCtx {
     std::vector<void*> owned;                 // table allocations
     std::map<uint32_t, float2*> tw_tables;    // size -> TW table (Stockham twiddles, oracle/so_fft.cpp)
     std::vector<SrTables> sr_host;
+    std::vector<StratumConfig> sr_cfg;        // configuration each sr_host entry was built for (the tables depend on it)
     SrTables* d_srtab = nullptr;
     static constexpr int MAX_SR = 32;
     float* fa = nullptr;
@@ -272,12 +273,12 @@ static uint32_t hz_to_bin(float hz, float res, uint32_t n_bins) {  // period/tem
 
 static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slot_out) {
     for (size_t i = 0; i < c.sr_host.size(); ++i)
-        if (c.sr_host[i].sr == sr) {
+        if (c.sr_host[i].sr == sr && memcmp(&c.sr_cfg[i], &cfg, sizeof cfg) == 0) {
             *slot_out = (int)i;
             return STRATUM_OK;
         }
     if ((int)c.sr_host.size() >= DeviceCtx::MAX_SR) {
-        set_error("too many distinct sample rates in one process (max 32)");
+        set_error("too many distinct (sample rate, configuration) pairs in one batch (max 32)");
         return STRATUM_NOT_IMPLEMENTED;
     }
     SrTables st{};
@@ -400,7 +401,61 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         set_error("sample rates below ~20 kHz are not supported (more than 512 HPCP peak slots per key frame)");
         return STRATUM_NOT_IMPLEMENTED;
     }
+    {   // chroma folding (extractor.rs:393-487): the bin -> pitch-class weights do not depend on the frame, so they are
+        // tabulated per pitch class in ascending-bin order (the order in which the reference adds them)
+        std::vector<int32_t> off(13, 0), bins;
+        std::vector<float> ws;
+        std::vector<std::vector<std::pair<int32_t, float>>> per(12);
+        const float res = (float)sr / 8192.0f;
+        uint32_t lo = 1, hi = 0;
+        bool first = true;
+        for (uint32_t b = 0; b < 4097; ++b) {
+            const float freq = (float)b * res;
+            if (freq < 100.0f) continue;
+            if (freq > fminf(5000.0f, (float)sr / 2.0f)) break;
+            if (freq >= (float)sr / 2.0f) break;
+            if (first) { lo = b; first = false; }
+            hi = b;
+            const float semitone = 12.0f * log2f(freq / 440.0f) + 57.0f - 0.0f;
+            if (cfg.soft_chroma_mapping) {
+                float spc = fmodf(semitone, 12.0f);
+                if (spc < 0.0f) spc += 12.0f;
+                float ppc = fmodf(roundf(spc), 12.0f);
+                if (ppc < 0.0f) ppc += 12.0f;
+                const int primary = (int)ppc;
+                for (int o = -1; o <= 1; ++o) {
+                    const int tc = ((primary + o) % 12 + 12) % 12;
+                    float dist = fabsf(spc - (float)tc);
+                    dist = fminf(dist, 12.0f - dist);
+                    const float sigma = fmaxf(cfg.soft_mapping_sigma, 1e-6f);
+                    per[tc].push_back({(int32_t)b, expf(-dist * dist / (2.0f * sigma * sigma))});
+                }
+            } else {
+                int cls = (int)roundf(semitone) % 12;
+                if (cls < 0) cls += 12;
+                per[cls].push_back({(int32_t)b, 1.0f});
+            }
+        }
+        for (int tc = 0; tc < 12; ++tc) {
+            for (auto& e : per[tc]) {
+                bins.push_back(e.first);
+                ws.push_back(e.second);
+            }
+            off[tc + 1] = (int32_t)bins.size();
+        }
+        if (bins.empty()) { bins.push_back(0); ws.push_back(0.0f); }
+        if (hi >= lo && hi - lo + 1 > 1024) {
+            set_error("sample rates below ~20 kHz are not supported (chroma band wider than 1024 key-STFT bins)");
+            return STRATUM_NOT_IMPLEMENTED;
+        }
+        st.fold_lo = lo;
+        st.fold_hi = hi;
+        st.fold_off = dev_upload(c, off);
+        st.fold_bin = dev_upload(c, bins);
+        st.fold_w = dev_upload(c, ws);
+    }
     c.sr_host.push_back(st);
+    c.sr_cfg.push_back(cfg);
     *slot_out = (int)c.sr_host.size() - 1;
     if (cudaMemcpy(c.d_srtab, c.sr_host.data(), sizeof(SrTables) * c.sr_host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("sr table upload failed");
@@ -488,6 +543,8 @@ static void config_default(StratumConfig* c) {  // src/config.rs:594-744
     c->key_hpcp_mag_power = 0.50f;
     c->chroma_sharpening_power = 1.0f;
     c->hpss_margin = 10;
+    c->soft_chroma_mapping = 1;
+    c->enable_key_spectrogram_time_smoothing = 1;
 }
 
 // Rejects configurations whose branch is not built instead of silently ignoring them.
@@ -510,7 +567,6 @@ static int config_validate(const StratumConfig& c) {
     if (!c.tempogram_band_seed_only) return ni("tempogram_band_seed_only = false");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
     if (!c.enable_key_stft_override || c.key_stft_frame_size != 8192 || c.key_stft_hop_size != 512) return ni("key STFT other than 8192/512");
-    if (!c.enable_key_hpcp) return ni("enable_key_hpcp = false (plain chroma folding)");
     if (c.key_spectrogram_smooth_margin > 15) return ni("key_spectrogram_smooth_margin > 15");
     if (c.key_hpcp_peaks_per_frame > 32) return ni("key_hpcp_peaks_per_frame > 32");
     if (c.key_hpcp_num_harmonics > 8) return ni("key_hpcp_num_harmonics > 8");
@@ -520,7 +576,6 @@ static int config_validate(const StratumConfig& c) {
         c.enable_key_median || c.enable_key_tuning_compensation || c.enable_key_edge_trim || c.enable_key_mode_heuristic || c.enable_key_hpcp_whitening ||
         c.enable_key_hpcp_bass_blend || c.enable_key_minor_harmonic_bonus)
         return ni("optional key-path variants (hpss/log-frequency/beat-sync/multi-scale/ensemble/median/tuning/edge-trim/mode-heuristic/whitening/bass-blend/minor-bonus)");
-    if (c.chroma_sharpening_power > 1.0f) return ni("chroma_sharpening_power > 1");
     if (!(c.min_bpm > 0.0f) || !(c.max_bpm > c.min_bpm) || !(c.bpm_resolution > 0.0f)) {
         set_error("Invalid BPM range");
         return STRATUM_INVALID_INPUT;
@@ -598,6 +653,9 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.key_margin = c.key_spectrogram_smooth_margin;
     d.key_mask_power = c.key_harmonic_mask_power;
     d.key_mask = c.enable_key_harmonic_mask;
+    d.key_smooth_only = !c.enable_key_harmonic_mask && c.enable_key_spectrogram_time_smoothing && c.key_spectrogram_smooth_margin > 0;
+    d.key_hpcp = c.enable_key_hpcp;
+    d.chroma_sharpen = c.chroma_sharpening_power;
     d.key_weighting = c.enable_key_frame_weighting;
     d.key_voting = c.enable_key_segment_voting;
     d.key_min_tonal = c.key_min_tonalness;
@@ -1201,6 +1259,12 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     std::lock_guard<std::mutex> lk(ctx->mu);
     CUDA_OK(cudaSetDevice(ctx->device));
     const DevCfg dcfg = make_devcfg(cfg);
+    // per-sample-rate tables are built for one configuration; a call with another one starts a fresh set when the
+    // table is getting full (slots are only referenced within a call)
+    if (!ctx->sr_cfg.empty() && ctx->sr_host.size() > DeviceCtx::MAX_SR / 2 && memcmp(&ctx->sr_cfg.back(), &cfg, sizeof cfg) != 0) {
+        ctx->sr_host.clear();
+        ctx->sr_cfg.clear();
+    }
     size_t free_b = 0, total_b = 0;
     CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
     // budget: what is free now plus what our own arena already holds, minus head room

@@ -56,6 +56,10 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
             const float denom = (float)max(en - st, 1u);
             h_est = sum / denom;
         }
+        if (cfg.key_smooth_only) {  // smooth_spectrogram_time alone (extractor.rs:1246-1290, lib.rs:1043-1060)
+            K[(uint64_t)t * KBINS] = h_est;
+            return;
+        }
         const float x = fmaxf(xt, 0.0f);
         const float h = fmaxf(h_est, 0.0f);
         const float r = fmaxf(x - h, 0.0f);
@@ -261,6 +265,65 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
     }
     if (lane < 12) fa[T.chroma + (uint64_t)f * 12 + lane] = pc;
     if (lane == 0) fa[T.kenergy + f] = e;
+}
+
+// ---- chroma folding (extractor.rs:393-487, enable_key_hpcp = false): one warp per frame ---------------------------
+// chroma[pc] = sum over band bins (ascending) of max(x,0)^0.6 * w[bin][pc]; the weights (Gaussian soft mapping in
+// circular pitch-class space, or the hard nearest-class assignment) depend only on the bin, so they come from a
+// per-sample-rate table grouped by pitch class in the reference's accumulation order.  The 0.6-power of every band bin
+// is evaluated once, in parallel, into shared memory; 12 lanes then fold their pitch class.
+constexpr int FOLD_MAX = 1024;  // band bins (912 at 44.1 kHz; the ABI rejects sample rates whose band is wider)
+
+__global__ void __launch_bounds__(128) chroma_fold_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
+                                                          float* fa) {
+    __shared__ float contrib[4][FOLD_MAX];
+    const int t = blockIdx.y;
+    const TrackDev& T = tr[t];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * 4 + w;
+    if (T.status != 0 || f >= T.Fk) return;
+    const SrTables& st = srtab[sr_index[t]];
+    const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
+    float e = 0.0f;  // frame energy: tree sum (tolerance-level consumer, see hpcp_kernel)
+    for (uint32_t k = lane; k < KBINS; k += 32) {
+        const float x = row[k];
+        e = e + x * x;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    const uint32_t lo = st.fold_lo, hi = st.fold_hi;
+    float pc = 0.0f;
+    if (lo <= hi) {
+        for (uint32_t b = lo + lane; b <= hi; b += 32) contrib[w][b - lo] = powf(fmaxf(row[b], 0.0f), 0.6f);  // extractor.rs:431
+        __syncwarp();
+        if (lane < 12) {
+            const int a = st.fold_off[lane], z = st.fold_off[lane + 1];
+            for (int q = a; q < z; ++q) pc = pc + contrib[w][st.fold_bin[q] - lo] * st.fold_w[q];
+        }
+        float ss = 0.0f;
+        for (int i = 0; i < 12; ++i) {
+            const float v = __shfl_sync(0xffffffffu, pc, i);
+            ss = ss + v * v;
+        }
+        const float norm = sqrtf(ss);
+        if (norm > 1e-10f) pc = pc / norm;
+    }
+    if (lane < 12) fa[T.chroma + (uint64_t)f * 12 + lane] = pc;
+    if (lane == 0) fa[T.kenergy + f] = e;
+}
+
+// ---- sharpen_chroma (chroma/normalization.rs:41-65): thread per frame ----------------------------------------------
+__global__ void __launch_bounds__(256) chroma_sharpen_kernel(const TrackDev* __restrict__ tr, float* fa, float power) {
+    const TrackDev& T = tr[blockIdx.y];
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T.status != 0 || f >= T.Fk) return;
+    float* ch = fa + T.chroma + (uint64_t)f * 12;
+    float v[12], ss = 0.0f;
+    for (int i = 0; i < 12; ++i) {
+        v[i] = powf(ch[i], power);
+        ss = ss + v[i] * v[i];
+    }
+    const float norm = sqrtf(ss);
+    for (int i = 0; i < 12; ++i) ch[i] = norm > 1e-10f ? v[i] / norm : 1.0f / sqrtf(12.0f);
 }
 
 // ---- 5-tap median over time per pitch class (smoothing.rs:37-94); applied when Fk > 5 --------------
@@ -557,7 +620,7 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
 }
 
 void launch_key_mask(const WaveCtx& c) {
-    if (c.max_Fk > 0 && c.cfg.key_mask) {
+    if (c.max_Fk > 0 && (c.cfg.key_mask || c.cfg.key_smooth_only)) {
         const dim3 g((KBINS + 127) / 128, c.n_tracks);
         if (c.cfg.key_margin == 12) mask_kernel<12><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // default margin (config.rs:669)
         else mask_kernel<0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
@@ -567,8 +630,14 @@ void launch_key_mask(const WaveCtx& c) {
 
 void launch_key_hpcp(const WaveCtx& c) {
     if (c.max_Fk > 0) {
-        hpcp_kernel<<<dim3((c.max_Fk + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+        const dim3 g((c.max_Fk + 3) / 4, c.n_tracks);
+        if (c.cfg.key_hpcp) hpcp_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+        else chroma_fold_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa);
         count_launch("key_hpcp");
+        if (c.cfg.chroma_sharpen > 1.0f) {  // lib.rs:1200-1208
+            chroma_sharpen_kernel<<<dim3((c.max_Fk + 255) / 256, c.n_tracks), 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg.chroma_sharpen);
+            count_launch("key_hpcp");
+        }
     }
 }
 

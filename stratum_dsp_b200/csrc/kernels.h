@@ -33,6 +33,9 @@ struct DevCfg {
     uint32_t key_margin;
     float key_mask_power;
     int32_t key_mask, key_weighting, key_voting;
+    int32_t key_smooth_only;      // harmonic mask off, time smoothing on: the key spectrogram is replaced by its +-margin mean (lib.rs:1043-1060)
+    int32_t key_hpcp;             // 0 = plain chroma folding (extractor.rs:393-487)
+    float chroma_sharpen;         // > 1: sharpen_chroma (chroma/normalization.rs:41-65)
     float key_min_tonal, key_tonal_pow, key_energy_pow;
     uint32_t key_seg_len, key_seg_hop;
     float key_seg_min_clarity;
@@ -50,6 +53,10 @@ struct SrTables {
     const int32_t* mel_bin;           // flat entries in ascending-bin order per band (centre bin twice: rising and falling slope)
     const float* mel_w;
     uint32_t key_bin_lo, key_bin_hi;  // HPCP peak search range in the key STFT (extractor.rs:584-591)
+    uint32_t fold_lo, fold_hi;        // chroma-folding bin range (extractor.rs:407-417); lo > hi = empty
+    const int32_t* fold_off;          // [13] entry ranges per pitch class
+    const int32_t* fold_bin;          // entries in ascending-bin order per pitch class
+    const float* fold_w;              // Gaussian (soft) or unit (hard) weights
     float kw_b0, kw_b1, kw_b2, kw_a1, kw_a2;  // K-weighting biquad (normalization.rs:127-155)
     uint32_t lufs_block;              // (sr * 0.4) as usize, normalization.rs:198
 };

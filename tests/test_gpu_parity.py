@@ -299,3 +299,19 @@ def test_percussive_tempogram_fallback():
         opt = lambda v: None if v < 0 else bool(v)
         assert g.metadata.tempogram_percussive_triggered == opt(o.percussive_triggered)
         assert g.metadata.tempogram_percussive_used == opt(o.percussive_used)
+
+
+@pytest.mark.parametrize("cfg", [
+    {"enable_key_hpcp": 0},                                 # a33: chroma folding, Gaussian soft mapping (extractor.rs:393-487)
+    {"enable_key_hpcp": 0, "soft_chroma_mapping": 0},       # hard nearest-class assignment
+    {"enable_key_hpcp": 0, "chroma_sharpening_power": 1.5}, # sharpen_chroma (chroma/normalization.rs:41-65)
+    {"enable_key_harmonic_mask": 0},                        # time smoothing alone (lib.rs:1043-1060)
+    {"enable_key_harmonic_mask": 0, "enable_key_spectrogram_time_smoothing": 0},  # raw key spectrogram
+    {"chroma_sharpening_power": 2.0},
+])
+def test_key_path_variants(cfg):
+    for i, sr in ((97, SR), (98, 48000)):
+        p = synth.c2_params(i, 22 * sr, sr)
+        p.sample_rate = sr
+        x = synth.render(p)
+        assert_parity(S.analyze_audio(x, sr, S.AnalysisConfig(**cfg)), O.analyze(x, sr, cfg, fast=True), f"{cfg} sr={sr}")
