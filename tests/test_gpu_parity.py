@@ -315,3 +315,35 @@ def test_key_path_variants(cfg):
         p.sample_rate = sr
         x = synth.render(p)
         assert_parity(S.analyze_audio(x, sr, S.AnalysisConfig(**cfg)), O.analyze(x, sr, cfg, fast=True), f"{cfg} sr={sr}")
+
+
+@pytest.mark.parametrize("cfg", [
+    {"force_legacy_bpm": 1},
+    {"enable_tempogram_multi_resolution": 0},
+    {"enable_tempogram_band_fusion": 0},
+    {"enable_tempogram_mel_novelty": 0},
+    {"enable_tempogram_band_fusion": 0, "enable_tempogram_mel_novelty": 0},
+    {"enable_onset_consensus": 0},
+    {"enable_silence_trimming": 0},
+    {"enable_normalization": 0},
+    {"enable_legacy_bpm_guardrails": 0, "force_legacy_bpm": 1},
+    {"onset_threshold_percentile": 0.9, "onset_consensus_tolerance_ms": 30},
+    {"enable_key_frame_weighting": 0},
+    {"enable_key_segment_voting": 0, "enable_key_frame_weighting": 0},
+    {"key_segment_len_frames": 512, "key_segment_hop_frames": 128, "key_segment_min_clarity": 0.5},
+    {"key_spectrogram_smooth_margin": 6, "key_harmonic_mask_power": 1.5},
+    {"key_hpcp_peaks_per_frame": 8, "key_hpcp_num_harmonics": 2, "key_hpcp_harmonic_decay": 0.4, "key_hpcp_mag_power": 0.8},
+    {"tempogram_superflux_max_filter_bins": 2, "tempogram_mel_max_filter_bins": 1, "tempogram_novelty_local_mean_window": 8,
+     "tempogram_novelty_smooth_window": 3},
+    {"min_bpm": 60.0, "max_bpm": 180.0, "bpm_resolution": 0.5},
+    {"tempogram_band_low_max_hz": 150.0, "tempogram_band_mid_max_hz": 1500.0, "tempogram_band_high_max_hz": 6000.0, "tempogram_mel_n_mels": 24},
+    {"min_amplitude_db": -30.0},
+    {"key_min_tonalness": 0.1, "key_tonalness_power": 1.5, "key_energy_power": 0.8},
+])
+def test_accepted_config_switches_match_the_oracle(cfg):
+    # every switch the ABI accepts selects a reference branch: check each against the oracle, not just the defaults
+    xs = [synth.render(synth.TrackParams(76.0, 4, 1, 0.4, 0.08, SR, 24 * SR)), synth.render(synth.c2_params(99, 18 * SR, SR))]
+    quiet = np.concatenate([np.zeros(SR, np.float32), xs[1][: 10 * SR] * np.float32(0.5), np.zeros(2 * SR, np.float32)])
+    res = S.analyze_batch(xs + [quiet], SR, S.AnalysisConfig(**cfg))
+    for i, (x, g) in enumerate(zip(xs + [quiet], res)):
+        assert_parity(g, O.analyze(x, SR, cfg, fast=True), f"{cfg} track {i}")
