@@ -90,7 +90,7 @@ typedef struct StratumConfig {
     uint32_t tempogram_mel_max_filter_bins;
     float tempogram_mel_weight;
     uint32_t tempogram_superflux_max_filter_bins;
-    int32_t emit_tempogram_candidates; /* must be 0 */
+    int32_t emit_tempogram_candidates;
     uint32_t tempogram_candidates_top_n;
     float legacy_bpm_preferred_min, legacy_bpm_preferred_max, legacy_bpm_soft_min, legacy_bpm_soft_max;
     float legacy_bpm_conf_mul_preferred, legacy_bpm_conf_mul_soft, legacy_bpm_conf_mul_extreme;
@@ -119,6 +119,12 @@ typedef struct StratumConfig {
     int32_t soft_chroma_mapping;   /* chroma folding (enable_key_hpcp = 0): Gaussian soft mapping (config.rs:244, default 1) */
     int32_t enable_key_spectrogram_time_smoothing; /* used when the harmonic mask is off (config.rs:261, default 1) */
 } StratumConfig;
+
+/* TempoCandidateDebug (src/analysis/result.rs:170-181). */
+typedef struct StratumTempoCandidate {
+    float bpm, score, fft_norm, autocorr_norm;
+    int32_t selected;
+} StratumTempoCandidate;
 
 /* AnalysisResult + AnalysisMetadata (src/analysis/result.rs:183-263; built at src/lib.rs:1592-1619). */
 typedef struct StratumResult {
@@ -151,6 +157,9 @@ typedef struct StratumResult {
     uint32_t n_hmm_beat_frames;
     int32_t time_sig_beats_per_bar;
     int32_t beats_refined;         /* 1 when the per-segment Bayesian refinement replaced the grid */
+    /* metadata.tempogram_candidates: Option<Vec<..>> — n = -1 is None (emit_tempogram_candidates off or tempogram failed) */
+    StratumTempoCandidate* tempogram_candidates;
+    int32_t n_tempogram_candidates;
 } StratumResult;
 
 /* AnalysisConfidence (src/analysis/confidence.rs:32-68). */

@@ -107,8 +107,12 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
         size_t base_top_n = std::max(std::max(c.tempogram_candidates_top_n, c.tempogram_multi_res_top_k), (size_t)10);
         BpmEstimate base;
         std::vector<TempoCand> base_c;
+        // lib.rs:378-410 / 714-737: with multi-resolution the base call keeps base_top_n candidates; without it candidates are
+        // only kept (top tempogram_candidates_top_n) when emit_tempogram_candidates is set
+        const size_t plain_top_n = c.emit_tempogram_candidates ? c.tempogram_candidates_top_n : 0;
         Error te_ = c.enable_tempogram_multi_resolution ? estimate_bpm_tempogram(S, sr, (uint32_t)c.hop_size, c, base_top_n, base, base_c, dump, "base.")
-                                                        : estimate_bpm_tempogram(S, sr, (uint32_t)c.hop_size, c, 0, base, base_c, dump, "base.");
+                                                        : estimate_bpm_tempogram(S, sr, (uint32_t)c.hop_size, c, plain_top_n, base, base_c, dump, "base.");
+        std::vector<TempoCand> chosen_c = base_c;
         if (!te_) {
             has_tempogram = true;
             tg = base;
@@ -139,6 +143,7 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
                                                    ((mr.bpm >= 70.0f && mr.bpm <= 180.0f) || base.bpm > 180.0f)));
                         if (better) {
                             tg = mr;
+                            chosen_c = mc;
                             used = true;
                         }
                     }
@@ -164,12 +169,17 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
                                                (pe.method_agreement > tg.method_agreement && pe.confidence >= tg.confidence * 0.92f));
                         if (p_better) {
                             tg = pe;
+                            chosen_c = pc;
                             r.percussive_used = 1;
                         }
                     }
                 } else if (c.enable_tempogram_percussive_fallback) {
                     r.percussive_used = 0;
                 }
+            }
+            if (c.emit_tempogram_candidates) {  // lib.rs:684-697, 740-752
+                r.has_candidates = true;
+                r.tempogram_candidates = chosen_c;
             }
         }
     }

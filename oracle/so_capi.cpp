@@ -17,7 +17,7 @@ struct SoHandle {
 
 #define SO_FIELDS(X)                                                                                                                     \
     X(min_amplitude_db) X(normalization) X(enable_normalization) X(enable_silence_trimming) X(enable_onset_consensus)                     \
-    X(onset_threshold_percentile) X(onset_consensus_tolerance_ms) X(enable_hpss_onsets) X(hpss_margin) X(enable_tempogram_percussive_fallback) X(force_legacy_bpm) X(enable_bpm_fusion) X(enable_legacy_bpm_guardrails) \
+    X(onset_threshold_percentile) X(onset_consensus_tolerance_ms) X(emit_tempogram_candidates) X(enable_hpss_onsets) X(hpss_margin) X(enable_tempogram_percussive_fallback) X(force_legacy_bpm) X(enable_bpm_fusion) X(enable_legacy_bpm_guardrails) \
     X(enable_tempogram_multi_resolution) X(tempogram_multi_res_top_k) X(tempogram_multi_res_w512) X(tempogram_multi_res_w256)             \
     X(tempogram_multi_res_w1024) X(tempogram_multi_res_structural_discount) X(tempogram_multi_res_double_time_512_factor)                 \
     X(tempogram_multi_res_margin_threshold) X(tempogram_multi_res_use_human_prior) X(enable_tempogram_band_fusion)                        \
@@ -69,6 +69,17 @@ void* so_analyze(const float* samples, uint64_t n, uint32_t sr, void* cfg, int w
     h->d.f["result.downbeats"] = r.downbeats;
     h->d.f["result.bars"] = r.bars;
     h->d.i["result.onsets"] = r.onsets;
+    if (r.has_candidates) {
+        std::vector<float> flat;
+        for (auto& c : r.tempogram_candidates) {
+            flat.push_back(c.bpm);
+            flat.push_back(c.score);
+            flat.push_back(c.fft_norm);
+            flat.push_back(c.autocorr_norm);
+            flat.push_back(c.selected ? 1.0f : 0.0f);
+        }
+        h->d.f["result.candidates"] = flat;
+    }
     h->d.i["result.hmm_beat_frames"] = std::vector<int64_t>(r.hmm_beat_frames.begin(), r.hmm_beat_frames.end());
     return h;
 }

@@ -82,6 +82,7 @@ struct Config {
     float onset_threshold_percentile = 0.80f;
     uint32_t onset_consensus_tolerance_ms = 50;
     float onset_consensus_weights[4] = {0.25f, 0.25f, 0.25f, 0.25f};
+    bool emit_tempogram_candidates = false;
     bool enable_hpss_onsets = false;
     size_t hpss_margin = 10;
     bool enable_tempogram_percussive_fallback = false;
@@ -203,6 +204,8 @@ struct Result {
     std::vector<int32_t> hmm_beat_frames;  // t indices kept by the first HMM pass
     int time_sig_beats_per_bar = 4;
     int beats_refined = 0;  // 1 if the Bayesian per-segment refinement replaced the grid
+    bool has_candidates = false;  // metadata.tempogram_candidates: Option<Vec<TempoCandidateDebug>> (lib.rs:684-697, 740-752)
+    std::vector<TempoCand> tempogram_candidates;
 };
 
 struct Confidence {  // analysis/confidence.rs:32-68

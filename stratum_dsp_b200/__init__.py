@@ -90,6 +90,10 @@ class StratumConfig(C.Structure):
     ]
 
 
+class StratumTempoCandidate(C.Structure):
+    _fields_ = [("bpm", _f), ("score", _f), ("fft_norm", _f), ("autocorr_norm", _f), ("selected", _i)]
+
+
 class StratumResult(C.Structure):
     _fields_ = [
         ("status", _i), ("error", C.c_char * 128), ("bpm", _f), ("bpm_confidence", _f), ("key_is_minor", _i), ("key_index", _u),
@@ -102,6 +106,7 @@ class StratumResult(C.Structure):
         ("tempogram_percussive_triggered", _i), ("tempogram_percussive_used", _i),
         ("trim_start", C.c_uint64), ("trim_end", C.c_uint64), ("onsets", C.POINTER(C.c_int64)), ("n_onsets", _u),
         ("hmm_beat_frames", C.POINTER(_i)), ("n_hmm_beat_frames", _u), ("time_sig_beats_per_bar", _i), ("beats_refined", _i),
+        ("tempogram_candidates", C.POINTER(StratumTempoCandidate)), ("n_tempogram_candidates", _i),
     ]
 
 
@@ -272,6 +277,7 @@ class AnalysisMetadata:
     tempogram_multi_res_used: bool | None
     tempogram_percussive_triggered: bool | None
     tempogram_percussive_used: bool | None
+    tempogram_candidates: list | None = None  # [(bpm, score, fft_norm, autocorr_norm, selected)] when emit_tempogram_candidates
 
 
 @dataclass
@@ -337,7 +343,9 @@ def _convert(r: StratumResult) -> AnalysisResult:
         methods_used=["energy_flux", "autocorrelation", "comb_filterbank"],  # lib.rs:1604-1608
         flags=_flags(r.flags), confidence_warnings=warnings,
         tempogram_multi_res_triggered=_opt(r.tempogram_multi_res_triggered), tempogram_multi_res_used=_opt(r.tempogram_multi_res_used),
-        tempogram_percussive_triggered=_opt(r.tempogram_percussive_triggered), tempogram_percussive_used=_opt(r.tempogram_percussive_used))
+        tempogram_percussive_triggered=_opt(r.tempogram_percussive_triggered), tempogram_percussive_used=_opt(r.tempogram_percussive_used),
+        tempogram_candidates=None if r.n_tempogram_candidates < 0 else [
+            (c.bpm, c.score, c.fft_norm, c.autocorr_norm, bool(c.selected)) for c in (r.tempogram_candidates[i] for i in range(r.n_tempogram_candidates))])
     grid = BeatGrid(_arr(r.beats, r.n_beats, np.float32), _arr(r.downbeats, r.n_downbeats, np.float32), _arr(r.bars, r.n_bars, np.float32))
     return AnalysisResult(
         bpm=r.bpm, bpm_confidence=r.bpm_confidence, key=Key(bool(r.key_is_minor), int(r.key_index)), key_confidence=r.key_confidence,

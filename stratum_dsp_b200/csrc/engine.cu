@@ -563,7 +563,7 @@ static int config_validate(const StratumConfig& c) {
     }
     if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
     if (c.enable_bpm_fusion) return ni("enable_bpm_fusion");
-    if (c.emit_tempogram_candidates) return ni("emit_tempogram_candidates");
+    if (c.emit_tempogram_candidates && c.tempogram_candidates_top_n > 200) return ni("tempogram_candidates_top_n > 200");
     if (!c.tempogram_band_seed_only) return ni("tempogram_band_seed_only = false");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
     if (!c.enable_key_stft_override || c.key_stft_frame_size != 8192 || c.key_stft_hop_size != 512) return ni("key STFT other than 8192/512");
@@ -631,7 +631,8 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.consensus_bonus = c.tempogram_band_consensus_bonus;
     // lib.rs:382-385 / multi_resolution.rs:230-234
     const uint32_t base_top_n = std::max(std::max(c.tempogram_candidates_top_n, c.tempogram_multi_res_top_k), 10u);
-    d.base_top_n = c.enable_tempogram_multi_resolution ? base_top_n : 0;
+    d.base_top_n = c.enable_tempogram_multi_resolution ? base_top_n : (c.emit_tempogram_candidates ? c.tempogram_candidates_top_n : 0);  // lib.rs:378-410, 714-737
+    d.emit_cands = c.emit_tempogram_candidates;
     d.mr_top_k = std::max(c.tempogram_multi_res_top_k, 1u);
     d.mr_aux_k = std::min(std::max(d.mr_top_k * 4, 25u), 200u);
     d.mr_w512 = c.tempogram_multi_res_w512;
@@ -758,6 +759,8 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.hmm_path = ia.take(T.hmm_cap);
     T.beats = oa.take(T.beat_cap);
     T.downbeats = oa.take(T.beat_cap);
+    T.cand_out = cfg.emit_tempogram_candidates ? oa.take((uint64_t)5 * MAX_TOPC) : 0;
+    T.n_cand_out = -1;
     // legacy ACF: next_pow2(2 * (max_frame + 1)), max_frame <= n / 512
     T.lg_fft = next_pow2_u32((uint32_t)(2 * (n / 512 + 1)));
     T.lg_work = fa.take((uint64_t)4 * T.lg_fft);
@@ -833,6 +836,7 @@ static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* 
     r->tempogram_multi_res_triggered = r->tempogram_multi_res_used = -1;
     r->tempogram_percussive_triggered = r->tempogram_percussive_used = -1;
     r->time_sig_beats_per_bar = 4;
+    r->n_tempogram_candidates = -1;
     if (T.status != 0) {
         snprintf(r->error, sizeof r->error, "%s", error_message(T.err_code));
         return;
@@ -886,6 +890,14 @@ static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* 
     }
     r->time_sig_beats_per_bar = T.time_sig;
     r->beats_refined = T.beats_refined;
+    r->n_tempogram_candidates = T.n_cand_out;
+    if (T.n_cand_out > 0) {
+        r->tempogram_candidates = (StratumTempoCandidate*)malloc(sizeof(StratumTempoCandidate) * T.n_cand_out);
+        for (int32_t i = 0; i < T.n_cand_out; ++i) {
+            const float* o = oa_host + T.cand_out + 5 * (size_t)i;
+            r->tempogram_candidates[i] = StratumTempoCandidate{o[0], o[1], o[2], o[3], o[4] != 0.0f ? 1 : 0};
+        }
+    }
 }
 
 static void debug_put(const char* name, const float* d, size_t n, cudaStream_t s) {
@@ -1162,7 +1174,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             CUDA_OK(cudaStreamSynchronize(s));  // `pl` is a stack-owned buffer
         }
     }
-    { StageTimer t(s, "final_bpm"); launch_final_bpm(w); }
+    { StageTimer t(s, "final_bpm"); launch_final_bpm(w); launch_emit_candidates(w); }
     { StageTimer t(s, "beats"); launch_beat_tracking(w); }
     if (split) {
         cudaStreamWaitEvent(s, ev_key, 0);
@@ -1639,6 +1651,9 @@ void stratum_b200_result_free(StratumResult* results, uint32_t n) {
         free(results[i].bars);
         free(results[i].onsets);
         free(results[i].hmm_beat_frames);
+        free(results[i].tempogram_candidates);
+        results[i].tempogram_candidates = nullptr;
+        results[i].n_tempogram_candidates = -1;
         results[i].beats = results[i].downbeats = results[i].bars = nullptr;
         results[i].onsets = nullptr;
         results[i].hmm_beat_frames = nullptr;

@@ -880,6 +880,43 @@ void launch_perc_accept(const WaveCtx& c, const int32_t* d_list, int n_list) {
     count_launch("hpss");
 }
 
+// ---- metadata.tempogram_candidates (lib.rs:684-697, 740-752): the candidate list of the chosen estimate ------------
+// base list, the hop-512 list re-flagged against the multi-resolution winner (multi_resolution.rs:888-891) or the
+// percussive list; `selected` = within 0.75 BPM of the chosen estimate.
+__global__ void emit_candidates_kernel(TrackDev* tr, const float* fa, float* oa, int n_tracks, DevCfg cfg) {
+    TrackDev& T = tr[blockIdx.x];
+    if ((int)blockIdx.x >= n_tracks) return;
+    if (threadIdx.x == 0) T.n_cand_out = -1;
+    if (T.status != 0 || !T.est[0].ok || cfg.force_legacy || !cfg.emit_cands) return;
+    int slot = 0;
+    uint32_t n = T.est[0].n_cands;
+    float best = T.est[0].bpm;
+    if (T.perc_used == 1) {
+        slot = SLOT_PERC;
+        n = T.est[SLOT_PERC].n_cands;
+        best = T.est[SLOT_PERC].bpm;
+    } else if (T.mr_used == 1) {
+        n = min(n, max(cfg.mr_top_k, 1u));
+        best = T.bpm;  // multi-resolution winner (written by multires_fusion_kernel)
+    }
+    const TempoCandDev* c = reinterpret_cast<const TempoCandDev*>(fa + T.cands[slot]);
+    float* o = oa + T.cand_out;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        o[5 * i + 0] = c[i].bpm;
+        o[5 * i + 1] = c[i].score;
+        o[5 * i + 2] = c[i].fft_norm;
+        o[5 * i + 3] = c[i].ac_norm;
+        o[5 * i + 4] = fabsf(__fsub_rn(c[i].bpm, best)) < 0.75f ? 1.0f : 0.0f;
+    }
+    if (threadIdx.x == 0) T.n_cand_out = (int32_t)n;
+}
+
+void launch_emit_candidates(const WaveCtx& c) {
+    if (!c.cfg.emit_cands) return;
+    emit_candidates_kernel<<<c.n_tracks, 64, 0, c.stream>>>(c.tracks, c.fa, c.oa, c.n_tracks, c.cfg);
+    count_launch("tempogram");
+}
+
 void launch_tempogram(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (n_list == 0 || c.max_F[h] < 2) return;
     dim3 g5(MAX_VARIANTS, n_list);

@@ -16,7 +16,7 @@ struct DevCfg {
     float onset_pct;
     uint32_t consensus_tol_ms;
     float cons_w[4];
-    int32_t hpss_onsets, perc_fallback;
+    int32_t hpss_onsets, perc_fallback, emit_cands;
     uint32_t hpss_margin;
     uint32_t sf_k, mel_k;
     float nov_ws, nov_we, nov_wh;
@@ -103,6 +103,7 @@ void launch_tempogram(const WaveCtx& c, int hop_idx, const int32_t* d_list, int 
 void launch_escalation_gate(const WaveCtx& c);
 void launch_multires_fusion(const WaveCtx& c, const int32_t* d_list, int n_list);
 void launch_final_bpm(const WaveCtx& c);
+void launch_emit_candidates(const WaveCtx& c);
 // k_legacy.cu
 void launch_legacy_bpm(const WaveCtx& c);
 // k_hpss.cu

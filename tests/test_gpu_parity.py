@@ -347,3 +347,21 @@ def test_accepted_config_switches_match_the_oracle(cfg):
     res = S.analyze_batch(xs + [quiet], SR, S.AnalysisConfig(**cfg))
     for i, (x, g) in enumerate(zip(xs + [quiet], res)):
         assert_parity(g, O.analyze(x, SR, cfg, fast=True), f"{cfg} track {i}")
+
+
+@pytest.mark.parametrize("cfg", [{"emit_tempogram_candidates": 1}, {"emit_tempogram_candidates": 1, "enable_tempogram_multi_resolution": 0},
+                                 {"emit_tempogram_candidates": 1, "tempogram_candidates_top_n": 40, "tempogram_multi_res_top_k": 12}])
+def test_tempogram_candidates_metadata(cfg):
+    # metadata.tempogram_candidates (analysis/result.rs:170-181, lib.rs:684-697, 740-752)
+    for bpm in (74.0, 121.0):
+        x = synth.render(synth.TrackParams(bpm, 2, 0, 0.25, 0.1, SR, 20 * SR))
+        o = O.analyze(x, SR, cfg, fast=True)
+        g = S.analyze_audio(x, SR, S.AnalysisConfig(**cfg))
+        assert_parity(g, o, f"{cfg} bpm={bpm}")
+        exp = o.farray("result.candidates").reshape(-1, 5)
+        got = g.metadata.tempogram_candidates
+        assert got is not None and len(got) == len(exp)
+        for (b, sc, fn, an, sel), e in zip(got, exp):
+            assert b == e[0] and abs(sc - e[1]) <= 1e-3 * max(abs(e[1]), 1e-6) + 1e-6 and bool(e[4]) == sel
+            assert abs(fn - e[2]) < 1e-3 and abs(an - e[3]) < 1e-3
+    assert S.analyze_audio(x, SR).metadata.tempogram_candidates is None
