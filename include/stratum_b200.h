@@ -67,7 +67,7 @@ typedef struct StratumConfig {
     float onset_consensus_weights[4];
     int32_t enable_hpss_onsets;
     int32_t force_legacy_bpm;
-    int32_t enable_bpm_fusion;             /* must be 0 */
+    int32_t enable_bpm_fusion;
     int32_t enable_legacy_bpm_guardrails;
     int32_t enable_tempogram_multi_resolution;
     uint32_t tempogram_multi_res_top_k;

@@ -190,6 +190,29 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
             bpm = legacy.bpm;
             bpm_conf = legacy.confidence;
         }
+    } else if (c.enable_bpm_fusion) {  // lib.rs:819-892: the legacy estimate only validates the tempogram's confidence
+        const float t_bpm = has_tempogram ? tg.bpm : 0.0f, t_conf = has_tempogram ? tg.confidence : 0.0f;
+        const float l_bpm = has_legacy ? legacy.bpm : 0.0f, l_conf = clamp_rs(has_legacy ? legacy.confidence : 0.0f, 0.0f, 1.0f);
+        if (t_bpm <= 0.0f) {
+            if (has_legacy) {
+                bpm = legacy.bpm;
+                bpm_conf = legacy.confidence;
+            }
+        } else {
+            float conf = clamp_rs(t_conf, 0.0f, 1.0f);
+            bool agreement = false;
+            if (l_bpm > 0.0f) {
+                const float diffs[5] = {fabsf(l_bpm - t_bpm), fabsf(l_bpm - (t_bpm * 0.5f)), fabsf(l_bpm - (t_bpm * 2.0f)),
+                                        fabsf(l_bpm - (t_bpm * (2.0f / 3.0f))), fabsf(l_bpm - (t_bpm * (3.0f / 2.0f)))};
+                for (float d : diffs) agreement |= d <= 2.0f;
+            }
+            if (agreement)
+                conf = clamp_rs(conf + 0.12f * l_conf, 0.0f, 1.0f);
+            else if (l_bpm > 0.0f)
+                conf = clamp_rs(conf * 0.90f, 0.0f, 1.0f);
+            bpm = t_bpm;
+            bpm_conf = conf;
+        }
     } else if (has_tempogram) {
         bpm = tg.bpm;
         bpm_conf = tg.confidence;

@@ -562,7 +562,6 @@ static int config_validate(const StratumConfig& c) {
         return STRATUM_INVALID_INPUT;
     }
     if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
-    if (c.enable_bpm_fusion) return ni("enable_bpm_fusion");
     if (c.emit_tempogram_candidates && c.tempogram_candidates_top_n > 200) return ni("tempogram_candidates_top_n > 200");
     if (!c.tempogram_band_seed_only) return ni("tempogram_band_seed_only = false");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
@@ -644,6 +643,7 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.mr_enabled = c.enable_tempogram_multi_resolution;
     d.force_legacy = c.force_legacy_bpm;
     d.legacy_guardrails = c.enable_legacy_bpm_guardrails;
+    d.bpm_fusion = c.enable_bpm_fusion;
     d.lg_pmin = c.legacy_bpm_preferred_min;
     d.lg_pmax = c.legacy_bpm_preferred_max;
     d.lg_smin = c.legacy_bpm_soft_min;

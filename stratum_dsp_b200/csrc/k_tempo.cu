@@ -841,6 +841,22 @@ __global__ void final_bpm_kernel(TrackDev* tr, int n_tracks, DevCfg cfg) {
         bpm = T.legacy.bpm;
         conf = T.legacy.confidence;
     }
+    if (!cfg.force_legacy && cfg.bpm_fusion) {  // lib.rs:819-892: validator mode — the tempogram BPM is never overridden
+        if (T.est[0].ok && bpm > 0.0f) {
+            const float l_bpm = T.legacy.ok ? T.legacy.bpm : 0.0f;
+            const float l_conf = clamp_rs(T.legacy.ok ? T.legacy.confidence : 0.0f, 0.0f, 1.0f);
+            float cf = clamp_rs(conf, 0.0f, 1.0f);
+            bool agreement = false;
+            if (l_bpm > 0.0f) {
+                const float d[5] = {fabsf(__fsub_rn(l_bpm, bpm)), fabsf(__fsub_rn(l_bpm, __fmul_rn(bpm, 0.5f))), fabsf(__fsub_rn(l_bpm, __fmul_rn(bpm, 2.0f))),
+                                    fabsf(__fsub_rn(l_bpm, __fmul_rn(bpm, 2.0f / 3.0f))), fabsf(__fsub_rn(l_bpm, __fmul_rn(bpm, 3.0f / 2.0f)))};
+                for (int q = 0; q < 5; ++q) agreement |= d[q] <= 2.0f;
+            }
+            if (agreement) cf = clamp_rs(__fadd_rn(cf, __fmul_rn(0.12f, l_conf)), 0.0f, 1.0f);
+            else if (l_bpm > 0.0f) cf = clamp_rs(__fmul_rn(cf, 0.90f), 0.0f, 1.0f);
+            conf = cf;
+        }  // tempogram unavailable: the legacy estimate chosen above stands
+    }
     T.bpm = bpm;
     T.bpm_confidence = conf;
 }

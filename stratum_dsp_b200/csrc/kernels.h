@@ -27,7 +27,7 @@ struct DevCfg {
     uint32_t base_top_n, mr_top_k, mr_aux_k;
     float mr_w512, mr_w256, mr_w1024, mr_dt, mr_margin;
     int32_t mr_human_prior, mr_enabled;
-    int32_t force_legacy, legacy_guardrails;
+    int32_t force_legacy, legacy_guardrails, bpm_fusion;
     float lg_pmin, lg_pmax, lg_smin, lg_smax, lg_mp, lg_ms, lg_me;
     // key
     uint32_t key_margin;

@@ -72,7 +72,7 @@ def test_errors_match_reference():
         S.analyze_audio(np.ones(100, np.float32), 0)
     assert e.value.kind == "InvalidInput"
     with pytest.raises(S.AnalysisError) as e:
-        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(enable_bpm_fusion=True))
+        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(enable_key_mode_heuristic=True))
     assert e.value.kind == "NotImplemented"  # unsupported switches are rejected, never silently ignored
 
 
@@ -319,6 +319,7 @@ def test_key_path_variants(cfg):
 
 @pytest.mark.parametrize("cfg", [
     {"force_legacy_bpm": 1},
+    {"enable_bpm_fusion": 1},
     {"enable_tempogram_multi_resolution": 0},
     {"enable_tempogram_band_fusion": 0},
     {"enable_tempogram_mel_novelty": 0},
