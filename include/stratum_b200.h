@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define STRATUM_B200_ABI_VERSION 1
+#define STRATUM_B200_ABI_VERSION 2
 
 /* AnalysisError variants (src/error.rs:7-22); 0 = Ok. */
 typedef enum StratumStatus {
@@ -110,7 +110,7 @@ typedef struct StratumConfig {
     int32_t enable_key_hpcp;
     uint32_t key_hpcp_peaks_per_frame, key_hpcp_num_harmonics;
     float key_hpcp_harmonic_decay, key_hpcp_mag_power;
-    /* key-path options that must keep their default (off) value for now: */
+    /* optional key-path variants (all off by default, config.rs:683-741); their parameters follow below */
     int32_t enable_key_hpss_harmonic, enable_key_log_frequency, enable_key_beat_synchronous, enable_key_multi_scale,
         enable_key_ensemble, enable_key_median, enable_key_tuning_compensation, enable_key_edge_trim, enable_key_mode_heuristic,
         enable_key_hpcp_whitening, enable_key_hpcp_bass_blend, enable_key_minor_harmonic_bonus;
@@ -118,6 +118,26 @@ typedef struct StratumConfig {
     uint32_t hpss_margin;          /* median half-width of the HPSS filters (config.rs:43, default 10; at most 10 here) */
     int32_t soft_chroma_mapping;   /* chroma folding (enable_key_hpcp = 0): Gaussian soft mapping (config.rs:244, default 1) */
     int32_t enable_key_spectrogram_time_smoothing; /* used when the harmonic mask is off (config.rs:261, default 1) */
+    /* parameters of the optional key-path variants (config.rs:683-741) */
+    int32_t key_template_set;              /* TemplateSet (key/templates.rs:16-22): 0 = KrumhanslKessler, 1 = Temperley */
+    float key_edge_trim_fraction;
+    float key_mode_third_ratio_margin, key_mode_flip_min_score_ratio;
+    float key_minor_leading_tone_bonus_weight;
+    float key_ensemble_kk_weight, key_ensemble_temperley_weight;
+    uint32_t key_multi_scale_n_lengths;    /* Vec<usize> key_multi_scale_lengths as count + fixed array (at most 8 scales) */
+    uint32_t key_multi_scale_lengths[8];
+    uint32_t key_multi_scale_hop;
+    float key_multi_scale_min_clarity;
+    uint32_t key_multi_scale_n_weights;    /* Vec<f32> key_multi_scale_weights; 0 = empty = equal weights */
+    float key_multi_scale_weights[8];
+    uint32_t key_median_segment_length_frames, key_median_segment_hop_frames, key_median_min_segments; /* carried, unused: analyze_audio never reads them */
+    float key_tuning_max_abs_semitones;
+    uint32_t key_tuning_frame_step;
+    float key_tuning_peak_rel_threshold;
+    uint32_t key_hpss_frame_step, key_hpss_time_margin, key_hpss_freq_margin;
+    float key_hpss_mask_power;
+    uint32_t key_hpcp_whitening_smooth_bins;
+    float key_hpcp_bass_fmin_hz, key_hpcp_bass_fmax_hz, key_hpcp_bass_weight;
 } StratumConfig;
 
 /* TempoCandidateDebug (src/analysis/result.rs:170-181). */

@@ -238,7 +238,7 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
         }
     }
 
-    if (Error e = detect_key_path(x, m, sr, c, S, r, dump)) return e;
+    if (Error e = detect_key_path(x, m, sr, c, S, r, dump, &r.beats)) return e;
 
     // warnings / flags — lib.rs:1567-1589
     if (bpm == 0.0f) r.warnings |= WARN_BPM_FAILED;

@@ -2,6 +2,7 @@
 // Plain C entry points so tests/ and bench.py can drive the oracle through ctypes.
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <thread>
 
@@ -32,7 +33,15 @@ struct SoHandle {
     X(key_spectrogram_smooth_margin) X(enable_key_frame_weighting) X(key_min_tonalness) X(key_tonalness_power) X(key_energy_power)        \
     X(enable_key_harmonic_mask) X(key_harmonic_mask_power) X(enable_key_stft_override) X(key_stft_frame_size) X(key_stft_hop_size)        \
     X(enable_key_segment_voting) X(key_segment_len_frames) X(key_segment_hop_frames) X(key_segment_min_clarity) X(enable_key_hpcp)        \
-    X(key_hpcp_peaks_per_frame) X(key_hpcp_num_harmonics) X(key_hpcp_harmonic_decay) X(key_hpcp_mag_power)
+    X(key_hpcp_peaks_per_frame) X(key_hpcp_num_harmonics) X(key_hpcp_harmonic_decay) X(key_hpcp_mag_power)                                \
+    X(key_template_set) X(enable_key_edge_trim) X(key_edge_trim_fraction) X(enable_key_mode_heuristic) X(key_mode_third_ratio_margin)     \
+    X(key_mode_flip_min_score_ratio) X(enable_key_minor_harmonic_bonus) X(key_minor_leading_tone_bonus_weight) X(enable_key_ensemble)     \
+    X(key_ensemble_kk_weight) X(key_ensemble_temperley_weight) X(enable_key_multi_scale) X(key_multi_scale_n_lengths)                     \
+    X(key_multi_scale_hop) X(key_multi_scale_min_clarity) X(key_multi_scale_n_weights) X(enable_key_median)                               \
+    X(enable_key_tuning_compensation) X(key_tuning_max_abs_semitones) X(key_tuning_frame_step) X(key_tuning_peak_rel_threshold)           \
+    X(enable_key_hpss_harmonic) X(key_hpss_frame_step) X(key_hpss_time_margin) X(key_hpss_freq_margin) X(key_hpss_mask_power)             \
+    X(enable_key_log_frequency) X(enable_key_beat_synchronous) X(enable_key_hpcp_whitening) X(key_hpcp_whitening_smooth_bins)             \
+    X(enable_key_hpcp_bass_blend) X(key_hpcp_bass_fmin_hz) X(key_hpcp_bass_fmax_hz) X(key_hpcp_bass_weight)
 
 template <class T>
 static void assign(T& dst, double v) { dst = (T)v; }
@@ -48,6 +57,11 @@ int so_config_set(void* cp, const char* name, double v) {
     if (!strcmp(name, #f)) { assign(c.f, v); return 0; }
     SO_FIELDS(X)
 #undef X
+    // array fields: "name[i]"
+    unsigned idx = 0;
+    if (sscanf(name, "key_multi_scale_lengths[%u]", &idx) == 1 && idx < 8) { c.key_multi_scale_lengths[idx] = (uint32_t)v; return 0; }
+    if (sscanf(name, "key_multi_scale_weights[%u]", &idx) == 1 && idx < 8) { c.key_multi_scale_weights[idx] = (float)v; return 0; }
+    if (sscanf(name, "onset_consensus_weights[%u]", &idx) == 1 && idx < 4) { c.onset_consensus_weights[idx] = (float)v; return 0; }
     return -1;
 }
 double so_config_get(void* cp, const char* name) {

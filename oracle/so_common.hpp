@@ -157,6 +157,43 @@ struct Config {
     size_t key_hpcp_num_harmonics = 4;
     float key_hpcp_harmonic_decay = 0.60f;
     float key_hpcp_mag_power = 0.50f;
+    // a39 variants (config.rs:683-741), all off by default
+    int key_template_set = 0;  // TemplateSet: 0 = KrumhanslKessler, 1 = Temperley
+    bool enable_key_edge_trim = false;
+    float key_edge_trim_fraction = 0.15f;
+    bool enable_key_mode_heuristic = false;
+    float key_mode_third_ratio_margin = 0.0f;
+    float key_mode_flip_min_score_ratio = 0.60f;
+    bool enable_key_minor_harmonic_bonus = false;
+    float key_minor_leading_tone_bonus_weight = 0.2f;
+    bool enable_key_ensemble = false;
+    float key_ensemble_kk_weight = 0.5f;
+    float key_ensemble_temperley_weight = 0.5f;
+    bool enable_key_multi_scale = false;
+    uint32_t key_multi_scale_n_lengths = 3;
+    uint32_t key_multi_scale_lengths[8] = {120, 360, 720, 0, 0, 0, 0, 0};
+    size_t key_multi_scale_hop = 60;
+    float key_multi_scale_min_clarity = 0.20f;
+    uint32_t key_multi_scale_n_weights = 0;
+    float key_multi_scale_weights[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool enable_key_median = false;  // read by nothing in analyze_audio (lib.rs never calls detect_key_median)
+    bool enable_key_tuning_compensation = false;
+    float key_tuning_max_abs_semitones = 0.08f;
+    size_t key_tuning_frame_step = 20;
+    float key_tuning_peak_rel_threshold = 0.35f;
+    bool enable_key_hpss_harmonic = false;
+    size_t key_hpss_frame_step = 4;
+    size_t key_hpss_time_margin = 8;
+    size_t key_hpss_freq_margin = 8;
+    float key_hpss_mask_power = 2.0f;
+    bool enable_key_log_frequency = false;
+    bool enable_key_beat_synchronous = false;
+    bool enable_key_hpcp_whitening = false;
+    size_t key_hpcp_whitening_smooth_bins = 31;
+    bool enable_key_hpcp_bass_blend = false;
+    float key_hpcp_bass_fmin_hz = 55.0f;
+    float key_hpcp_bass_fmax_hz = 300.0f;
+    float key_hpcp_bass_weight = 0.35f;
 };
 
 // ---- result (reference src/analysis/result.rs:7-263) ----------------------
@@ -287,10 +324,13 @@ struct KeyScores {
     int key;
     float confidence;
 };
-Error detect_key_weighted(const float* chroma, size_t frames, const float* w /*nullable*/, KeyScores& out);
+Error detect_key_weighted(const float* chroma, size_t frames, const float* w /*nullable*/, KeyScores& out, int template_set = 0);
+Error detect_key_weighted_mode_heuristic(const float* chroma, size_t frames, const float* w /*nullable*/, int template_set, float third_ratio_margin,
+                                         float flip_min_score_ratio, bool minor_bonus, float minor_bonus_weight, KeyScores& out);
 float compute_key_clarity(const float* sorted_scores, size_t n);
-void key_templates(float major[12][12], float minor[12][12]);
-Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, const Spec& S_base, Result& r, Dump* dump = nullptr);
+void key_templates(float major[12][12], float minor[12][12], int template_set = 0);
+Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, const Spec& S_base, Result& r, Dump* dump = nullptr,
+                      const std::vector<float>* beat_times = nullptr);
 
 // ---- top level -----------------------------------------------------------------------
 Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c, Result& r, Dump* dump = nullptr);

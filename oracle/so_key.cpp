@@ -226,10 +226,14 @@ void smooth_chroma(std::vector<float>& chroma, size_t frames, size_t window) {
     chroma.swap(out);
 }
 
-// KeyTemplates::new_krumhansl_kessler — templates.rs:64-143
-void key_templates(float major[12][12], float minor[12][12]) {
-    const float cmaj[12] = {6.35f, 2.23f, 3.48f, 2.33f, 4.38f, 4.09f, 2.52f, 5.19f, 2.39f, 3.66f, 2.29f, 2.88f};
-    const float cmin[12] = {6.33f, 2.68f, 3.52f, 5.38f, 2.60f, 3.53f, 2.54f, 4.75f, 3.98f, 2.69f, 3.34f, 3.17f};
+// KeyTemplates::new_krumhansl_kessler — templates.rs:64-143; new_temperley — templates.rs:145-222
+void key_templates(float major[12][12], float minor[12][12], int template_set) {
+    const float kk_maj[12] = {6.35f, 2.23f, 3.48f, 2.33f, 4.38f, 4.09f, 2.52f, 5.19f, 2.39f, 3.66f, 2.29f, 2.88f};
+    const float kk_min[12] = {6.33f, 2.68f, 3.52f, 5.38f, 2.60f, 3.53f, 2.54f, 4.75f, 3.98f, 2.69f, 3.34f, 3.17f};
+    const float tp_maj[12] = {5.0f, 2.0f, 3.5f, 2.0f, 4.5f, 4.0f, 2.0f, 4.5f, 2.0f, 3.5f, 1.5f, 4.0f};
+    const float tp_min[12] = {5.0f, 2.0f, 3.5f, 5.0f, 2.0f, 3.5f, 2.0f, 4.5f, 3.5f, 2.0f, 4.0f, 3.5f};
+    const float* cmaj = template_set == 1 ? tp_maj : kk_maj;
+    const float* cmin = template_set == 1 ? tp_min : kk_min;
     for (int k = 0; k < 12; ++k)
         for (int s = 0; s < 12; ++s) {
             major[k][s] = cmaj[(s + 12 - k) % 12];
@@ -265,10 +269,10 @@ float compute_key_clarity(const float* sc, size_t n) {
 }
 
 // detect_key_weighted — detector.rs:68-313.  Key ids: 0..11 major, 12..23 minor.
-Error detect_key_weighted(const float* chroma, size_t frames, const float* w, KeyScores& out) {
+Error detect_key_weighted(const float* chroma, size_t frames, const float* w, KeyScores& out, int template_set) {
     if (frames == 0) return Error{INVALID_INPUT, "Empty chroma vectors"};
     float maj[12][12], mnr[12][12];
-    key_templates(maj, mnr);
+    key_templates(maj, mnr, template_set);
     float sc[24];
     for (int k = 0; k < 24; ++k) {
         const float* tpl = k < 12 ? maj[k] : mnr[k - 12];
@@ -338,6 +342,173 @@ Error detect_key_weighted(const float* chroma, size_t frames, const float* w, Ke
     return Error{};
 }
 
+// detect_key_weighted_mode_heuristic — detector.rs:326-518.  out.keys/out.scores = the post-bonus score table in
+// ranked order (stable re-sort of the base ranking), out.key = chosen key (after the optional parallel-mode flip).
+Error detect_key_weighted_mode_heuristic(const float* chroma, size_t frames, const float* w, int template_set, float third_ratio_margin,
+                                         float flip_min_score_ratio, bool minor_bonus, float minor_bonus_weight, KeyScores& out) {
+    KeyScores base;
+    if (Error e = detect_key_weighted(chroma, frames, w, base, template_set)) return e;
+    const float flip_ratio = clamp_rs(flip_min_score_ratio, 0.0f, 1.0f);
+    const bool enable_flip = flip_ratio > 0.0f;
+    out = base;
+    if (!minor_bonus && !enable_flip) return Error{};
+    float avg[12];
+    for (int i = 0; i < 12; ++i) avg[i] = 0.0f;
+    float wsum = 0.0f;
+    if (!w) {
+        for (size_t t = 0; t < frames; ++t)
+            for (int i = 0; i < 12; ++i) avg[i] += chroma[t * 12 + i];
+        wsum = (float)frames;
+    } else {
+        for (size_t t = 0; t < frames; ++t) {
+            const float wt = w[t];
+            if (wt <= 0.0f) continue;
+            for (int i = 0; i < 12; ++i) avg[i] += wt * chroma[t * 12 + i];
+            wsum += wt;
+        }
+    }
+    if (wsum <= 1e-9f) return Error{};
+    float sum = 0.0f;
+    for (int i = 0; i < 12; ++i) sum += avg[i];
+    if (sum > 1e-9f)
+        for (int i = 0; i < 12; ++i) avg[i] /= sum;
+    int keys[24];
+    float sc[24];
+    for (int i = 0; i < 24; ++i) {
+        keys[i] = base.keys[i];
+        sc[i] = base.scores[i];
+    }
+    if (minor_bonus) {
+        const float bw = fmax_rs(minor_bonus_weight, 0.0f);
+        if (bw > 0.0f)
+            for (int i = 0; i < 24; ++i)
+                if (keys[i] >= 12) {
+                    const int tonic = keys[i] - 12;
+                    const int lt = (tonic + 11) % 12, b7 = (tonic + 10) % 12;
+                    sc[i] += wsum * bw * (avg[lt] - avg[b7]);
+                }
+    }
+    int order[24];
+    for (int i = 0; i < 24; ++i) order[i] = i;
+    std::stable_sort(order, order + 24, [&](int a, int b) { return sc[a] > sc[b]; });
+    float by_key[24];
+    for (int i = 0; i < 24; ++i) {
+        out.keys[i] = keys[order[i]];
+        out.scores[i] = sc[order[i]];
+        by_key[out.keys[i]] = out.scores[i];
+    }
+    const int best_key = out.keys[0];
+    const int tonic = best_key % 12;
+    const bool best_is_major = best_key < 12;
+    const float p_min3 = avg[(tonic + 3) % 12], p_maj3 = avg[(tonic + 4) % 12];
+    const float p_min6 = avg[(tonic + 8) % 12], p_maj6 = avg[(tonic + 9) % 12];
+    const float p_min7 = avg[(tonic + 10) % 12], p_maj7 = avg[(tonic + 11) % 12];
+    const float margin = fmax_rs(third_ratio_margin, 0.0f);
+    float minor_score = 0.0f, major_score = 0.0f;
+    const float third_diff = fabsf(p_min3 - p_maj3);
+    if (p_min3 > (p_maj3 * (1.0f + margin))) minor_score += third_diff * 2.0f;
+    else if (p_maj3 > (p_min3 * (1.0f + margin))) major_score += third_diff * 2.0f;
+    const float sixth_diff = fabsf(p_min6 - p_maj6);
+    if (p_min6 > (p_maj6 * (1.0f + margin))) minor_score += sixth_diff * 1.0f;
+    else if (p_maj6 > (p_min6 * (1.0f + margin))) major_score += sixth_diff * 1.0f;
+    const float seventh_diff = fabsf(p_min7 - p_maj7);
+    if (p_min7 > (p_maj7 * (1.0f + margin))) minor_score += seventh_diff * 1.0f;
+    else if (p_maj7 > (p_min7 * (1.0f + margin))) major_score += seventh_diff * 1.0f;
+    const float total = minor_score + major_score;
+    const bool minor_pref = total > 1e-9f ? minor_score > major_score * (1.0f + margin * 0.5f) : false;
+    const bool major_pref = total > 1e-9f ? major_score > minor_score * (1.0f + margin * 0.5f) : false;
+    int chosen = best_key;
+    if (enable_flip) {
+        if (best_is_major && minor_pref) {
+            const float s_best = by_key[tonic], s_alt = by_key[12 + tonic];
+            if (s_best > 0.0f && s_alt >= s_best * flip_ratio) chosen = 12 + tonic;
+        } else if (!best_is_major && major_pref) {
+            const float s_best = by_key[12 + tonic], s_alt = by_key[tonic];
+            if (s_best > 0.0f && s_alt >= s_best * flip_ratio) chosen = tonic;
+        }
+    }
+    const float chosen_score = by_key[chosen];
+    float best_other = 0.0f;
+    for (int i = 0; i < 24; ++i)
+        if (out.keys[i] != chosen) best_other = fmax_rs(best_other, out.scores[i]);
+    out.key = chosen;
+    out.confidence = chosen_score > 0.0f ? clamp_rs((chosen_score - best_other) / chosen_score, 0.0f, 1.0f) : 0.0f;
+    return Error{};
+}
+
+// Segment/whole-track detector selected by the config (lib.rs:1353-1372, 1386-1410, 1437-1453)
+static Error detect_one(const float* chroma, size_t frames, const float* w, const Config& c, KeyScores& out) {
+    if (c.enable_key_mode_heuristic || c.enable_key_minor_harmonic_bonus)
+        return detect_key_weighted_mode_heuristic(chroma, frames, w, c.key_template_set, c.key_mode_third_ratio_margin,
+                                                  c.enable_key_mode_heuristic ? c.key_mode_flip_min_score_ratio : 0.0f, c.enable_key_minor_harmonic_bonus,
+                                                  c.key_minor_leading_tone_bonus_weight, out);
+    return detect_key_weighted(chroma, frames, w, out, c.key_template_set);
+}
+
+// Final table from 24 accumulated scores indexed by key id: stable sort, confidence (lib.rs:1412-1435, detector.rs:672-699)
+static void finish_accumulated(const float* acc, KeyScores& out) {
+    int order[24];
+    for (int k = 0; k < 24; ++k) order[k] = k;
+    std::stable_sort(order, order + 24, [&](int a, int b) { return acc[a] > acc[b]; });
+    for (int i = 0; i < 24; ++i) {
+        out.keys[i] = order[i];
+        out.scores[i] = acc[order[i]];
+    }
+    out.key = out.keys[0];
+    out.confidence = out.scores[0] > 0.0f ? clamp_rs((out.scores[0] - out.scores[1]) / out.scores[0], 0.0f, 1.0f) : 0.0f;
+}
+
+// detect_key_multi_scale — detector.rs:546-700
+static Error detect_key_multi_scale(const float* chroma, size_t frames, const float* w, const Config& c, KeyScores& out) {
+    if (frames == 0) return Error{INVALID_INPUT, "Empty chroma vectors"};
+    if (c.key_multi_scale_n_lengths == 0) return Error{INVALID_INPUT, "No segment lengths provided for multi-scale detection"};
+    float acc[24];
+    for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
+    float total_weight = 0.0f;
+    size_t used = 0;
+    const float min_cl = clamp_rs(c.key_multi_scale_min_clarity, 0.0f, 1.0f);
+    const size_t hop = std::max<size_t>(c.key_multi_scale_hop, 1);
+    for (uint32_t si = 0; si < c.key_multi_scale_n_lengths; ++si) {
+        const size_t seg_len = c.key_multi_scale_lengths[si];
+        if (seg_len == 0 || seg_len > frames) continue;
+        const float scale_weight = (c.key_multi_scale_n_weights > 0 && si < c.key_multi_scale_n_weights) ? c.key_multi_scale_weights[si] : 1.0f;
+        if (scale_weight <= 0.0f) continue;
+        for (size_t st = 0; st + seg_len <= frames; st += hop) {
+            KeyScores ks;
+            if (Error e = detect_one(chroma + st * 12, seg_len, w ? w + st : nullptr, c, ks)) return e;
+            const float cl = compute_key_clarity(ks.scores, 24);
+            if (cl >= min_cl) {
+                ++used;
+                const float cw = cl * scale_weight;
+                total_weight += cw;
+                for (int i = 0; i < 24; ++i) acc[ks.keys[i]] += ks.scores[i] * cw;
+            }
+        }
+    }
+    if (used == 0 || total_weight <= 1e-12f) return detect_one(chroma, frames, w, c, out);
+    for (int k = 0; k < 24; ++k) acc[k] /= total_weight;
+    finish_accumulated(acc, out);
+    return Error{};
+}
+
+// detect_key_ensemble — detector.rs:881-976
+static Error detect_key_ensemble(const float* chroma, size_t frames, const float* w, float kk_weight, float temperley_weight, KeyScores& out) {
+    const float total = kk_weight + temperley_weight;
+    const float kk_norm = total > 1e-9f ? kk_weight / total : 0.5f;
+    const float tp_norm = total > 1e-9f ? temperley_weight / total : 0.5f;
+    KeyScores kk, tp;
+    if (Error e = detect_key_weighted(chroma, frames, w, kk, 0)) return e;
+    if (Error e = detect_key_weighted(chroma, frames, w, tp, 1)) return e;
+    float a[24], b[24], comb[24];
+    for (int i = 0; i < 24; ++i) {
+        a[kk.keys[i]] = kk.scores[i];
+        b[tp.keys[i]] = tp.scores[i];
+    }
+    for (int k = 0; k < 24; ++k) comb[k] = kk_norm * a[k] + tp_norm * b[k];
+    finish_accumulated(comb, out);
+    return Error{};
+}
+
 static float chroma_tonalness(const float* ch) {  // lib.rs:1236-1251
     float sum = 0.0f;
     for (int i = 0; i < 12; ++i) sum += ch[i];
@@ -352,7 +523,7 @@ static float chroma_tonalness(const float* ch) {  // lib.rs:1236-1251
 }
 
 // Key section of analyze_audio — lib.rs:961-1559, default-config branches only.
-Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, const Spec& S_base, Result& r, Dump* dump) {
+Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, const Spec& S_base, Result& r, Dump* dump, const std::vector<float>* beat_times) {
     r.key_is_minor = 0;
     r.key_index = 0;
     r.key_confidence = 0.0f;
@@ -399,19 +570,32 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
     if (nf > 5) smooth_chroma(chroma, nf, 5);
     if (dump) dump->f["key.hpcp_smooth"] = chroma;
 
+    // optional edge trimming (lib.rs:1216-1233): the chroma / energy slices every later step works on
+    size_t f0 = 0;
+    if (c.enable_key_edge_trim && nf >= 200) {
+        const float frac = clamp_rs(c.key_edge_trim_fraction, 0.0f, 0.49f);
+        const size_t start = as_usize(roundf((float)nf * frac));
+        const size_t end = as_usize(roundf((float)nf * (1.0f - frac)));
+        if (end > start + 50 && end <= nf) {
+            f0 = start;
+            nf = end - start;
+        }
+    }
+    const float* ch = chroma.data() + f0 * 12;
+    const float* en = energy.data() + f0;
     std::vector<float> weights;
     bool have_w = false;
     if (c.enable_key_frame_weighting && nf > 0) {  // lib.rs:1253-1287
-        std::vector<float> sorted = energy;
+        std::vector<float> sorted(en, en + nf);
         std::stable_sort(sorted.begin(), sorted.end());
         float median = fmax_rs(sorted[sorted.size() / 2], 1e-12f);
         weights.resize(nf);
         for (size_t t = 0; t < nf; ++t) {
-            float tonal = chroma_tonalness(&chroma[t * 12]);
+            float tonal = chroma_tonalness(&ch[t * 12]);
             if (tonal < c.key_min_tonalness) tonal = 0.0f;
-            float en = fmax_rs(energy[t] / median, 0.0f);
+            float e_norm = fmax_rs(en[t] / median, 0.0f);
             float wt = powf(tonal, fmax_rs(c.key_tonalness_power, 0.0f));
-            float we = powf(en, fmax_rs(c.key_energy_power, 0.0f));
+            float we = powf(e_norm, fmax_rs(c.key_energy_power, 0.0f));
             weights[t] = fmax_rs(wt * we, 0.0f);
         }
         float sw = 0.0f;
@@ -430,9 +614,17 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
     int all_keys[24];
     float confidence;
     int key;
-    bool voted = false;
-    if (c.enable_key_segment_voting && nf >= std::max<size_t>(c.key_segment_len_frames, 1) && c.key_segment_len_frames >= 120 &&
-        c.key_segment_hop_frames >= 1) {  // lib.rs:1332-1436
+    bool done = false;
+    size_t ms_min = 0;
+    for (uint32_t i = 0; i < c.key_multi_scale_n_lengths; ++i) ms_min = i == 0 ? c.key_multi_scale_lengths[0] : std::min<size_t>(ms_min, c.key_multi_scale_lengths[i]);
+    if (c.enable_key_ensemble) {  // lib.rs:1290-1298
+        if (detect_key_ensemble(ch, nf, wp, c.key_ensemble_kk_weight, c.key_ensemble_temperley_weight, ks)) return Error{};
+        done = true;
+    } else if (c.enable_key_multi_scale && c.key_multi_scale_n_lengths > 0 && nf >= ms_min) {  // lib.rs:1304-1330
+        if (detect_key_multi_scale(ch, nf, wp, c, ks)) return Error{};
+        done = true;
+    } else if (c.enable_key_segment_voting && nf >= std::max<size_t>(c.key_segment_len_frames, 1) && c.key_segment_len_frames >= 120 &&
+               c.key_segment_hop_frames >= 1) {  // lib.rs:1332-1436
         size_t seg_len = std::min(c.key_segment_len_frames, nf);
         size_t hop = std::max<size_t>(std::min(c.key_segment_hop_frames, seg_len), 1);
         float min_cl = clamp_rs(c.key_segment_min_clarity, 0.0f, 1.0f);
@@ -441,7 +633,7 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
         size_t used = 0;
         std::vector<float> seg_dump;
         for (size_t st = 0; st + seg_len <= nf; st += hop) {
-            if (Error e = detect_key_weighted(&chroma[st * 12], seg_len, wp ? wp + st : nullptr, ks)) return e;
+            if (Error e = detect_one(&ch[st * 12], seg_len, wp ? wp + st : nullptr, c, ks)) return e;  // `?` at lib.rs:1369/1371
             float cl = compute_key_clarity(ks.scores, 24);
             if (dump) {
                 seg_dump.push_back((float)ks.keys[0]);
@@ -454,30 +646,20 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
         }
         if (dump) dump->f["key.segments"] = seg_dump;
         if (used > 0) {
-            int order[24];
-            for (int k = 0; k < 24; ++k) order[k] = k;
-            std::stable_sort(order, order + 24, [&](int a, int b) { return acc[a] > acc[b]; });
-            for (int i = 0; i < 24; ++i) {
-                all_keys[i] = order[i];
-                all_scores[i] = acc[order[i]];
-            }
-            key = all_keys[0];
-            confidence = all_scores[0] > 0.0f ? clamp_rs((all_scores[0] - all_scores[1]) / all_scores[0], 0.0f, 1.0f) : 0.0f;
-            voted = true;
+            finish_accumulated(acc, ks);
+            done = true;
         }
     }
-    if (!voted) {
-        if (Error e = detect_key_weighted(chroma.data(), nf, wp, ks)) {
-            // chroma extraction/key detection failure degrades to the default key (lib.rs:1542-1551)
-            return Error{};
-        }
-        for (int i = 0; i < 24; ++i) {
-            all_keys[i] = ks.keys[i];
-            all_scores[i] = ks.scores[i];
-        }
-        key = ks.key;
-        confidence = ks.confidence;
+    if (!done) {
+        // chroma extraction/key detection failure degrades to the default key (lib.rs:1542-1551)
+        if (detect_one(ch, nf, wp, c, ks)) return Error{};
     }
+    for (int i = 0; i < 24; ++i) {
+        all_keys[i] = ks.keys[i];
+        all_scores[i] = ks.scores[i];
+    }
+    key = ks.key;
+    confidence = ks.confidence;
     float clarity = compute_key_clarity(all_scores, 24);
     r.key_is_minor = key >= 12;
     r.key_index = (uint32_t)(key % 12);

@@ -25,7 +25,7 @@ import numpy as np
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_build" / "libstratum_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # StratumStatus / AnalysisError variants (src/error.rs:7-22)
 OK, INVALID_INPUT, DECODING_ERROR, PROCESSING_ERROR, NOT_IMPLEMENTED, NUMERICAL_ERROR = range(6)
@@ -87,6 +87,15 @@ class StratumConfig(C.Structure):
         ("enable_key_hpcp_whitening", _i), ("enable_key_hpcp_bass_blend", _i), ("enable_key_minor_harmonic_bonus", _i),
         ("chroma_sharpening_power", _f), ("hpss_margin", _u), ("soft_chroma_mapping", _i),
         ("enable_key_spectrogram_time_smoothing", _i),
+        ("key_template_set", _i), ("key_edge_trim_fraction", _f), ("key_mode_third_ratio_margin", _f),
+        ("key_mode_flip_min_score_ratio", _f), ("key_minor_leading_tone_bonus_weight", _f), ("key_ensemble_kk_weight", _f),
+        ("key_ensemble_temperley_weight", _f), ("key_multi_scale_n_lengths", _u), ("key_multi_scale_lengths", _u * 8),
+        ("key_multi_scale_hop", _u), ("key_multi_scale_min_clarity", _f), ("key_multi_scale_n_weights", _u),
+        ("key_multi_scale_weights", _f * 8), ("key_median_segment_length_frames", _u), ("key_median_segment_hop_frames", _u),
+        ("key_median_min_segments", _u), ("key_tuning_max_abs_semitones", _f), ("key_tuning_frame_step", _u),
+        ("key_tuning_peak_rel_threshold", _f), ("key_hpss_frame_step", _u), ("key_hpss_time_margin", _u), ("key_hpss_freq_margin", _u),
+        ("key_hpss_mask_power", _f), ("key_hpcp_whitening_smooth_bins", _u), ("key_hpcp_bass_fmin_hz", _f),
+        ("key_hpcp_bass_fmax_hz", _f), ("key_hpcp_bass_weight", _f),
     ]
 
 
@@ -213,9 +222,14 @@ class AnalysisConfig:
         for k, v in overrides.items():
             setattr(self, k, v)
 
+    # Vec<_> fields of the reference (config.rs:432-444) travel as a fixed array + count
+    _vecs = {"key_multi_scale_lengths": "key_multi_scale_n_lengths", "key_multi_scale_weights": "key_multi_scale_n_weights"}
+
     def __getattr__(self, name):
         if name in AnalysisConfig._names:
             v = getattr(self._c, name)
+            if name in AnalysisConfig._vecs:
+                return list(v)[: getattr(self._c, AnalysisConfig._vecs[name])]
             return list(v) if name == "onset_consensus_weights" else v
         raise AttributeError(name)
 
@@ -225,6 +239,14 @@ class AnalysisConfig:
         if name == "onset_consensus_weights":
             for i, w in enumerate(value):
                 self._c.onset_consensus_weights[i] = float(w)
+        elif name in AnalysisConfig._vecs:
+            value = list(value)
+            if len(value) > 8:
+                raise ValueError(f"{name}: at most 8 entries")
+            arr = getattr(self._c, name)
+            for i in range(8):
+                arr[i] = (value[i] if i < len(value) else 0)
+            setattr(self._c, AnalysisConfig._vecs[name], len(value))
         else:
             setattr(self._c, name, int(value) if isinstance(value, bool) else value)
 

@@ -21,7 +21,7 @@
 #include <thread>
 #include <vector>
 
-#include "kernels.h"
+#include "key_rows.cuh"
 
 namespace sb {
 
@@ -173,9 +173,13 @@ static std::vector<float> make_hann(uint32_t n) {  // chroma/extractor.rs:318-32
     return w;
 }
 
-static void make_key_templates(std::vector<float>& major, std::vector<float>& minor) {  // key/templates.rs:64-143
-    const float cmaj[12] = {6.35f, 2.23f, 3.48f, 2.33f, 4.38f, 4.09f, 2.52f, 5.19f, 2.39f, 3.66f, 2.29f, 2.88f};
-    const float cmin[12] = {6.33f, 2.68f, 3.52f, 5.38f, 2.60f, 3.53f, 2.54f, 4.75f, 3.98f, 2.69f, 3.34f, 3.17f};
+static void make_key_templates(std::vector<float>& major, std::vector<float>& minor, int template_set) {  // key/templates.rs:64-143 (K-K), 145-222 (Temperley)
+    const float kk_maj[12] = {6.35f, 2.23f, 3.48f, 2.33f, 4.38f, 4.09f, 2.52f, 5.19f, 2.39f, 3.66f, 2.29f, 2.88f};
+    const float kk_min[12] = {6.33f, 2.68f, 3.52f, 5.38f, 2.60f, 3.53f, 2.54f, 4.75f, 3.98f, 2.69f, 3.34f, 3.17f};
+    const float tp_maj[12] = {5.0f, 2.0f, 3.5f, 2.0f, 4.5f, 4.0f, 2.0f, 4.5f, 2.0f, 3.5f, 1.5f, 4.0f};
+    const float tp_min[12] = {5.0f, 2.0f, 3.5f, 5.0f, 2.0f, 3.5f, 2.0f, 4.5f, 3.5f, 2.0f, 4.0f, 3.5f};
+    const float* cmaj = template_set == 1 ? tp_maj : kk_maj;
+    const float* cmin = template_set == 1 ? tp_min : kk_min;
     major.assign(144, 0.0f);
     minor.assign(144, 0.0f);
     for (int k = 0; k < 12; ++k) {
@@ -215,11 +219,15 @@ static int ctx_init(DeviceCtx& c, int device) {
     c.tab.win2048 = dev_upload(c, make_hann(2048));
     c.tab.win8192 = dev_upload(c, make_hann(8192));
     std::vector<float> mj, mn;
-    make_key_templates(mj, mn);
+    make_key_templates(mj, mn, 0);
     c.tab.key_major = dev_upload(c, mj);
     c.tab.key_minor = dev_upload(c, mn);
+    make_key_templates(mj, mn, 1);
+    c.tab.key_major_tp = dev_upload(c, mj);
+    c.tab.key_minor_tp = dev_upload(c, mn);
     CUDA_OK(cudaMalloc(&c.d_srtab, sizeof(SrTables) * DeviceCtx::MAX_SR));
-    if (!c.tab.tw1024 || !c.tab.tw4096 || !c.tab.ptw1024 || !c.tab.ptw4096 || !c.tab.rw2048 || !c.tab.rw8192 || !c.tab.win2048 || !c.tab.win8192 || !c.tab.key_major || !c.tab.key_minor) {
+    if (!c.tab.tw1024 || !c.tab.tw4096 || !c.tab.ptw1024 || !c.tab.ptw4096 || !c.tab.rw2048 || !c.tab.rw8192 || !c.tab.win2048 || !c.tab.win8192 || !c.tab.key_major || !c.tab.key_minor ||
+        !c.tab.key_major_tp || !c.tab.key_minor_tp) {
         set_error("device table allocation failed");
         return STRATUM_PROCESSING_ERROR;
     }
@@ -545,6 +553,34 @@ static void config_default(StratumConfig* c) {  // src/config.rs:594-744
     c->hpss_margin = 10;
     c->soft_chroma_mapping = 1;
     c->enable_key_spectrogram_time_smoothing = 1;
+    c->key_template_set = 0;
+    c->key_edge_trim_fraction = 0.15f;
+    c->key_mode_third_ratio_margin = 0.0f;
+    c->key_mode_flip_min_score_ratio = 0.60f;
+    c->key_minor_leading_tone_bonus_weight = 0.2f;
+    c->key_ensemble_kk_weight = 0.5f;
+    c->key_ensemble_temperley_weight = 0.5f;
+    c->key_multi_scale_n_lengths = 3;
+    c->key_multi_scale_lengths[0] = 120;
+    c->key_multi_scale_lengths[1] = 360;
+    c->key_multi_scale_lengths[2] = 720;
+    c->key_multi_scale_hop = 60;
+    c->key_multi_scale_min_clarity = 0.20f;
+    c->key_multi_scale_n_weights = 0;
+    c->key_median_segment_length_frames = 480;
+    c->key_median_segment_hop_frames = 120;
+    c->key_median_min_segments = 3;
+    c->key_tuning_max_abs_semitones = 0.08f;
+    c->key_tuning_frame_step = 20;
+    c->key_tuning_peak_rel_threshold = 0.35f;
+    c->key_hpss_frame_step = 4;
+    c->key_hpss_time_margin = 8;
+    c->key_hpss_freq_margin = 8;
+    c->key_hpss_mask_power = 2.0f;
+    c->key_hpcp_whitening_smooth_bins = 31;
+    c->key_hpcp_bass_fmin_hz = 55.0f;
+    c->key_hpcp_bass_fmax_hz = 300.0f;
+    c->key_hpcp_bass_weight = 0.35f;
 }
 
 // Rejects configurations whose branch is not built instead of silently ignoring them.
@@ -571,10 +607,15 @@ static int config_validate(const StratumConfig& c) {
     if (c.key_hpcp_num_harmonics > 8) return ni("key_hpcp_num_harmonics > 8");
     if (c.tempogram_superflux_max_filter_bins > 8) return ni("tempogram_superflux_max_filter_bins > 8");
     if (c.tempogram_multi_res_top_k > 32) return ni("tempogram_multi_res_top_k > 32");
-    if (c.enable_key_hpss_harmonic || c.enable_key_log_frequency || c.enable_key_beat_synchronous || c.enable_key_multi_scale || c.enable_key_ensemble ||
-        c.enable_key_median || c.enable_key_tuning_compensation || c.enable_key_edge_trim || c.enable_key_mode_heuristic || c.enable_key_hpcp_whitening ||
-        c.enable_key_hpcp_bass_blend || c.enable_key_minor_harmonic_bonus)
-        return ni("optional key-path variants (hpss/log-frequency/beat-sync/multi-scale/ensemble/median/tuning/edge-trim/mode-heuristic/whitening/bass-blend/minor-bonus)");
+    // enable_key_median is accepted and has no effect, as in the reference: analyze_audio never reads it (lib.rs imports no detect_key_median)
+    if (c.enable_key_hpss_harmonic || c.enable_key_log_frequency || c.enable_key_beat_synchronous || c.enable_key_tuning_compensation ||
+        c.enable_key_hpcp_whitening || c.enable_key_hpcp_bass_blend)
+        return ni("optional key-path variants (hpss/log-frequency/beat-sync/tuning/whitening/bass-blend)");
+    if (c.key_template_set != 0 && c.key_template_set != 1) {
+        set_error("unknown key_template_set");
+        return STRATUM_INVALID_INPUT;
+    }
+    if (c.key_multi_scale_n_lengths > 8 || c.key_multi_scale_n_weights > 8) return ni("more than 8 multi-scale lengths / weights");
     if (!(c.min_bpm > 0.0f) || !(c.max_bpm > c.min_bpm) || !(c.bpm_resolution > 0.0f)) {
         set_error("Invalid BPM range");
         return STRATUM_INVALID_INPUT;
@@ -670,6 +711,25 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.hpcp_decay = c.key_hpcp_harmonic_decay;
     d.hpcp_pow = c.key_hpcp_mag_power;
     d.hpcp_sigma = c.soft_mapping_sigma;
+    d.key_mode = c.enable_key_ensemble ? KEY_ROWS_ENSEMBLE : (c.enable_key_multi_scale ? KEY_ROWS_MULTI_SCALE : KEY_ROWS_VOTE);
+    d.key_template_set = c.key_template_set;
+    d.key_edge_trim = c.enable_key_edge_trim;
+    d.key_edge_frac = c.key_edge_trim_fraction;
+    d.key_heur = c.enable_key_mode_heuristic || c.enable_key_minor_harmonic_bonus;
+    d.key_third_margin = c.key_mode_third_ratio_margin;
+    d.key_flip_ratio = c.enable_key_mode_heuristic ? c.key_mode_flip_min_score_ratio : 0.0f;
+    d.key_minor_bonus = c.enable_key_minor_harmonic_bonus;
+    d.key_minor_bonus_w = c.key_minor_leading_tone_bonus_weight;
+    d.key_ens_kk = c.key_ensemble_kk_weight;
+    d.key_ens_tp = c.key_ensemble_temperley_weight;
+    d.ms_n = std::min<uint32_t>(c.key_multi_scale_n_lengths, 8);
+    d.ms_nw = std::min<uint32_t>(c.key_multi_scale_n_weights, 8);
+    for (int i = 0; i < 8; ++i) {
+        d.ms_len[i] = c.key_multi_scale_lengths[i];
+        d.ms_w[i] = c.key_multi_scale_weights[i];
+    }
+    d.ms_hop = c.key_multi_scale_hop;
+    d.ms_min_clarity = c.key_multi_scale_min_clarity;
     return d;
 }
 
@@ -721,14 +781,11 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.chroma2 = fa.take((uint64_t)Fk * 12 + 12);
     T.kenergy = fa.take(Fk + 1);
     T.kweights = fa.take(Fk + 1);
-    uint32_t nseg = 0;
-    if (cfg.enable_key_segment_voting && cfg.key_segment_len_frames >= 120 && cfg.key_segment_hop_frames >= 1 && Fk >= cfg.key_segment_len_frames) {
-        const uint32_t seg_len = std::min(cfg.key_segment_len_frames, Fk);
-        const uint32_t hop = std::max(std::min(cfg.key_segment_hop_frames, seg_len), 1u);
-        nseg = (Fk - seg_len) / hop + 1;
-    }
-    T.seg_cap = nseg + 1;
+    // score rows (key_rows.cuh); the row count is monotone in the frame count, so the untrimmed Fk bounds every trimmed / edge-trimmed slice
+    T.seg_cap = key_rows(Fk, make_devcfg(cfg)).nrows + 1;
     T.seg_scores = fa.take((uint64_t)T.seg_cap * 24);
+    T.seg_avg = fa.take((uint64_t)T.seg_cap * 13);
+    T.seg_rank = fa.take((uint64_t)T.seg_cap * 28);
     // onsets: each detector yields at most every other flux sample
     const uint32_t on_cap = F512 / 2 + 8;
     T.on_energy = ia.take(on_cap);

@@ -11,7 +11,7 @@
 // in place by the mask and read once by the HPCP kernel (4 x 16 KB); everything after that is 12 floats
 // per frame.
 #include "framed.cuh"
-#include "kernels.h"
+#include "key_rows.cuh"
 
 namespace sb {
 
@@ -358,18 +358,21 @@ __global__ void __launch_bounds__(256) chroma_smooth_kernel(const TrackDev* __re
 }
 
 // ---- frame weights (lib.rs:1236-1287): one CTA per track -------------------------------------------
+// Works on the (optionally edge-trimmed, lib.rs:1216-1233) slice [f0, f0 + nf) of the smoothed chroma; weights are
+// stored at slice-relative indices.
 __global__ void __launch_bounds__(256) key_weights_kernel(TrackDev* tr, float* fa, DevCfg cfg) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t bc[2];
     __shared__ float sred[32];
     __shared__ uint32_t sused[32];
     TrackDev& T = tr[blockIdx.x];
-    const uint32_t nf = T.Fk;
+    uint32_t f0, nf;
+    key_slice(T.Fk, cfg, &f0, &nf);
     if (threadIdx.x == 0) T.have_w = 0;
     if (T.status != 0 || nf == 0 || !cfg.key_weighting) return;
-    const float* en = fa + T.kenergy;
+    const float* en = fa + T.kenergy + f0;
     const float median = fmaxf(block_select_kth(en, nf, nf / 2, hist, bc), 1e-12f);
-    const float* ch = fa + T.chroma2;
+    const float* ch = fa + T.chroma2 + (uint64_t)f0 * 12;
     float* wv = fa + T.kweights;
     const float tp = fmaxf(cfg.key_tonal_pow, 0.0f), ep = fmaxf(cfg.key_energy_pow, 0.0f);
     const float ln12 = logf(12.0f);
@@ -417,47 +420,52 @@ __global__ void __launch_bounds__(256) key_weights_kernel(TrackDev* tr, float* f
     }
 }
 
-// Segment geometry shared by the two kernels below (lib.rs:1332-1352).
-__device__ __forceinline__ bool seg_geometry(const TrackDev& T, const DevCfg& cfg, uint32_t* seg_len, uint32_t* hop, uint32_t* nseg) {
-    const uint32_t nf = T.Fk;
-    const bool voting = cfg.key_voting && nf >= max(cfg.key_seg_len, 1u) && cfg.key_seg_len >= 120 && cfg.key_seg_hop >= 1;
-    if (!voting) {
-        *seg_len = nf;
-        *hop = 1;
-        *nseg = 0;
-        return false;
+// Rows a launch covers: the first pass scores every window row (and both whole-track rows of the ensemble); the
+// whole-track row of a voting / multi-scale track is only needed when no window passes the clarity gate
+// (lib.rs:1385-1411, detector.rs:648-668), so it is computed by a second pass (fallback_only) for the tracks
+// key_vote_kernel flagged.  Returns false when this (track, row, pass) has nothing to do.
+__device__ __forceinline__ bool key_row_for_pass(const TrackDev& T, const DevCfg& cfg, uint32_t bx, int fallback_only, uint32_t* f0, uint32_t* nf, KeyRows* R,
+                                                 uint32_t* row) {
+    if (T.status != 0 || T.Fk == 0) return false;
+    key_slice(T.Fk, cfg, f0, nf);
+    if (*nf == 0) return false;
+    *R = key_rows(*nf, cfg);
+    if (R->mode == KEY_ROWS_ENSEMBLE) {
+        *row = bx;
+        return !fallback_only && bx < 2 && bx < T.seg_cap;
     }
-    *seg_len = min(cfg.key_seg_len, nf);
-    *hop = max(min(cfg.key_seg_hop, *seg_len), 1u);
-    *nseg = (nf - *seg_len) / *hop + 1;
-    return true;
+    if (fallback_only) {
+        *row = R->nseg;
+        return bx == 0 && T.key_fallback && *row < T.seg_cap;
+    }
+    *row = bx;
+    if (R->nseg == 0) return bx == 0;  // no windows: the whole-track row is the result
+    return bx < R->nseg && bx < T.seg_cap;
 }
 
-// ---- template scores: one warp per (segment, key) ------------------------------------------------------
+// ---- template scores: one warp per (row, key) -----------------------------------------------------------
 // score = sum over frames (in frame order) of w_t * <c_t, T_k> (detector.rs:984-1001).  The 32 lanes
 // evaluate the 12-term dot products of 32 consecutive frames in parallel (each in the reference's term
 // order); the running sum then absorbs the 32 products strictly in frame order through shuffles, so the
 // result equals the serial fold bit for bit while the chain per frame is one add instead of ~25 ops.
-// blockIdx.x = segment index; the extra index `nseg` is the whole-track score used when no segment
-// passes the clarity gate (lib.rs:1385-1411) or voting is off.  blockDim = 24 warps, warp = key.
-// The whole-track row of a track that votes by segments is only needed when no segment passes the clarity gate, so the
-// first launch skips it and a second launch (fallback_only) computes it for the tracks key_vote_kernel flagged.
+// blockIdx.x = row (key_rows.cuh); blockDim = 24 warps, warp = key.
 __global__ void __launch_bounds__(768) segment_score_kernel(const TrackDev* __restrict__ tr, float* fa, Tables tab, DevCfg cfg, int fallback_only) {
     const TrackDev& T = tr[blockIdx.y];
-    if (T.status != 0 || T.Fk == 0) return;
-    uint32_t seg_len, hop, nseg;
-    const bool voting = seg_geometry(T, cfg, &seg_len, &hop, &nseg);
-    const uint32_t s = fallback_only ? nseg : blockIdx.x;
-    if (s > nseg || s >= T.seg_cap) return;
-    if (fallback_only ? !T.key_fallback : (voting && s == nseg)) return;
-    const uint32_t start = s < nseg ? s * hop : 0;
-    const uint32_t len = s < nseg ? seg_len : T.Fk;
+    uint32_t f0, nf, row;
+    KeyRows R;
+    if (!key_row_for_pass(T, cfg, blockIdx.x, fallback_only, &f0, &nf, &R, &row)) return;
+    uint32_t start, len;
+    float scale_w;
+    int tset;
+    key_row_range(R, row, nf, cfg, &start, &len, &scale_w, &tset);
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* tpl = (k < 12 ? tab.key_major + k * 12 : tab.key_minor + (k - 12) * 12);
+    const float* tmaj = tset == 1 ? tab.key_major_tp : tab.key_major;
+    const float* tmin = tset == 1 ? tab.key_minor_tp : tab.key_minor;
+    const float* tpl = (k < 12 ? tmaj + k * 12 : tmin + (k - 12) * 12);
     float tp[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) tp[i] = tpl[i];
-    const float* ch = fa + T.chroma2 + (uint64_t)start * 12;
+    const float* ch = fa + T.chroma2 + (uint64_t)(f0 + start) * 12;
     const float* wv = T.have_w ? fa + T.kweights + start : nullptr;
     float acc = 0.0f;
     for (uint32_t t0 = 0; t0 < len; t0 += 32) {
@@ -485,7 +493,52 @@ __global__ void __launch_bounds__(768) segment_score_kernel(const TrackDev* __re
             if ((um >> l) & 1u) acc = acc + p;
         }
     }
-    if (lane == 0) fa[T.seg_scores + (uint64_t)s * 24 + k] = acc;
+    if (lane == 0) fa[T.seg_scores + (uint64_t)row * 24 + k] = acc;
+}
+
+// ---- weighted chroma sums of a row (mode heuristic, detector.rs:345-371): warp i < 12 folds avg[i] += w_t * c_t[i] over the
+// frames with w_t > 0 in frame order (or avg[i] += c_t[i] without weights); warp 12 folds the weight sum.  Same
+// "parallel products, ordered absorption" scheme as the score kernel.  blockDim = 13 warps.
+__global__ void __launch_bounds__(416) segment_avg_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg, int fallback_only) {
+    const TrackDev& T = tr[blockIdx.y];
+    uint32_t f0, nf, row;
+    KeyRows R;
+    if (!key_row_for_pass(T, cfg, blockIdx.x, fallback_only, &f0, &nf, &R, &row)) return;
+    uint32_t start, len;
+    float scale_w;
+    int tset;
+    key_row_range(R, row, nf, cfg, &start, &len, &scale_w, &tset);
+    const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* ch = fa + T.chroma2 + (uint64_t)(f0 + start) * 12;
+    const float* wv = T.have_w ? fa + T.kweights + start : nullptr;
+    float acc = 0.0f;
+    if (!wv && i == 12) {
+        acc = (float)len;  // wsum = chroma_vectors.len() as f32
+    } else {
+        for (uint32_t t0 = 0; t0 < len; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            float prod = 0.0f;
+            bool use = false;
+            if (t < len) {
+                const float c = i < 12 ? ch[(uint64_t)t * 12 + i] : 1.0f;
+                if (wv) {
+                    const float wt = wv[t];
+                    use = wt > 0.0f;
+                    prod = i < 12 ? wt * c : wt;
+                } else {
+                    use = true;
+                    prod = c;
+                }
+            }
+            const uint32_t um = __ballot_sync(0xffffffffu, use);
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const float p = __shfl_sync(0xffffffffu, prod, l);
+                if ((um >> l) & 1u) acc = acc + p;
+            }
+        }
+    }
+    if (lane == 0) fa[T.seg_avg + (uint64_t)row * 13 + i] = acc;
 }
 
 // detect_key_weighted steps 1.5 - 2 on 24 raw scores: ranked keys/scores out (detector.rs:135-250) and the
@@ -550,7 +603,129 @@ __device__ __noinline__ float key_clarity(const float* sc, int n) {  // key_clar
     return 0.0f;
 }
 
-// ---- per-track vote (lib.rs:1353-1436, 1461): one thread per track -----------------------------------
+// Stable descending sort of 24 (key, score) pairs already in some order (Rust sort_by is stable).
+__device__ __forceinline__ void stable_sort_desc(int* keys, float* scores) {
+    for (int a = 1; a < 24; ++a) {
+        const float x = scores[a];
+        const int kx = keys[a];
+        int j = a;
+        while (j > 0 && scores[j - 1] < x) {
+            scores[j] = scores[j - 1];
+            keys[j] = keys[j - 1];
+            --j;
+        }
+        scores[j] = x;
+        keys[j] = kx;
+    }
+}
+
+// detect_key_weighted_mode_heuristic after the base scoring (detector.rs:338-517): minor-key leading-tone bonus, stable
+// re-sort, scale-degree mode preference, optional parallel-mode flip.  keys/scores (ranked) and by_key are updated in
+// place; returns the chosen key and its confidence.
+__device__ __noinline__ void mode_heuristic(const float* avg13, const DevCfg& cfg, int* keys, float* scores, float* by_key, int* chosen_out, float* conf_out) {
+    const float flip_ratio = clamp_rs(cfg.key_flip_ratio, 0.0f, 1.0f);
+    const bool enable_flip = flip_ratio > 0.0f;
+    const float wsum = avg13[12];
+    if ((!cfg.key_minor_bonus && !enable_flip) || wsum <= 1e-9f) return;  // base result stands
+    float avg[12];
+    float sum = 0.0f;
+    for (int i = 0; i < 12; ++i) {
+        avg[i] = avg13[i];
+        sum = sum + avg[i];
+    }
+    if (sum > 1e-9f)
+        for (int i = 0; i < 12; ++i) avg[i] = avg[i] / sum;
+    if (cfg.key_minor_bonus) {
+        const float bw = fmaxf(cfg.key_minor_bonus_w, 0.0f);
+        if (bw > 0.0f)
+            for (int i = 0; i < 24; ++i)
+                if (keys[i] >= 12) {
+                    const int tonic = keys[i] - 12;
+                    scores[i] = scores[i] + wsum * bw * (avg[(tonic + 11) % 12] - avg[(tonic + 10) % 12]);
+                }
+    }
+    stable_sort_desc(keys, scores);
+    for (int i = 0; i < 24; ++i) by_key[keys[i]] = scores[i];
+    const int best_key = keys[0];
+    const int tonic = best_key % 12;
+    const bool best_is_major = best_key < 12;
+    const float p_min3 = avg[(tonic + 3) % 12], p_maj3 = avg[(tonic + 4) % 12];
+    const float p_min6 = avg[(tonic + 8) % 12], p_maj6 = avg[(tonic + 9) % 12];
+    const float p_min7 = avg[(tonic + 10) % 12], p_maj7 = avg[(tonic + 11) % 12];
+    const float margin = fmaxf(cfg.key_third_margin, 0.0f);
+    float minor_score = 0.0f, major_score = 0.0f;
+    const float d3 = fabsf(p_min3 - p_maj3);
+    if (p_min3 > (p_maj3 * (1.0f + margin))) minor_score = minor_score + d3 * 2.0f;
+    else if (p_maj3 > (p_min3 * (1.0f + margin))) major_score = major_score + d3 * 2.0f;
+    const float d6 = fabsf(p_min6 - p_maj6);
+    if (p_min6 > (p_maj6 * (1.0f + margin))) minor_score = minor_score + d6 * 1.0f;
+    else if (p_maj6 > (p_min6 * (1.0f + margin))) major_score = major_score + d6 * 1.0f;
+    const float d7 = fabsf(p_min7 - p_maj7);
+    if (p_min7 > (p_maj7 * (1.0f + margin))) minor_score = minor_score + d7 * 1.0f;
+    else if (p_maj7 > (p_min7 * (1.0f + margin))) major_score = major_score + d7 * 1.0f;
+    const float total = minor_score + major_score;
+    const bool minor_pref = total > 1e-9f ? minor_score > major_score * (1.0f + margin * 0.5f) : false;
+    const bool major_pref = total > 1e-9f ? major_score > minor_score * (1.0f + margin * 0.5f) : false;
+    int chosen = best_key;
+    if (enable_flip) {
+        if (best_is_major && minor_pref) {
+            const float s_best = by_key[tonic], s_alt = by_key[12 + tonic];
+            if (s_best > 0.0f && s_alt >= s_best * flip_ratio) chosen = 12 + tonic;
+        } else if (!best_is_major && major_pref) {
+            const float s_best = by_key[12 + tonic], s_alt = by_key[tonic];
+            if (s_best > 0.0f && s_alt >= s_best * flip_ratio) chosen = tonic;
+        }
+    }
+    const float chosen_score = by_key[chosen];
+    float best_other = 0.0f;
+    for (int i = 0; i < 24; ++i)
+        if (keys[i] != chosen) best_other = fmaxf(best_other, scores[i]);
+    *chosen_out = chosen;
+    *conf_out = chosen_score > 0.0f ? clamp_rs((chosen_score - best_other) / chosen_score, 0.0f, 1.0f) : 0.0f;
+}
+
+// ---- per-row detection result: one thread per (row, track) ----------------------------------------------------------------
+// seg_rank[row] = { refined score by key id [24], clarity of the ranked table, chosen key, confidence, 0 }
+__global__ void __launch_bounds__(64) row_rank_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg, uint32_t max_rows, int fallback_only) {
+    const TrackDev& T = tr[blockIdx.y];
+    const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bx >= max_rows) return;
+    uint32_t f0, nf, row;
+    KeyRows R;
+    if (!key_row_for_pass(T, cfg, bx, fallback_only, &f0, &nf, &R, &row)) return;
+    int keys[24];
+    float scores[24], by_key[24];
+    rank_keys(fa + T.seg_scores + (uint64_t)row * 24, keys, scores, by_key);
+    // weighted top-3 vote (detector.rs:254-275): three distinct keys, so the first-ranked key wins
+    int chosen = keys[0];
+    float conf = scores[0] > 0.0f ? clamp_rs((scores[0] - scores[1]) / scores[0], 0.0f, 1.0f) : 0.0f;
+    if (cfg.key_heur && R.mode != KEY_ROWS_ENSEMBLE) mode_heuristic(fa + T.seg_avg + (uint64_t)row * 13, cfg, keys, scores, by_key, &chosen, &conf);
+    float* out = fa + T.seg_rank + (uint64_t)row * 28;
+    for (int k = 0; k < 24; ++k) out[k] = by_key[k];
+    out[24] = key_clarity(scores, 24);
+    out[25] = (float)chosen;
+    out[26] = conf;
+    out[27] = 0.0f;
+}
+
+// Sort 24 accumulated scores (by key id) descending, stable in key-id order; confidence as lib.rs:1412-1425.
+__device__ __forceinline__ void finish_accumulated(const float* acc, int* keys, float* fin, int* key, float* confidence) {
+    for (int k = 0; k < 24; ++k) {
+        const float x = acc[k];
+        int j = k;
+        while (j > 0 && fin[j - 1] < x) {
+            fin[j] = fin[j - 1];
+            keys[j] = keys[j - 1];
+            --j;
+        }
+        fin[j] = x;
+        keys[j] = k;
+    }
+    *key = keys[0];
+    *confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;
+}
+
+// ---- per-track decision (lib.rs:1290-1461): one thread per track ---------------------------------------------------------
 __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, DevCfg cfg, int fallback_only) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
@@ -564,59 +739,70 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
         T.key_fallback = 0;
     }
     if (T.status != 0 || T.Fk == 0 || T.m < 2048) return;
-    uint32_t seg_len, hop, nseg;
-    const bool voting = seg_geometry(T, cfg, &seg_len, &hop, &nseg);
-    nseg = min(nseg, T.seg_cap > 0 ? T.seg_cap - 1 : 0u);
-    const float* ss = fa + T.seg_scores;
+    uint32_t f0, nf;
+    key_slice(T.Fk, cfg, &f0, &nf);
+    if (nf == 0) return;
+    const KeyRows R = key_rows(nf, cfg);
+    const float* rk = fa + T.seg_rank;
     int keys[24];
-    float scores[24], by_key[24];
-    bool voted = false;
+    float fin[24];
     int key = 0;
     float confidence = 0.0f;
-    float fin[24];
-    if (voting && !fallback_only) {
-        const float min_cl = clamp_rs(cfg.key_seg_min_clarity, 0.0f, 1.0f);
+    if (R.mode == KEY_ROWS_ENSEMBLE) {  // detector.rs:881-976
+        const float total = cfg.key_ens_kk + cfg.key_ens_tp;
+        const float kk_norm = total > 1e-9f ? cfg.key_ens_kk / total : 0.5f;
+        const float tp_norm = total > 1e-9f ? cfg.key_ens_tp / total : 0.5f;
+        float comb[24];
+        for (int k = 0; k < 24; ++k) comb[k] = kk_norm * rk[k] + tp_norm * rk[28 + k];
+        finish_accumulated(comb, keys, fin, &key, &confidence);
+        T.key = key;
+        T.key_confidence = confidence;
+        T.key_clarity = key_clarity(fin, 24);
+        return;
+    }
+    const uint32_t nseg = min(R.nseg, T.seg_cap > 0 ? T.seg_cap - 1 : 0u);
+    if (nseg > 0 && !fallback_only) {
+        const bool ms = R.mode == KEY_ROWS_MULTI_SCALE;
+        const float min_cl = clamp_rs(ms ? cfg.ms_min_clarity : cfg.key_seg_min_clarity, 0.0f, 1.0f);
         float acc[24];
         for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
         uint32_t used = 0;
+        float total_weight = 0.0f;
         for (uint32_t s = 0; s < nseg; ++s) {
-            rank_keys(ss + (uint64_t)s * 24, keys, scores, by_key);
-            const float cl = key_clarity(scores, 24);
+            const float* r = rk + (uint64_t)s * 28;
+            const float cl = r[24];
             if (cl >= min_cl) {
                 ++used;
-                for (int k = 0; k < 24; ++k) acc[k] = acc[k] + by_key[k] * cl;  // one add per key and segment, as lib.rs:1375-1381
-            }
-        }
-        if (used > 0) {
-            for (int k = 0; k < 24; ++k) {
-                const float x = acc[k];
-                int j = k;
-                while (j > 0 && fin[j - 1] < x) {
-                    fin[j] = fin[j - 1];
-                    keys[j] = keys[j - 1];
-                    --j;
+                float cw = cl;
+                if (ms) {  // detector.rs:634-645: clarity x scale weight
+                    uint32_t start, len;
+                    float scale_w;
+                    int tset;
+                    key_row_range(R, s, nf, cfg, &start, &len, &scale_w, &tset);
+                    cw = cl * scale_w;
+                    total_weight = total_weight + cw;
                 }
-                fin[j] = x;
-                keys[j] = k;
+                for (int k = 0; k < 24; ++k) acc[k] = acc[k] + r[k] * cw;  // one add per key and row, as lib.rs:1375-1381
             }
-            key = keys[0];
-            confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;
-            voted = true;
         }
-    }
-    if (!voted && voting && !fallback_only) {
-        T.key_fallback = 1;  // no segment passed the clarity gate (lib.rs:1385-1411): the whole-track row is computed on demand
+        const bool ok = ms ? (used > 0 && !(total_weight <= 1e-12f)) : used > 0;
+        if (!ok) {
+            T.key_fallback = 1;  // every window rejected: the whole-track row is computed on demand
+            return;
+        }
+        if (ms)
+            for (int k = 0; k < 24; ++k) acc[k] = acc[k] / total_weight;
+        finish_accumulated(acc, keys, fin, &key, &confidence);
+        T.key = key;
+        T.key_confidence = confidence;
+        T.key_clarity = key_clarity(fin, 24);
         return;
     }
-    if (!voted) {
-        rank_keys(ss + (uint64_t)nseg * 24, keys, fin, by_key);
-        // weighted top-3 vote (detector.rs:254-275): three distinct keys, so the first-ranked key wins
-        key = keys[0];
-        confidence = fin[0] > 0.0f ? clamp_rs((fin[0] - fin[1]) / fin[0], 0.0f, 1.0f) : 0.0f;
-    }
-    T.key = key;
-    T.key_confidence = confidence;
-    T.key_clarity = key_clarity(fin, 24);
+    // whole-track detection: the row's own result; its ranked table gives the clarity (lib.rs:1461)
+    const float* r = rk + (uint64_t)nseg * 28;
+    T.key = (int)r[25];
+    T.key_confidence = r[26];
+    T.key_clarity = r[24];
 }
 
 void launch_key_mask(const WaveCtx& c) {
@@ -642,19 +828,30 @@ void launch_key_hpcp(const WaveCtx& c) {
 }
 
 void launch_key_vote(const WaveCtx& c) {
+    const uint32_t rows = c.max_seg_cap;
+    auto pass = [&](int fallback_only) {
+        const uint32_t gx = fallback_only ? 1u : rows;
+        segment_score_kernel<<<dim3(gx, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg, fallback_only);
+        count_launch("key_vote");
+        if (c.cfg.key_heur && c.cfg.key_mode != KEY_ROWS_ENSEMBLE) {
+            segment_avg_kernel<<<dim3(gx, c.n_tracks), 416, 0, c.stream>>>(c.tracks, c.fa, c.cfg, fallback_only);
+            count_launch("key_vote");
+        }
+        row_rank_kernel<<<dim3((gx + 63) / 64, c.n_tracks), 64, 0, c.stream>>>(c.tracks, c.fa, c.cfg, gx, fallback_only);
+        count_launch("key_vote");
+    };
     if (c.max_Fk > 0) {
         chroma_smooth_kernel<<<dim3((c.max_Fk * 12 + 255) / 256, c.n_tracks), 256, 0, c.stream>>>(c.tracks, c.fa);
         count_launch("key_vote");
         key_weights_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         count_launch("key_vote");
-        segment_score_kernel<<<dim3(c.max_seg_cap, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg, 0);
-        count_launch("key_vote");
+        pass(0);
     }
     key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg, 0);
     count_launch("key_vote");
-    if (c.max_Fk > 0 && c.cfg.key_voting) {  // rare path: tracks whose segments were all rejected
-        segment_score_kernel<<<dim3(1, c.n_tracks), 768, 0, c.stream>>>(c.tracks, c.fa, c.tab, c.cfg, 1);
-        count_launch("key_vote");
+    if (c.max_Fk > 0 && c.cfg.key_mode != KEY_ROWS_ENSEMBLE && (c.cfg.key_voting || c.cfg.key_mode == KEY_ROWS_MULTI_SCALE)) {
+        // rare path: tracks whose windows were all rejected
+        pass(1);
         key_vote_kernel<<<(c.n_tracks + 63) / 64, 64, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg, 1);
         count_launch("key_vote");
     }

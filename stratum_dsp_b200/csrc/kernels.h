@@ -41,6 +41,18 @@ struct DevCfg {
     float key_seg_min_clarity;
     uint32_t hpcp_peaks, hpcp_harm;
     float hpcp_decay, hpcp_pow, hpcp_sigma;
+    // optional key scoring variants
+    int32_t key_mode;             // KEY_ROWS_* (key_rows.cuh): segment voting / multi-scale / ensemble
+    int32_t key_template_set;     // 0 = Krumhansl-Kessler, 1 = Temperley (key/templates.rs:16-22)
+    int32_t key_edge_trim;
+    float key_edge_frac;
+    int32_t key_heur;             // detect_key_weighted_mode_heuristic replaces detect_key_weighted (lib.rs:1353-1372)
+    float key_third_margin, key_flip_ratio;  // flip ratio is 0 unless enable_key_mode_heuristic (lib.rs:1361-1365)
+    int32_t key_minor_bonus;
+    float key_minor_bonus_w;
+    float key_ens_kk, key_ens_tp;
+    uint32_t ms_n, ms_len[8], ms_hop, ms_nw;
+    float ms_w[8], ms_min_clarity;
 };
 
 // Per-sample-rate tables (band edges, mel filterbank) — novelty.rs:72-190, tempogram.rs:364-372.

@@ -201,3 +201,60 @@ def fixture_mixed_silence(sr: int = 44100) -> np.ndarray:
     t = np.arange(5 * sr) / sr
     tone = (np.sin(2 * np.pi * 440.0 * t).astype(np.float32)) * 0.5
     return _pcm16_roundtrip(np.concatenate([sil, tone, sil]))
+
+
+# ---- richer tonal material for the optional key-path variants ---------------------------------------
+# A chord progression with harmonics, a bass line, a scale melody, clicks and a little noise: template scores no longer
+# tie between the modes, tuning offsets are measurable (detune_cents), and the bass band carries its own pitch content.
+def render_progression(seed: int, duration_s: float, sr: int = 44100, tonic: int = 0, minor: bool = False, bpm: float = 120.0,
+                       detune_cents: float = 0.0, noise: float = 0.003) -> np.ndarray:
+    rng = np.random.RandomState(seed)
+    n = int(duration_s * sr)
+    t = np.arange(n, dtype=np.float64) / sr
+    x = np.zeros(n, dtype=np.float64)
+    scale = [0, 2, 3, 5, 7, 8, 10] if minor else [0, 2, 4, 5, 7, 9, 11]
+    degrees = [0, 5, 3, 4] if not minor else [0, 5, 2, 6]  # I-vi-IV-V / i-VI-III-VII
+    tune = 2.0 ** (detune_cents / 1200.0)
+    beat = 60.0 / bpm
+    bar = 4 * beat
+    nbars = int(math.ceil(duration_s / bar))
+
+    def hz(semi_from_c4):
+        return C4_HZ * tune * 2.0 ** (semi_from_c4 / 12.0)
+
+    for b in range(nbars):
+        s0, s1 = int(b * bar * sr), min(int((b + 1) * bar * sr), n)
+        if s0 >= n:
+            break
+        d = degrees[b % 4]
+        triad = [scale[d % 7] + 12 * (d // 7), scale[(d + 2) % 7] + 12 * ((d + 2) // 7), scale[(d + 4) % 7] + 12 * ((d + 4) // 7)]
+        tt = t[s0:s1]
+        env = np.minimum(1.0, (tt - tt[0]) / 0.02) * np.minimum(1.0, (tt[-1] - tt) / 0.02 + 1e-3)
+        for semi in triad:
+            f = hz(tonic + semi)
+            for h in range(1, 5):
+                x[s0:s1] += env * 0.06 / h * np.sin(2.0 * np.pi * f * h * tt + 0.3 * h)
+        fb = hz(tonic + triad[0] - 24)  # bass: chord root two octaves down
+        for h in range(1, 4):
+            x[s0:s1] += env * 0.12 / h * np.sin(2.0 * np.pi * fb * h * tt)
+        for q in range(8):  # eighth-note melody from the scale, one octave up
+            m0, m1 = s0 + int(q * beat / 2 * sr), min(s0 + int((q + 1) * beat / 2 * sr), n)
+            if m0 >= n:
+                break
+            deg = rng.randint(0, 7)
+            f = hz(tonic + scale[deg] + 12)
+            mt = t[m0:m1] - t[m0]
+            x[m0:m1] += 0.05 * np.exp(-mt / 0.15) * np.sin(2.0 * np.pi * f * mt)
+    clen = int(CLICK_LEN_S * sr)
+    ct = np.arange(clen, dtype=np.float64) / sr
+    click = 0.5 * np.sin(2.0 * np.pi * CLICK_HZ * ct) * np.exp(-ct / CLICK_TAU_S)
+    k = 0
+    while True:
+        s = int(round(k * beat * sr))
+        if s >= n:
+            break
+        e = min(s + clen, n)
+        x[s:e] += click[: e - s]
+        k += 1
+    x += noise * rng.standard_normal(n)
+    return x.astype(np.float32)

@@ -72,7 +72,7 @@ def test_errors_match_reference():
         S.analyze_audio(np.ones(100, np.float32), 0)
     assert e.value.kind == "InvalidInput"
     with pytest.raises(S.AnalysisError) as e:
-        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(enable_key_mode_heuristic=True))
+        S.analyze_audio(np.ones(100000, np.float32), SR, S.AnalysisConfig(frame_size=1024))
     assert e.value.kind == "NotImplemented"  # unsupported switches are rejected, never silently ignored
 
 
@@ -315,6 +315,42 @@ def test_key_path_variants(cfg):
         p.sample_rate = sr
         x = synth.render(p)
         assert_parity(S.analyze_audio(x, sr, S.AnalysisConfig(**cfg)), O.analyze(x, sr, cfg, fast=True), f"{cfg} sr={sr}")
+
+
+@pytest.mark.parametrize("cfg", [
+    {"key_template_set": 1},                                 # Temperley profiles (key/templates.rs:145-222)
+    {"enable_key_edge_trim": 1},                             # lib.rs:1216-1233
+    {"enable_key_edge_trim": 1, "key_edge_trim_fraction": 0.3, "enable_key_segment_voting": 0},
+    {"enable_key_mode_heuristic": 1},                        # detector.rs:326-518 (flip only reaches the result through whole-track detection)
+    {"enable_key_minor_harmonic_bonus": 1},
+    {"enable_key_mode_heuristic": 1, "enable_key_minor_harmonic_bonus": 1, "key_mode_third_ratio_margin": 0.1, "key_minor_leading_tone_bonus_weight": 0.5},
+    {"enable_key_segment_voting": 0, "enable_key_mode_heuristic": 1, "key_mode_flip_min_score_ratio": 0.3},
+    {"enable_key_segment_voting": 0, "enable_key_mode_heuristic": 1, "enable_key_frame_weighting": 0, "key_template_set": 1},
+    {"enable_key_ensemble": 1},                              # detector.rs:881-976
+    {"enable_key_ensemble": 1, "key_ensemble_kk_weight": 0.8, "key_ensemble_temperley_weight": 0.1, "enable_key_edge_trim": 1},
+    {"enable_key_multi_scale": 1},                           # detector.rs:546-700
+    {"enable_key_multi_scale": 1, "enable_key_mode_heuristic": 1, "enable_key_minor_harmonic_bonus": 1, "key_multi_scale_weights": [0.5, 1.0, 0.0],
+     "key_multi_scale_hop": 45},
+    {"enable_key_multi_scale": 1, "key_multi_scale_lengths": [5000, 200], "key_multi_scale_min_clarity": 0.6},
+    {"enable_key_multi_scale": 1, "key_multi_scale_lengths": [100000]},   # shorter than every scale: falls through to segment voting (lib.rs:1304-1308)
+    {"enable_key_multi_scale": 1, "key_multi_scale_min_clarity": 1.0},   # every window rejected: whole-track fallback (detector.rs:648-668)
+    {"enable_key_median": 1},                                # read by nothing in analyze_audio: no effect, as in the reference
+])
+def test_key_scoring_variants(cfg):
+    # template set, edge trim, mode heuristic / minor bonus, ensemble, multi-scale — on material whose modes do not tie
+    ocfg = {}
+    for k, v in cfg.items():
+        if isinstance(v, list):
+            ocfg["key_multi_scale_n_" + k.rsplit("_", 1)[1]] = len(v)
+            for i, e in enumerate(v):
+                ocfg[f"{k}[{i}]"] = e
+        else:
+            ocfg[k] = v
+    xs = [synth.render_progression(1, 30, SR, tonic=2, minor=True, bpm=124), synth.render_progression(2, 26, 48000, tonic=9, minor=False, bpm=96)]
+    srs = [SR, 48000]
+    res = [S.analyze_audio(x, sr, S.AnalysisConfig(**cfg)) for x, sr in zip(xs, srs)]
+    for i, (x, sr, g) in enumerate(zip(xs, srs, res)):
+        assert_parity(g, O.analyze(x, sr, ocfg, fast=True), f"{cfg} track {i}")
 
 
 @pytest.mark.parametrize("cfg", [
