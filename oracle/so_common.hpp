@@ -315,8 +315,16 @@ Error generate_beat_grid(float bpm, float bpm_conf, const std::vector<float>& on
 // ---- key ---------------------------------------------------------------------------
 Spec harmonic_spectrogram_time_mask(const Spec& K, size_t margin, float power);
 Spec smooth_spectrogram_time(const Spec& K, size_t margin);
-void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, float sigma, std::vector<float>& chroma, std::vector<float>& energy);
-void extract_hpcp(const Spec& K, uint32_t sr, size_t fft_size, const Config& c, std::vector<float>& chroma /*frames*12*/, std::vector<float>& energy);
+void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, float sigma, std::vector<float>& chroma, std::vector<float>& energy, float tuning = 0.0f);
+void extract_hpcp(const Spec& K, uint32_t sr, size_t fft_size, const Config& c, std::vector<float>& chroma /*frames*12*/, std::vector<float>& energy,
+                  float tuning = 0.0f);
+float estimate_tuning_offset(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, size_t frame_step, float peak_rel_threshold);
+Spec linear_to_log_frequency(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, int* semitone_bin_min_out);
+void extract_chroma_log_frequency(const Spec& L, int semitone_offset, std::vector<float>& chroma, std::vector<float>& energy);
+void extract_beat_synchronous_chroma(const Spec& K, uint32_t sr, size_t fft_size, size_t hop, const std::vector<float>& beats, bool soft, float sigma,
+                                     float tuning, std::vector<float>& chroma, std::vector<float>& energy);
+Spec harmonic_spectrogram_hpss_median_mask(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, size_t frame_step, size_t time_margin,
+                                           size_t freq_margin, float mask_power);
 void smooth_chroma(std::vector<float>& chroma, size_t frames, size_t window);
 struct KeyScores {
     int keys[24];  // 0..11 major, 12..23 minor, in ranked order

@@ -75,27 +75,47 @@ static float rem_euclid(float a, float b) {
     return r < 0.0f ? r + fabsf(b) : r;
 }
 
-// frame_to_hpcp_tuned_band — extractor.rs:529-680 with whitening off, tuning 0, band 100..5000 Hz.
+// frame_to_hpcp_tuned_band — extractor.rs:529-680.
 // Top-K ordering: `select_nth_unstable_by` leaves the K selected peaks in an unspecified order
 // (which only changes f32 accumulation order).  The oracle fixes it as: selected set = the K
-// largest by (magnitude desc, bin asc); accumulation in ascending bin order.
-static void frame_to_hpcp(const float* mag, size_t nb, uint32_t sr, size_t fft_size, const Config& c, float pc[12]) {
+// largest by (selection value desc, bin asc); accumulation in ascending bin order.
+static void frame_to_hpcp_band(const float* mag, size_t nb, uint32_t sr, size_t fft_size, const Config& c, float tuning, size_t peaks_per_frame,
+                               float fmin_hz, float fmax_hz, float pc[12]) {
     for (int i = 0; i < 12; ++i) pc[i] = 0.0f;
     if (nb == 0 || sr == 0 || fft_size == 0) return;
     float res = (float)sr / (float)fft_size;
-    float fmin = fmax_rs(100.0f, 20.0f), fmax = fmin_rs(5000.0f, (float)sr / 2.0f);
+    float fmin = fmax_rs(fmin_hz, 20.0f), fmax = fmin_rs(fmax_hz, (float)sr / 2.0f);
     if (fmax <= fmin) return;
+    // optional per-frame spectral whitening (:558-580): moving-average over bins from a sequential f32 prefix
+    std::vector<float> whitened;
+    const bool use_whitening = c.enable_key_hpcp_whitening && c.key_hpcp_whitening_smooth_bins >= 3;
+    if (use_whitening) {
+        const size_t win = std::max<size_t>(c.key_hpcp_whitening_smooth_bins, 3) | 1;
+        const size_t half = win / 2;
+        std::vector<float> prefix(nb + 1, 0.0f);
+        for (size_t i = 0; i < nb; ++i) prefix[i + 1] = prefix[i] + fmax_rs(mag[i], 0.0f);
+        whitened.assign(nb, 0.0f);
+        for (size_t i = 0; i < nb; ++i) {
+            const size_t l = i >= half ? i - half : 0;
+            const size_t r = std::min(i + half, nb - 1);
+            const float denom = (float)(r + 1 - l);
+            const float mean = (prefix[r + 1] - prefix[l]) / fmax_rs(denom, 1.0f);
+            const float v = fmax_rs(mag[i], 0.0f) / (mean + 1e-12f);
+            whitened[i] = fmin_rs(v, 20.0f);
+        }
+    }
+    const float* selv = use_whitening ? whitened.data() : mag;
     std::vector<std::pair<size_t, float>> peaks;
     for (size_t b = 1; b + 1 < nb; ++b) {
         float f = (float)b * res;
         if (f < fmin) continue;
         if (f > fmax) break;
-        float m = mag[b];
-        if (m <= mag[b - 1] || m < mag[b + 1]) continue;
+        float m = selv[b];
+        if (m <= selv[b - 1] || m < selv[b + 1]) continue;
         peaks.emplace_back(b, m);
     }
     if (peaks.empty()) return;
-    size_t k = std::min(std::max<size_t>(c.key_hpcp_peaks_per_frame, 1), peaks.size());
+    size_t k = std::min(std::max<size_t>(peaks_per_frame, 1), peaks.size());
     if (peaks.size() > k) {
         std::vector<std::pair<size_t, float>> byv = peaks;
         std::stable_sort(byv.begin(), byv.end(), [](const std::pair<size_t, float>& a, const std::pair<size_t, float>& b) { return a.second > b.second; });
@@ -110,13 +130,13 @@ static void frame_to_hpcp(const float* mag, size_t nb, uint32_t sr, size_t fft_s
     for (auto& pk : peaks) {
         float f0 = (float)pk.first * res;
         if (f0 <= 0.0f) continue;
-        float w0 = powf(fmax_rs(mag[pk.first], 0.0f), p);
+        float w0 = powf(fmax_rs(mag[pk.first], 0.0f), p);  // original magnitude even when whitening selected the peak (:628-637)
         if (w0 <= 0.0f) continue;
         for (size_t h = 1; h <= hmax; ++h) {
             float fh = f0 * (float)h;
             if (fh > fmax) break;
             if (fh < fmin) continue;
-            float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f - 0.0f;
+            float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f - tuning;
             float spc = rem_euclid(semitone, 12.0f);
             float ppc = rem_euclid(roundf(spc), 12.0f);
             int primary = as_i32(ppc);
@@ -141,8 +161,8 @@ static void frame_to_hpcp(const float* mag, size_t nb, uint32_t sr, size_t fft_s
         for (int i = 0; i < 12; ++i) pc[i] /= norm;
 }
 
-// frame_to_chroma_tuned ("chroma folding") — extractor.rs:393-487, tuning offset 0
-static void frame_to_chroma(const float* mag, size_t nb, uint32_t sr, size_t fft_size, bool soft, float sigma_in, float pc[12]) {
+// frame_to_chroma_tuned ("chroma folding") — extractor.rs:393-487
+static void frame_to_chroma(const float* mag, size_t nb, uint32_t sr, size_t fft_size, bool soft, float sigma_in, float tuning, float pc[12]) {
     for (int i = 0; i < 12; ++i) pc[i] = 0.0f;
     float res = (float)sr / (float)fft_size;
     for (size_t b = 0; b < nb; ++b) {
@@ -150,7 +170,7 @@ static void frame_to_chroma(const float* mag, size_t nb, uint32_t sr, size_t fft
         if (freq < 100.0f) continue;
         if (freq > fmin_rs(5000.0f, (float)sr / 2.0f)) break;
         if (freq >= (float)sr / 2.0f) break;
-        float semitone = 12.0f * log2f(freq / 440.0f) + 57.0f - 0.0f;
+        float semitone = 12.0f * log2f(freq / 440.0f) + 57.0f - tuning;
         float contrib = powf(fmax_rs(mag[b], 0.0f), 0.6f);
         if (soft) {
             float spc = rem_euclid(semitone, 12.0f);
@@ -177,8 +197,8 @@ static void frame_to_chroma(const float* mag, size_t nb, uint32_t sr, size_t fft
         for (int i = 0; i < 12; ++i) pc[i] /= norm;
 }
 
-// extract_chroma_from_spectrogram_with_options_and_energy — extractor.rs:1028-1091
-void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, float sigma, std::vector<float>& chroma, std::vector<float>& energy) {
+// extract_chroma_from_spectrogram_with_options_and_energy(_tuned) — extractor.rs:1028-1091
+void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, float sigma, std::vector<float>& chroma, std::vector<float>& energy, float tuning) {
     chroma.assign(K.frames * 12, 0.0f);
     energy.assign(K.frames, 0.0f);
     for (size_t t = 0; t < K.frames; ++t) {
@@ -186,21 +206,241 @@ void extract_chroma(const Spec& K, uint32_t sr, size_t fft_size, bool soft, floa
         float e = 0.0f;
         for (size_t b = 0; b < K.bins; ++b) e += r[b] * r[b];
         energy[t] = e;
-        frame_to_chroma(r, K.bins, sr, fft_size, soft, sigma, &chroma[t * 12]);
+        frame_to_chroma(r, K.bins, sr, fft_size, soft, sigma, tuning, &chroma[t * 12]);
     }
 }
 
-// extract_hpcp_from_spectrogram_with_options_and_energy_tuned — extractor.rs:1097-1150
-void extract_hpcp(const Spec& K, uint32_t sr, size_t fft_size, const Config& c, std::vector<float>& chroma, std::vector<float>& energy) {
+// extract_hpcp_from_spectrogram_with_options_and_energy_tuned — extractor.rs:1097-1150;
+// extract_hpcp_bass_blend_from_spectrogram_with_options_and_energy_tuned — extractor.rs:1154-1239
+void extract_hpcp(const Spec& K, uint32_t sr, size_t fft_size, const Config& c, std::vector<float>& chroma, std::vector<float>& energy, float tuning) {
     chroma.assign(K.frames * 12, 0.0f);
     energy.assign(K.frames, 0.0f);
+    const float bw = clamp_rs(c.key_hpcp_bass_weight, 0.0f, 1.0f);
     for (size_t t = 0; t < K.frames; ++t) {
         const float* r = K.row(t);
         float e = 0.0f;
         for (size_t b = 0; b < K.bins; ++b) e += r[b] * r[b];
         energy[t] = e;
-        frame_to_hpcp(r, K.bins, sr, fft_size, c, &chroma[t * 12]);
+        float* out = &chroma[t * 12];
+        frame_to_hpcp_band(r, K.bins, sr, fft_size, c, tuning, c.key_hpcp_peaks_per_frame, 100.0f, 5000.0f, out);
+        if (c.enable_key_hpcp_bass_blend) {
+            float bass[12];
+            const size_t kb = std::min<size_t>(std::max<size_t>(c.key_hpcp_peaks_per_frame, 1), 12);  // peaks_per_frame.clamp(1, 12)
+            frame_to_hpcp_band(r, K.bins, sr, fft_size, c, tuning, kb, c.key_hpcp_bass_fmin_hz, c.key_hpcp_bass_fmax_hz, bass);
+            float ss = 0.0f;
+            for (int i = 0; i < 12; ++i) {
+                out[i] = (1.0f - bw) * out[i] + bw * bass[i];
+                ss += out[i] * out[i];
+            }
+            const float norm = sqrtf(ss);
+            if (norm > 1e-10f)
+                for (int i = 0; i < 12; ++i) out[i] /= norm;
+        }
     }
+}
+
+// estimate_tuning_offset_semitones_from_spectrogram — extractor.rs:66-170
+float estimate_tuning_offset(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, size_t frame_step, float peak_rel_threshold) {
+    if (K.frames == 0 || sr == 0 || fft_size == 0) return 0.0f;
+    const float res = (float)sr / (float)fft_size;
+    const float fmin = fmax_rs(fmin_hz, 20.0f);
+    const float fmax = clamp_rs(fmax_hz, fmin + 1.0f, (float)sr / 2.0f);
+    const size_t step = std::max<size_t>(frame_step, 1);
+    const float thr = clamp_rs(peak_rel_threshold, 0.0f, 1.0f);
+    float sum_sin = 0.0f, sum_cos = 0.0f, sum_w = 0.0f;
+    for (size_t t = 0; t < K.frames; t += step) {
+        const float* fr = K.row(t);
+        float peak = 0.0f;
+        for (size_t b = 0; b < K.bins; ++b) {
+            const float f = (float)b * res;
+            if (f < fmin) continue;
+            if (f > fmax) break;
+            peak = fmax_rs(peak, fr[b]);
+        }
+        if (peak <= 1e-12f) continue;
+        const float abs_thr = peak * thr;
+        for (size_t b = 0; b < K.bins; ++b) {
+            const float mag = fr[b];
+            if (mag < abs_thr) continue;
+            const float f = (float)b * res;
+            if (f < fmin) continue;
+            if (f > fmax) break;
+            const float semitone = 12.0f * log2f(f / 440.0f) + 57.0f;
+            const float residual = semitone - roundf(semitone);
+            const float w = powf(fmax_rs(mag, 0.0f), 0.5f);
+            if (w <= 0.0f) continue;
+            const float angle = 2.0f * PI_F * residual;
+            sum_sin += w * sinf(angle);
+            sum_cos += w * cosf(angle);
+            sum_w += w;
+        }
+    }
+    if (sum_w <= 1e-6f) return 0.0f;
+    const float r = sqrtf(sum_sin * sum_sin + sum_cos * sum_cos) / sum_w;
+    if (r < 0.05f) return 0.0f;
+    return atan2f(sum_sin, sum_cos) / (2.0f * PI_F);
+}
+
+// convert_linear_to_log_frequency_spectrogram — extractor.rs:701-807
+Spec linear_to_log_frequency(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, int* semitone_bin_min_out) {
+    Spec out;
+    const float res = (float)sr / (float)fft_size;
+    const float nyq = (float)sr / 2.0f;
+    const float fmin = fmax_rs(fmin_hz, 20.0f), fmax = fmin_rs(fmax_hz, nyq - 1.0f);
+    const float smin = 12.0f * log2f(fmin / 440.0f) + 57.0f, smax = 12.0f * log2f(fmax / 440.0f) + 57.0f;
+    const int bmin = as_i32(floorf(smin)), bmax = as_i32(ceilf(smax));
+    const long nbl = (long)bmax - (long)bmin + 1;
+    *semitone_bin_min_out = bmin;
+    if (nbl <= 0) return out;  // (the reference's `as usize` of a negative count would allocate absurdly; unreachable for fmin < fmax)
+    const size_t n_semi = (size_t)nbl;
+    out.frames = K.frames;
+    out.bins = n_semi;
+    out.d.assign(K.frames * n_semi, 0.0f);
+    for (size_t t = 0; t < K.frames; ++t) {
+        const float* fr = K.row(t);
+        float* lf = out.row(t);
+        for (size_t b = 0; b < K.bins; ++b) {
+            const float m = fr[b];
+            if (m <= 0.0f) continue;
+            const float f = (float)b * res;
+            if (f < fmin || f >= fmax || f >= nyq) continue;
+            const float semitone = 12.0f * log2f(f / 440.0f) + 57.0f;
+            const float x = semitone - (float)bmin;
+            const size_t lo = as_usize(floorf(x));
+            const size_t hi = std::min(as_usize(ceilf(x)), n_semi - 1);
+            if (lo < n_semi) {
+                const float wh = x - (float)lo, wl = 1.0f - wh;
+                lf[lo] += m * wl;
+                if (hi != lo && hi < n_semi) lf[hi] += m * wh;
+            }
+        }
+    }
+    return out;
+}
+
+// extract_chroma_from_log_frequency_spectrogram — extractor.rs:941-984 (+ energies, lib.rs:1124-1132)
+void extract_chroma_log_frequency(const Spec& L, int semitone_offset, std::vector<float>& chroma, std::vector<float>& energy) {
+    chroma.assign(L.frames * 12, 0.0f);
+    energy.assign(L.frames, 0.0f);
+    for (size_t t = 0; t < L.frames; ++t) {
+        const float* fr = L.row(t);
+        float* ch = &chroma[t * 12];
+        for (size_t b = 0; b < L.bins; ++b) {
+            if (fr[b] <= 0.0f) continue;
+            int pc = (semitone_offset + (int)b) % 12;
+            if (pc < 0) pc += 12;
+            ch[pc] += fr[b];
+        }
+        float ss = 0.0f;
+        for (int i = 0; i < 12; ++i) ss += ch[i] * ch[i];
+        const float norm = sqrtf(ss);
+        if (norm > EPSILON)
+            for (int i = 0; i < 12; ++i) ch[i] /= norm;
+        float e = 0.0f;
+        for (size_t b = 0; b < L.bins; ++b) e += fr[b] * fr[b];
+        energy[t] = e;
+    }
+}
+
+// extract_beat_synchronous_chroma — extractor.rs:830-922
+void extract_beat_synchronous_chroma(const Spec& K, uint32_t sr, size_t fft_size, size_t hop, const std::vector<float>& beats, bool soft, float sigma,
+                                     float tuning, std::vector<float>& chroma, std::vector<float>& energy) {
+    chroma.clear();
+    energy.clear();
+    if (K.frames == 0 || beats.empty()) return;
+    const float dur = (float)hop / (float)sr;
+    const size_t ni = beats.size() - 1;
+    chroma.assign(ni * 12, 0.0f);
+    energy.assign(ni, 0.0f);
+    for (size_t i = 0; i < ni; ++i) {
+        const float b0 = beats[i], b1 = beats[i + 1];
+        float acc[12];
+        for (int j = 0; j < 12; ++j) acc[j] = 0.0f;
+        float e_int = 0.0f;
+        size_t cnt = 0;
+        for (size_t f = 0; f < K.frames; ++f) {
+            const float ft = (float)f * dur;
+            if (ft >= b0 && ft < b1) {
+                float ch[12];
+                frame_to_chroma(K.row(f), K.bins, sr, fft_size, soft, sigma, tuning, ch);
+                float e = 0.0f;
+                const float* r = K.row(f);
+                for (size_t b = 0; b < K.bins; ++b) e += r[b] * r[b];
+                for (int j = 0; j < 12; ++j) acc[j] += ch[j];
+                e_int += e;
+                ++cnt;
+            }
+        }
+        if (cnt > 0) {
+            const float n = (float)cnt;
+            float ss = 0.0f;
+            for (int j = 0; j < 12; ++j) {
+                acc[j] /= n;
+                ss += acc[j] * acc[j];
+            }
+            const float norm = sqrtf(ss);
+            if (norm > EPSILON)
+                for (int j = 0; j < 12; ++j) acc[j] /= norm;
+            for (int j = 0; j < 12; ++j) chroma[i * 12 + j] = acc[j];
+            energy[i] = e_int;
+        }
+    }
+}
+
+// harmonic_spectrogram_hpss_median_mask — extractor.rs:1369-1501
+Spec harmonic_spectrogram_hpss_median_mask(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, size_t frame_step, size_t time_margin,
+                                           size_t freq_margin, float mask_power) {
+    if (K.frames == 0 || sr == 0 || fft_size == 0) return K;
+    const size_t nf = K.frames, nb = K.bins;
+    const float res = (float)sr / (float)fft_size;
+    const float fmin = fmax_rs(fmin_hz, 20.0f);
+    const float fmax = clamp_rs(fmax_hz, fmin + 1.0f, (float)sr / 2.0f);
+    long bs = (long)floorf(fmin / res), be = (long)ceilf(fmax / res);
+    bs = std::min<long>(std::max<long>(bs, 0), (long)nb);
+    be = std::min<long>(std::max<long>(be, 0), (long)nb);
+    if (be <= bs) return K;
+    const size_t b0 = (size_t)bs, band = (size_t)(be - bs);
+    const size_t step = std::max<size_t>(frame_step, 1);
+    const size_t n_ds = std::max<size_t>((nf + step - 1) / step, 1);
+    auto san = [](float x) { return std::isfinite(x) ? fmax_rs(x, 0.0f) : 0.0f; };
+    std::vector<float> ds(n_ds * band), h_est(n_ds * band), p_est(n_ds * band);
+    for (size_t k = 0; k < n_ds; ++k)
+        for (size_t b = 0; b < band; ++b) ds[k * band + b] = K.d[(k * step) * nb + b0 + b];
+    std::vector<float> scratch;
+    auto median = [&](std::vector<float>& v) {  // select_nth_unstable_by(len/2): the value is order-independent
+        if (v.empty()) return 0.0f;
+        std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+        return v[v.size() / 2];
+    };
+    for (size_t b = 0; b < band; ++b)
+        for (size_t t = 0; t < n_ds; ++t) {
+            scratch.clear();
+            const size_t st = t >= time_margin ? t - time_margin : 0, en = std::min(t + time_margin + 1, n_ds);
+            for (size_t q = st; q < en; ++q) scratch.push_back(san(ds[q * band + b]));
+            h_est[t * band + b] = median(scratch);
+        }
+    for (size_t t = 0; t < n_ds; ++t)
+        for (size_t b = 0; b < band; ++b) {
+            scratch.clear();
+            const size_t st = b >= freq_margin ? b - freq_margin : 0, en = std::min(b + freq_margin + 1, band);
+            for (size_t q = st; q < en; ++q) scratch.push_back(san(ds[t * band + q]));
+            p_est[t * band + b] = median(scratch);
+        }
+    const float p = fmax_rs(mask_power, 1.0f);
+    Spec out;
+    out.frames = nf;
+    out.bins = nb;
+    out.d.assign(nf * nb, 0.0f);
+    for (size_t t = 0; t < nf; ++t) {
+        const size_t k = std::min(t / step, n_ds - 1);
+        for (size_t b = 0; b < band; ++b) {
+            const float h = fmax_rs(h_est[k * band + b], 0.0f), per = fmax_rs(p_est[k * band + b], 0.0f);
+            const float hp = powf(h, p), pp = powf(per, p);
+            const float m = hp / (hp + pp + 1e-12f);
+            out.d[t * nb + b0 + b] = san(K.d[t * nb + b0 + b]) * m;
+        }
+    }
+    return out;
 }
 
 // smooth_chroma (median) — smoothing.rs:37-94
@@ -536,19 +776,51 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
     const Spec& K = c.enable_key_stft_override ? Kown : S_base;
     Spec masked;
     const Spec* forkey = &K;
-    if (!K.empty() && c.enable_key_harmonic_mask) {  // lib.rs:1011-1060
+    if (!K.empty() && c.enable_key_hpss_harmonic) {  // lib.rs:1011-1030
+        masked = harmonic_spectrogram_hpss_median_mask(K, sr, kfft, 100.0f, 5000.0f, c.key_hpss_frame_step, c.key_hpss_time_margin, c.key_hpss_freq_margin,
+                                                       c.key_hpss_mask_power);
+        forkey = &masked;
+    } else if (!K.empty() && c.enable_key_harmonic_mask) {  // lib.rs:1031-1042
         masked = harmonic_spectrogram_time_mask(K, c.key_spectrogram_smooth_margin, c.key_harmonic_mask_power);
         forkey = &masked;
     } else if (!K.empty() && c.enable_key_spectrogram_time_smoothing) {
         masked = smooth_spectrogram_time(K, c.key_spectrogram_smooth_margin);
         forkey = &masked;
     }
+    // optional log-frequency (semitone-aligned) spectrogram (lib.rs:1064-1094); disables HPCP, tuning and beat-sync
+    bool use_log = false;
+    Spec logspec;
+    int semitone_offset = 0;
+    if (c.enable_key_log_frequency && !forkey->empty()) {
+        int bmin = 0;
+        logspec = linear_to_log_frequency(*forkey, sr, kfft, 100.0f, 5000.0f, &bmin);
+        use_log = true;
+        // lib.rs:1076-1079 recomputes the offset from fmin = 100 (same value as the converter's)
+        semitone_offset = as_i32(floorf(12.0f * log2f(100.0f / 440.0f) + 57.0f));
+        (void)bmin;
+    }
+    float tuning = 0.0f;
+    if (c.enable_key_tuning_compensation && !forkey->empty() && !use_log) {  // lib.rs:1098-1121
+        const float d = estimate_tuning_offset(*forkey, sr, kfft, 80.0f, 2000.0f, c.key_tuning_frame_step, c.key_tuning_peak_rel_threshold);
+        const float lim = fabsf(c.key_tuning_max_abs_semitones);
+        tuning = clamp_rs(d, -lim, lim);
+    }
+    if (dump) dump->f["key.tuning"] = std::vector<float>(1, tuning);
     std::vector<float> chroma, energy;
-    if (c.enable_key_hpcp)
-        extract_hpcp(*forkey, sr, kfft, c, chroma, energy);
-    else  // lib.rs:1188-1196 (tuning compensation off)
-        extract_chroma(*forkey, sr, kfft, c.soft_chroma_mapping, c.soft_mapping_sigma, chroma, energy);
-    size_t nf = forkey->frames;
+    size_t nf_chroma = forkey->frames;
+    if (c.enable_key_beat_synchronous && beat_times && !beat_times->empty() && !use_log) {  // lib.rs:1124-1136
+        if (forkey->empty()) return Error{};
+        extract_beat_synchronous_chroma(*forkey, sr, kfft, khop, *beat_times, c.soft_chroma_mapping, c.soft_mapping_sigma, tuning, chroma, energy);
+        nf_chroma = energy.size();
+    } else if (use_log) {
+        extract_chroma_log_frequency(logspec, semitone_offset, chroma, energy);
+    } else if (c.enable_key_hpcp) {
+        extract_hpcp(*forkey, sr, kfft, c, chroma, energy, tuning);
+    } else {  // lib.rs:1178-1196: the tuned variant with |tuning| <= 1e-6 equals the untuned one up to `semitone - 0.0`
+        const float tn = (c.enable_key_tuning_compensation && fabsf(tuning) > 1e-6f) ? tuning : 0.0f;
+        extract_chroma(*forkey, sr, kfft, c.soft_chroma_mapping, c.soft_mapping_sigma, chroma, energy, tn);
+    }
+    size_t nf = nf_chroma;
     if (c.chroma_sharpening_power > 1.0f)  // lib.rs:1200-1208, chroma/normalization.rs:41-65
         for (size_t t = 0; t < nf; ++t) {
             float* ch = &chroma[t * 12];

@@ -390,6 +390,98 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         st.key_bin_lo = lo;
         st.key_bin_hi = hi;
     }
+    {   // bands and tables of the optional key-path variants, key-STFT bins
+        const float res = (float)sr / 8192.0f;
+        const float nyq = (float)sr / 2.0f;
+        // bass-band HPCP: same peak loop as above on [bass_fmin, bass_fmax] (extractor.rs:1206-1220 -> 551-556, 584-591)
+        st.bass_fmin = fmaxf(cfg.key_hpcp_bass_fmin_hz, 20.0f);
+        st.bass_fmax = fminf(cfg.key_hpcp_bass_fmax_hz, nyq);
+        st.bass_bin_lo = 1;
+        st.bass_bin_hi = 0;
+        if (st.bass_fmax > st.bass_fmin) {
+            uint32_t lo = 0, hi = 0;
+            for (uint32_t b = 1; b + 1 < 4097; ++b) {
+                const float f = (float)b * res;
+                if (f < st.bass_fmin) continue;
+                if (f > st.bass_fmax) break;
+                if (lo == 0) lo = b;
+                hi = b;
+            }
+            if (lo != 0) {
+                st.bass_bin_lo = lo;
+                st.bass_bin_hi = hi;
+            }
+        }
+        st.white_n = std::min<uint32_t>(std::max(st.key_bin_hi, st.bass_bin_hi) + 2, 4097);
+        // tuning estimator band (extractor.rs:100-121): all bins with fmin <= f <= fmax
+        {
+            const float fmin = fmaxf(80.0f, 20.0f);
+            const float fmax = fminf(fmaxf(2000.0f, fmin + 1.0f), nyq);  // clamp(fmin + 1, nyq)
+            st.tune_bin_lo = 1;
+            st.tune_bin_hi = 0;
+            bool first = true;
+            for (uint32_t b = 0; b < 4097; ++b) {
+                const float f = (float)b * res;
+                if (f < fmin) continue;
+                if (f > fmax) break;
+                if (first) { st.tune_bin_lo = b; first = false; }
+                st.tune_bin_hi = b;
+            }
+        }
+        // median-HPSS band (extractor.rs:1408-1420)
+        {
+            const float fmin = fmaxf(100.0f, 20.0f);
+            const float fmax = fminf(fmaxf(5000.0f, fmin + 1.0f), nyq);
+            long bs = (long)floorf(fmin / res), be = (long)ceilf(fmax / res);
+            bs = std::min<long>(std::max<long>(bs, 0), 4097);
+            be = std::min<long>(std::max<long>(be, 0), 4097);
+            st.hpss_b0 = (uint32_t)bs;
+            st.hpss_band = be > bs ? (uint32_t)(be - bs) : 0u;
+        }
+        // log-frequency resampling (extractor.rs:733-803): per semitone bin, the (linear bin, weight) entries in ascending
+        // linear-bin order — the order in which the reference adds them
+        {
+            const float fmin = fmaxf(100.0f, 20.0f), fmax = fminf(5000.0f, nyq - 1.0f);
+            const float smin = 12.0f * log2f(fmin / 440.0f) + 57.0f, smax = 12.0f * log2f(fmax / 440.0f) + 57.0f;
+            const long bmin = (long)floorf(smin), bmax = (long)ceilf(smax);
+            const long nsl = bmax - bmin + 1;
+            const uint32_t n_semi = nsl > 0 ? (uint32_t)nsl : 0u;
+            st.log_n = n_semi;
+            st.log_offset = (int32_t)floorf(12.0f * log2f(100.0f / 440.0f) + 57.0f);  // lib.rs:1076-1079
+            std::vector<std::vector<std::pair<int32_t, float>>> per(n_semi);
+            for (uint32_t b = 0; b < 4097 && n_semi > 0; ++b) {
+                const float f = (float)b * res;
+                if (f < fmin || f >= fmax || f >= nyq) continue;
+                const float semitone = 12.0f * log2f(f / 440.0f) + 57.0f;
+                const float x = semitone - (float)bmin;
+                const float fl = floorf(x), ce = ceilf(x);
+                const uint32_t lo = fl > 0.0f ? (uint32_t)fl : 0u;
+                const uint32_t hi = std::min<uint32_t>(ce > 0.0f ? (uint32_t)ce : 0u, n_semi - 1);
+                if (lo < n_semi) {
+                    const float wh = x - (float)lo, wl = 1.0f - wh;
+                    per[lo].push_back({(int32_t)b, wl});
+                    if (hi != lo && hi < n_semi) per[hi].push_back({(int32_t)b, wh});
+                }
+            }
+            std::vector<int32_t> off(n_semi + 1, 0), bins;
+            std::vector<float> ws;
+            for (uint32_t q = 0; q < n_semi; ++q) {
+                for (auto& e : per[q]) {
+                    bins.push_back(e.first);
+                    ws.push_back(e.second);
+                }
+                off[q + 1] = (int32_t)bins.size();
+            }
+            if (bins.empty()) { bins.push_back(0); ws.push_back(0.0f); }
+            if (cfg.enable_key_log_frequency && n_semi > 128) {
+                set_error("log-frequency key spectrogram with more than 128 semitone bins is not supported");
+                return STRATUM_NOT_IMPLEMENTED;
+            }
+            st.log_off = dev_upload(c, off);
+            st.log_bin = dev_upload(c, bins);
+            st.log_w = dev_upload(c, ws);
+        }
+    }
     {   // KWeightingFilter::new — normalization.rs:127-155 (single RBJ high-pass biquad), f32 like the reference
         const float pi = 3.14159265358979323846f;
         const float w0 = 2.0f * pi * 1681.9745f / (float)sr;
@@ -608,9 +700,8 @@ static int config_validate(const StratumConfig& c) {
     if (c.tempogram_superflux_max_filter_bins > 8) return ni("tempogram_superflux_max_filter_bins > 8");
     if (c.tempogram_multi_res_top_k > 32) return ni("tempogram_multi_res_top_k > 32");
     // enable_key_median is accepted and has no effect, as in the reference: analyze_audio never reads it (lib.rs imports no detect_key_median)
-    if (c.enable_key_hpss_harmonic || c.enable_key_log_frequency || c.enable_key_beat_synchronous || c.enable_key_tuning_compensation ||
-        c.enable_key_hpcp_whitening || c.enable_key_hpcp_bass_blend)
-        return ni("optional key-path variants (hpss/log-frequency/beat-sync/tuning/whitening/bass-blend)");
+    if (c.enable_key_hpss_harmonic && (c.key_hpss_time_margin > 10 || c.key_hpss_freq_margin > 10)) return ni("key_hpss_time_margin / key_hpss_freq_margin > 10");
+    if (c.enable_key_hpcp_whitening && c.key_hpcp_whitening_smooth_bins > 63) return ni("key_hpcp_whitening_smooth_bins > 63");
     if (c.key_template_set != 0 && c.key_template_set != 1) {
         set_error("unknown key_template_set");
         return STRATUM_INVALID_INPUT;
@@ -730,6 +821,22 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     }
     d.ms_hop = c.key_multi_scale_hop;
     d.ms_min_clarity = c.key_multi_scale_min_clarity;
+    d.key_tuning = c.enable_key_tuning_compensation;
+    d.tune_max_abs = c.key_tuning_max_abs_semitones;
+    d.tune_thr = c.key_tuning_peak_rel_threshold;
+    d.tune_step = c.key_tuning_frame_step;
+    d.key_whiten = c.enable_key_hpcp_whitening && c.key_hpcp_whitening_smooth_bins >= 3;
+    d.whiten_half = (std::max<uint32_t>(c.key_hpcp_whitening_smooth_bins, 3) | 1u) / 2;
+    d.key_bass_blend = c.enable_key_hpcp_bass_blend;
+    d.bass_weight = c.key_hpcp_bass_weight;
+    d.key_log_freq = c.enable_key_log_frequency;
+    d.key_beat_sync = c.enable_key_beat_synchronous;
+    d.key_soft_mapping = c.soft_chroma_mapping;
+    d.key_hpss = c.enable_key_hpss_harmonic;
+    d.khpss_step = c.key_hpss_frame_step;
+    d.khpss_tm = c.key_hpss_time_margin;
+    d.khpss_fm = c.key_hpss_freq_margin;
+    d.khpss_power = c.key_hpss_mask_power;
     return d;
 }
 
@@ -782,6 +889,18 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.kenergy = fa.take(Fk + 1);
     T.kweights = fa.take(Fk + 1);
     // score rows (key_rows.cuh); the row count is monotone in the frame count, so the untrimmed Fk bounds every trimmed / edge-trimmed slice
+    if (cfg.enable_key_hpcp_whitening && cfg.enable_key_hpcp && !cfg.enable_key_log_frequency) {  // whitened magnitudes of the peak bands
+        T.kwhite_stride = 1056;  // >= white_n (the 100..5000 Hz band is at most 1024 key-STFT bins wide at the accepted sample rates)
+        T.kwhite = fa.take((uint64_t)Fk * T.kwhite_stride + 8);
+    }
+    if (cfg.enable_key_hpss_harmonic) {  // harmonic soft mask on the time-downsampled band
+        const uint32_t step = std::max<uint32_t>(cfg.key_hpss_frame_step, 1);
+        T.khpss_mask = fa.take((uint64_t)((Fk + step - 1) / step + 1) * 1032);
+    }
+    if (cfg.enable_key_tuning_compensation) {  // per-track chroma-folding lists (tuned mapping)
+        T.kfold_w = fa.take((uint64_t)12 * 1024);
+        T.kfold_bin = ia.take((uint64_t)12 * 1024 + 16);
+    }
     T.seg_cap = key_rows(Fk, make_devcfg(cfg)).nrows + 1;
     T.seg_scores = fa.take((uint64_t)T.seg_cap * 24);
     T.seg_avg = fa.take((uint64_t)T.seg_cap * 13);
@@ -1120,7 +1239,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     // tracks/s with the two paths overlapped vs 970 one after the other — both are bound by the same SM resources
     // (issue slots, L1/shared pipe), so overlap only adds cache pressure.  Off unless STRATUM_B200_DUAL_STREAM is set.
     static const bool dual_stream = getenv("STRATUM_B200_DUAL_STREAM") != nullptr;
-    const bool split = dual_stream && !(g_debug.load() && nt == 1);
+    const bool split = dual_stream && !(g_debug.load() && nt == 1) && !dcfg.key_beat_sync;  // beat-synchronous chroma reads the beat grid
     cudaEvent_t ev_pre = nullptr, ev_key = nullptr;
     auto run_key_path = [&](cudaStream_t ks) {
         WaveCtx wk = w;

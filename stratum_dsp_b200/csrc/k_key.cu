@@ -117,27 +117,12 @@ __device__ __forceinline__ float rem_euclid_f(float a, float b) {
     return r < 0.0f ? r + fabsf(b) : r;
 }
 
-__global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
-                                                   float* fa, DevCfg cfg) {
-    __shared__ HpcpSmem sm[4];
-    const int t = blockIdx.y;
-    const TrackDev& T = tr[t];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t f = blockIdx.x * 4 + w;
-    if (T.status != 0 || f >= T.Fk) return;
-    HpcpSmem& S = sm[w];
-    const SrTables& st = srtab[sr_index[t]];
-    const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
-    // frame energy (extractor.rs:1132-1134).  Consumed only through (E/median)^0.5 frame weights, a
-    // tolerance-level quantity, so the 4097-term sum is a warp tree instead of a serial fold.
-    float e = 0.0f;
-    for (uint32_t k = lane; k < KBINS; k += 32) {
-        const float x = row[k];
-        e = e + x * x;
-    }
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+// One band of frame_to_hpcp_tuned_band (extractor.rs:529-680) for the calling warp.  `sel` = the row peaks are picked and ranked
+// on (whitened magnitudes when whitening is on, else the magnitudes), `mag` = the magnitudes that weight the peaks.
+// Returns the L2-normalised profile in lanes 0..11.
+__device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const float* __restrict__ mag, uint32_t lo, uint32_t hi, float fmin, float fmax,
+                                           uint32_t peaks_per_frame, float tuning, float res, HpcpSmem& S, int lane, const DevCfg& cfg) {
     // local maxima in the band, compacted in ascending bin order (extractor.rs:582-606)
-    const uint32_t lo = st.key_bin_lo, hi = st.key_bin_hi;  // inclusive; lo > hi = empty band
     uint32_t np = 0;
     if (lo <= hi) {
         for (uint32_t base = lo; base <= hi; base += 32) {
@@ -145,8 +130,8 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
             bool pk = false;
             float m = 0.0f;
             if (b <= hi) {
-                m = row[b];
-                pk = !(m <= row[b - 1] || m < row[b + 1]);
+                m = sel[b];
+                pk = !(m <= sel[b - 1] || m < sel[b + 1]);
             }
             const uint32_t mask = __ballot_sync(0xffffffffu, pk);
             if (pk) {
@@ -163,12 +148,12 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
     __syncwarp();
     float pc = 0.0f;  // lanes 0..11 own one pitch class each
     if (np > 0) {
-        // top-K by (magnitude desc, bin asc); the reference's select_nth_unstable_by leaves the K
+        // top-K by (value desc, bin asc); the reference's select_nth_unstable_by leaves the K
         // survivors in unspecified order — the documented rule is "accumulate in ascending bin order".
-        // The K-th largest magnitude is found by a bitwise search on the (positive) float bit patterns:
+        // The K-th largest value is found by a bitwise search on the (positive) float bit patterns:
         // 31 rounds of "how many peaks are >= candidate", each a register compare + one warp reduction.
-        const uint32_t K = min(max(cfg.hpcp_peaks, 1u), np);
-        uint32_t thr = 0, need = 0;  // keep magnitudes > thr, plus the first `need` ties in bin order
+        const uint32_t K = min(max(peaks_per_frame, 1u), np);
+        uint32_t thr = 0, need = 0;  // keep values > thr, plus the first `need` ties in bin order
         if (np > K) {
             uint32_t e[HPCP_MAX_PEAKS / 32];
 #pragma unroll
@@ -209,8 +194,6 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
             nsel += __popc(mask);
         }
         __syncwarp();
-        const float res = (float)T.sr / 8192.0f;
-        const float fmin = fmaxf(100.0f, 20.0f), fmax = fminf(5000.0f, (float)T.sr / 2.0f);
         const float sigma = fmaxf(cfg.hpcp_sigma, 1e-6f);
         const uint32_t hmax = min(max(cfg.hpcp_harm, 1u), (uint32_t)HPCP_MAX_HARM);
         const float decay = clamp_rs(cfg.hpcp_decay, 0.0f, 1.0f);
@@ -219,8 +202,9 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
         for (uint32_t it = lane; it < items; it += 32) {
             const uint32_t pi = it / hmax, h = it % hmax + 1;
             const uint32_t idx = S.sel[pi];
-            const float f0 = (float)S.bin[idx] * res;
-            const float mg = fmaxf(S.mag[idx], 0.0f);
+            const uint32_t bin = S.bin[idx];
+            const float f0 = (float)bin * res;
+            const float mg = fmaxf(mag[bin], 0.0f);  // the original magnitude weights the peak even when whitening picked it (:628-637)
             const float w0 = (pw == 0.5f) ? sqrtf(mg) : powf(mg, pw);
             const float fh = f0 * (float)h;
             int8_t* tcs = S.tc + it * 3;
@@ -230,7 +214,7 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
                 tcs[0] = tcs[1] = tcs[2] = -1;
                 continue;
             }
-            const float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f;
+            const float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f - tuning;
             const float spc = rem_euclid_f(semitone, 12.0f);
             const float ppc = rem_euclid_f(roundf(spc), 12.0f);
             const int primary = as_i32(ppc);
@@ -263,42 +247,38 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
         const float norm = sqrtf(ss);
         if (norm > 1e-10f) pc = pc / norm;
     }
-    if (lane < 12) fa[T.chroma + (uint64_t)f * 12 + lane] = pc;
-    if (lane == 0) fa[T.kenergy + f] = e;
+    __syncwarp();
+    return pc;
 }
 
-// ---- chroma folding (extractor.rs:393-487, enable_key_hpcp = false): one warp per frame ---------------------------
-// chroma[pc] = sum over band bins (ascending) of max(x,0)^0.6 * w[bin][pc]; the weights (Gaussian soft mapping in
-// circular pitch-class space, or the hard nearest-class assignment) depend only on the bin, so they come from a
-// per-sample-rate table grouped by pitch class in the reference's accumulation order.  The 0.6-power of every band bin
-// is evaluated once, in parallel, into shared memory; 12 lanes then fold their pitch class.
-constexpr int FOLD_MAX = 1024;  // band bins (912 at 44.1 kHz; the ABI rejects sample rates whose band is wider)
-
-__global__ void __launch_bounds__(128) chroma_fold_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
-                                                          float* fa) {
-    __shared__ float contrib[4][FOLD_MAX];
+__global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
+                                                   float* fa, DevCfg cfg) {
+    __shared__ HpcpSmem sm[4];
     const int t = blockIdx.y;
     const TrackDev& T = tr[t];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * 4 + w;
-    if (T.status != 0 || f >= T.Fk) return;
+    if (T.status != 0 || f >= T.Fk || T.beat_sync) return;
+    HpcpSmem& S = sm[w];
     const SrTables& st = srtab[sr_index[t]];
     const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
-    float e = 0.0f;  // frame energy: tree sum (tolerance-level consumer, see hpcp_kernel)
+    const float* sel = cfg.key_whiten ? fa + T.kwhite + (uint64_t)f * T.kwhite_stride : row;
+    // frame energy (extractor.rs:1132-1134).  Consumed only through (E/median)^0.5 frame weights, a
+    // tolerance-level quantity, so the 4097-term sum is a warp tree instead of a serial fold.
+    float e = 0.0f;
     for (uint32_t k = lane; k < KBINS; k += 32) {
         const float x = row[k];
         e = e + x * x;
     }
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    const uint32_t lo = st.fold_lo, hi = st.fold_hi;
-    float pc = 0.0f;
-    if (lo <= hi) {
-        for (uint32_t b = lo + lane; b <= hi; b += 32) contrib[w][b - lo] = powf(fmaxf(row[b], 0.0f), 0.6f);  // extractor.rs:431
-        __syncwarp();
-        if (lane < 12) {
-            const int a = st.fold_off[lane], z = st.fold_off[lane + 1];
-            for (int q = a; q < z; ++q) pc = pc + contrib[w][st.fold_bin[q] - lo] * st.fold_w[q];
-        }
+    const float res = (float)T.sr / 8192.0f;
+    const float nyq = (float)T.sr / 2.0f;
+    float pc = hpcp_band(sel, row, st.key_bin_lo, st.key_bin_hi, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), cfg.hpcp_peaks, T.key_tuning, res, S, lane, cfg);
+    if (cfg.key_bass_blend) {  // extractor.rs:1154-1239: (1-w) full + w bass, renormalised
+        const float bass = hpcp_band(sel, row, st.bass_bin_lo, st.bass_bin_hi, st.bass_fmin, st.bass_fmax, min(max(cfg.hpcp_peaks, 1u), 12u), T.key_tuning, res, S,
+                                     lane, cfg);
+        const float bw = clamp_rs(cfg.bass_weight, 0.0f, 1.0f);
+        pc = (1.0f - bw) * pc + bw * bass;
         float ss = 0.0f;
         for (int i = 0; i < 12; ++i) {
             const float v = __shfl_sync(0xffffffffu, pc, i);
@@ -311,11 +291,66 @@ __global__ void __launch_bounds__(128) chroma_fold_kernel(const TrackDev* __rest
     if (lane == 0) fa[T.kenergy + f] = e;
 }
 
+// ---- chroma folding (extractor.rs:393-487, enable_key_hpcp = false): one warp per frame ---------------------------
+// chroma[pc] = sum over band bins (ascending) of max(x,0)^0.6 * w[bin][pc]; the weights (Gaussian soft mapping in
+// circular pitch-class space, or the hard nearest-class assignment) depend only on the bin, so they come from a
+// per-sample-rate table grouped by pitch class in the reference's accumulation order.  The 0.6-power of every band bin
+// is evaluated once, in parallel, into shared memory; 12 lanes then fold their pitch class.
+constexpr int FOLD_MAX = 1024;  // band bins (912 at 44.1 kHz; the ABI rejects sample rates whose band is wider)
+
+// Tracks with a non-zero tuning offset (lib.rs:1098-1121) use per-track lists built by fold_table_kernel (k_keyvar.cu) in the same layout.
+// Beat-synchronous tracks (extractor.rs:830-922) fold every frame into chroma2 / kweights, which beat_sync_kernel then averages per beat interval.
+__global__ void __launch_bounds__(128) chroma_fold_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
+                                                          float* fa, const int32_t* __restrict__ ia, DevCfg cfg) {
+    __shared__ float contrib[4][FOLD_MAX];
+    const int t = blockIdx.y;
+    const TrackDev& T = tr[t];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * 4 + w;
+    if (T.status != 0 || f >= T.Fk) return;
+    if (!T.beat_sync && (cfg.key_hpcp || cfg.key_log_freq)) return;
+    const SrTables& st = srtab[sr_index[t]];
+    const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
+    float e = 0.0f;  // frame energy: tree sum (tolerance-level consumer, see hpcp_kernel)
+    for (uint32_t k = lane; k < KBINS; k += 32) {
+        const float x = row[k];
+        e = e + x * x;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    const uint32_t lo = st.fold_lo, hi = st.fold_hi;
+    const bool tuned = cfg.key_tuning && ia[T.kfold_bin + 12 * FOLD_MAX + 12] != 0;
+    float pc = 0.0f;
+    if (lo <= hi) {
+        for (uint32_t b = lo + lane; b <= hi; b += 32) contrib[w][b - lo] = powf(fmaxf(row[b], 0.0f), 0.6f);  // extractor.rs:431
+        __syncwarp();
+        if (lane < 12) {
+            if (tuned) {
+                const int32_t* bins = ia + T.kfold_bin + lane * FOLD_MAX;
+                const float* ws = fa + T.kfold_w + lane * FOLD_MAX;
+                const int n = ia[T.kfold_bin + 12 * FOLD_MAX + lane];
+                for (int q = 0; q < n; ++q) pc = pc + contrib[w][bins[q] - lo] * ws[q];
+            } else {
+                const int a = st.fold_off[lane], z = st.fold_off[lane + 1];
+                for (int q = a; q < z; ++q) pc = pc + contrib[w][st.fold_bin[q] - lo] * st.fold_w[q];
+            }
+        }
+        float ss = 0.0f;
+        for (int i = 0; i < 12; ++i) {
+            const float v = __shfl_sync(0xffffffffu, pc, i);
+            ss = ss + v * v;
+        }
+        const float norm = sqrtf(ss);
+        if (norm > 1e-10f) pc = pc / norm;
+    }
+    if (lane < 12) fa[(T.beat_sync ? T.chroma2 : T.chroma) + (uint64_t)f * 12 + lane] = pc;
+    if (lane == 0) fa[(T.beat_sync ? T.kweights : T.kenergy) + f] = e;
+}
+
 // ---- sharpen_chroma (chroma/normalization.rs:41-65): thread per frame ----------------------------------------------
 __global__ void __launch_bounds__(256) chroma_sharpen_kernel(const TrackDev* __restrict__ tr, float* fa, float power) {
     const TrackDev& T = tr[blockIdx.y];
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (T.status != 0 || f >= T.Fk) return;
+    if (T.status != 0 || f >= T.kf) return;
     float* ch = fa + T.chroma + (uint64_t)f * 12;
     float v[12], ss = 0.0f;
     for (int i = 0; i < 12; ++i) {
@@ -329,7 +364,7 @@ __global__ void __launch_bounds__(256) chroma_sharpen_kernel(const TrackDev* __r
 // ---- 5-tap median over time per pitch class (smoothing.rs:37-94); applied when Fk > 5 --------------
 __global__ void __launch_bounds__(256) chroma_smooth_kernel(const TrackDev* __restrict__ tr, float* fa) {
     const TrackDev& T = tr[blockIdx.y];
-    const uint32_t nf = T.Fk;
+    const uint32_t nf = T.kf;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (T.status != 0 || i >= nf * 12) return;
     const float* src = fa + T.chroma;
@@ -367,7 +402,7 @@ __global__ void __launch_bounds__(256) key_weights_kernel(TrackDev* tr, float* f
     __shared__ uint32_t sused[32];
     TrackDev& T = tr[blockIdx.x];
     uint32_t f0, nf;
-    key_slice(T.Fk, cfg, &f0, &nf);
+    key_slice(T.kf, cfg, &f0, &nf);
     if (threadIdx.x == 0) T.have_w = 0;
     if (T.status != 0 || nf == 0 || !cfg.key_weighting) return;
     const float* en = fa + T.kenergy + f0;
@@ -426,8 +461,8 @@ __global__ void __launch_bounds__(256) key_weights_kernel(TrackDev* tr, float* f
 // key_vote_kernel flagged.  Returns false when this (track, row, pass) has nothing to do.
 __device__ __forceinline__ bool key_row_for_pass(const TrackDev& T, const DevCfg& cfg, uint32_t bx, int fallback_only, uint32_t* f0, uint32_t* nf, KeyRows* R,
                                                  uint32_t* row) {
-    if (T.status != 0 || T.Fk == 0) return false;
-    key_slice(T.Fk, cfg, f0, nf);
+    if (T.status != 0 || T.kf == 0) return false;
+    key_slice(T.kf, cfg, f0, nf);
     if (*nf == 0) return false;
     *R = key_rows(*nf, cfg);
     if (R->mode == KEY_ROWS_ENSEMBLE) {
@@ -738,9 +773,9 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
         T.key_clarity = 0.0f;
         T.key_fallback = 0;
     }
-    if (T.status != 0 || T.Fk == 0 || T.m < 2048) return;
+    if (T.status != 0 || T.kf == 0 || T.m < 2048) return;
     uint32_t f0, nf;
-    key_slice(T.Fk, cfg, &f0, &nf);
+    key_slice(T.kf, cfg, &f0, &nf);
     if (nf == 0) return;
     const KeyRows R = key_rows(nf, cfg);
     const float* rk = fa + T.seg_rank;
@@ -806,20 +841,29 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
 }
 
 void launch_key_mask(const WaveCtx& c) {
-    if (c.max_Fk > 0 && (c.cfg.key_mask || c.cfg.key_smooth_only)) {
+    if (c.max_Fk > 0 && !c.cfg.key_hpss && (c.cfg.key_mask || c.cfg.key_smooth_only)) {  // the median-HPSS mask takes precedence (lib.rs:1011-1030)
         const dim3 g((KBINS + 127) / 128, c.n_tracks);
         if (c.cfg.key_margin == 12) mask_kernel<12><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // default margin (config.rs:669)
         else mask_kernel<0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         count_launch("key_mask");
     }
+    if (c.max_Fk > 0) launch_key_variants_pre(c);
 }
 
 void launch_key_hpcp(const WaveCtx& c) {
     if (c.max_Fk > 0) {
         const dim3 g((c.max_Fk + 3) / 4, c.n_tracks);
-        if (c.cfg.key_hpcp) hpcp_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
-        else chroma_fold_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa);
-        count_launch("key_hpcp");
+        // which chroma front end a track takes is decided per track (lib.rs:1123-1197): beat-synchronous tracks and plain chroma
+        // folding go through chroma_fold_kernel, log-frequency through k_keyvar.cu, everything else through HPCP
+        if (c.cfg.key_hpcp && !c.cfg.key_log_freq) {
+            hpcp_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+            count_launch("key_hpcp");
+        }
+        if (c.cfg.key_beat_sync || (!c.cfg.key_hpcp && !c.cfg.key_log_freq)) {
+            chroma_fold_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.ia, c.cfg);
+            count_launch("key_hpcp");
+        }
+        launch_key_chroma_variants(c);
         if (c.cfg.chroma_sharpen > 1.0f) {  // lib.rs:1200-1208
             chroma_sharpen_kernel<<<dim3((c.max_Fk + 255) / 256, c.n_tracks), 256, 0, c.stream>>>(c.tracks, c.fa, c.cfg.chroma_sharpen);
             count_launch("key_hpcp");

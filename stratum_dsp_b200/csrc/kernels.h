@@ -53,6 +53,18 @@ struct DevCfg {
     float key_ens_kk, key_ens_tp;
     uint32_t ms_n, ms_len[8], ms_hop, ms_nw;
     float ms_w[8], ms_min_clarity;
+    // optional chroma-side variants
+    int32_t key_tuning;           // estimate_tuning_offset_semitones_from_spectrogram (extractor.rs:66-170)
+    float tune_max_abs, tune_thr;
+    uint32_t tune_step;
+    int32_t key_whiten;           // enable_whitening && smooth_bins >= 3 (extractor.rs:562)
+    uint32_t whiten_half;         // (max(smooth_bins, 3) | 1) / 2
+    int32_t key_bass_blend;
+    float bass_weight;
+    int32_t key_log_freq, key_beat_sync, key_soft_mapping;
+    int32_t key_hpss;             // harmonic_spectrogram_hpss_median_mask (extractor.rs:1369-1501)
+    uint32_t khpss_step, khpss_tm, khpss_fm;
+    float khpss_power;
 };
 
 // Per-sample-rate tables (band edges, mel filterbank) — novelty.rs:72-190, tempogram.rs:364-372.
@@ -69,6 +81,17 @@ struct SrTables {
     const int32_t* fold_off;          // [13] entry ranges per pitch class
     const int32_t* fold_bin;          // entries in ascending-bin order per pitch class
     const float* fold_w;              // Gaussian (soft) or unit (hard) weights
+    // optional key-path variants, all in key-STFT bins
+    uint32_t bass_bin_lo, bass_bin_hi;  // bass-band HPCP peak range (extractor.rs:1206-1220); lo > hi = empty
+    float bass_fmin, bass_fmax;         // band edges after the clamps of extractor.rs:551-556
+    uint32_t tune_bin_lo, tune_bin_hi;  // tuning estimator band, 80..2000 Hz (extractor.rs:100-121)
+    uint32_t white_n;                   // whitened bins [0, white_n) a frame needs (peak tests read one bin past each band)
+    uint32_t hpss_b0, hpss_band;        // median-HPSS band (extractor.rs:1408-1420); band = 0: spectrogram passes through
+    uint32_t log_n;                     // semitone bins of the log-frequency spectrogram (extractor.rs:741-745)
+    int32_t log_offset;                 // semitone index of bin 0 (lib.rs:1076-1079)
+    const int32_t* log_off;             // [log_n + 1] entry ranges per semitone bin
+    const int32_t* log_bin;             // linear bins in ascending order per semitone bin
+    const float* log_w;                 // interpolation weights (extractor.rs:786-797)
     float kw_b0, kw_b1, kw_b2, kw_a1, kw_a2;  // K-weighting biquad (normalization.rs:127-155)
     uint32_t lufs_block;              // (sr * 0.4) as usize, normalization.rs:198
 };
@@ -129,6 +152,8 @@ void launch_beat_tracking(const WaveCtx& c);
 void launch_key_mask(const WaveCtx& c);
 void launch_key_hpcp(const WaveCtx& c);
 void launch_key_vote(const WaveCtx& c);
+void launch_key_variants_pre(const WaveCtx& c);  // k_keyvar.cu: median-HPSS mask, tuning estimate, whitening, per-track fold tables
+void launch_key_chroma_variants(const WaveCtx& c);  // k_keyvar.cu: log-frequency chroma, beat-synchronous chroma
 // k_synth.cu
 void launch_pcm16_to_mono(cudaStream_t s, const int16_t* d_pcm, float* d_out, const uint64_t* d_pcm_off, const uint64_t* d_out_off, const uint32_t* d_channels,
                           uint32_t n_tracks, uint64_t max_frames);

@@ -338,6 +338,15 @@ def test_key_path_variants(cfg):
 ])
 def test_key_scoring_variants(cfg):
     # template set, edge trim, mode heuristic / minor bonus, ensemble, multi-scale — on material whose modes do not tie
+    ocfg = _oracle_cfg(cfg)
+    xs = [synth.render_progression(1, 30, SR, tonic=2, minor=True, bpm=124), synth.render_progression(2, 26, 48000, tonic=9, minor=False, bpm=96)]
+    srs = [SR, 48000]
+    res = [S.analyze_audio(x, sr, S.AnalysisConfig(**cfg)) for x, sr in zip(xs, srs)]
+    for i, (x, sr, g) in enumerate(zip(xs, srs, res)):
+        assert_parity(g, O.analyze(x, sr, ocfg, fast=True), f"{cfg} track {i}")
+
+
+def _oracle_cfg(cfg):
     ocfg = {}
     for k, v in cfg.items():
         if isinstance(v, list):
@@ -346,11 +355,52 @@ def test_key_scoring_variants(cfg):
                 ocfg[f"{k}[{i}]"] = e
         else:
             ocfg[k] = v
-    xs = [synth.render_progression(1, 30, SR, tonic=2, minor=True, bpm=124), synth.render_progression(2, 26, 48000, tonic=9, minor=False, bpm=96)]
-    srs = [SR, 48000]
-    res = [S.analyze_audio(x, sr, S.AnalysisConfig(**cfg)) for x, sr in zip(xs, srs)]
-    for i, (x, sr, g) in enumerate(zip(xs, srs, res)):
+    return ocfg
+
+
+@pytest.mark.parametrize("cfg", [
+    {"enable_key_tuning_compensation": 1},                                           # extractor.rs:66-170; clamps to +-0.08 (lib.rs:1109-1113)
+    {"enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5},
+    {"enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "enable_key_hpcp": 0},   # tuned chroma folding
+    {"enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "enable_key_hpcp": 0, "soft_chroma_mapping": 0,
+     "key_tuning_frame_step": 7, "key_tuning_peak_rel_threshold": 0.6},
+    {"enable_key_hpcp_whitening": 1},                                                # extractor.rs:558-580
+    {"enable_key_hpcp_whitening": 1, "key_hpcp_whitening_smooth_bins": 9, "key_hpcp_peaks_per_frame": 12},
+    {"enable_key_hpcp_whitening": 1, "key_hpcp_whitening_smooth_bins": 2},           # < 3: whitening stays off (extractor.rs:562)
+    {"enable_key_hpcp_bass_blend": 1},                                               # extractor.rs:1154-1239
+    {"enable_key_hpcp_bass_blend": 1, "enable_key_hpcp_whitening": 1, "key_hpcp_bass_weight": 0.6, "key_hpcp_bass_fmin_hz": 40.0,
+     "key_hpcp_bass_fmax_hz": 400.0, "enable_key_tuning_compensation": 1},
+    {"enable_key_log_frequency": 1},                                                 # extractor.rs:701-807, 941-984
+    {"enable_key_log_frequency": 1, "enable_key_tuning_compensation": 1, "enable_key_beat_synchronous": 1, "enable_key_harmonic_mask": 0},
+    {"enable_key_beat_synchronous": 1},                                              # extractor.rs:830-922
+    {"enable_key_beat_synchronous": 1, "enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "soft_chroma_mapping": 0,
+     "enable_key_segment_voting": 0},
+    {"enable_key_hpss_harmonic": 1},                                                 # extractor.rs:1369-1501
+    {"enable_key_hpss_harmonic": 1, "key_hpss_frame_step": 2, "key_hpss_time_margin": 5, "key_hpss_freq_margin": 10, "key_hpss_mask_power": 1.5},
+    {"enable_key_hpss_harmonic": 1, "key_hpss_frame_step": 1, "enable_key_hpcp": 0, "enable_key_multi_scale": 1},
+])
+def test_key_chroma_variants(cfg):
+    # tuning estimate, HPCP whitening / bass blend, log-frequency and beat-synchronous chroma, median-HPSS mask
+    ocfg = _oracle_cfg(cfg)
+    xs = [synth.render_progression(3, 30, SR, tonic=2, minor=True, bpm=124, detune_cents=30),
+          synth.render_progression(4, 24, 48000, tonic=7, minor=False, bpm=100, detune_cents=-20),
+          synth.render(synth.c2_params(41, 20 * SR, SR))]   # click track: a dense beat grid for the beat-synchronous branch
+    srs = [SR, 48000, SR]
+    for i, (x, sr) in enumerate(zip(xs, srs)):
+        g = S.analyze_audio(x, sr, S.AnalysisConfig(**cfg))
         assert_parity(g, O.analyze(x, sr, ocfg, fast=True), f"{cfg} track {i}")
+
+
+def test_key_variants_in_a_ragged_batch():
+    # per-track decisions (beat grid present or not, tuned or untuned lists, window counts) inside one wave
+    cfg = {"enable_key_beat_synchronous": 1, "enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "enable_key_mode_heuristic": 1,
+           "enable_key_edge_trim": 1}
+    xs = [synth.render_progression(5, 28, SR, tonic=4, minor=False, bpm=110, detune_cents=25), synth.render(synth.c2_params(42, 16 * SR, SR)),
+          (0.2 * np.sin(2 * np.pi * 220.0 * np.arange(6 * SR) / SR)).astype(np.float32),   # no beats: falls back to the HPCP front end
+          synth.render(synth.c2_params(43, 9 * SR, SR))]
+    res = S.analyze_batch(xs, SR, S.AnalysisConfig(**cfg))
+    for i, (x, g) in enumerate(zip(xs, res)):
+        assert_parity(g, O.analyze(x, SR, cfg, fast=True), f"ragged key variants track {i}")
 
 
 @pytest.mark.parametrize("cfg", [
