@@ -691,7 +691,6 @@ static int config_validate(const StratumConfig& c) {
     }
     if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
     if (c.emit_tempogram_candidates && c.tempogram_candidates_top_n > 200) return ni("tempogram_candidates_top_n > 200");
-    if (!c.tempogram_band_seed_only) return ni("tempogram_band_seed_only = false");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
     if (!c.enable_key_stft_override || c.key_stft_frame_size != 8192 || c.key_stft_hop_size != 512) return ni("key STFT other than 8192/512");
     if (c.key_spectrogram_smooth_margin > 15) return ni("key_spectrogram_smooth_margin > 15");

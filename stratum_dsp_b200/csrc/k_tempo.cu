@@ -421,21 +421,33 @@ __global__ void __launch_bounds__(256) score_kernel(TrackDev* tr, const int32_t*
     __syncthreads();
     const int nu = n_uniq;
     const float ac_tol = fmaxf(cfg.bpm_resolution, 0.5f);
-    const float max_fft0 = fmaxf(ntop_fft[0] > 0 ? fl[0].p[top_fft[0][0]] : 1.0f, 1e-12f);
-    const float max_ac0 = fmaxf(ntop_ac[0] > 0 ? ac_full[top_ac[0][0]] : 1.0f, 1e-12f);
     const float support_thr = clamp_rs(cfg.support_thr, 0.0f, 1.0f);
     const float bonus = fmaxf(cfg.consensus_bonus, 0.0f);
-    // scoring variants: seed_only -> full only (tempogram.rs:467-476); the ABI rejects seed_only = false
-    const float w_full = cfg.w_full;
-    const float w_sum = fmaxf(fmaxf(w_full, 0.0f), 1e-6f);
+    // scoring variants (tempogram.rs:464-484): seed_only -> the full-band variant alone; otherwise every active variant, weighted,
+    // in the reference's order full, low, mid, high, mel
+    const float vw[MAX_VARIANTS] = {cfg.w_full, cfg.w_low, cfg.w_mid, cfg.w_high, cfg.w_mel};
+    const int n_score = cfg.seed_only ? 1 : MAX_VARIANTS;
+    float vmax_fft[MAX_VARIANTS], vmax_ac[MAX_VARIANTS];
+    float w_sum = 0.0f;
+    for (int v = 0; v < n_score; ++v) {
+        vmax_fft[v] = vmax_ac[v] = 1.0f;
+        if (!variant_on(st, v)) continue;
+        const float* acv = fa + HL.tgac + (uint64_t)v * AC_CAP;
+        vmax_fft[v] = fmaxf(ntop_fft[v] > 0 ? fl[v].p[top_fft[v][0]] : 1.0f, 1e-12f);
+        vmax_ac[v] = fmaxf(ntop_ac[v] > 0 ? acv[top_ac[v][0]] : 1.0f, 1e-12f);
+        w_sum = __fadd_rn(w_sum, fmaxf(vw[v], 0.0f));
+    }
+    w_sum = fmaxf(w_sum, 1e-6f);
     for (int i = threadIdx.x; i < nu; i += blockDim.x) {
         const float bpm = cand[i];
         float fft_acc = 0.0f, ac_acc = 0.0f;
-        if (w_full > 0.0f) {
-            float fv = lookup_fft(fl[0], bpm, 0.75f);
-            float av = lookup_ac(ac_full, nb, cfg, acb, bpm, ac_tol);
-            fft_acc = __fadd_rn(fft_acc, __fmul_rn(w_full, clamp_rs(__fdiv_rn(fv, max_fft0), 0.0f, 1.0f)));
-            ac_acc = __fadd_rn(ac_acc, __fmul_rn(w_full, clamp_rs(__fdiv_rn(av, max_ac0), 0.0f, 1.0f)));
+        for (int v = 0; v < n_score; ++v) {
+            if (!variant_on(st, v) || !(vw[v] > 0.0f)) continue;
+            const float* acv = fa + HL.tgac + (uint64_t)v * AC_CAP;
+            float fv = lookup_fft(fl[v], bpm, 0.75f);
+            float av = lookup_ac(acv, nb, cfg, acb, bpm, ac_tol);
+            fft_acc = __fadd_rn(fft_acc, __fmul_rn(vw[v], clamp_rs(__fdiv_rn(fv, vmax_fft[v]), 0.0f, 1.0f)));
+            ac_acc = __fadd_rn(ac_acc, __fmul_rn(vw[v], clamp_rs(__fdiv_rn(av, vmax_ac[v]), 0.0f, 1.0f)));
         }
         const float fft_norm = clamp_rs(__fdiv_rn(fft_acc, w_sum), 0.0f, 1.0f);
         const float ac_norm = clamp_rs(__fdiv_rn(ac_acc, w_sum), 0.0f, 1.0f);

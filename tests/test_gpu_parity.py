@@ -410,6 +410,8 @@ def test_key_variants_in_a_ragged_batch():
     {"enable_tempogram_band_fusion": 0},
     {"enable_tempogram_mel_novelty": 0},
     {"enable_tempogram_band_fusion": 0, "enable_tempogram_mel_novelty": 0},
+    {"tempogram_band_seed_only": 0},                         # bands and mel take part in the scoring (tempogram.rs:464-484, 590-603)
+    {"tempogram_band_seed_only": 0, "tempogram_band_w_low": 0.5, "tempogram_band_w_high": 0.0, "tempogram_mel_weight": 0.3, "emit_tempogram_candidates": 1},
     {"enable_onset_consensus": 0},
     {"enable_silence_trimming": 0},
     {"enable_normalization": 0},
