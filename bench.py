@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=1024, help="tracks per GPU and step (BASELINE.json configs[1]: 1024)")
-    ap.add_argument("--e2e-tracks", type=int, default=256, help="tracks per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-tracks", type=int, default=512, help="tracks per step of the host-buffer (e2e) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -236,19 +236,32 @@ def main():
     # ---- e2e: host buffers through the reference-facing call, H2D + result D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        ne = min(args.e2e_tracks if world == 1 else min(args.e2e_tracks, 128), nt)  # N ranks pin N host buffers: keep them modest
+        ne = min(args.e2e_tracks if world == 1 else min(args.e2e_tracks, 256), nt)  # N ranks pin N host buffers: keep them modest
         host = torch.empty(ne * N_SAMPLES, dtype=torch.float32, pin_memory=True)
         host.copy_(buf[: ne * N_SAMPLES])
         torch.cuda.synchronize()
         hnp = host.numpy()
         eoff = np.arange(ne + 1, dtype=np.uint64) * np.uint64(N_SAMPLES)
-        S.analyze_batch_packed(hnp, eoff, [SR] * ne, None, [local_rank])  # warm-up (staging buffer allocation)
+        import ctypes as _C
+        srs_e = np.full(ne, SR, np.uint32)
+
+        def host_step():
+            # the reference-facing C-ABI call itself (include/stratum_b200.h): host samples in, StratumResult array out
+            res = (S.StratumResult * ne)()
+            st = S.lib().stratum_b200_analyze_batch(hnp.ctypes.data, eoff.ctypes.data_as(_C.POINTER(_C.c_uint64)), srs_e.ctypes.data_as(_C.POINTER(_C.c_uint32)), ne,
+                                                    None, (_C.c_int32 * 1)(local_rank), 1, res)
+            assert st == 0, S.last_error()
+            n_ok = sum(1 for r in res if r.status == 0)
+            S.free_results(res)
+            return n_ok
+
+        host_step()  # warm-up (staging buffer allocation)
         h0, d0 = S.transfer_bytes()
         barrier()
         te0 = time.perf_counter()
         e_steps = max(1, min(args.steps, 3))
         for _ in range(e_steps):
-            S.analyze_batch_packed(hnp, eoff, [SR] * ne, None, [local_rank])
+            assert host_step() == ne
         barrier()
         e_ms = (time.perf_counter() - te0) * 1000.0 / e_steps
         h1, d1 = S.transfer_bytes()
@@ -261,9 +274,7 @@ def main():
         torch.cuda.synchronize()
         pnp = pcm.numpy()
         ptracks = [pnp[i * N_SAMPLES:(i + 1) * N_SAMPLES] for i in range(ne)]
-        import ctypes as _C
         chans = np.ones(ne, np.uint32)
-        srs_e = np.full(ne, SR, np.uint32)
 
         def pcm_step():
             res = (S.StratumResult * ne)()

@@ -88,6 +88,24 @@ static void resolve_stage_times() {  // call after the stream has been synchroni
     g_pending.clear();
 }
 
+// Host-side time during which the device has nothing queued (planning, the escalation round trip, result gathering):
+// reported next to the device stages as "host_*" when stage timing is on.
+struct HostSpan {
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit HostSpan(const char* n) : name(n), t0(std::chrono::steady_clock::now()), on(g_timing.load() != 0) {}
+    void stop() {
+        if (!on) return;
+        on = false;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        if (!g_stage_ms.count(name)) g_stage_order.push_back(name);
+        g_stage_ms[name] += ms;
+    }
+    ~HostSpan() { stop(); }
+};
+
 static std::atomic<uint64_t> g_last_call_us{0};
 static std::atomic<uint32_t> g_last_call_waves{0};
 static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // host<->device traffic of this process (results, staging)  // device time of the most recent batch call (all waves), microseconds
@@ -1101,6 +1119,7 @@ struct WavePlan {
 static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample_off, const uint64_t* lens, const uint32_t* srs, const WavePlan& wp,
                     const StratumConfig& cfg, const DevCfg& dcfg, size_t fa_budget, StratumResult* out, double* wave_ms) {
     const int nt = (int)wp.idx.size();
+    HostSpan span_plan("host_plan");
     std::vector<TrackDev> tracks(nt);
     std::vector<int32_t> sr_index(nt, 0);
     Bump fa, oa, ia;
@@ -1187,6 +1206,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     cudaEventRecord(ev0, s);
     CUDA_OK(cudaMemcpyAsync(c.d_tracks, tracks.data(), sizeof(TrackDev) * nt, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(c.d_sr_index, sr_index.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
+    span_plan.stop();
     {
         StageTimer t(s, "preprocess");
         launch_peak(w);
@@ -1284,6 +1304,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         // escalation decision needs the host: read the records back, hand out arena slots
         CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaStreamSynchronize(s));
+        HostSpan span_esc("host_escalation");
         std::vector<int32_t> esc;
         for (int i = 0; i < nt; ++i)
             if (tracks[i].status == 0 && tracks[i].escalate) esc.push_back(i);
@@ -1308,6 +1329,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
                 launch_stft_hop(w, 1, c.d_list, nl);
                 launch_stft_hop(w, 2, c.d_list, nl);
             }
+            span_esc.stop();
             {
                 StageTimer t(s, "multires_features");
                 launch_spec_features(w, 1, c.d_list, nl);
@@ -1365,6 +1387,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     g_h2d_bytes.fetch_add((sizeof(TrackDev) + sizeof(int32_t)) * nt);
     cudaEventRecord(ev1, s);
     CUDA_OK(cudaStreamSynchronize(s));
+    HostSpan span_gather("host_gather");
     CUDA_OK(cudaGetLastError());
     resolve_stage_times();
     float ms = 0.0f;
@@ -1461,8 +1484,14 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     double cap_gb = 100.0;
     if (const char* e = getenv("STRATUM_B200_ARENA_GB")) cap_gb = atof(e);
     budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(cap_gb * 1e9 / 4));
-    uint32_t wave_max = 1u << 20;
-    if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) wave_max = std::max(1, atoi(e));
+    // waves of 128-160 three-minute tracks measured fastest (982-989 tracks/s against 959 in waves of 256, 913 in waves of 64)
+    // (the cap is expressed in samples so that batches of short tracks still fill the device)
+    uint32_t wave_max = 1u << 16;
+    uint64_t wave_max_samples = (uint64_t)128 * 7938000;
+    if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) {
+        wave_max = std::max(1, atoi(e));
+        wave_max_samples = ~0ull;
+    }
     std::vector<uint64_t> lens(n_tracks), offs(n_tracks);
     for (uint32_t i = 0; i < n_tracks; ++i) {
         offs[i] = offsets[i];
@@ -1475,9 +1504,22 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     cudaEventCreate(&call_b);
     cudaEventRecord(call_a, ctx->stream);
     while (i < n_tracks) {
+        HostSpan span_pack("host_wave_pack");
         WavePlan wp;
         uint64_t used = 0, esc_max = 0;
+        uint64_t wave_samples = 0;
+        // balanced waves: the remaining samples are spread over ceil(remaining / cap) waves, so a batch slightly larger
+        // than the cap does not end in a tiny (latency-bound) wave
+        uint64_t remaining = 0;
+        for (uint32_t q = i; q < n_tracks; ++q) remaining += lens[q];
+        uint64_t wave_target = wave_max_samples;
+        if (wave_max_samples != ~0ull && remaining > 0) {
+            const uint64_t nw = (remaining + wave_max_samples - 1) / wave_max_samples;
+            wave_target = (remaining + nw - 1) / nw;
+        }
         while (i < n_tracks && wp.idx.size() < wave_max) {
+            if (!wp.idx.empty() && wave_samples + lens[i] / 2 > wave_target) break;
+            wave_samples += lens[i];
             const uint64_t need = track_floats(lens[i], srs[i], cfg);
             const uint64_t esc = esc_floats(lens[i]);
             const uint64_t esc_new = std::max(esc_max, esc);
@@ -1493,6 +1535,7 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
             // a single track larger than the arena budget: let cudaMalloc decide
             budget_floats = used + esc_max;
         }
+        span_pack.stop();
         st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out, &call_ms);
         if (st != STRATUM_OK) return st;
         ++n_waves;
@@ -1575,10 +1618,12 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             return;
         }
         cudaSetDevice(ctx->device);
-        // chunk size: STRATUM_B200_STAGE_MB of mono f32 per chunk (default 2048 MB ~ 64 three-minute tracks: measured 732 vs 679
-        // tracks/s end to end against 1024 MB), at least one track
-        uint64_t chunk_frames = (uint64_t)2048 * 1024 * 1024 / 4;
+        // Chunk sizes ramp up: a small first chunk keeps the un-overlapped first upload short, later chunks grow to
+        // STRATUM_B200_STAGE_MB of mono f32 (default 3876 MB = 128 three-minute tracks, the most efficient wave size measured:
+        // 999 tracks/s device-resident in waves of 128 vs 933 in waves of 64); at least one track per chunk
+        uint64_t chunk_frames = (uint64_t)128 * 7938000;  // = the wave cap of analyze_device: one full-size chunk is one wave
         if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_frames = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
+        static const bool no_ramp = getenv("STRATUM_B200_STAGE_NO_RAMP") != nullptr;
         struct Chunk {
             uint32_t i, j;
             uint64_t elems, frames;
@@ -1586,10 +1631,11 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
         auto frames_of_track = [&](uint32_t q) { return (offsets[q + 1] - offsets[q]) / (pcm16 ? channels[q] : 1u); };
         std::vector<Chunk> chunks;
         uint64_t max_el = 0, max_fr = 0;
+        uint64_t cur_frames = no_ramp ? chunk_frames : std::max<uint64_t>(chunk_frames / 4, 1u << 16);
         for (uint32_t i = a; i < b;) {
             uint32_t j = i;
             uint64_t fr = 0;
-            while (j < b && (j == i || fr + frames_of_track(j) <= chunk_frames)) {
+            while (j < b && (j == i || fr + frames_of_track(j) <= cur_frames)) {
                 fr += frames_of_track(j);
                 ++j;
             }
@@ -1598,6 +1644,7 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             max_el = std::max(max_el, el);
             max_fr = std::max(max_fr, fr);
             i = j;
+            cur_frames = std::min<uint64_t>(chunk_frames, chunks.size() == 1 ? cur_frames * 2 : cur_frames + cur_frames / 2);
         }
         const size_t buf_bytes = (size_t)align_up(max_el * elt + 64, 256);
         {
@@ -1625,22 +1672,32 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             }
         }
         char* bufs[2] = {reinterpret_cast<char*>(ctx->d_stage), reinterpret_cast<char*>(ctx->d_stage) + buf_bytes};
-        std::vector<cudaEvent_t> ev(chunks.size(), nullptr);
+        // Uploads run on a helper thread, in pieces of 128 MB with a stream synchronisation after each piece: the analysis of
+        // chunk k issues small host<->device copies of its own (track records, escalation lists) that would otherwise queue
+        // behind a multi-gigabyte transfer on the copy engine and stall the wave until the next chunk has landed (measured: no
+        // overlap at all with 2 GB transfers enqueued in one piece).
         auto upload = [&](size_t k) -> bool {
             const Chunk& ch = chunks[k];
-            cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+            if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
             g_h2d_bytes.fetch_add(ch.elems * elt);
-            if (ch.elems && cudaMemcpyAsync(bufs[k & 1], static_cast<const char*>(src) + offsets[ch.i] * elt, ch.elems * elt, cudaMemcpyHostToDevice,
-                                            ctx->copy_stream) != cudaSuccess)
-                return false;
-            return cudaEventRecord(ev[k], ctx->copy_stream) == cudaSuccess;
+            const char* hsrc = static_cast<const char*>(src) + offsets[ch.i] * elt;
+            const size_t total = ch.elems * elt, piece = (size_t)128 << 20;
+            for (size_t o = 0; o < total; o += piece) {
+                if (cudaMemcpyAsync(bufs[k & 1] + o, hsrc + o, std::min(piece, total - o), cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess) return false;
+                if (cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) return false;
+            }
+            return true;
         };
         bool ok = upload(0);
         for (size_t k = 0; ok && k < chunks.size(); ++k) {
             // chunk k-1 has been analysed (the call below is synchronous), so its buffer is free for chunk k+1
-            if (k + 1 < chunks.size()) ok = upload(k + 1);
-            if (!ok) break;
-            cudaStreamWaitEvent(ctx->stream, ev[k], 0);
+            bool up_ok = true;
+            std::thread uploader;
+            if (k + 1 < chunks.size()) uploader = std::thread([&, k] { up_ok = upload(k + 1); });
+            struct Joiner {
+                std::thread& t;
+                ~Joiner() { if (t.joinable()) t.join(); }
+            } joiner{uploader};
             const Chunk& ch = chunks[k];
             const uint32_t cn = ch.j - ch.i;
             std::vector<uint64_t> rel(cn + 1, 0);  // per-track offsets in mono frames inside the chunk
@@ -1685,10 +1742,10 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 ok = false;
                 break;
             }
+            if (uploader.joinable()) uploader.join();
+            if (!up_ok) ok = false;
         }
         cudaStreamSynchronize(ctx->copy_stream);
-        for (cudaEvent_t e : ev)
-            if (e) cudaEventDestroy(e);
         if (!ok && status[d] == STRATUM_OK) {
             status[d] = STRATUM_PROCESSING_ERROR;
             errs[d] = "host to device copy failed";
