@@ -92,6 +92,35 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pins this process (and the library's upload thread, which inherits the mask) to the CPUs of the NUMA node the GPU hangs
+    off, before any pinned host buffer is allocated: pinned pages are placed on the allocating thread's node, and an upload
+    that has to cross the socket interconnect runs at about half the PCIe rate.  Returns a short note for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        if node < 0:
+            return "gpu numa node unknown (-1)"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"gpu on numa node {node}, none of its cpus in this process's cpuset"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to numa node {node} ({len(allowed)} cpus) of GPU {device_index}"
+    except Exception as e:  # placement is an optimisation, never a reason to fail the measurement
+        return f"not bound ({type(e).__name__})"
+
+
 def track_params(first: int, count: int) -> np.ndarray:
     import synth
 
@@ -172,6 +201,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_note = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -255,6 +285,15 @@ def main():
             S.free_results(res)
             return n_ok
 
+        # pinned H2D rate of this box (outside the timed region): the ceiling of the f32 leg is this rate / 31.75 MB per track
+        probe = torch.empty(min(ne, 32) * N_SAMPLES, dtype=torch.float32, device="cuda")
+        probe.copy_(host[: probe.numel()], non_blocking=True)
+        torch.cuda.synchronize()
+        tb0 = time.perf_counter()
+        probe.copy_(host[: probe.numel()], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = probe.numel() * 4 / (time.perf_counter() - tb0) / 1e9
+        del probe
         host_step()  # warm-up (staging buffer allocation)
         h0, d0 = S.transfer_bytes()
         barrier()
@@ -265,7 +304,7 @@ def main():
         barrier()
         e_ms = (time.perf_counter() - te0) * 1000.0 / e_steps
         h1, d1 = S.transfer_bytes()
-        e2e = {"tracks_per_step": ne, "ms_per_step": e_ms, "h2d": (h1 - h0) // e_steps, "d2h": (d1 - d0) // e_steps}
+        e2e = {"tracks_per_step": ne, "ms_per_step": e_ms, "h2d": (h1 - h0) // e_steps, "d2h": (d1 - d0) // e_steps, "h2d_gbs": h2d_gbs}
         # informational: the decoder-side entry (16-bit PCM uploaded as is, converted on the device): half the H2D bytes
         pcm = torch.empty(ne * N_SAMPLES, dtype=torch.int16, pin_memory=True)
         for i in range(0, ne, 8):  # converted in slices: the analysis arenas own most of the device memory
@@ -348,7 +387,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C2: batch of synthetic 3-min 44.1 kHz mono tracks, BPM 70-180, random keys (BASELINE.json configs[1]); analyze_audio defaults",
                        "tracks_per_gpu_per_step": nt, "samples_per_track": N_SAMPLES, "l2": "inputs (32.5 GB per GPU) far larger than L2; no flush needed",
-                       "timing": "CUDA events on the library stream around each batch call, max over ranks"},
+                       "timing": "CUDA events on the library stream around each batch call, max over ranks", "host_placement": numa_note},
             "ms_per_track": ms_step / nt, "wall_ms_per_step": wall_step,
             "gpu_launches": launches, "clocks": clocks,
             "stages_ms_per_step": {k: v / args.steps for k, v in stages.items()},
@@ -357,7 +396,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": ({"value": e2e["tracks_per_step"] * world / (e_ms_step / 1000.0), "unit": "tracks/s", "h2d_bytes_per_step": int(e2e["h2d"]),
                      "d2h_bytes_per_step": int(e2e["d2h"]), "tracks_per_step": e2e["tracks_per_step"], "ms_per_step": e_ms_step,
-                     "pcm16_value": e2e["tracks_per_step"] * world / (p_ms_step / 1000.0),
+                     "pcm16_value": e2e["tracks_per_step"] * world / (p_ms_step / 1000.0), "pinned_h2d_gbs_rank0": e2e["h2d_gbs"],
                      "note": "stratum_b200_analyze_batch on pinned host f32 samples: H2D of the samples and D2H of the results inside the timed region; "
                              "pcm16_value = same through stratum_b200_analyze_batch_pcm16 (int16 upload, conversion on the device)"}
                     if e2e else None),

@@ -230,8 +230,12 @@ static int ctx_init(DeviceCtx& c, int device) {
     CUDA_OK(cudaStreamCreateWithFlags(&c.key_stream, cudaStreamNonBlocking));
     c.tab.tw1024 = get_tw(c, 1024);
     c.tab.tw4096 = get_tw(c, 4096);
-    c.tab.ptw1024 = dev_upload(c, make_pass_tw(1024));
-    c.tab.ptw4096 = dev_upload(c, make_pass_tw(4096));
+    {
+        const std::vector<float2> p1 = make_pass_tw(1024), p4 = make_pass_tw(4096);
+        c.tab.ptw1024 = dev_upload(c, p1);
+        c.tab.ptw4096 = dev_upload(c, p4);
+        stft_upload_constants(p1.data(), p4.data());
+    }
     c.tab.rw2048 = get_tw(c, 2048);  // RW_N[k] = TW_N[k], k <= N/2
     c.tab.rw8192 = get_tw(c, 8192);
     c.tab.win2048 = dev_upload(c, make_hann(2048));

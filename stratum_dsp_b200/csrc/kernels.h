@@ -127,6 +127,7 @@ void launch_silence_trim(const WaveCtx& c);
 // k_stft.cu
 void launch_stft_hop(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);
 void launch_stft_key(const WaveCtx& c);
+void stft_upload_constants(const float2* ptw1024_host, const float2* ptw4096_host);  // per device, before the first STFT launch
 void launch_stft_raw(cudaStream_t s, const float* d_samples, uint64_t n, uint32_t frame_size, uint32_t hop, float gain, const Tables& tab,
                      float* d_out, uint32_t frames);
 // k_onset.cu

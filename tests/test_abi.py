@@ -147,3 +147,17 @@ def test_product_does_not_touch_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", str(S.LIB_PATH)], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_rust_binding_is_generated_from_the_header():
+    # rust/stratum-dsp-b200/src/sys.rs mirrors include/stratum_b200.h field for field (the crate ships as source: no Rust toolchain here)
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, str(ROOT / "tools" / "gen_rust_sys.py"), "--check"]).returncode == 0, "run tools/gen_rust_sys.py"
+    rs = (ROOT / "rust" / "stratum-dsp-b200" / "src" / "sys.rs").read_text()
+    names = [n for n, _ in S.StratumConfig._fields_]
+    got = re.findall(r"pub (\w+):", rs[rs.index("pub struct StratumConfig {"):rs.index("pub struct StratumTempoCandidate {")])
+    assert got == names
+    wrapper = (ROOT / "rust" / "stratum-dsp-b200" / "src" / "lib.rs").read_text()
+    for sym in re.findall(r"(stratum_b200_\w+)\(", wrapper):
+        assert sym in HEADER and f"pub fn {sym}(" in rs, sym
