@@ -31,7 +31,8 @@ constexpr int HPCP_MAX_HARM = 8;     // key_hpcp_num_harmonics upper bound accep
 // x[t - MG] is then a register; MG = 0: run-time margin with a shared-memory ring for the samples.
 constexpr int MASK_G = 16;
 
-template <int MG>
+// FAST: the default exponent 2 with the mask on — `h*h`, `r*r` and no per-element mode tests.
+template <int MG, bool FAST>
 __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
     __shared__ float ringP[RING][128];
     __shared__ float ringX[MG > 0 ? 1 : RING][128];
@@ -42,21 +43,14 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
     const uint32_t mg = MG > 0 ? (uint32_t)MG : cfg.key_margin;
     float* K = fa + T.keyspec + b;
     const int tx = threadIdx.x;
-    const float p = fmaxf(cfg.key_mask_power, 1.0f);
-    const bool square = (p == 2.0f);
+    const float p = FAST ? 2.0f : fmaxf(cfg.key_mask_power, 1.0f);
+    const bool square = FAST || (p == 2.0f);
     float P = 0.0f;
     ringP[0][tx] = 0.0f;
-    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt) {
-        float h_est;
-        if (mg == 0) {
-            h_est = xt;
-        } else {
-            const uint32_t st = t >= mg ? t - mg : 0;
-            const float sum = Pen - ringP[st & (RING - 1)][tx];
-            const float denom = (float)max(en - st, 1u);
-            h_est = sum / denom;
-        }
-        if (cfg.key_smooth_only) {  // smooth_spectrogram_time alone (extractor.rs:1246-1290, lib.rs:1043-1060)
+    // steady = the window [t - mg, t + mg] lies inside the track: the divisor is the compile-time constant 2*MG + 1 (an IEEE
+    // division by a constant needs no reciprocal approximation or range check), no clamping of the window edges
+    auto emit_h = [&](uint32_t t, float h_est, float xt) {
+        if (!FAST && cfg.key_smooth_only) {  // smooth_spectrogram_time alone (extractor.rs:1246-1290, lib.rs:1043-1060)
             K[(uint64_t)t * KBINS] = h_est;
             return;
         }
@@ -68,6 +62,18 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
         const float m = hp / (hp + rp + 1e-12f);
         K[(uint64_t)t * KBINS] = x * m;
     };
+    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt) {
+        float h_est;
+        if (mg == 0) {
+            h_est = xt;
+        } else {
+            const uint32_t st = t >= mg ? t - mg : 0;
+            const float sum = Pen - ringP[st & (RING - 1)][tx];
+            const float denom = (float)max(en - st, 1u);
+            h_est = sum / denom;
+        }
+        emit_h(t, h_est, xt);
+    };
     float xp[MASK_G];  // previous group (compile-time margin only)
 #pragma unroll
     for (int q = 0; q < MASK_G; ++q) xp[q] = 0.0f;
@@ -76,6 +82,7 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
         float xs[MASK_G];
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) xs[q] = K[(uint64_t)(i + q) * KBINS];
+        const bool steady = MG > 0 && i >= 2 * (uint32_t)MG;  // every frame this group emits has its full window (uniform over the CTA)
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) {
             const uint32_t ii = i + q;
@@ -85,7 +92,8 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
                 float xt;
                 if (MG > 0) xt = (q >= MG) ? xs[q >= MG ? q - MG : 0] : xp[q + MASK_G - MG < MASK_G ? q + MASK_G - MG : 0];
                 else xt = ringX[(ii - mg) & (RING - 1)][tx];
-                emit(ii - mg, ii + 1, P, xt);
+                if (steady) emit_h(ii - MG, (P - ringP[(ii - 2 * MG) & (RING - 1)][tx]) / (float)(2 * MG + 1), xt);
+                else emit(ii - mg, ii + 1, P, xt);
             }
             ringP[(ii + 1) & (RING - 1)][tx] = P;
         }
@@ -843,8 +851,10 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
 void launch_key_mask(const WaveCtx& c) {
     if (c.max_Fk > 0 && !c.cfg.key_hpss && (c.cfg.key_mask || c.cfg.key_smooth_only)) {  // the median-HPSS mask takes precedence (lib.rs:1011-1030)
         const dim3 g((KBINS + 127) / 128, c.n_tracks);
-        if (c.cfg.key_margin == 12) mask_kernel<12><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // default margin (config.rs:669)
-        else mask_kernel<0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        const bool fast = !c.cfg.key_smooth_only && fmaxf(c.cfg.key_mask_power, 1.0f) == 2.0f;
+        if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680)
+        else if (c.cfg.key_margin == 12) mask_kernel<12, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        else mask_kernel<0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         count_launch("key_mask");
     }
     if (c.max_Fk > 0) launch_key_variants_pre(c);
