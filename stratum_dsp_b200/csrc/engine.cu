@@ -313,6 +313,8 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
     }
     SrTables st{};
     st.sr = sr;
+    const uint32_t key_frame = cfg.enable_key_stft_override ? std::max<uint32_t>(cfg.key_stft_frame_size, 256) : cfg.frame_size;  // lib.rs:984-989
+    const uint32_t key_bins = key_frame / 2 + 1;
     const uint32_t n_bins = 1025;
     const float freq_res = (float)sr / 2048.0f;
     uint32_t vm = 1u;  // full
@@ -392,12 +394,12 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
     st.mel_w = dev_upload(c, mel_w);
     // HPCP band in key-STFT bins — chroma/extractor.rs:584-591 (b from 1 to n_bins-2)
     {
-        const float res = (float)sr / 8192.0f;
+        const float res = (float)sr / (float)key_frame;
         const float fmin = fmaxf(100.0f, 20.0f), fmax = fminf(5000.0f, (float)sr / 2.0f);
         uint32_t lo = 1, hi = 0;
         if (fmax > fmin) {
             lo = 0;
-            for (uint32_t b = 1; b + 1 < 4097; ++b) {
+            for (uint32_t b = 1; b + 1 < key_bins; ++b) {
                 const float f = (float)b * res;
                 if (f < fmin) continue;
                 if (f > fmax) break;
@@ -413,7 +415,7 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         st.key_bin_hi = hi;
     }
     {   // bands and tables of the optional key-path variants, key-STFT bins
-        const float res = (float)sr / 8192.0f;
+        const float res = (float)sr / (float)key_frame;
         const float nyq = (float)sr / 2.0f;
         // bass-band HPCP: same peak loop as above on [bass_fmin, bass_fmax] (extractor.rs:1206-1220 -> 551-556, 584-591)
         st.bass_fmin = fmaxf(cfg.key_hpcp_bass_fmin_hz, 20.0f);
@@ -422,7 +424,7 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         st.bass_bin_hi = 0;
         if (st.bass_fmax > st.bass_fmin) {
             uint32_t lo = 0, hi = 0;
-            for (uint32_t b = 1; b + 1 < 4097; ++b) {
+            for (uint32_t b = 1; b + 1 < key_bins; ++b) {
                 const float f = (float)b * res;
                 if (f < st.bass_fmin) continue;
                 if (f > st.bass_fmax) break;
@@ -434,7 +436,7 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
                 st.bass_bin_hi = hi;
             }
         }
-        st.white_n = std::min<uint32_t>(std::max(st.key_bin_hi, st.bass_bin_hi) + 2, 4097);
+        st.white_n = std::min<uint32_t>(std::max(st.key_bin_hi, st.bass_bin_hi) + 2, key_bins);
         // tuning estimator band (extractor.rs:100-121): all bins with fmin <= f <= fmax
         {
             const float fmin = fmaxf(80.0f, 20.0f);
@@ -442,7 +444,7 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
             st.tune_bin_lo = 1;
             st.tune_bin_hi = 0;
             bool first = true;
-            for (uint32_t b = 0; b < 4097; ++b) {
+            for (uint32_t b = 0; b < key_bins; ++b) {
                 const float f = (float)b * res;
                 if (f < fmin) continue;
                 if (f > fmax) break;
@@ -455,8 +457,8 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
             const float fmin = fmaxf(100.0f, 20.0f);
             const float fmax = fminf(fmaxf(5000.0f, fmin + 1.0f), nyq);
             long bs = (long)floorf(fmin / res), be = (long)ceilf(fmax / res);
-            bs = std::min<long>(std::max<long>(bs, 0), 4097);
-            be = std::min<long>(std::max<long>(be, 0), 4097);
+            bs = std::min<long>(std::max<long>(bs, 0), (long)key_bins);
+            be = std::min<long>(std::max<long>(be, 0), (long)key_bins);
             st.hpss_b0 = (uint32_t)bs;
             st.hpss_band = be > bs ? (uint32_t)(be - bs) : 0u;
         }
@@ -471,7 +473,7 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
             st.log_n = n_semi;
             st.log_offset = (int32_t)floorf(12.0f * log2f(100.0f / 440.0f) + 57.0f);  // lib.rs:1076-1079
             std::vector<std::vector<std::pair<int32_t, float>>> per(n_semi);
-            for (uint32_t b = 0; b < 4097 && n_semi > 0; ++b) {
+            for (uint32_t b = 0; b < key_bins && n_semi > 0; ++b) {
                 const float f = (float)b * res;
                 if (f < fmin || f >= fmax || f >= nyq) continue;
                 const float semitone = 12.0f * log2f(f / 440.0f) + 57.0f;
@@ -528,10 +530,10 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         std::vector<int32_t> off(13, 0), bins;
         std::vector<float> ws;
         std::vector<std::vector<std::pair<int32_t, float>>> per(12);
-        const float res = (float)sr / 8192.0f;
+        const float res = (float)sr / (float)key_frame;
         uint32_t lo = 1, hi = 0;
         bool first = true;
-        for (uint32_t b = 0; b < 4097; ++b) {
+        for (uint32_t b = 0; b < key_bins; ++b) {
             const float freq = (float)b * res;
             if (freq < 100.0f) continue;
             if (freq > fminf(5000.0f, (float)sr / 2.0f)) break;
@@ -714,7 +716,8 @@ static int config_validate(const StratumConfig& c) {
     if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
     if (c.emit_tempogram_candidates && c.tempogram_candidates_top_n > 200) return ni("tempogram_candidates_top_n > 200");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
-    if (!c.enable_key_stft_override || c.key_stft_frame_size != 8192 || c.key_stft_hop_size != 512) return ni("key STFT other than 8192/512");
+    if (c.enable_key_stft_override && std::max<uint32_t>(c.key_stft_frame_size, 256) != 8192 && std::max<uint32_t>(c.key_stft_frame_size, 256) != 2048)
+        return ni("key_stft_frame_size other than 2048 or 8192");
     if (c.key_spectrogram_smooth_margin > 15) return ni("key_spectrogram_smooth_margin > 15");
     if (c.key_hpcp_peaks_per_frame > 32) return ni("key_hpcp_peaks_per_frame > 32");
     if (c.key_hpcp_num_harmonics > 8) return ni("key_hpcp_num_harmonics > 8");
@@ -823,6 +826,9 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.hpcp_decay = c.key_hpcp_harmonic_decay;
     d.hpcp_pow = c.key_hpcp_mag_power;
     d.hpcp_sigma = c.soft_mapping_sigma;
+    d.key_frame = c.enable_key_stft_override ? std::max<uint32_t>(c.key_stft_frame_size, 256) : c.frame_size;  // lib.rs:984-995
+    d.key_hop = c.enable_key_stft_override ? std::max<uint32_t>(c.key_stft_hop_size, 1) : c.hop_size;
+    d.key_bins = d.key_frame / 2 + 1;
     d.key_mode = c.enable_key_ensemble ? KEY_ROWS_ENSEMBLE : (c.enable_key_multi_scale ? KEY_ROWS_MULTI_SCALE : KEY_ROWS_VOTE);
     d.key_template_set = c.key_template_set;
     d.key_edge_trim = c.enable_key_edge_trim;
@@ -894,7 +900,8 @@ static void plan_hop(Bump& fa, HopLayout& H, uint32_t fcap, uint32_t hop, bool w
 static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumConfig& cfg) {
     const uint64_t n = T.n;
     const uint32_t F512 = frames_of(n, 2048, 512), F256 = frames_of(n, 2048, 256), F1024 = frames_of(n, 2048, 1024);
-    const uint32_t Fk = frames_of(n, 8192, 512);
+    const DevCfg kd = make_devcfg(cfg);
+    const uint32_t Fk = frames_of(n, kd.key_frame, kd.key_hop);
     const uint32_t Fsil = n >= 2048 ? frames_of(n, 2048, 1024) : 1;
     T.fall = std::max(std::max(F256, F512), std::max(F1024, 1u));
     T.fkmax = Fk;
@@ -903,7 +910,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.sil_rms = fa.take(Fsil + 1);
     T.erms = fa.take(F512 + 2);
     T.scratch = fa.take((uint64_t)12 * T.fall);
-    T.keyspec = fa.take((uint64_t)Fk * 4097 + 8);
+    T.keyspec = fa.take((uint64_t)Fk * kd.key_bins + 8);
     T.keymask = T.keyspec;  // the mask is applied in place
     T.chroma = fa.take((uint64_t)Fk * 12 + 12);
     T.chroma2 = fa.take((uint64_t)Fk * 12 + 12);
@@ -922,7 +929,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
         T.kfold_w = fa.take((uint64_t)12 * 1024);
         T.kfold_bin = ia.take((uint64_t)12 * 1024 + 16);
     }
-    T.seg_cap = key_rows(Fk, make_devcfg(cfg)).nrows + 1;
+    T.seg_cap = key_rows(Fk, kd).nrows + 1;
     T.seg_scores = fa.take((uint64_t)T.seg_cap * 24);
     T.seg_avg = fa.take((uint64_t)T.seg_cap * 13);
     T.seg_rank = fa.take((uint64_t)T.seg_cap * 28);
@@ -1172,7 +1179,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         w.max_F[1] = std::max(w.max_F[1], frames_of(T.n, 2048, 256));
         w.max_F[2] = std::max(w.max_F[2], frames_of(T.n, 2048, 1024));
         w.max_F[SLOT_PERC] = w.max_F[0];
-        w.max_Fk = std::max(w.max_Fk, frames_of(T.n, 8192, 512));
+        w.max_Fk = std::max(w.max_Fk, frames_of(T.n, dcfg.key_frame, dcfg.key_hop));
         w.max_Fsil = std::max(w.max_Fsil, Fsil);
         w.max_n = std::max<uint64_t>(w.max_n, T.n);
         w.max_beat_cap = std::max(w.max_beat_cap, T.beat_cap);
@@ -1273,7 +1280,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             cudaStreamSynchronize(ks);
             const TrackDev& T = tracks[0];
             const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
-            debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * 4097, ks);
+            debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * dcfg.key_bins, ks);
         }
         { StageTimer t(ks, "key_mask"); launch_key_mask(wk); }
         { StageTimer t(ks, "key_hpcp"); launch_key_hpcp(wk); }
@@ -1441,7 +1448,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             debug_put("key.energy", c.fa + T.kenergy, T.Fk, s);
             debug_put("key.weights", c.fa + T.kweights, T.Fk, s);
             debug_put("key.seg_scores", c.fa + T.seg_scores, (size_t)T.seg_cap * 24, s);
-            debug_put("key.mask_head", c.fa + T.keyspec, (size_t)std::min<uint32_t>(T.Fk, 64) * 4097, s);
+            debug_put("key.mask_head", c.fa + T.keyspec, (size_t)std::min<uint32_t>(T.Fk, 64) * dcfg.key_bins, s);
             debug_put_i("hmm.path", c.ia + T.hmm_path, T.hmm_T, s);
         }
     }

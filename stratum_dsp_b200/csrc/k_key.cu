@@ -15,7 +15,6 @@
 
 namespace sb {
 
-constexpr int KBINS = 4097;
 constexpr int RING = 32;           // mask ring: supports margin <= 15
 constexpr int HPCP_MAX_PEAKS = 512;  // local maxima in the 100..5000 Hz band (<= (hi-lo+2)/2 = 456 at 44.1 kHz)
 constexpr int HPCP_MAX_SEL = 32;     // key_hpcp_peaks_per_frame upper bound accepted by the ABI
@@ -32,8 +31,11 @@ constexpr int HPCP_MAX_HARM = 8;     // key_hpcp_num_harmonics upper bound accep
 constexpr int MASK_G = 16;
 
 // FAST: the default exponent 2 with the mask on — `h*h`, `r*r` and no per-element mode tests.
-template <int MG, bool FAST>
+// KB: bins per key-spectrogram row when known at compile time (4097 for the default 8192-point key STFT: row offsets become
+// immediates), 0 = cfg.key_bins.
+template <int MG, bool FAST, int KB>
 __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
+    const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
     __shared__ float ringP[RING][128];
     __shared__ float ringX[MG > 0 ? 1 : RING][128];
     const TrackDev& T = tr[blockIdx.y];
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
     if (T.status != 0 || f >= T.Fk || T.beat_sync) return;
     HpcpSmem& S = sm[w];
     const SrTables& st = srtab[sr_index[t]];
+    const uint32_t KBINS = cfg.key_bins;
     const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
     const float* sel = cfg.key_whiten ? fa + T.kwhite + (uint64_t)f * T.kwhite_stride : row;
     // frame energy (extractor.rs:1132-1134).  Consumed only through (E/median)^0.5 frame weights, a
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ 
         e = e + x * x;
     }
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    const float res = (float)T.sr / 8192.0f;
+    const float res = (float)T.sr / (float)cfg.key_frame;
     const float nyq = (float)T.sr / 2.0f;
     float pc = hpcp_band(sel, row, st.key_bin_lo, st.key_bin_hi, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), cfg.hpcp_peaks, T.key_tuning, res, S, lane, cfg);
     if (cfg.key_bass_blend) {  // extractor.rs:1154-1239: (1-w) full + w bass, renormalised
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(128) chroma_fold_kernel(const TrackDev* __rest
     if (T.status != 0 || f >= T.Fk) return;
     if (!T.beat_sync && (cfg.key_hpcp || cfg.key_log_freq)) return;
     const SrTables& st = srtab[sr_index[t]];
+    const uint32_t KBINS = cfg.key_bins;
     const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
     float e = 0.0f;  // frame energy: tree sum (tolerance-level consumer, see hpcp_kernel)
     for (uint32_t k = lane; k < KBINS; k += 32) {
@@ -850,11 +854,11 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
 
 void launch_key_mask(const WaveCtx& c) {
     if (c.max_Fk > 0 && !c.cfg.key_hpss && (c.cfg.key_mask || c.cfg.key_smooth_only)) {  // the median-HPSS mask takes precedence (lib.rs:1011-1030)
-        const dim3 g((KBINS + 127) / 128, c.n_tracks);
-        const bool fast = !c.cfg.key_smooth_only && fmaxf(c.cfg.key_mask_power, 1.0f) == 2.0f;
-        if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680)
-        else if (c.cfg.key_margin == 12) mask_kernel<12, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-        else mask_kernel<0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        const dim3 g((c.cfg.key_bins + 127) / 128, c.n_tracks);
+        const bool fast = !c.cfg.key_smooth_only && fmaxf(c.cfg.key_mask_power, 1.0f) == 2.0f && c.cfg.key_bins == 4097;
+        if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680, 688)
+        else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        else mask_kernel<0, false, 0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         count_launch("key_mask");
     }
     if (c.max_Fk > 0) launch_key_variants_pre(c);

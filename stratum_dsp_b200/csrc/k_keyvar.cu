@@ -14,7 +14,6 @@
 
 namespace sb {
 
-constexpr int KBINS = 4097;
 constexpr int FOLD_MAX = 1024;   // chroma band bins (k_key.cu)
 constexpr int LOG_MAX = 128;     // semitone bins of the log-frequency spectrogram (70 at 44.1 kHz)
 constexpr int WHITE_RING = 64;   // whitening window <= 63 bins (the ABI rejects wider ones)
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(128) khpss_mask_kernel(const TrackDev* __restr
     const SrTables& st = srtab[sr_index[t]];
     const uint32_t band = st.hpss_band, b0 = st.hpss_b0;
     const uint32_t step = max(cfg.khpss_step, 1u);
-    const uint32_t nf = T.Fk;
+    const uint32_t nf = T.Fk, KBINS = cfg.key_bins;
     if (T.status != 0 || nf == 0 || band == 0) return;
     const uint32_t n_ds = (nf + step - 1) / step;
     const uint32_t b = blockIdx.y * blockDim.x + threadIdx.x, k = blockIdx.x;
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(256) khpss_apply_kernel(const TrackDev* __rest
     const uint32_t nf = T.Fk;
     if (T.status != 0 || nf == 0 || band == 0) return;
     const uint32_t n_ds = (nf + step - 1) / step;
-    const uint32_t f = blockIdx.x;
+    const uint32_t f = blockIdx.x, KBINS = cfg.key_bins;
     if (f >= nf) return;
     float* row = fa + T.keyspec + (uint64_t)f * KBINS;
     const float* m = fa + T.khpss_mask + (uint64_t)min(f / step, n_ds - 1) * band;
@@ -133,7 +132,8 @@ __global__ void __launch_bounds__(256) tuning_kernel(TrackDev* tr, const SrTable
     const uint32_t lo = st.tune_bin_lo, hi = st.tune_bin_hi;
     const uint32_t step = max(cfg.tune_step, 1u);
     const float thr = clamp_rs(cfg.tune_thr, 0.0f, 1.0f);
-    const float res = (float)T.sr / 8192.0f;
+    const float res = (float)T.sr / (float)cfg.key_frame;
+    const uint32_t KBINS = cfg.key_bins;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float ss = 0.0f, sc = 0.0f, sw = 0.0f;
     if (lo <= hi) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(32) fold_table_kernel(const TrackDev* __restri
     const SrTables& st = srtab[sr_index[t]];
     if (pc == 12) ia[T.kfold_bin + 12 * FOLD_MAX + 12] = 1;
     if (pc >= 12) return;
-    const float res = (float)T.sr / 8192.0f;
+    const float res = (float)T.sr / (float)cfg.key_frame;
     int32_t* bins = ia + T.kfold_bin + pc * FOLD_MAX;
     float* ws = fa + T.kfold_w + pc * FOLD_MAX;
     const float sigma = fmaxf(cfg.hpcp_sigma, 1e-6f);
@@ -255,12 +255,12 @@ __global__ void __launch_bounds__(32) whiten_kernel(const TrackDev* __restrict__
     if (T.status != 0 || f0 >= T.Fk) return;
     const SrTables& st = srtab[sr_index[t]];
     const uint32_t wn = st.white_n, half = cfg.whiten_half, WS = T.kwhite_stride;
-    const uint32_t nf = T.Fk;
+    const uint32_t nf = T.Fk, KBINS = cfg.key_bins;
     const float* K = fa + T.keyspec;
     float* W = fa + T.kwhite;
     float P = 0.0f;
     ringP[w][0][lane] = 0.0f;
-    const uint32_t last = min(wn + half, (uint32_t)KBINS);  // bins to walk
+    const uint32_t last = min(wn + half, KBINS);  // bins to walk
     for (uint32_t jb = 0; jb < last; jb += 32) {
         for (int r = 0; r < 32; ++r) {
             const uint32_t f = f0 + r, b = jb + lane;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(32) whiten_kernel(const TrackDev* __restrict__
 
 // ---- log-frequency chroma: one warp per frame --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) logfreq_chroma_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
-                                                             float* fa) {
+                                                             float* fa, uint32_t KBINS) {
     __shared__ float lf[4][LOG_MAX];
     const int t = blockIdx.y;
     const TrackDev& T = tr[t];
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) logfreq_chroma_kernel(const TrackDev* __r
 // Interval i = [beats[i], beats[i+1]): the frames with start time (f as f32 * hop/sr) inside it form a contiguous run because
 // the frame times are non-decreasing; their chroma vectors (chroma_fold_kernel -> chroma2) are added in frame order, divided
 // by the count and L2-normalised; energies (kweights) are added in frame order (extractor.rs:872-919).
-__global__ void __launch_bounds__(128) beat_sync_kernel(TrackDev* tr, float* fa, const float* __restrict__ oa) {
+__global__ void __launch_bounds__(128) beat_sync_kernel(TrackDev* tr, float* fa, const float* __restrict__ oa, uint32_t key_hop) {
     const int t = blockIdx.y;
     TrackDev& T = tr[t];
     if (T.status != 0 || !T.beat_sync) return;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) beat_sync_kernel(TrackDev* tr, float* fa,
     if (i >= ni) return;
     const float* beats = oa + T.beats;
     const float b0 = beats[i], b1 = beats[i + 1];
-    const float dur = (float)512 / (float)T.sr;
+    const float dur = (float)key_hop / (float)T.sr;  // hop_size as f32 / sample_rate as f32 (extractor.rs:859)
     const uint32_t nf = T.Fk;
     auto first_ge = [&](float x) {  // first frame with (float)f * dur >= x
         uint32_t lo = 0, hi = nf;
@@ -421,11 +421,11 @@ void launch_key_variants_pre(const WaveCtx& c) {
 void launch_key_chroma_variants(const WaveCtx& c) {
     if (c.max_Fk == 0) return;
     if (c.cfg.key_log_freq) {
-        logfreq_chroma_kernel<<<dim3((c.max_Fk + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa);
+        logfreq_chroma_kernel<<<dim3((c.max_Fk + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg.key_bins);
         count_launch("key_hpcp");
     }
     if (c.cfg.key_beat_sync && !c.cfg.key_log_freq) {
-        beat_sync_kernel<<<dim3((c.max_beat_cap + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.fa, c.oa);
+        beat_sync_kernel<<<dim3((c.max_beat_cap + 3) / 4, c.n_tracks), 128, 0, c.stream>>>(c.tracks, c.fa, c.oa, c.cfg.key_hop);
         count_launch("key_hpcp");
     }
 }

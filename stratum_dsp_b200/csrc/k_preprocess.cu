@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) trim_kernel(TrackDev* tr, const float* fa
     const uint32_t hops[N_HOPS] = {512, 256, 1024};
     for (int h = 0; h < N_HOPS; ++h) T.F[h] = m >= 2048 ? (uint32_t)((m - 2048) / hops[h] + 1) : 0;
     T.F[SLOT_PERC] = T.F[0];
-    T.Fk = m >= 8192 ? (uint32_t)((m - 8192) / 512 + 1) : 0;
+    T.Fk = m >= cfg.key_frame ? (uint32_t)((m - cfg.key_frame) / cfg.key_hop + 1) : 0;
     if (m == 0 && T.status == 0) {
         T.status = STRATUM_PROCESSING_ERROR;
         T.err_code = 3;  // "Audio is entirely silent after trimming" (lib.rs:143-147)

@@ -391,6 +391,26 @@ def test_key_chroma_variants(cfg):
         assert_parity(g, O.analyze(x, sr, ocfg, fast=True), f"{cfg} track {i}")
 
 
+@pytest.mark.parametrize("cfg", [
+    {"enable_key_stft_override": 0},                                      # key path on the shared 2048/512 geometry (lib.rs:984-1009)
+    {"key_stft_frame_size": 2048, "key_stft_hop_size": 256},
+    {"key_stft_hop_size": 1024},
+    {"key_stft_hop_size": 333, "key_segment_len_frames": 600, "key_segment_hop_frames": 200},   # odd hop: unaligned frame starts
+    {"enable_key_stft_override": 0, "enable_key_hpcp_whitening": 1, "enable_key_hpcp_bass_blend": 1, "enable_key_tuning_compensation": 1,
+     "key_tuning_max_abs_semitones": 0.5},
+    {"enable_key_stft_override": 0, "enable_key_beat_synchronous": 1, "enable_key_harmonic_mask": 0},
+    {"key_stft_frame_size": 2048, "key_stft_hop_size": 1024, "enable_key_hpss_harmonic": 1, "enable_key_hpcp": 0},
+    {"key_stft_hop_size": 2048, "enable_key_log_frequency": 1, "enable_key_multi_scale": 1},
+])
+def test_key_stft_geometry(cfg):
+    # key STFT frame 2048 / 8192 at any hop, or no override at all: every key kernel takes the geometry from the configuration
+    xs = [synth.render_progression(6, 26, SR, tonic=5, minor=True, bpm=118, detune_cents=15), synth.render(synth.c2_params(44, 14 * 48000, 48000))]
+    srs = [SR, 48000]
+    for i, (x, sr) in enumerate(zip(xs, srs)):
+        g = S.analyze_audio(x, sr, S.AnalysisConfig(**cfg))
+        assert_parity(g, O.analyze(x, sr, _oracle_cfg(cfg), fast=True), f"{cfg} track {i}")
+
+
 def test_key_variants_in_a_ragged_batch():
     # per-track decisions (beat grid present or not, tuned or untuned lists, window counts) inside one wave
     cfg = {"enable_key_beat_synchronous": 1, "enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "enable_key_mode_heuristic": 1,
