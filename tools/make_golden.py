@@ -33,6 +33,18 @@ def cases():
     out["fixture_mixed_silence"] = (synth.fixture_mixed_silence(), SR, {})
     out["c2_6_rms"] = (synth.render(synth.c2_params(6, 14 * SR, SR)) * np.float32(0.3), SR, {"normalization": 1})
     out["c2_7_lufs"] = (synth.render(synth.c2_params(7, 14 * SR, SR)) * np.float32(0.3), SR, {"normalization": 2})
+    # optional key-path variants on material whose modes do not tie
+    prog = synth.render_progression(11, 16, SR, tonic=2, minor=True, bpm=124, detune_cents=30)
+    out["prog_default"] = (prog, SR, {})
+    out["prog_mode_heuristic_bonus"] = (prog, SR, {"enable_key_mode_heuristic": 1, "enable_key_minor_harmonic_bonus": 1, "enable_key_segment_voting": 0})
+    out["prog_ensemble"] = (prog, SR, {"enable_key_ensemble": 1, "key_ensemble_kk_weight": 0.7, "key_ensemble_temperley_weight": 0.3})
+    out["prog_multi_scale_temperley"] = (prog, SR, {"enable_key_multi_scale": 1, "key_template_set": 1, "enable_key_edge_trim": 1})
+    out["prog_tuning_whiten_bass"] = (prog, SR, {"enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "enable_key_hpcp_whitening": 1,
+                                                 "enable_key_hpcp_bass_blend": 1})
+    out["prog_log_frequency"] = (prog, SR, {"enable_key_log_frequency": 1})
+    out["prog_hpss_mask_fold"] = (prog, SR, {"enable_key_hpss_harmonic": 1, "enable_key_hpcp": 0})
+    out["prog_no_override_beat_sync"] = (synth.render(synth.c2_params(9, 14 * SR, SR)), SR, {"enable_key_stft_override": 0, "enable_key_beat_synchronous": 1})
+    out["prog_bpm_fusion_band_scoring"] = (prog, SR, {"enable_bpm_fusion": 1, "tempogram_band_seed_only": 0})
     return out
 
 
