@@ -39,6 +39,61 @@ __device__ __forceinline__ void framed_rms_warp(const float* __restrict__ x, uin
 }
 
 
+// ---- the same sums, streamed: every sample is fetched once ------------------------------------------------------
+// Frames of FRAME samples at hop HOP overlap FRAME/HOP-fold; the tile scheme above fetches every sample once per frame
+// that contains it (4x at hop 512), which makes the kernel L2-bandwidth bound.  Here a track is cut into segments of SEG
+// hop-blocks; PH = FRAME/HOP lanes share a segment and walk its blocks together: lane p owns the frames f = p (mod PH), so at
+// any block all PH lanes consume the same samples (a shared-memory broadcast), each into its own frame's running sum at a
+// different position inside that frame.  A warp carries 32/PH segments; per 32 samples it issues 32/PH coalesced row loads
+// (the next tile is fetched into registers while the current one is summed).  Per-frame order stays strictly left to right.
+// Only full frames (tracks with at least FRAME samples); the single short frame of a shorter track stays on framed_rms_warp.
+template <int FRAME, int HOP, int SEG>
+__device__ __forceinline__ void framed_rms_stream_warp(const float* __restrict__ x, uint64_t limit, float g, uint32_t nf, uint32_t seg_first,
+                                                       float (*tile)[32 / (FRAME / HOP)][33], float* out) {
+    constexpr int PH = FRAME / HOP, GPW = 32 / PH, TILES = HOP / 32;
+    static_assert(SEG % PH == 0 && HOP % 32 == 0, "segment / hop geometry");
+    const int lane = threadIdx.x & 31;
+    const int gq = lane / PH, p = lane % PH;
+    const uint32_t tau0 = (seg_first + gq) * SEG;  // first hop-block (= first frame) of this lane's segment
+    auto fetch = [&](uint32_t beta, int s, float (&r)[GPW]) {  // row q of the tile: 32 samples of block (segment q start + beta)
+#pragma unroll
+        for (int q = 0; q < GPW; ++q) {
+            const uint64_t idx = ((uint64_t)(seg_first + q) * SEG + beta) * HOP + (uint32_t)s * 32 + lane;
+            r[q] = idx < limit ? __fmul_rn(x[idx], g) : 0.0f;
+        }
+    };
+    float nxt[GPW];
+    fetch(0, 0, nxt);
+    float sum = 0.0f;
+    int buf = 0;
+    for (uint32_t beta = 0; beta < SEG + PH - 1; ++beta) {
+        // lane p joins at block p; its k-th frame spans blocks p + PH*k .. p + PH*k + PH-1 of the segment
+        const int rel = (int)beta - p;
+        const bool in_seg = rel >= 0 && rel < SEG;
+        const uint32_t f = tau0 + p + (in_seg ? (uint32_t)(rel / PH) * PH : 0u);
+        const bool active = in_seg && f < nf;
+        const int c = in_seg ? rel % PH : 0;
+        if (c == 0) sum = 0.0f;
+        for (int s = 0; s < TILES; ++s) {
+#pragma unroll
+            for (int q = 0; q < GPW; ++q) tile[buf][q][lane] = nxt[q];
+            __syncwarp();
+            const int s2 = s + 1 < TILES ? s + 1 : 0;
+            const uint32_t b2 = s + 1 < TILES ? beta : beta + 1;
+            if (b2 < SEG + PH - 1) fetch(b2, s2, nxt);  // in flight while this tile is summed
+            if (active) {
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const float v = tile[buf][gq][j];
+                    sum = __fadd_rn(sum, __fmul_rn(v, v));
+                }
+            }
+            buf ^= 1;
+        }
+        if (active && c == PH - 1) out[f] = sqrtf(__fdiv_rn(sum, (float)FRAME));
+    }
+}
+
 // Block-wide exclusive scan of one uint per thread (blockDim.x <= 1024, multiple of 32).
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums /* >= 33 */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -18,13 +18,14 @@ constexpr int PQ_SFLUX = 0, PQ_SF = 1, PQ_SFB = 2, PQ_MEL = 5;
 constexpr int MEL_MAX = 40;
 
 // ---- energy flux onsets ------------------------------------------------------------------------
+constexpr int ERMS_SEG = 32;  // hop-blocks per segment of the streamed frame-RMS (framed.cuh)
 __global__ void __launch_bounds__(128) energy_rms_kernel(const float* __restrict__ x, const TrackDev* tr, float* fa) {
-    __shared__ float tiles[4][32][33];
+    __shared__ float tiles[4][2][8][33];
     const TrackDev& T = tr[blockIdx.y];
-    const uint32_t nf = T.F[0];
-    const uint32_t f0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 32;
-    if (f0 >= nf || T.status != 0) return;
-    framed_rms_warp<2048>(x + T.off + T.trim_start, T.m, T.gain, 512, f0, nf, tiles[threadIdx.x >> 5], fa + T.erms);
+    const uint32_t nf = T.F[0];  // > 0 only when the trimmed track holds a full frame
+    const uint32_t seg_first = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 8;  // 8 segments per warp (4 lanes each)
+    if (seg_first * ERMS_SEG >= nf || T.status != 0) return;
+    framed_rms_stream_warp<2048, 512, ERMS_SEG>(x + T.off + T.trim_start, T.m, T.gain, nf, seg_first, tiles[threadIdx.x >> 5], fa + T.erms);
 }
 
 // Shared peak rule of the three detectors (energy_flux.rs:176-217, spectral_flux.rs:183-210, hfc.rs:180-204).
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
 
 void launch_energy_onsets(const WaveCtx& c) {
     if (c.max_F[0] > 0) {
-        energy_rms_kernel<<<dim3((c.max_F[0] + 127) / 128, c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
+        energy_rms_kernel<<<dim3((c.max_F[0] + ERMS_SEG * 32 - 1) / (ERMS_SEG * 32), c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
         count_launch("onsets");
     }
     energy_onset_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg);

@@ -226,14 +226,19 @@ __global__ void __launch_bounds__(32) lufs_scan_kernel(const TrackDev* __restric
     }
 }
 
+constexpr int SRMS_SEG = 16;  // hop-blocks per segment of the streamed frame-RMS (framed.cuh)
 __global__ void __launch_bounds__(128) silence_rms_kernel(const float* __restrict__ x, TrackDev* tr, float* fa) {
-    __shared__ float tiles[4][32][33];
+    __shared__ float tiles[4][2][16][33];
     const int t = blockIdx.y;
     const TrackDev& T = tr[t];
     const uint32_t nf = T.Fsil;
-    const uint32_t f0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 32;
-    if (f0 >= nf) return;
-    framed_rms_warp<2048>(x + T.off, T.n, T.gain, 1024, f0, nf, tiles[threadIdx.x >> 5], fa + T.sil_rms);
+    if (T.n < 2048) {  // one short frame (silence.rs:154-169 on a track shorter than the frame): the tile scheme with its length-aware divisor
+        if (blockIdx.x == 0 && threadIdx.x < 32 && nf > 0) framed_rms_warp<2048>(x + T.off, T.n, T.gain, 1024, 0, nf, reinterpret_cast<float(*)[33]>(&tiles[0][0][0][0]), fa + T.sil_rms);
+        return;
+    }
+    const uint32_t seg_first = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 16;  // 16 segments per warp (2 lanes each)
+    if (seg_first * SRMS_SEG >= nf) return;
+    framed_rms_stream_warp<2048, 1024, SRMS_SEG>(x + T.off, T.n, T.gain, nf, seg_first, tiles[threadIdx.x >> 5], fa + T.sil_rms);
 }
 
 // detect_and_trim region logic — silence.rs:171-256.  One CTA per track.
@@ -327,7 +332,7 @@ void launch_gain(const WaveCtx& c, const float* d_lufs_gain) {
 
 void launch_silence_trim(const WaveCtx& c) {
     if (c.cfg.enable_trim && c.max_Fsil > 0) {
-        silence_rms_kernel<<<dim3((c.max_Fsil + 127) / 128, c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
+        silence_rms_kernel<<<dim3((c.max_Fsil + SRMS_SEG * 64 - 1) / (SRMS_SEG * 64), c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
         count_launch("preprocess");
     }
     trim_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);
