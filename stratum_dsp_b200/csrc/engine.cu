@@ -1699,7 +1699,11 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             }
             return true;
         };
-        bool ok = upload(0);
+        bool ok;
+        {
+            HostSpan span_first("host_first_upload");
+            ok = upload(0);
+        }
         for (size_t k = 0; ok && k < chunks.size(); ++k) {
             // chunk k-1 has been analysed (the call below is synchronous), so its buffer is free for chunk k+1
             bool up_ok = true;
@@ -1746,14 +1750,21 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 }
                 d_mono = ctx->d_conv;
             }
-            const int s2 = analyze_device(ctx->device, d_mono, rel.data(), sample_rates + ch.i, cn, c, out + ch.i);
+            int s2;
+            {
+                HostSpan span_an("host_chunk_analyze");  // wall time of the synchronous analysis call (device time + its host gaps)
+                s2 = analyze_device(ctx->device, d_mono, rel.data(), sample_rates + ch.i, cn, c, out + ch.i);
+            }
             if (s2 != STRATUM_OK) {
                 status[d] = s2;
                 errs[d] = g_last_error;
                 ok = false;
                 break;
             }
-            if (uploader.joinable()) uploader.join();
+            {
+                HostSpan span_up("host_chunk_wait_upload");  // > 0 only when the next chunk's upload outlasts this chunk's analysis
+                if (uploader.joinable()) uploader.join();
+            }
             if (!up_ok) ok = false;
         }
         cudaStreamSynchronize(ctx->copy_stream);

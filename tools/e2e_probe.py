@@ -62,11 +62,18 @@ os.environ.pop("STRATUM_B200_WAVE_MAX_TRACKS")
 for extra in sys.argv[2:]:
     k, v = extra.split("=")
     os.environ[k] = v
-for mb in (1024, 2048, 4096, 8192):
+for mb in (2048, 3876):
     os.environ["STRATUM_B200_STAGE_MB"] = str(mb)
     host_step()
     ms = min(host_step() for _ in range(2))
     print(f"host f32 {ne} tracks, stage {mb} MB: {ms:.1f} ms  ({ne / ms * 1000:.0f} tracks/s)")
+    S.stage_timing(True)
+    S.stage_times(reset=True)
+    ms = host_step()
+    st = S.stage_times(reset=True)
+    S.stage_timing(False)
+    dev = sum(v for k, v in st.items() if not k.startswith("host_"))
+    print(f"   one call {ms:.1f} ms: device stages {dev:.1f} ms; host spans:", {k: round(v, 1) for k, v in st.items() if k.startswith("host_")})
 
 # decoder-side entry: int16 PCM uploaded as is, converted on the device
 pcm = torch.empty(ne * N_SAMPLES, dtype=torch.int16, pin_memory=True)
