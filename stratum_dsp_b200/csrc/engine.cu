@@ -1270,7 +1270,24 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     // (issue slots, L1/shared pipe), so overlap only adds cache pressure.  Off unless STRATUM_B200_DUAL_STREAM is set.
     static const bool dual_stream = getenv("STRATUM_B200_DUAL_STREAM") != nullptr;
     const bool split = dual_stream && !(g_debug.load() && nt == 1) && !dcfg.key_beat_sync;  // beat-synchronous chroma reads the beat grid
-    cudaEvent_t ev_pre = nullptr, ev_key = nullptr;
+    // Late split (default): the key path and the legacy estimator are independent of the tempo path's tail, whose kernels are
+    // small latency-bound grids (one CTA or warp per track: legacy ACF/comb, the hop-256/1024 tempograms and their fusion,
+    // the final BPM, the beat tracker — about 45 ms of a 980 ms step).  The legacy estimator starts on the second stream as
+    // soon as the consensus onsets exist; the key path is forked there after the last heavy tempo kernel (the multi-resolution
+    // features), so those tails run beside the key STFT instead of in front of it.  Unlike the early split above, no two
+    // bandwidth- or issue-heavy kernels ever overlap.
+    static const bool no_late_split = getenv("STRATUM_B200_NO_LATE_SPLIT") != nullptr;
+    const bool late = !split && !no_late_split && !(g_debug.load() && nt == 1) && !dcfg.key_beat_sync;
+    cudaEvent_t ev_pre = nullptr, ev_key = nullptr, ev_legacy = nullptr;
+    bool key_forked = false;
+    auto fork_key_path = [&]() {  // late split: everything the key path needs (gain, trim) was produced long ago on s
+        if (!late || key_forked) return;
+        key_forked = true;
+        cudaEventCreateWithFlags(&ev_pre, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_key, cudaEventDisableTiming);
+        cudaEventRecord(ev_pre, s);
+        cudaStreamWaitEvent(c.key_stream, ev_pre, 0);
+    };
     auto run_key_path = [&](cudaStream_t ks) {
         WaveCtx wk = w;
         wk.stream = ks;
@@ -1310,7 +1327,21 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         launch_tempogram(w, 0, nullptr, nt);
         launch_escalation_gate(w);
     }
-    { StageTimer t(s, "legacy_bpm"); launch_legacy_bpm(w); }
+    if (late) {  // needs the consensus onsets only; its result is read by final_bpm
+        cudaEvent_t ev_on;
+        cudaEventCreateWithFlags(&ev_on, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_legacy, cudaEventDisableTiming);
+        cudaEventRecord(ev_on, s);
+        cudaStreamWaitEvent(c.key_stream, ev_on, 0);
+        cudaEventDestroy(ev_on);
+        WaveCtx wl = w;
+        wl.stream = c.key_stream;
+        { StageTimer t(c.key_stream, "legacy_bpm"); launch_legacy_bpm(wl); }
+        cudaEventRecord(ev_legacy, c.key_stream);
+    } else {
+        StageTimer t(s, "legacy_bpm");
+        launch_legacy_bpm(w);
+    }
     if (want_tempogram && dcfg.mr_enabled) {
         // escalation decision needs the host: read the records back, hand out arena slots
         CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
@@ -1345,6 +1376,11 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
                 StageTimer t(s, "multires_features");
                 launch_spec_features(w, 1, c.d_list, nl);
                 launch_spec_features(w, 2, c.d_list, nl);
+            }
+            if (late && p1 == esc.size()) {  // last heavy kernel of the tempo path is queued: the key path starts behind it
+                fork_key_path();
+                run_key_path(c.key_stream);
+                cudaEventRecord(ev_key, c.key_stream);
             }
             {
                 StageTimer t(s, "multires_tempogram");
@@ -1382,9 +1418,15 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             CUDA_OK(cudaStreamSynchronize(s));  // `pl` is a stack-owned buffer
         }
     }
+    if (late && !key_forked) {  // nothing escalated (or multi-resolution off): fork here
+        fork_key_path();
+        run_key_path(c.key_stream);
+        cudaEventRecord(ev_key, c.key_stream);
+    }
+    if (late) cudaStreamWaitEvent(s, ev_legacy, 0);
     { StageTimer t(s, "final_bpm"); launch_final_bpm(w); launch_emit_candidates(w); }
     { StageTimer t(s, "beats"); launch_beat_tracking(w); }
-    if (split) {
+    if (split || late) {
         cudaStreamWaitEvent(s, ev_key, 0);
     } else {
         run_key_path(s);
@@ -1407,6 +1449,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     cudaEventDestroy(ev1);
     if (ev_pre) cudaEventDestroy(ev_pre);
     if (ev_key) cudaEventDestroy(ev_key);
+    if (ev_legacy) cudaEventDestroy(ev_legacy);
     if (wave_ms) *wave_ms += ms;
     for (int i = 0; i < nt; ++i) fill_result(tracks[i], oa_host.data(), ia_host.data(), ms / (float)nt, &out[wp.idx[i]]);
     if (g_debug.load() && nt == 1) {
