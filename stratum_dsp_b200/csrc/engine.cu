@@ -1311,7 +1311,22 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         run_key_path(c.key_stream);
         cudaEventRecord(ev_key, c.key_stream);
     }
-    { StageTimer t(s, "onsets_energy"); launch_energy_onsets(w); }
+    cudaEvent_t ev_eon = nullptr;
+    if (late) {  // the energy-flux detector (a latency-bound add chain per frame) only feeds the consensus: beside the STFT
+        cudaEvent_t ev_trim;
+        cudaEventCreateWithFlags(&ev_trim, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_eon, cudaEventDisableTiming);
+        cudaEventRecord(ev_trim, s);
+        cudaStreamWaitEvent(c.key_stream, ev_trim, 0);
+        cudaEventDestroy(ev_trim);
+        WaveCtx we = w;
+        we.stream = c.key_stream;
+        { StageTimer t(c.key_stream, "onsets_energy"); launch_energy_onsets(we); }
+        cudaEventRecord(ev_eon, c.key_stream);
+    } else {
+        StageTimer t(s, "onsets_energy");
+        launch_energy_onsets(w);
+    }
     { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, 0, nullptr, nt); }
     { StageTimer t(s, "spec_features"); launch_spec_features(w, 0, nullptr, nt); }
     if (dcfg.hpss_onsets) {  // lib.rs:222-235: onsets of the percussive component as the fourth detector
@@ -1319,6 +1334,10 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         launch_hpss(w, nullptr, nt);
         launch_seq_features(w, SLOT_PERC, nullptr, nt);
         launch_hpss_onsets(w);
+    }
+    if (ev_eon) {
+        cudaStreamWaitEvent(s, ev_eon, 0);
+        cudaEventDestroy(ev_eon);
     }
     { StageTimer t(s, "onsets_consensus"); launch_spectral_onsets_consensus(w); }
     const bool want_tempogram = !dcfg.force_legacy;
