@@ -133,25 +133,41 @@ __device__ __forceinline__ float rem_euclid_f(float a, float b) {
 __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const float* __restrict__ mag, uint32_t lo, uint32_t hi, float fmin, float fmax,
                                            uint32_t peaks_per_frame, float tuning, float res, HpcpSmem& S, int lane, const DevCfg& cfg) {
     // local maxima in the band, compacted in ascending bin order (extractor.rs:582-606)
+    // Eight 32-bin slices at a time: their values are fetched first (eight independent loads in flight instead of three
+    // dependent ones per slice), neighbours come from the adjacent lanes / slices by shuffle, then the compare-ballot-compact
+    // chain runs on registers.
     uint32_t np = 0;
     if (lo <= hi) {
-        for (uint32_t base = lo; base <= hi; base += 32) {
-            const uint32_t b = base + lane;
-            bool pk = false;
-            float m = 0.0f;
-            if (b <= hi) {
-                m = sel[b];
-                pk = !(m <= sel[b - 1] || m < sel[b + 1]);
+        for (uint32_t base0 = lo; base0 <= hi; base0 += 256) {
+            float mv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t b = base0 + 32 * k + lane;
+                mv[k] = b <= hi + 1 ? sel[b] : 0.0f;  // hi + 1 is a valid bin (the band loop stops two bins short of the row end)
             }
-            const uint32_t mask = __ballot_sync(0xffffffffu, pk);
-            if (pk) {
-                const uint32_t pos = np + __popc(mask & ((1u << lane) - 1u));
-                if (pos < HPCP_MAX_PEAKS) {
-                    S.mag[pos] = m;
-                    S.bin[pos] = (uint16_t)b;
+            const float left_edge = sel[base0 - 1];
+            const float right_edge = base0 + 256 <= hi + 1 ? sel[base0 + 256] : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t b = base0 + 32 * k + lane;
+                const float m = mv[k];
+                float l = __shfl_up_sync(0xffffffffu, m, 1);
+                const float lc = k == 0 ? left_edge : __shfl_sync(0xffffffffu, mv[k > 0 ? k - 1 : 0], 31);
+                if (lane == 0) l = lc;
+                float r = __shfl_down_sync(0xffffffffu, m, 1);
+                const float rc = k == 7 ? right_edge : __shfl_sync(0xffffffffu, mv[k < 7 ? k + 1 : 7], 0);
+                if (lane == 31) r = rc;
+                const bool pk = b <= hi && !(m <= l || m < r);
+                const uint32_t mask = __ballot_sync(0xffffffffu, pk);
+                if (pk) {
+                    const uint32_t pos = np + __popc(mask & ((1u << lane) - 1u));
+                    if (pos < HPCP_MAX_PEAKS) {
+                        S.mag[pos] = m;
+                        S.bin[pos] = (uint16_t)b;
+                    }
                 }
+                np += __popc(mask);
             }
-            np += __popc(mask);
         }
         np = min(np, (uint32_t)HPCP_MAX_PEAKS);
     }
