@@ -257,6 +257,11 @@ int32_t stratum_b200_synth_batch(float* d_out, uint32_t n_tracks, uint64_t n_sam
 int64_t stratum_b200_debug_array(const char* name, float* out, int64_t cap);
 void stratum_b200_debug_enable(int32_t on);
 
+/* Host-side wave planner on its own (no device work): wave index of every track for an arena budget of budget_gb
+ * gigabytes; returns the number of waves.  Lets the packing logic be tested without a GPU. */
+uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg, double budget_gb,
+                                       uint32_t* wave_of_track);
+
 /* Per-stage device time (ms) accumulated since the last reset; names newline separated. */
 int32_t stratum_b200_stage_times(char* names, size_t cap, double* ms, int32_t max_stages);
 void stratum_b200_stage_times_reset(void);

@@ -1534,6 +1534,40 @@ static uint64_t esc_floats(uint64_t n) {
     return align_up(b.pos, 64);
 }
 
+// Wave packing (host logic, unit-tested through stratum_b200_debug_plan_waves): tracks are taken in order until the wave
+// reaches its sample target or the arena budget.  The target balances the remaining samples over ceil(remaining / cap)
+// waves, so a batch slightly larger than the cap does not end in a tiny (latency-bound) wave.
+struct WaveLimits {
+    uint64_t budget_floats;     // float arena budget; raised when a single track alone exceeds it
+    uint32_t wave_max;          // track-count cap
+    uint64_t wave_max_samples;  // sample cap (~0 = none)
+};
+
+static void pack_wave(uint32_t& i, uint32_t n_tracks, const uint64_t* lens, const uint32_t* srs, const StratumConfig& cfg, WaveLimits& L, WavePlan& wp) {
+    uint64_t used = 0, esc_max = 0, wave_samples = 0, remaining = 0;
+    for (uint32_t q = i; q < n_tracks; ++q) remaining += lens[q];
+    uint64_t wave_target = L.wave_max_samples;
+    if (L.wave_max_samples != ~0ull && remaining > 0) {
+        const uint64_t nw = (remaining + L.wave_max_samples - 1) / L.wave_max_samples;
+        wave_target = (remaining + nw - 1) / nw;
+    }
+    while (i < n_tracks && wp.idx.size() < L.wave_max) {
+        if (!wp.idx.empty() && wave_samples + lens[i] / 2 > wave_target) break;
+        const uint64_t need = track_floats(lens[i], srs[i], cfg);
+        const uint64_t esc = esc_floats(lens[i]);
+        const uint64_t esc_new = std::max(esc_max, esc);
+        // keep room for escalating about a quarter of the wave at a time (at least one track)
+        const uint64_t esc_room = esc_new * std::max<uint64_t>(1, (wp.idx.size() + 4) / 4);
+        if (!wp.idx.empty() && used + need + esc_room > L.budget_floats) break;
+        wave_samples += lens[i];
+        used += need;
+        esc_max = esc_new;
+        wp.idx.push_back(i);
+        ++i;
+    }
+    if (used + esc_max > L.budget_floats && wp.idx.size() == 1) L.budget_floats = used + esc_max;  // a single track larger than the budget: let cudaMalloc decide
+}
+
 static int analyze_device(int device_id, const float* d_samples, const uint64_t* offsets, const uint32_t* srs, uint32_t n_tracks, const StratumConfig& cfg,
                           StratumResult* out) {
     int st;
@@ -1576,38 +1610,12 @@ static int analyze_device(int device_id, const float* d_samples, const uint64_t*
     cudaEventCreate(&call_a);
     cudaEventCreate(&call_b);
     cudaEventRecord(call_a, ctx->stream);
+    WaveLimits lim{budget_floats, wave_max, wave_max_samples};
     while (i < n_tracks) {
         HostSpan span_pack("host_wave_pack");
         WavePlan wp;
-        uint64_t used = 0, esc_max = 0;
-        uint64_t wave_samples = 0;
-        // balanced waves: the remaining samples are spread over ceil(remaining / cap) waves, so a batch slightly larger
-        // than the cap does not end in a tiny (latency-bound) wave
-        uint64_t remaining = 0;
-        for (uint32_t q = i; q < n_tracks; ++q) remaining += lens[q];
-        uint64_t wave_target = wave_max_samples;
-        if (wave_max_samples != ~0ull && remaining > 0) {
-            const uint64_t nw = (remaining + wave_max_samples - 1) / wave_max_samples;
-            wave_target = (remaining + nw - 1) / nw;
-        }
-        while (i < n_tracks && wp.idx.size() < wave_max) {
-            if (!wp.idx.empty() && wave_samples + lens[i] / 2 > wave_target) break;
-            wave_samples += lens[i];
-            const uint64_t need = track_floats(lens[i], srs[i], cfg);
-            const uint64_t esc = esc_floats(lens[i]);
-            const uint64_t esc_new = std::max(esc_max, esc);
-            // keep room for escalating about a quarter of the wave at a time (at least one track)
-            const uint64_t esc_room = esc_new * std::max<uint64_t>(1, (wp.idx.size() + 4) / 4);
-            if (!wp.idx.empty() && used + need + esc_room > budget_floats) break;
-            used += need;
-            esc_max = esc_new;
-            wp.idx.push_back(i);
-            ++i;
-        }
-        if (used + esc_max > budget_floats && wp.idx.size() == 1) {
-            // a single track larger than the arena budget: let cudaMalloc decide
-            budget_floats = used + esc_max;
-        }
+        pack_wave(i, n_tracks, lens.data(), srs, cfg, lim, wp);
+        budget_floats = lim.budget_floats;
         span_pack.stop();
         st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out, &call_ms);
         if (st != STRATUM_OK) return st;
@@ -1848,6 +1856,24 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             return status[d];
         }
     return STRATUM_OK;
+}
+
+uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg, double budget_gb,
+                                       uint32_t* wave_of_track) {
+    StratumConfig def;
+    config_default(&def);
+    const StratumConfig& c = cfg ? *cfg : def;
+    std::vector<uint64_t> lens(n_tracks);
+    for (uint32_t q = 0; q < n_tracks; ++q) lens[q] = offsets[q + 1] - offsets[q];
+    WaveLimits lim{(uint64_t)(budget_gb * 1e9 / 4), 1u << 16, (uint64_t)128 * 7938000};
+    uint32_t i = 0, nw = 0;
+    while (i < n_tracks) {
+        WavePlan wp;
+        pack_wave(i, n_tracks, lens.data(), sample_rates, c, lim, wp);
+        for (uint32_t q : wp.idx) wave_of_track[q] = nw;
+        ++nw;
+    }
+    return nw;
 }
 
 int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg,

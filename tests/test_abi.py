@@ -161,3 +161,38 @@ def test_rust_binding_is_generated_from_the_header():
     wrapper = (ROOT / "rust" / "stratum-dsp-b200" / "src" / "lib.rs").read_text()
     for sym in re.findall(r"(stratum_b200_\w+)\(", wrapper):
         assert sym in HEADER and f"pub fn {sym}(" in rs, sym
+
+
+def _plan(lens, srs=None, budget_gb=100.0, cfg=None):
+    L = S.lib()
+    L.stratum_b200_debug_plan_waves.restype = C.c_uint32
+    n = len(lens)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(np.asarray(lens, np.uint64))
+    sr = np.full(n, 44100, np.uint32) if srs is None else np.asarray(srs, np.uint32)
+    out = np.zeros(n, np.uint32)
+    nw = L.stratum_b200_debug_plan_waves(off.ctypes.data_as(C.POINTER(C.c_uint64)), sr.ctypes.data_as(C.POINTER(C.c_uint32)), n,
+                                         C.byref(cfg._c) if cfg else None, C.c_double(budget_gb), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return nw, out
+
+
+def test_wave_planner_balances_and_respects_the_budget():
+    T3 = 7_938_000  # 3 minutes at 44.1 kHz
+    nw, w = _plan([T3] * 1024)
+    assert nw == 8 and np.bincount(w).tolist() == [128] * 8
+    nw, w = _plan([T3] * 135)                       # a little over one full wave: two balanced waves, not 128 + 7
+    assert nw == 2 and sorted(np.bincount(w).tolist()) == [67, 68]
+    nw, w = _plan([T3] * 64)
+    assert nw == 1
+    nw, w = _plan([T3 // 6] * 3000)                 # short tracks: the cap is in samples, not in tracks
+    assert nw == 4 and np.bincount(w).min() >= 700
+    nw, w = _plan([T3] * 200, budget_gb=10.0)       # a 10 GB arena holds ~25 three-minute tracks with their escalation room
+    assert nw >= 8 and np.bincount(w).max() <= 32 and np.all(np.diff(w) >= 0)
+    rng = np.random.RandomState(3)
+    lens = (np.exp(rng.uniform(np.log(30), np.log(600), 256)) * 44100).astype(np.uint64)   # C5: ragged 30 s - 10 min
+    nw, w = _plan(lens, srs=[44100, 48000] * 128)
+    assert np.all(np.diff(w) >= 0) and w[0] == 0 and w[-1] == nw - 1                       # contiguous, in order, every track placed
+    per = [int(lens[w == k].sum()) for k in range(nw)]
+    assert max(per) <= 1.5 * 128 * T3 and (nw == 1 or min(per) >= 0.3 * max(per))          # no tiny tail wave
+    nw, w = _plan([200 * T3])                       # one 10-hour track: still planned (the budget is raised for a single track)
+    assert nw == 1
