@@ -103,12 +103,17 @@ constexpr int FEAT_RUN = 32;
 constexpr int HALO = 8;  // superflux radius upper bound (the ABI rejects larger values)
 
 __global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, int h, float* fa) {
-    __shared__ float tiles[4][33][33];
+    // A warp owns 32 consecutive frames f0 .. f0+31 and produces the flux of the 31 pairs inside them: the normalised value
+    // x[f][k] / max[f] that frame f contributes as "current" is the same number frame f+1 needs as "previous", so every lane
+    // divides once and hands its quotient to the next lane by shuffle (bit-identical to dividing again, half the IEEE
+    // divisions).  Consecutive warps overlap by one frame (31 new frames per warp); the duplicated frame's E / H are the
+    // same values written twice.
+    __shared__ float tiles[4][32][33];
     const int t = list ? list[blockIdx.y] : blockIdx.y;
     const TrackDev& T = tr[t];
     const uint32_t F = T.F[h];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t f0 = (blockIdx.x * 4 + w) * 32;
+    const uint32_t f0 = (blockIdx.x * 4 + w) * 31;
     if (f0 >= F || T.status != 0) return;
     float(*tile)[33] = tiles[w];
     const HopLayout& HL = T.hop[h];
@@ -116,37 +121,34 @@ __global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const
     float* fr = fa + HL.frame;
     const uint64_t fm = HL.fmax;
     const uint32_t f = f0 + lane;
-    const bool valid = f < F, has_prev = valid && f >= 1;
+    const bool valid = f < F;
     const float maxc = valid ? fr[FQ_ROWMAX * fm + f] : 0.0f;
-    const float maxp = has_prev ? fr[FQ_ROWMAX * fm + f - 1] : 0.0f;
-    const bool nc = maxc > 1e-10f, np = maxp > 1e-10f;
+    const bool nc = maxc > 1e-10f;
     float sflux = 0.0f, E = 0.0f, H = 0.0f;
-    auto step = [&](uint32_t k, float cur, float prev) {
+    auto step = [&](uint32_t k, float cur) {
         const float xc = nc ? __fdiv_rn(cur, maxc) : 0.0f;   // spectral_flux.rs:120-157
-        const float xp = np ? __fdiv_rn(prev, maxp) : 0.0f;
+        const float xp = __shfl_up_sync(0xffffffffu, xc, 1);  // the previous frame's normalised bin (lane 0: unused)
         const float d0 = fmaxf(__fsub_rn(xc, xp), 0.0f);
         sflux = __fadd_rn(sflux, __fmul_rn(d0, d0));
         E = __fadd_rn(E, __fmul_rn(cur, cur));
         H = __fadd_rn(H, __fmul_rn(__fmul_rn((float)k, cur), cur));  // hfc.rs:137
     };
     for (uint32_t jb = 0; jb < 32; ++jb) {
-#pragma unroll 3
-        for (int r = 0; r < 33; ++r) {
-            const int64_t fr_ = (int64_t)f0 - 1 + r;
-            tile[r][lane] = (fr_ >= 0 && fr_ < (int64_t)F) ? spec[(uint64_t)fr_ * 1025 + jb * 32 + lane] : 0.0f;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const uint32_t fr_ = f0 + r;
+            tile[r][lane] = fr_ < F ? spec[(uint64_t)fr_ * 1025 + jb * 32 + lane] : 0.0f;
         }
         __syncwarp();
 #pragma unroll 4
-        for (int j = 0; j < 32; ++j) step(jb * 32 + j, tile[lane + 1][j], tile[lane][j]);
+        for (int j = 0; j < 32; ++j) step(jb * 32 + j, tile[lane][j]);
         __syncwarp();
     }
+    step(1024, valid ? spec[(uint64_t)f * 1025 + 1024] : 0.0f);  // all lanes: the shuffle inside is warp-wide
     if (valid) {
-        const float cur = spec[(uint64_t)f * 1025 + 1024];
-        const float prev = has_prev ? spec[(uint64_t)(f - 1) * 1025 + 1024] : 0.0f;
-        step(1024, cur, prev);
         fr[FQ_E * fm + f] = E;
         fr[FQ_H * fm + f] = H;
-        if (has_prev) fa[HL.pair + PQ_SFLUX * fm + f - 1] = __fadd_rn(sqrtf(sflux), 0.0f);
+        if (lane >= 1) fa[HL.pair + PQ_SFLUX * fm + f - 1] = __fadd_rn(sqrtf(sflux), 0.0f);
     }
 }
 
@@ -483,7 +485,7 @@ void launch_hpss_onsets(const WaveCtx& c) {
 
 void launch_seq_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (c.max_F[h] == 0 || n_list == 0) return;
-    dim3 grid((c.max_F[h] + 127) / 128, n_list);
+    dim3 grid((c.max_F[h] + 123) / 124, n_list);  // 4 warps x 31 new frames
     seq_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
     count_launch("spec_features");
 }
@@ -491,7 +493,7 @@ void launch_seq_features(const WaveCtx& c, int h, const int32_t* d_list, int n_l
 void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (c.max_F[h] == 0 || n_list == 0) return;
     dim3 grid((c.max_F[h] + 127) / 128, n_list);
-    seq_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
+    seq_feat_kernel<<<dim3((c.max_F[h] + 123) / 124, n_list), 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
     count_launch("spec_features");
     par_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
     count_launch("spec_features");
