@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tracks", type=int, default=1024, help="tracks per GPU and step (BASELINE.json configs[1]: 1024)")
-    ap.add_argument("--e2e-tracks", type=int, default=512, help="tracks per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-tracks", type=int, default=1024, help="tracks per step of the host-buffer (e2e) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
