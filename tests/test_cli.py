@@ -121,3 +121,58 @@ def test_analyze_file_cli_end_to_end(tmp_path):
     assert len(doc["bpm_candidates"]) == len(r.metadata.tempogram_candidates) >= 1
     assert [cd["selected"] for cd in doc["bpm_candidates"]] == [bool(t[4]) for t in r.metadata.tempogram_candidates]
     assert list(doc)[:6] == ["bpm", "bpm_confidence", "key", "key_confidence", "key_clarity", "grid_stability"] and list(doc)[-1] == "processing_time_ms"
+
+
+def _build_cpp_example():
+    import subprocess
+
+    subprocess.run(["make", "-s", "-C", str(ROOT / "stratum_dsp_b200"), "example"], check=True)
+    return ROOT / "stratum_dsp_b200" / "_build" / "analyze_batch"
+
+
+def _write_wav(path, x, sr=44100, channels=1):
+    pcm = np.clip(np.round(np.asarray(x, np.float64) * 32768.0), -32768, 32767).astype("<i2")
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(channels)
+        w.setsampwidth(2)
+        w.setframerate(sr)
+        w.writeframes(pcm.tobytes())
+    return pcm
+
+
+def test_cpp_example_links_against_the_c_abi_and_fails_loudly_without_a_device(tmp_path):
+    # compiled host code over include/stratum_b200.h alone (what a Rust / Go / Java binding would link): builds, prints usage,
+    # and on a box without a GPU reports the library's error instead of computing anything on the CPU
+    import subprocess
+
+    import stratum_dsp_b200 as S
+
+    exe = _build_cpp_example()
+    assert subprocess.run([str(exe), "--help"], capture_output=True, text=True).returncode == 0
+    if S.device_count() == 0:
+        _write_wav(tmp_path / "a.wav", 0.3 * np.sin(2 * np.pi * 440 * np.arange(44100) / 44100))
+        out = subprocess.run([str(exe), "--json", str(tmp_path / "a.wav")], capture_output=True, text=True)
+        assert out.returncode == 1 and "no CPU fallback" in out.stderr and out.stdout == ""
+
+
+@pytest.mark.gpu
+def test_cpp_example_matches_the_python_mirror(tmp_path):
+    import json
+    import subprocess
+
+    import stratum_dsp_b200 as S
+    import synth
+
+    exe = _build_cpp_example()
+    xs = [synth.render(synth.c2_params(31, 10 * 44100, 44100)), synth.render(synth.c2_params(32, 8 * 44100, 44100))]
+    pcms = [_write_wav(tmp_path / f"t{i}.wav", x) for i, x in enumerate(xs)]
+    out = subprocess.run([str(exe), "--json"] + [str(tmp_path / f"t{i}.wav") for i in range(2)] + [str(tmp_path / "missing.wav")], capture_output=True, text=True)
+    lines = [json.loads(l) for l in out.stdout.splitlines()]
+    assert len(lines) == 3 and out.returncode == 1                      # one file could not be read: reported per item, the batch went on
+    assert lines[2]["file"].endswith("missing.wav") and lines[2]["error"].startswith("decode failed:")
+    for doc, pcm in zip(lines, pcms):
+        r = S.analyze_audio(pcm.astype(np.float32) / np.float32(32768.0), 44100)
+        c = S.compute_confidence(r)
+        assert doc["bpm"] == float(f"{r.bpm:.2f}") and doc["key"] == r.key.name() and doc["bpm_confidence"] == float(f"{c.bpm_confidence:.4f}")
+        assert list(doc) == ["file", "bpm", "bpm_confidence", "key", "key_confidence", "processing_time_ms", "tempogram_multi_res_triggered",
+                             "tempogram_multi_res_used", "tempogram_percussive_triggered", "tempogram_percussive_used"]
