@@ -206,3 +206,21 @@ def test_hpss_known_answers():
     spec[:, 30] = 1.0
     assert L.so_hpss_decompose(O.f32ptr(spec), 40, 64, 10, O.f32ptr(h), O.f32ptr(p)) == 0
     assert h[:, 30].sum() > 10 * p[:, 30].sum()
+
+
+def test_tuning_estimate_recovers_a_known_detune():
+    # estimate_tuning_offset_semitones_from_spectrogram (chroma/extractor.rs:66-170) has no unit test in the reference; its
+    # intent is checkable: material detuned by +/-30 cents must come out near +/-0.3 semitones, and the clamp of
+    # lib.rs:1109-1113 must hold it at key_tuning_max_abs_semitones
+    import synth
+
+    for cents in (30.0, -30.0):
+        x = synth.render_progression(7, 12, 44100, tonic=0, minor=False, bpm=120, detune_cents=cents)
+        o = O.analyze(x, 44100, {"enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5}, dump=True, fast=True)
+        t = float(o.farray("key.tuning")[0])
+        assert abs(t - cents / 100.0) < 0.06, (cents, t)
+        o = O.analyze(x, 44100, {"enable_key_tuning_compensation": 1}, dump=True, fast=True)
+        assert float(o.farray("key.tuning")[0]) == pytest.approx(np.sign(cents) * 0.08, abs=1e-7)
+    x = synth.render_progression(7, 12, 44100, tonic=0, minor=False, bpm=120, detune_cents=0.0)
+    o = O.analyze(x, 44100, {"enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5}, dump=True, fast=True)
+    assert abs(float(o.farray("key.tuning")[0])) < 0.1  # bin-centre quantisation leaves a small bias
