@@ -12,7 +12,7 @@
 namespace sb {
 
 // frame-region layout (q * fmax + t): 0 rowmax, 1 E, 2 H, 3..5 E_low/mid/high, 6..8 H_low/mid/high
-constexpr int FQ_ROWMAX = 0, FQ_E = 1, FQ_H = 2, FQ_EB = 3, FQ_HB = 6, FQ_MEL = 9;
+constexpr int FQ_ROWMAX = 0, FQ_E = 1, FQ_H = 2, FQ_EB = 3, FQ_HB = 6;
 // pair-region layout: 0 onset spectral flux, 1 SF_full, 2..4 SF_low/mid/high, 5 SF_mel
 constexpr int PQ_SFLUX = 0, PQ_SF = 1, PQ_SFB = 2, PQ_MEL = 5;
 constexpr int MEL_MAX = 40;
@@ -334,7 +334,7 @@ __device__ __forceinline__ uint32_t count_less(const int32_t* a, uint32_t n, int
 __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* ia, int n_tracks, DevCfg cfg) {
     extern __shared__ int32_t cs[];
     __shared__ uint32_t sc[34];
-    __shared__ uint32_t s_nfinal, s_strong;
+    __shared__ uint32_t s_strong;
     const int t = blockIdx.x;
     if (t >= n_tracks) return;
     TrackDev& T = tr[t];

@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(256) score_kernel(TrackDev* tr, const int32_t*
         if (threadIdx.x == 0) { ntop_fft[v] = c1; ntop_ac[v] = c2; }
     }
     __syncthreads();
-    const float* ac_full = fa + HL.tgac;
     const float fft_primary = ntop_fft[0] > 0 ? fft_bpm(fl[0], (uint32_t)top_fft[0][0]) : 0.0f;
     const float ac_primary = ntop_ac[0] > 0 ? acb[top_ac[0][0]] : 0.0f;
     if (threadIdx.x == 0) {
