@@ -34,6 +34,13 @@ def read_wav_pcm16(path: str):
     return (x.reshape(-1, ch) if ch > 1 else x), sr
 
 
+def _display(e) -> str:
+    """Display of AnalysisError (src/error.rs:24-34)."""
+    names = {"InvalidInput": "Invalid input", "DecodingError": "Decoding error", "ProcessingError": "Processing error", "NotImplemented": "Not implemented",
+             "NumericalError": "Numerical error"}
+    return f"{names.get(e.kind, e.kind)}: {e.message}"
+
+
 def percentile(xs, p):
     xs = sorted(xs)
     idx = int(round((len(xs) - 1) * min(max(p, 0.0), 1.0)))
@@ -77,17 +84,18 @@ def main(argv):
     times = []
     for i, p in enumerate(paths):
         r = results.get(i)
-        err = errors.get(i) or (str(r.error.message) if r is not None and r.error is not None else None)
+        err = ("decode failed: " + errors[i]) if i in errors else (("analysis failed: " + _display(r.error)) if r is not None and r.error is not None else None)
         if err is None:
             m = r.metadata
+            c = S.compute_confidence(r)  # the reference prints compute_confidence's values (analyze_batch.rs:271-279)
             times.append(m.processing_time_ms)
             if as_json:
-                print("{" + f'"file":{json.dumps(p)},"bpm":{r.bpm:.2f},"bpm_confidence":{r.bpm_confidence:.4f},"key":{json.dumps(r.key.name())},'
-                      f'"key_confidence":{r.key_confidence:.4f},"processing_time_ms":{m.processing_time_ms:.2f},'
+                print("{" + f'"file":{json.dumps(p)},"bpm":{r.bpm:.2f},"bpm_confidence":{c.bpm_confidence:.4f},"key":{json.dumps(r.key.name())},'
+                      f'"key_confidence":{c.key_confidence:.4f},"processing_time_ms":{m.processing_time_ms:.2f},'
                       f'"tempogram_multi_res_triggered":{opt(m.tempogram_multi_res_triggered)},"tempogram_multi_res_used":{opt(m.tempogram_multi_res_used)},'
                       f'"tempogram_percussive_triggered":{opt(m.tempogram_percussive_triggered)},"tempogram_percussive_used":{opt(m.tempogram_percussive_used)}' + "}")
             else:
-                print(f"[{i + 1}/{len(paths)}] {p}: BPM={r.bpm:.2f} (conf={r.bpm_confidence:.3f}) Key={r.key.name()} (conf={r.key_confidence:.3f}) "
+                print(f"[{i + 1}/{len(paths)}] {p}: BPM={r.bpm:.2f} (conf={c.bpm_confidence:.3f}) Key={r.key.name()} (conf={c.key_confidence:.3f}) "
                       f"time={m.processing_time_ms:.2f}ms")
         elif as_json:
             print("{" + f'"file":{json.dumps(p)},"error":{json.dumps(err)}' + "}")
