@@ -257,6 +257,10 @@ int32_t stratum_b200_synth_batch(float* d_out, uint32_t n_tracks, uint64_t n_sam
 int64_t stratum_b200_debug_array(const char* name, float* out, int64_t cap);
 void stratum_b200_debug_enable(int32_t on);
 
+/* Measured FP32 FMA rate of the device in TFLOP/s (8 independent chains per thread, 2 flops per FMA): the second
+ * roofline denominator of bench.py (the path is FP32-bound).  0 when no device is usable. */
+double stratum_b200_fp32_peak_tflops(int32_t device_id);
+
 /* Host-side wave planner on its own (no device work): wave index of every track for an arena budget of budget_gb
  * gigabytes; returns the number of waves.  Lets the packing logic be tested without a GPU. */
 uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg, double budget_gb,

@@ -2097,6 +2097,19 @@ int64_t stratum_b200_stft(const float* samples, uint64_t n, uint32_t frame_size,
     return frames;
 }
 
+double stratum_b200_fp32_peak_tflops(int32_t device_id) {
+    int st;
+    DeviceCtx* ctx = get_ctx(device_id, &st);
+    if (!ctx) return 0.0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return 0.0;
+    float* d = nullptr;
+    if (cudaMalloc(&d, 256) != cudaSuccess) return 0.0;
+    const double tf = measure_fp32_peak_tflops(ctx->stream, d);
+    cudaFree(d);
+    return tf;
+}
+
 int32_t stratum_b200_synth_batch(float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sample_rate, const float* params5, int32_t device_id) {
     int st;
     DeviceCtx* ctx = get_ctx(device_id, &st);

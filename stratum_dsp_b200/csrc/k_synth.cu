@@ -66,6 +66,37 @@ void launch_pcm16_to_mono(cudaStream_t s, const int16_t* d_pcm, float* d_out, co
     count_launch("pcm16");
 }
 
+// FP32 FMA microbenchmark for the second roofline denominator (the non-tensor FP32 peak is not in
+// MEASURED_PEAKS.json): 8 independent FMA chains per thread, 2 flops per FMA.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.0f, a2 = a0 + 2.0f, a3 = a0 + 3.0f, a4 = a0 + 4.0f, a5 = a0 + 5.0f, a6 = a0 + 6.0f, a7 = a0 + 7.0f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+        a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456f) out[0] = r;  // keeps the chains alive
+}
+
+double measure_fp32_peak_tflops(cudaStream_t s, float* d_scratch) {
+    const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+    fma_peak_kernel<<<blocks, threads, 0, s>>>(d_scratch, 1 << 8);  // warm-up
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    fma_peak_kernel<<<blocks, threads, 0, s>>>(d_scratch, iters);
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    if (!(ms > 0.0f)) return 0.0;
+    return (double)blocks * threads * 8.0 * 2.0 * iters / (ms * 1e-3) / 1e12;
+}
+
 void launch_synth(cudaStream_t s, float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sr, const float* d_params5) {
     if (n_tracks == 0 || n_samples == 0) return;
     unsigned gx = (unsigned)((n_samples + 256 * 16 - 1) / (256 * 16));
