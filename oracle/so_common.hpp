@@ -27,6 +27,18 @@ namespace so {
 // f32::max / f32::min ignore NaN; for non-NaN inputs they are plain max/min.
 static inline float fmax_rs(float a, float b) { return (a != a) ? b : ((b != b) ? a : (a > b ? a : b)); }
 static inline float fmin_rs(float a, float b) { return (a != a) ? b : ((b != b) ? a : (a < b ? a : b)); }
+// f32::powi with a run-time exponent: llvm.powi.f32 -> compiler-rt __powisf2 (square-and-multiply, reciprocal for b < 0)
+static inline float powi_rs(float a, int b) {
+    const bool recip = b < 0;
+    float r = 1.0f;
+    for (;;) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0f / r : r;
+}
 static inline float clamp_rs(float x, float lo, float hi) {
     // f32::clamp: NaN stays NaN; else if x < lo -> lo; if x > hi -> hi.
     if (x < lo) return lo;

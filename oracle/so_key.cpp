@@ -140,9 +140,9 @@ static void frame_to_hpcp_band(const float* mag, size_t nb, uint32_t sr, size_t 
             float spc = rem_euclid(semitone, 12.0f);
             float ppc = rem_euclid(roundf(spc), 12.0f);
             int primary = as_i32(ppc);
-            // decay.powi(h-1): repeated multiplication (powi lowers to llvm.powi: x*x*...)
-            float dp = 1.0f;
-            for (size_t i = 1; i < h; ++i) dp *= decay;
+            // decay.powi(h-1): llvm.powi.f32 with a run-time exponent lowers to compiler-rt's __powisf2, square-and-multiply
+            // (identical to a left-to-right product up to h = 4, the default; different roundings from h = 5 on)
+            float dp = powi_rs(decay, (int)h - 1);
             float hw = dp / (float)h;
             float contrib = w0 * hw;
             for (int off = -1; off <= 1; ++off) {

@@ -75,7 +75,7 @@ fn opt_bool(v: i32) -> Option<bool> {
 }
 
 /// One `StratumResult` to the reference's `AnalysisResult` (built like `src/lib.rs:1592-1619`).
-fn from_c(r: &StratumResult, cfg: &AnalysisConfig) -> AnalysisResult {
+fn from_c(r: &StratumResult, _cfg: &AnalysisConfig) -> AnalysisResult {
     let mut wbuf = [0 as c_char; 2048];
     unsafe { stratum_b200_warning_strings(r, wbuf.as_mut_ptr(), wbuf.len()) };
     // the exact strings of lib.rs:1567-1589 — compute_confidence matches on them (confidence.rs:231-297)
@@ -103,11 +103,8 @@ fn from_c(r: &StratumResult, cfg: &AnalysisConfig) -> AnalysisResult {
                 .collect(),
         )
     };
-    let mut methods_used = vec!["energy_flux".to_string()]; // lib.rs:1604-1608
-    if cfg.enable_onset_consensus {
-        methods_used.push("spectral_flux".to_string());
-        methods_used.push("hfc".to_string());
-    }
+    // the same three strings for every track, whatever the configuration (lib.rs:1604-1608)
+    let methods_used = vec!["energy_flux".to_string(), "chroma_extraction".to_string(), "key_detection".to_string()];
     AnalysisResult {
         bpm: r.bpm,
         bpm_confidence: r.bpm_confidence,
@@ -180,7 +177,9 @@ pub fn analyze_batch(tracks: &[&[f32]], sample_rates: &[u32], config: AnalysisCo
                                    if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() }, devices.len() as u32, res.as_mut_ptr())
     };
     if st != 0 {
-        return Err(to_error(st, last_error()));
+        let e = to_error(st, last_error());
+        unsafe { stratum_b200_result_free(res.as_mut_ptr(), n as u32) }; // waves that completed before the error own heap arrays
+        return Err(e);
     }
     let out = res.iter().map(|r| if r.status == 0 { Ok(from_c(r, &config)) } else { Err(to_error(r.status, c_string(&r.error))) }).collect();
     unsafe { stratum_b200_result_free(res.as_mut_ptr(), n as u32) };
@@ -210,7 +209,9 @@ pub fn analyze_batch_pcm16(tracks: &[&[i16]], sample_rates: &[u32], channels: &[
                                          if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() }, devices.len() as u32, res.as_mut_ptr())
     };
     if st != 0 {
-        return Err(to_error(st, last_error()));
+        let e = to_error(st, last_error());
+        unsafe { stratum_b200_result_free(res.as_mut_ptr(), n as u32) }; // waves that completed before the error own heap arrays
+        return Err(e);
     }
     let out = res.iter().map(|r| if r.status == 0 { Ok(from_c(r, &config)) } else { Err(to_error(r.status, c_string(&r.error))) }).collect();
     unsafe { stratum_b200_result_free(res.as_mut_ptr(), n as u32) };

@@ -302,6 +302,11 @@ class AnalysisMetadata:
     tempogram_candidates: list | None = None  # [(bpm, score, fft_norm, autocorr_norm, selected)] when emit_tempogram_candidates
 
 
+# AnalysisMetadata literals the reference writes at lib.rs:1603-1608 (the same three strings for every track)
+ALGORITHM_VERSION = "0.1.0-alpha"
+METHODS_USED = ("energy_flux", "chroma_extraction", "key_detection")
+
+
 @dataclass
 class AnalysisConfidence:
     bpm_confidence: float
@@ -353,7 +358,7 @@ def _convert(r: StratumResult) -> AnalysisResult:
     L = lib()
     if r.status != OK:
         err = AnalysisError(r.status, r.error.decode(errors="replace"))
-        meta = AnalysisMetadata(0.0, 0, 0.0, "0.1.0-alpha", 0.0, [], [], [], None, None, None, None)
+        meta = AnalysisMetadata(0.0, 0, 0.0, ALGORITHM_VERSION, 0.0, [], [], [], None, None, None, None)
         return AnalysisResult(0.0, 0.0, Key(False, 0), 0.0, 0.0, BeatGrid(np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float32)),
                               0.0, meta, error=err)
     wb = C.create_string_buffer(2048)
@@ -361,8 +366,8 @@ def _convert(r: StratumResult) -> AnalysisResult:
     warnings = [w for w in wb.value.decode().split("\n") if w]
     meta = AnalysisMetadata(
         duration_seconds=r.duration_seconds, sample_rate=r.sample_rate, processing_time_ms=r.processing_time_ms,
-        algorithm_version="0.1.0-alpha", onset_method_consensus=r.onset_method_consensus,
-        methods_used=["energy_flux", "autocorrelation", "comb_filterbank"],  # lib.rs:1604-1608
+        algorithm_version=ALGORITHM_VERSION, onset_method_consensus=r.onset_method_consensus,
+        methods_used=list(METHODS_USED),  # lib.rs:1604-1608
         flags=_flags(r.flags), confidence_warnings=warnings,
         tempogram_multi_res_triggered=_opt(r.tempogram_multi_res_triggered), tempogram_multi_res_used=_opt(r.tempogram_multi_res_used),
         tempogram_percussive_triggered=_opt(r.tempogram_percussive_triggered), tempogram_percussive_used=_opt(r.tempogram_percussive_used),
@@ -404,6 +409,13 @@ def compute_confidence(result: AnalysisResult) -> AnalysisConfidence:
     return AnalysisConfidence(out.bpm_confidence, out.key_confidence, out.grid_stability, out.overall_confidence, _flags(out.flags))
 
 
+def _fail(st: int, res, n: int):
+    """Batch-level error: results of waves that completed before it own heap arrays — release them, then raise."""
+    msg = last_error()
+    lib().stratum_b200_result_free(res, n)
+    raise AnalysisError(st, msg)
+
+
 def _collect(res, n) -> list:
     try:
         return [_convert(res[i]) for i in range(n)]
@@ -439,7 +451,7 @@ def analyze_batch_packed(samples: np.ndarray, offsets: np.ndarray, sample_rates:
     st = lib().stratum_b200_analyze_batch(samples.ctypes.data if samples.size else None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
                                           srs.ctypes.data_as(C.POINTER(_u)), n, _cfg_ptr(config), dev, len(devices) if devices else 0, res)
     if st != OK:
-        _raise(st)
+        _fail(st, res, n)
     return _collect(res, n)
 
 
@@ -464,7 +476,7 @@ def analyze_batch_pcm16(tracks: Sequence, sample_rates: int | Iterable[int], con
                                                 srs.ctypes.data_as(C.POINTER(_u)), chans.ctypes.data_as(C.POINTER(_u)), n, _cfg_ptr(config), dev,
                                                 len(devices) if devices else 0, res)
     if st != OK:
-        _raise(st)
+        _fail(st, res, n)
     return _collect(res, n)
 
 
@@ -480,7 +492,7 @@ def analyze_batch_device(d_samples_ptr: int, offsets: np.ndarray, sample_rates: 
     st = lib().stratum_b200_analyze_batch_device(C.c_void_p(d_samples_ptr), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                  srs.ctypes.data_as(C.POINTER(_u)), n, _cfg_ptr(config), device, res)
     if st != OK:
-        _raise(st)
+        _fail(st, res, n)
     if not convert:
         return res
     return _collect(res, n)

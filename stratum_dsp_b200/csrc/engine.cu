@@ -11,6 +11,11 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <future>
+#include <memory>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +29,8 @@
 #include "key_rows.cuh"
 
 namespace sb {
+
+static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // ---- errors ---------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
@@ -73,10 +80,10 @@ struct StageTimer {
     }
 };
 
-static void resolve_stage_times() {  // call after the stream has been synchronised
-    if (g_pending.empty()) return;
+static void resolve_stage_times(std::vector<PendingStage>& pending) {  // call once the wave that recorded them has completed
+    if (pending.empty()) return;
     std::lock_guard<std::mutex> lk(g_stage_mu);
-    for (PendingStage& p : g_pending) {
+    for (PendingStage& p : pending) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
             if (!g_stage_ms.count(p.name)) g_stage_order.push_back(p.name);
@@ -85,7 +92,7 @@ static void resolve_stage_times() {  // call after the stream has been synchroni
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
     }
-    g_pending.clear();
+    pending.clear();
 }
 
 // Host-side time during which the device has nothing queued (planning, the escalation round trip, result gathering):
@@ -114,6 +121,92 @@ static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // host<->device t
 static std::atomic<int> g_debug{0};
 static std::mutex g_debug_mu;
 static std::map<std::string, std::vector<float>> g_debug_arrays;
+
+// Grow-only pinned host buffer (asynchronous copy source / target).
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* need(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            const size_t n = bytes + bytes / 2 + 4096;
+            if (cudaHostAlloc(&p, n, cudaHostAllocDefault) != cudaSuccess) {
+                p = nullptr;
+                return nullptr;
+            }
+            cap = n;
+        }
+        return p;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// One long-lived helper thread per device (the sample uploads of host batches): tasks run in order.
+class Worker {
+public:
+    Worker() : th_([this] { run(); }) {}
+    ~Worker() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        if (th_.joinable()) th_.join();
+    }
+    std::future<bool> post(std::function<bool()> f) {
+        std::packaged_task<bool()> task(std::move(f));
+        std::future<bool> fut = task.get_future();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            q_.push_back(std::move(task));
+        }
+        cv_.notify_one();
+        return fut;
+    }
+
+private:
+    void run() {
+        for (;;) {
+            std::packaged_task<bool()> task;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return quit_ || !q_.empty(); });
+                if (q_.empty()) return;
+                task = std::move(q_.front());
+                q_.pop_front();
+            }
+            task();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::packaged_task<bool()>> q_;
+    bool quit_ = false;
+    std::thread th_;
+};
+
+// A wave whose launches are queued and whose results have not been gathered yet.  Two slots per device context: while wave k
+// runs, the host gathers wave k-1 and plans wave k+1.  The read-back targets are pinned, so the final copies are
+// asynchronous and the stream keeps running into the next wave.
+struct WaveJob {
+    bool active = false;
+    int nt = 0;
+    std::vector<uint32_t> idx;
+    std::vector<std::string> track_err;  // message of a failure found while planning a track (unsupported sample rate ...)
+    PinnedBuf h_tracks, h_oa, h_ia, h_small;
+    uint64_t oa_n = 0, ia_n = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of the wave
+    StratumResult* out = nullptr;
+    std::vector<PendingStage> stages;
+    bool debug_single = false;
+    DevCfg dcfg{};
+};
 
 // ---- per-device context ------------------------------------------------------------------------------
 struct DeviceCtx {
@@ -144,9 +237,15 @@ struct DeviceCtx {
     size_t stage_cap = 0;  // bytes
     float* d_conv = nullptr;  // mono f32 buffer the PCM16 chunks are converted into
     size_t conv_cap = 0;   // bytes
-    char* d_meta = nullptr;   // per-chunk offset / channel tables of the PCM16 path
+    char* d_meta = nullptr;   // per-chunk offset / channel tables of the PCM16 path (two sets)
     size_t meta_cap = 0;
-    std::mutex mu;
+    PinnedBuf h_meta[2];      // their pinned host images
+    int32_t* d_count = nullptr;  // escalated tracks of the wave being queued (escalation_compact_kernel)
+    PinnedBuf h_count;
+    cudaEvent_t ev_legacy = nullptr;  // legacy estimator finished on the key stream
+    WaveJob jobs[2];          // two wave slots (one queued ahead of the gather)
+    std::unique_ptr<Worker> uploader;
+    std::recursive_mutex mu;  // one call at a time per device; held for a whole batch call (upload, conversion, analysis)
 };
 
 static std::mutex g_ctx_mu;
@@ -248,6 +347,8 @@ static int ctx_init(DeviceCtx& c, int device) {
     c.tab.key_major_tp = dev_upload(c, mj);
     c.tab.key_minor_tp = dev_upload(c, mn);
     CUDA_OK(cudaMalloc(&c.d_srtab, sizeof(SrTables) * DeviceCtx::MAX_SR));
+    CUDA_OK(cudaMalloc(&c.d_count, sizeof(int32_t) * 4));
+    CUDA_OK(cudaEventCreateWithFlags(&c.ev_legacy, cudaEventDisableTiming));
     if (!c.tab.tw1024 || !c.tab.tw4096 || !c.tab.ptw1024 || !c.tab.ptw4096 || !c.tab.rw2048 || !c.tab.rw8192 || !c.tab.win2048 || !c.tab.win8192 || !c.tab.key_major || !c.tab.key_minor ||
         !c.tab.key_major_tp || !c.tab.key_minor_tp) {
         set_error("device table allocation failed");
@@ -299,6 +400,62 @@ static uint32_t hz_to_bin(float hz, float res, uint32_t n_bins) {  // period/tem
     long hi = (long)n_bins - 1;
     if (hi < 0) hi = 0;
     return (uint32_t)std::max<long>(0, std::min<long>(b, hi));
+}
+
+// Bins b in [1, key_bins - 2] with fmin <= b * res <= fmax, the peak-search range of frame_to_hpcp (chroma/extractor.rs:584-591);
+// lo > hi = empty.
+static void hpcp_band_bins(uint32_t sr, uint32_t key_frame, float fmin, float fmax, uint32_t* lo_out, uint32_t* hi_out) {
+    const uint32_t key_bins = key_frame / 2 + 1;
+    const float res = (float)sr / (float)key_frame;
+    uint32_t lo = 1, hi = 0;
+    if (fmax > fmin) {
+        lo = 0;
+        for (uint32_t b = 1; b + 1 < key_bins; ++b) {
+            const float f = (float)b * res;
+            if (f < fmin) continue;
+            if (f > fmax) break;
+            if (lo == 0) lo = b;
+            hi = b;
+        }
+        if (lo == 0) {
+            lo = 1;
+            hi = 0;
+        }
+    }
+    *lo_out = lo;
+    *hi_out = hi;
+}
+
+// Columns of the compact masked band (k_key.cu, key_compact): the HPCP peak search reads one bin either side of its band(s); the
+// first column is rounded down to a multiple of 32 bins so that a warp of the mask kernel stores one full 128-byte line.
+static void compact_band(uint32_t sr, const StratumConfig& cfg, uint32_t key_frame, uint32_t* lo_out, uint32_t* stride_out) {
+    const uint32_t key_bins = key_frame / 2 + 1;
+    const float nyq = (float)sr / 2.0f;
+    uint32_t lo, hi;
+    hpcp_band_bins(sr, key_frame, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), &lo, &hi);
+    if (cfg.enable_key_hpcp_bass_blend) {
+        uint32_t bl, bh;
+        hpcp_band_bins(sr, key_frame, fmaxf(cfg.key_hpcp_bass_fmin_hz, 20.0f), fminf(cfg.key_hpcp_bass_fmax_hz, nyq), &bl, &bh);
+        if (bl <= bh) {
+            if (lo > hi) { lo = bl; hi = bh; }
+            else { lo = std::min(lo, bl); hi = std::max(hi, bh); }
+        }
+    }
+    if (lo > hi) {
+        *lo_out = 0;
+        *stride_out = 32;
+        return;
+    }
+    const uint32_t first = (lo - 1) & ~31u;
+    const uint32_t end = std::min(hi + 2, key_bins);  // one past the last column read
+    *lo_out = first;
+    *stride_out = (uint32_t)align_up(end - first, 32);
+}
+
+static bool key_compact_mode(const StratumConfig& c) {  // see DevCfg::key_compact
+    const bool mask_runs = !c.enable_key_hpss_harmonic && (c.enable_key_harmonic_mask || (c.enable_key_spectrogram_time_smoothing && c.key_spectrogram_smooth_margin > 0));
+    return mask_runs && c.enable_key_hpcp && !c.enable_key_log_frequency && !c.enable_key_beat_synchronous && !c.enable_key_hpcp_whitening &&
+           !c.enable_key_tuning_compensation;
 }
 
 static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slot_out) {
@@ -393,49 +550,14 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
     st.mel_bin = dev_upload(c, mel_bin);
     st.mel_w = dev_upload(c, mel_w);
     // HPCP band in key-STFT bins — chroma/extractor.rs:584-591 (b from 1 to n_bins-2)
-    {
-        const float res = (float)sr / (float)key_frame;
-        const float fmin = fmaxf(100.0f, 20.0f), fmax = fminf(5000.0f, (float)sr / 2.0f);
-        uint32_t lo = 1, hi = 0;
-        if (fmax > fmin) {
-            lo = 0;
-            for (uint32_t b = 1; b + 1 < key_bins; ++b) {
-                const float f = (float)b * res;
-                if (f < fmin) continue;
-                if (f > fmax) break;
-                if (lo == 0) lo = b;
-                hi = b;
-            }
-            if (lo == 0) {
-                lo = 1;
-                hi = 0;
-            }
-        }
-        st.key_bin_lo = lo;
-        st.key_bin_hi = hi;
-    }
+    hpcp_band_bins(sr, key_frame, fmaxf(100.0f, 20.0f), fminf(5000.0f, (float)sr / 2.0f), &st.key_bin_lo, &st.key_bin_hi);
     {   // bands and tables of the optional key-path variants, key-STFT bins
         const float res = (float)sr / (float)key_frame;
         const float nyq = (float)sr / 2.0f;
         // bass-band HPCP: same peak loop as above on [bass_fmin, bass_fmax] (extractor.rs:1206-1220 -> 551-556, 584-591)
         st.bass_fmin = fmaxf(cfg.key_hpcp_bass_fmin_hz, 20.0f);
         st.bass_fmax = fminf(cfg.key_hpcp_bass_fmax_hz, nyq);
-        st.bass_bin_lo = 1;
-        st.bass_bin_hi = 0;
-        if (st.bass_fmax > st.bass_fmin) {
-            uint32_t lo = 0, hi = 0;
-            for (uint32_t b = 1; b + 1 < key_bins; ++b) {
-                const float f = (float)b * res;
-                if (f < st.bass_fmin) continue;
-                if (f > st.bass_fmax) break;
-                if (lo == 0) lo = b;
-                hi = b;
-            }
-            if (lo != 0) {
-                st.bass_bin_lo = lo;
-                st.bass_bin_hi = hi;
-            }
-        }
+        hpcp_band_bins(sr, key_frame, st.bass_fmin, st.bass_fmax, &st.bass_bin_lo, &st.bass_bin_hi);
         st.white_n = std::min<uint32_t>(std::max(st.key_bin_hi, st.bass_bin_hi) + 2, key_bins);
         // tuning estimator band (extractor.rs:100-121): all bins with fmin <= f <= fmax
         {
@@ -521,10 +643,6 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
         const float blk = (float)sr * 400.0f / 1000.0f;  // normalization.rs:198
         st.lufs_block = blk > 0.0f ? (uint32_t)blk : 0u;
     }
-    if ((st.key_bin_hi >= st.key_bin_lo ? (st.key_bin_hi - st.key_bin_lo + 2) / 2 : 0) > 512) {
-        set_error("sample rates below ~20 kHz are not supported (more than 512 HPCP peak slots per key frame)");
-        return STRATUM_NOT_IMPLEMENTED;
-    }
     {   // chroma folding (extractor.rs:393-487): the bin -> pitch-class weights do not depend on the frame, so they are
         // tabulated per pitch class in ascending-bin order (the order in which the reference adds them)
         std::vector<int32_t> off(13, 0), bins;
@@ -568,8 +686,17 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
             off[tc + 1] = (int32_t)bins.size();
         }
         if (bins.empty()) { bins.push_back(0); ws.push_back(0.0f); }
-        if (hi >= lo && hi - lo + 1 > 1024) {
-            set_error("sample rates below ~20 kHz are not supported (chroma band wider than 1024 key-STFT bins)");
+        // The HPCP front end handles any band (2048 peak slots cover a whole 8192-point row).  Plain chroma folding, its tuned and
+        // beat-synchronous forms, HPCP whitening and the median-HPSS key mask keep per-frame tables of 1024 band bins, which the
+        // 100..5000 Hz band exceeds when sr / key_frame < 4.79 Hz (below 39.2 kHz with the default 8192-point key STFT).
+        const bool fixed_tables = !cfg.enable_key_hpcp || cfg.enable_key_beat_synchronous || cfg.enable_key_tuning_compensation || cfg.enable_key_hpcp_whitening ||
+                                  cfg.enable_key_hpss_harmonic;
+        if (fixed_tables && hi >= lo && hi - lo + 1 > 1024) {
+            char msg[256];
+            snprintf(msg, sizeof msg,
+                     "sample rate %u Hz is not supported with this key configuration: the 100..5000 Hz band spans %u key-STFT bins (max 1024; the default HPCP key path has no such limit)",
+                     sr, hi - lo + 1);
+            set_error(msg);
             return STRATUM_NOT_IMPLEMENTED;
         }
         st.fold_lo = lo;
@@ -812,6 +939,7 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.key_mask = c.enable_key_harmonic_mask;
     d.key_smooth_only = !c.enable_key_harmonic_mask && c.enable_key_spectrogram_time_smoothing && c.key_spectrogram_smooth_margin > 0;
     d.key_hpcp = c.enable_key_hpcp;
+    d.key_compact = key_compact_mode(c);
     d.chroma_sharpen = c.chroma_sharpening_power;
     d.key_weighting = c.enable_key_frame_weighting;
     d.key_voting = c.enable_key_segment_voting;
@@ -868,7 +996,6 @@ static DevCfg make_devcfg(const StratumConfig& c) {
 }
 
 // ---- arena planning -----------------------------------------------------------------------------------------
-static inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 static inline uint32_t frames_of(uint64_t n, uint32_t frame, uint32_t hop) { return n >= frame ? (uint32_t)((n - frame) / hop + 1) : 0; }
 
 struct Bump {
@@ -911,7 +1038,13 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.erms = fa.take(F512 + 2);
     T.scratch = fa.take((uint64_t)12 * T.fall);
     T.keyspec = fa.take((uint64_t)Fk * kd.key_bins + 8);
-    T.keymask = T.keyspec;  // the mask is applied in place
+    T.keymask = T.keyspec;  // the mask is applied in place (or, key_compact: only its HPCP band is kept, in kband)
+    if (kd.key_compact) {
+        compact_band(T.sr, cfg, kd.key_frame, &T.kband_lo, &T.kband_stride);
+        T.kband = fa.take((uint64_t)Fk * T.kband_stride + 32, 32);
+        T.kepart_stride = (uint32_t)align_up(Fk + 1, 32);
+        T.kepart = fa.take((uint64_t)((kd.key_bins + 127) / 128) * T.kepart_stride, 32);
+    }
     T.chroma = fa.take((uint64_t)Fk * 12 + 12);
     T.chroma2 = fa.take((uint64_t)Fk * 12 + 12);
     T.kenergy = fa.take(Fk + 1);
@@ -1034,7 +1167,7 @@ static const char* error_message(int code) {
     }
 }
 
-static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* ia_host, float ms_per_track, StratumResult* r) {
+static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* ia_host, float ms_per_track, const char* custom_err, StratumResult* r) {
     memset(r, 0, sizeof *r);
     r->status = T.status;
     r->tempogram_multi_res_triggered = r->tempogram_multi_res_used = -1;
@@ -1042,7 +1175,7 @@ static void fill_result(const TrackDev& T, const float* oa_host, const int32_t* 
     r->time_sig_beats_per_bar = 4;
     r->n_tempogram_candidates = -1;
     if (T.status != 0) {
-        snprintf(r->error, sizeof r->error, "%s", error_message(T.err_code));
+        snprintf(r->error, sizeof r->error, "%s", custom_err ? custom_err : error_message(T.err_code));
         return;
     }
     r->bpm = T.bpm;
@@ -1120,6 +1253,14 @@ static void debug_put_i(const char* name, const int32_t* d, size_t n, cudaStream
     g_debug_arrays[name] = std::move(f);
 }
 
+static uint64_t esc_floats(uint64_t n) {
+    TrackDev T{};
+    T.n = n;
+    Bump b;
+    plan_escalation(b, T);
+    return align_up(b.pos, 64);
+}
+
 // ---- one wave ----------------------------------------------------------------------------------------------------
 struct WavePlan {
     std::vector<uint32_t> idx;  // track indices of the batch in this wave
@@ -1127,12 +1268,59 @@ struct WavePlan {
     uint64_t esc_each_max = 0;  // largest escalation footprint of a track in the wave
 };
 
-static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample_off, const uint64_t* lens, const uint32_t* srs, const WavePlan& wp,
-                    const StratumConfig& cfg, const DevCfg& dcfg, size_t fa_budget, StratumResult* out, double* wave_ms) {
+// stream `waiter` continues only after everything queued on `signaller` so far
+static void stream_wait(cudaStream_t waiter, cudaStream_t signaller) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord(e, signaller);
+    cudaStreamWaitEvent(waiter, e, 0);
+    cudaEventDestroy(e);  // released once the record has completed
+}
+
+// On an error return from the middle of a wave: let both streams drain (queued kernels still reference the arenas and the
+// host buffers of this call) and drop the stage-timer events of the launches made so far.
+struct WaveAbortGuard {
+    DeviceCtx& c;
+    bool armed = true;
+    explicit WaveAbortGuard(DeviceCtx& c_) : c(c_) {}
+    ~WaveAbortGuard() {
+        if (!armed) return;
+        cudaStreamSynchronize(c.stream);
+        cudaStreamSynchronize(c.key_stream);
+        for (PendingStage& p : g_pending) {
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        g_pending.clear();
+    }
+};
+
+static void debug_dump_wave(DeviceCtx& c, const WaveJob& job);
+
+// Queues every launch of one wave and its final read-back.  `mid` runs on the host once the first part of the wave (everything up
+// to the escalation gate) is queued and before the host waits for the escalated-track count — the one point inside a wave where
+// the host needs a device value; the caller gathers the previous wave and starts the next upload there.
+static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* sample_off, const uint64_t* lens, const uint32_t* srs, const WavePlan& wp,
+                      const StratumConfig& cfg, const DevCfg& dcfg, size_t fa_budget, StratumResult* out, WaveJob& job, const std::function<int()>& mid) {
     const int nt = (int)wp.idx.size();
     HostSpan span_plan("host_plan");
-    std::vector<TrackDev> tracks(nt);
-    std::vector<int32_t> sr_index(nt, 0);
+    job.nt = nt;
+    job.idx = wp.idx;
+    job.out = out;
+    job.dcfg = dcfg;
+    job.track_err.assign(nt, std::string());
+    job.debug_single = g_debug.load() && nt == 1;
+    TrackDev* tracks = static_cast<TrackDev*>(job.h_tracks.need(sizeof(TrackDev) * nt));
+    if (!tracks) {
+        set_error("pinned host allocation failed");
+        return STRATUM_PROCESSING_ERROR;
+    }
+    int32_t* sr_index = static_cast<int32_t*>(job.h_small.need(sizeof(int32_t) * nt));  // pinned: a pageable source would make the copy wait for the stream
+    if (!sr_index) {
+        set_error("pinned host allocation failed");
+        return STRATUM_PROCESSING_ERROR;
+    }
+    memset(sr_index, 0, sizeof(int32_t) * nt);
     Bump fa, oa, ia;
     WaveCtx w{};
     w.stream = c.stream;
@@ -1140,6 +1328,8 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     w.n_tracks = nt;
     w.tab = c.tab;
     w.cfg = dcfg;
+    w.max_key_peaks = 1;
+    const bool mr_on = dcfg.mr_enabled && !dcfg.force_legacy;
     for (int i = 0; i < nt; ++i) {
         TrackDev& T = tracks[i];
         memset(&T, 0, sizeof T);
@@ -1155,9 +1345,18 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         if (T.status == 0) {
             int slot = 0;
             const int st = sr_slot(c, T.sr, cfg, &slot);
-            if (st != STRATUM_OK) return st;
-            sr_index[i] = slot;
-        } else {
+            if (st == STRATUM_OK) {
+                sr_index[i] = slot;
+                const SrTables& S = c.sr_host[slot];
+                w.max_key_peaks = std::max(w.max_key_peaks, S.key_bin_hi >= S.key_bin_lo ? (S.key_bin_hi - S.key_bin_lo + 2) / 2 : 0u);
+                w.max_key_peaks = std::max(w.max_key_peaks, S.bass_bin_hi >= S.bass_bin_lo ? (S.bass_bin_hi - S.bass_bin_lo + 2) / 2 : 0u);
+            } else {  // this track fails with the table builder's message; the rest of the wave carries on (analyze_batch.rs:293-322)
+                T.status = st;
+                T.err_code = 6;
+                job.track_err[i] = g_last_error;
+            }
+        }
+        if (T.status != 0) {
             T.n = 0;
             T.sr = T.sr ? T.sr : 1;
         }
@@ -1165,7 +1364,13 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         T.hop[0].tgtw = get_tw(c, T.hop[0].fft_cap);
         if (dcfg.hpss_onsets || dcfg.perc_fallback) T.hop[SLOT_PERC].tgtw = get_tw(c, T.hop[SLOT_PERC].fft_cap);
         T.lg_tw = get_tw(c, T.lg_fft);
-        if (!T.hop[0].tgtw || !T.lg_tw) {
+        if (mr_on) {  // escalation work areas, relative to the start of whichever arena slot escalation_compact_kernel assigns
+            Bump b;
+            plan_escalation(b, T);
+            T.hop[1].tgtw = get_tw(c, T.hop[1].fft_cap);
+            T.hop[2].tgtw = get_tw(c, T.hop[2].fft_cap);
+        }
+        if (!T.hop[0].tgtw || !T.lg_tw || (mr_on && (!T.hop[1].tgtw || !T.hop[2].tgtw))) {
             set_error("twiddle table allocation failed");
             return STRATUM_PROCESSING_ERROR;
         }
@@ -1190,20 +1395,27 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     const uint64_t fa_base_end = align_up(fa.pos, 64);
     // escalation pool: whatever is left of the budget (at least one track's worth)
     uint64_t esc_each = 0;
-    for (int i = 0; i < nt; ++i) {
-        Bump b;
-        TrackDev tmp = tracks[i];
-        plan_escalation(b, tmp);
-        esc_each = std::max<uint64_t>(esc_each, align_up(b.pos, 64));
-    }
+    for (int i = 0; i < nt; ++i) esc_each = std::max<uint64_t>(esc_each, esc_floats(tracks[i].n));
     uint64_t esc_slots = 0;
-    if (dcfg.mr_enabled && !dcfg.force_legacy) {
+    if (mr_on) {
         const uint64_t room = fa_budget > fa_base_end ? fa_budget - fa_base_end : 0;
         esc_slots = esc_each ? std::min<uint64_t>(std::max<uint64_t>(room / esc_each, 1), (uint64_t)nt) : 0;
     }
     const uint64_t fa_total = fa_base_end + esc_slots * esc_each;
     int st = ensure_capacity(c, fa_total + 64, oa.pos + 64, ia.pos + 64, nt);
     if (st != STRATUM_OK) return st;
+    job.oa_n = oa.pos;
+    job.ia_n = ia.pos;
+    float* oa_host = static_cast<float*>(job.h_oa.need(sizeof(float) * (oa.pos + 1)));
+    int32_t* ia_host = static_cast<int32_t*>(job.h_ia.need(sizeof(int32_t) * (ia.pos + 1)));
+    if (!oa_host || !ia_host) {
+        set_error("pinned host allocation failed");
+        return STRATUM_PROCESSING_ERROR;
+    }
+    if (!job.ev0 && (cudaEventCreate(&job.ev0) != cudaSuccess || cudaEventCreate(&job.ev1) != cudaSuccess)) {
+        set_error("event creation failed");
+        return STRATUM_PROCESSING_ERROR;
+    }
     w.fa = c.fa;
     w.oa = c.oa;
     w.ia = c.ia;
@@ -1211,12 +1423,10 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     w.srtab = c.d_srtab;
     w.sr_index = c.d_sr_index;
     cudaStream_t s = c.stream;
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, s);
-    CUDA_OK(cudaMemcpyAsync(c.d_tracks, tracks.data(), sizeof(TrackDev) * nt, cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(c.d_sr_index, sr_index.data(), sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
+    WaveAbortGuard guard(c);
+    cudaEventRecord(job.ev0, s);
+    CUDA_OK(cudaMemcpyAsync(c.d_tracks, tracks, sizeof(TrackDev) * nt, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(c.d_sr_index, sr_index, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, s));
     span_plan.stop();
     {
         StageTimer t(s, "preprocess");
@@ -1225,10 +1435,11 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         if (dcfg.enable_normalization && dcfg.normalization == STRATUM_NORM_LOUDNESS) {
             // normalize_lufs (normalization.rs:401-484): gate, mean, log10 and the dB -> linear powf are evaluated on
             // the host (same libm as the reference's platform) from the device's block energies and peaks
-            CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
+            std::vector<TrackDev> rb(nt);
+            CUDA_OK(cudaMemcpyAsync(rb.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
             std::vector<std::vector<float>> en(nt);
             for (int i = 0; i < nt; ++i) {
-                en[i].resize(tracks[i].lufs_nb);  // layout fields are host-planned, valid before the copy lands
+                en[i].resize(tracks[i].lufs_nb);  // layout fields are host-planned
                 if (tracks[i].lufs_nb && tracks[i].status == 0)
                     CUDA_OK(cudaMemcpyAsync(en[i].data(), c.fa + tracks[i].lufs_e, sizeof(float) * tracks[i].lufs_nb, cudaMemcpyDeviceToHost, s));
             }
@@ -1237,8 +1448,8 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             const float gate = powf(10.0f, (-70.0f + 0.691f) / 10.0f);
             const float target_peak = powf(10.0f, (0.0f - 1.0f) / 20.0f);
             for (int i = 0; i < nt; ++i) {
-                if (tracks[i].status != 0) continue;
-                const float peak = tracks[i].peak;
+                if (rb[i].status != 0) continue;
+                const float peak = rb[i].peak;
                 float acc = 0.0f;
                 size_t cnt = 0;
                 for (float e : en[i])
@@ -1269,7 +1480,7 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     // tracks/s with the two paths overlapped vs 970 one after the other — both are bound by the same SM resources
     // (issue slots, L1/shared pipe), so overlap only adds cache pressure.  Off unless STRATUM_B200_DUAL_STREAM is set.
     static const bool dual_stream = getenv("STRATUM_B200_DUAL_STREAM") != nullptr;
-    const bool split = dual_stream && !(g_debug.load() && nt == 1) && !dcfg.key_beat_sync;  // beat-synchronous chroma reads the beat grid
+    const bool split = dual_stream && !job.debug_single && !dcfg.key_beat_sync;  // beat-synchronous chroma reads the beat grid
     // Late split (default): the key path and the legacy estimator are independent of the tempo path's tail, whose kernels are
     // small latency-bound grids (one CTA or warp per track: legacy ACF/comb, the hop-256/1024 tempograms and their fusion,
     // the final BPM, the beat tracker — about 45 ms of a 980 ms step).  The legacy estimator starts on the second stream as
@@ -1277,25 +1488,16 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
     // features), so those tails run beside the key STFT instead of in front of it.  Unlike the early split above, no two
     // bandwidth- or issue-heavy kernels ever overlap.
     static const bool no_late_split = getenv("STRATUM_B200_NO_LATE_SPLIT") != nullptr;
-    const bool late = !split && !no_late_split && !(g_debug.load() && nt == 1) && !dcfg.key_beat_sync;
-    cudaEvent_t ev_pre = nullptr, ev_key = nullptr, ev_legacy = nullptr;
+    const bool late = !split && !no_late_split && !job.debug_single && !dcfg.key_beat_sync;
     bool key_forked = false;
-    auto fork_key_path = [&]() {  // late split: everything the key path needs (gain, trim) was produced long ago on s
-        if (!late || key_forked) return;
-        key_forked = true;
-        cudaEventCreateWithFlags(&ev_pre, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_key, cudaEventDisableTiming);
-        cudaEventRecord(ev_pre, s);
-        cudaStreamWaitEvent(c.key_stream, ev_pre, 0);
-    };
     auto run_key_path = [&](cudaStream_t ks) {
         WaveCtx wk = w;
         wk.stream = ks;
         { StageTimer t(ks, "stft_8192_key"); launch_stft_key(wk); }
-        if (g_debug.load() && nt == 1) {
-            cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, ks);
+        if (job.debug_single) {
+            TrackDev T;
+            cudaMemcpyAsync(&T, c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, ks);
             cudaStreamSynchronize(ks);
-            const TrackDev& T = tracks[0];
             const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
             debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * dcfg.key_bins, ks);
         }
@@ -1303,26 +1505,21 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         { StageTimer t(ks, "key_hpcp"); launch_key_hpcp(wk); }
         { StageTimer t(ks, "key_vote"); launch_key_vote(wk); }
     };
-    if (split) {
-        cudaEventCreateWithFlags(&ev_pre, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_key, cudaEventDisableTiming);
-        cudaEventRecord(ev_pre, s);
-        cudaStreamWaitEvent(c.key_stream, ev_pre, 0);
+    auto fork_key_path = [&]() {  // late split: everything the key path needs (gain, trim) was produced long ago on s
+        if (!late || key_forked) return;
+        key_forked = true;
+        stream_wait(c.key_stream, s);
         run_key_path(c.key_stream);
-        cudaEventRecord(ev_key, c.key_stream);
+    };
+    if (split) {
+        stream_wait(c.key_stream, s);
+        run_key_path(c.key_stream);
     }
-    cudaEvent_t ev_eon = nullptr;
     if (late) {  // the energy-flux detector (a latency-bound add chain per frame) only feeds the consensus: beside the STFT
-        cudaEvent_t ev_trim;
-        cudaEventCreateWithFlags(&ev_trim, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_eon, cudaEventDisableTiming);
-        cudaEventRecord(ev_trim, s);
-        cudaStreamWaitEvent(c.key_stream, ev_trim, 0);
-        cudaEventDestroy(ev_trim);
+        stream_wait(c.key_stream, s);
         WaveCtx we = w;
         we.stream = c.key_stream;
         { StageTimer t(c.key_stream, "onsets_energy"); launch_energy_onsets(we); }
-        cudaEventRecord(ev_eon, c.key_stream);
     } else {
         StageTimer t(s, "onsets_energy");
         launch_energy_onsets(w);
@@ -1335,80 +1532,78 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         launch_seq_features(w, SLOT_PERC, nullptr, nt);
         launch_hpss_onsets(w);
     }
-    if (ev_eon) {
-        cudaStreamWaitEvent(s, ev_eon, 0);
-        cudaEventDestroy(ev_eon);
-    }
+    if (late) stream_wait(s, c.key_stream);  // energy onsets
     { StageTimer t(s, "onsets_consensus"); launch_spectral_onsets_consensus(w); }
     const bool want_tempogram = !dcfg.force_legacy;
     if (want_tempogram) {
         StageTimer t(s, "tempogram");
         launch_tempogram(w, 0, nullptr, nt);
         launch_escalation_gate(w);
+        if (dcfg.mr_enabled) launch_escalation_compact(w, c.d_list, c.d_count, fa_base_end, esc_each, (uint32_t)esc_slots);
     }
+    bool legacy_on_key_stream = false;
     if (late) {  // needs the consensus onsets only; its result is read by final_bpm
-        cudaEvent_t ev_on;
-        cudaEventCreateWithFlags(&ev_on, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_legacy, cudaEventDisableTiming);
-        cudaEventRecord(ev_on, s);
-        cudaStreamWaitEvent(c.key_stream, ev_on, 0);
-        cudaEventDestroy(ev_on);
+        stream_wait(c.key_stream, s);
         WaveCtx wl = w;
         wl.stream = c.key_stream;
         { StageTimer t(c.key_stream, "legacy_bpm"); launch_legacy_bpm(wl); }
-        cudaEventRecord(ev_legacy, c.key_stream);
+        cudaEventRecord(c.ev_legacy, c.key_stream);
+        legacy_on_key_stream = true;
     } else {
         StageTimer t(s, "legacy_bpm");
         launch_legacy_bpm(w);
     }
+    bool mid_done = false;
+    auto run_mid = [&]() -> int {
+        if (mid_done) return STRATUM_OK;
+        mid_done = true;
+        return mid ? mid() : (int)STRATUM_OK;
+    };
+    std::vector<TrackDev> gate_rb;  // records as of the gate (percussive fallback / debug only)
     if (want_tempogram && dcfg.mr_enabled) {
-        // escalation decision needs the host: read the records back, hand out arena slots
-        CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
-        CUDA_OK(cudaStreamSynchronize(s));
-        HostSpan span_esc("host_escalation");
-        std::vector<int32_t> esc;
-        for (int i = 0; i < nt; ++i)
-            if (tracks[i].status == 0 && tracks[i].escalate) esc.push_back(i);
-        for (size_t p0 = 0; p0 < esc.size(); p0 += esc_slots) {
-            const size_t p1 = std::min(esc.size(), p0 + (size_t)esc_slots);
-            for (size_t p = p0; p < p1; ++p) {
-                TrackDev& T = tracks[esc[p]];
-                Bump b;
-                b.pos = fa_base_end + (p - p0) * esc_each;
-                plan_escalation(b, T);
-                T.hop[1].tgtw = get_tw(c, T.hop[1].fft_cap);
-                T.hop[2].tgtw = get_tw(c, T.hop[2].fft_cap);
-                // only the escalation layouts are rewritten: the key path may be updating other fields of the record concurrently
-                char* drec = reinterpret_cast<char*>(c.d_tracks + esc[p]);
-                CUDA_OK(cudaMemcpyAsync(drec + offsetof(TrackDev, hop) + sizeof(HopLayout), &T.hop[1], 2 * sizeof(HopLayout), cudaMemcpyHostToDevice, s));
-                CUDA_OK(cudaMemcpyAsync(drec + offsetof(TrackDev, cands) + sizeof(uint64_t), &T.cands[1], 2 * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-            }
+        // the only device value the host needs inside a wave: how many tracks escalate (sizes the multi-resolution grids)
+        int32_t* h_count = static_cast<int32_t*>(c.h_count.need(sizeof(int32_t) * 4));
+        if (!h_count) {
+            set_error("pinned host allocation failed");
+            return STRATUM_PROCESSING_ERROR;
+        }
+        CUDA_OK(cudaMemcpyAsync(h_count, c.d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (dcfg.perc_fallback || job.debug_single) {
+            gate_rb.resize(nt);
+            CUDA_OK(cudaMemcpyAsync(gate_rb.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
+        }
+        if ((st = run_mid()) != STRATUM_OK) return st;
+        {
+            HostSpan span_esc("host_escalation");  // time the host waits for the count with nothing else to do
+            CUDA_OK(cudaStreamSynchronize(s));
+        }
+        const size_t n_esc = (size_t)std::max(0, std::min(h_count[0], nt));
+        g_d2h_bytes.fetch_add(sizeof(int32_t));
+        for (size_t p0 = 0; p0 < n_esc; p0 += esc_slots) {
+            const size_t p1 = std::min(n_esc, p0 + (size_t)esc_slots);
             const int nl = (int)(p1 - p0);
-            CUDA_OK(cudaMemcpyAsync(c.d_list, esc.data() + p0, sizeof(int32_t) * nl, cudaMemcpyHostToDevice, s));
+            const int32_t* lst = c.d_list + p0;
             {
                 StageTimer t(s, "stft_multires");
-                launch_stft_hop(w, 1, c.d_list, nl);
-                launch_stft_hop(w, 2, c.d_list, nl);
+                launch_stft_hop(w, 1, lst, nl);
+                launch_stft_hop(w, 2, lst, nl);
             }
-            span_esc.stop();
             {
                 StageTimer t(s, "multires_features");
-                launch_spec_features(w, 1, c.d_list, nl);
-                launch_spec_features(w, 2, c.d_list, nl);
+                launch_spec_features(w, 1, lst, nl);
+                launch_spec_features(w, 2, lst, nl);
             }
-            if (late && p1 == esc.size()) {  // last heavy kernel of the tempo path is queued: the key path starts behind it
-                fork_key_path();
-                run_key_path(c.key_stream);
-                cudaEventRecord(ev_key, c.key_stream);
-            }
+            if (late && p1 == n_esc) fork_key_path();  // last heavy kernel of the tempo path is queued: the key path starts behind it
             {
                 StageTimer t(s, "multires_tempogram");
-                launch_tempogram(w, 1, c.d_list, nl);
-                launch_tempogram(w, 2, c.d_list, nl);
-                launch_multires_fusion(w, c.d_list, nl);
+                launch_tempogram(w, 1, lst, nl);
+                launch_tempogram(w, 2, lst, nl);
+                launch_multires_fusion(w, lst, nl);
             }
-            if (g_debug.load() && nt == 1) {
-                const TrackDev& T = tracks[0];
+            if (job.debug_single) {
+                TrackDev T;
+                cudaMemcpyAsync(&T, c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
                 for (int h = 1; h < 3; ++h) {
                     const uint32_t L = T.F[h] > 0 ? T.F[h] - 1 : 0;
                     const std::string tag = h == 1 ? "h256." : "h1024.";
@@ -1421,11 +1616,11 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
         }
     }
     if (want_tempogram && dcfg.mr_enabled && dcfg.perc_fallback) {
-        // percussive tempogram fallback (lib.rs:587-683) for the tracks the gate put in the low-tempo trap; `tracks` was
+        // percussive tempogram fallback (lib.rs:587-683) for the tracks the gate put in the low-tempo trap; gate_rb was
         // read back after the gate, so perc_triggered is valid on the host
         std::vector<int32_t> pl;
         for (int i = 0; i < nt; ++i)
-            if (tracks[i].status == 0 && tracks[i].perc_triggered == 1) pl.push_back(i);
+            if (gate_rb[i].status == 0 && gate_rb[i].perc_triggered == 1) pl.push_back(i);
         if (!pl.empty()) {
             StageTimer t(s, "percussive_fallback");
             const int nl = (int)pl.size();
@@ -1437,84 +1632,92 @@ static int run_wave(DeviceCtx& c, const float* d_samples, const uint64_t* sample
             CUDA_OK(cudaStreamSynchronize(s));  // `pl` is a stack-owned buffer
         }
     }
-    if (late && !key_forked) {  // nothing escalated (or multi-resolution off): fork here
-        fork_key_path();
-        run_key_path(c.key_stream);
-        cudaEventRecord(ev_key, c.key_stream);
-    }
-    if (late) cudaStreamWaitEvent(s, ev_legacy, 0);
+    if (late && !key_forked) fork_key_path();  // nothing escalated (or multi-resolution off): fork here
+    if (legacy_on_key_stream) cudaStreamWaitEvent(s, c.ev_legacy, 0);  // not the whole key stream: the key path is queued behind the legacy estimator
     { StageTimer t(s, "final_bpm"); launch_final_bpm(w); launch_emit_candidates(w); }
     { StageTimer t(s, "beats"); launch_beat_tracking(w); }
-    if (split || late) {
-        cudaStreamWaitEvent(s, ev_key, 0);
-    } else {
-        run_key_path(s);
-    }
-    CUDA_OK(cudaMemcpyAsync(tracks.data(), c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
-    std::vector<float> oa_host(oa.pos + 1);
-    std::vector<int32_t> ia_host(ia.pos + 1);
-    CUDA_OK(cudaMemcpyAsync(oa_host.data(), c.oa, sizeof(float) * oa.pos, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(ia_host.data(), c.ia, sizeof(int32_t) * ia.pos, cudaMemcpyDeviceToHost, s));
-    g_d2h_bytes.fetch_add(sizeof(TrackDev) * nt * (dcfg.mr_enabled && want_tempogram ? 2 : 1) + sizeof(float) * oa.pos + sizeof(int32_t) * ia.pos);
+    if (split || late) stream_wait(s, c.key_stream);
+    else run_key_path(s);
+    CUDA_OK(cudaMemcpyAsync(tracks, c.d_tracks, sizeof(TrackDev) * nt, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(oa_host, c.oa, sizeof(float) * oa.pos, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(ia_host, c.ia, sizeof(int32_t) * ia.pos, cudaMemcpyDeviceToHost, s));
+    g_d2h_bytes.fetch_add(sizeof(TrackDev) * nt + sizeof(float) * oa.pos + sizeof(int32_t) * ia.pos);
     g_h2d_bytes.fetch_add((sizeof(TrackDev) + sizeof(int32_t)) * nt);
-    cudaEventRecord(ev1, s);
-    CUDA_OK(cudaStreamSynchronize(s));
+    cudaEventRecord(job.ev1, s);
+    job.stages.swap(g_pending);
+    g_pending.clear();
+    guard.armed = false;
+    job.active = true;
+    return run_mid();  // waves without an escalation wait gather the previous wave here
+}
+
+// Waits for a queued wave and gathers its results.
+static int wave_end(DeviceCtx& c, WaveJob& job, double* wave_ms) {
+    if (!job.active) return STRATUM_OK;
+    job.active = false;
+    const cudaError_t e = cudaEventSynchronize(job.ev1);
     HostSpan span_gather("host_gather");
-    CUDA_OK(cudaGetLastError());
-    resolve_stage_times();
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    if (ev_pre) cudaEventDestroy(ev_pre);
-    if (ev_key) cudaEventDestroy(ev_key);
-    if (ev_legacy) cudaEventDestroy(ev_legacy);
-    if (wave_ms) *wave_ms += ms;
-    for (int i = 0; i < nt; ++i) fill_result(tracks[i], oa_host.data(), ia_host.data(), ms / (float)nt, &out[wp.idx[i]]);
-    if (g_debug.load() && nt == 1) {
-        const TrackDev& T = tracks[0];
-        if (T.status == 0) {
-            const HopLayout& H = T.hop[0];
-            const uint32_t F = T.F[0], L = F > 0 ? F - 1 : 0;
-            const uint64_t fm = H.fmax;
-            debug_put("gain", &c.d_tracks[0].gain, 1, s);
-            debug_put("spec512_head", c.fa + H.spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
-            debug_put("onset.spectral_flux", c.fa + H.pair + 0 * fm, L, s);
-            debug_put("frame.hfc", c.fa + H.frame + 2 * fm, F, s);
-            debug_put("frame.energy", c.fa + H.frame + 1 * fm, F, s);
-            debug_put("pair.superflux", c.fa + H.pair + 1 * fm, L, s);
-            debug_put("pair.mel", c.fa + H.pair + 5 * fm, L, s);
-            debug_put_i("onset.energy", c.ia + T.on_energy, T.n_on_energy, s);
-            debug_put_i("onset.spectral", c.ia + T.on_spectral, T.n_on_spectral, s);
-            debug_put_i("onset.hfc", c.ia + T.on_hfc, T.n_on_hfc, s);
-            if (dcfg.hpss_onsets) debug_put_i("onset.hpss", c.ia + T.on_hpss, T.n_on_hpss, s);
-            if (T.hpss_ready) {
-                debug_put("hpss.perc_head", c.fa + T.hop[SLOT_PERC].spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
-                float pe[4] = {T.est[SLOT_PERC].bpm, T.est[SLOT_PERC].confidence, (float)T.est[SLOT_PERC].agreement, (float)T.est[SLOT_PERC].ok};
-                std::lock_guard<std::mutex> lk(g_debug_mu);
-                g_debug_arrays["perc.est"] = std::vector<float>(pe, pe + 4);
-            }
-            const char* vn[5] = {"base.nov.full", "base.nov.low", "base.nov.mid", "base.nov.high", "base.nov.mel"};
-            for (int v = 0; v < 5; ++v) debug_put(vn[v], c.fa + H.nov + (uint64_t)v * fm, L, s);
-            debug_put("base.tg.fft.full", c.fa + H.tgfft, H.fft_cap / 2 + 1, s);
-            debug_put("base.tg.ac.full", c.fa + H.tgac, AC_CAP, s);
-            debug_put("base.cands", c.fa + T.cands[0], (size_t)MAX_CANDS * 4, s);
-            float est[12] = {T.est[0].bpm, T.est[0].confidence, (float)T.est[0].agreement, (float)T.est[0].ok, (float)T.est[0].n_cands,
-                             T.legacy.bpm, T.legacy.confidence, (float)T.legacy.ok, (float)T.escalate, T.est[1].bpm, T.est[2].bpm, 0.0f};
-            {
-                std::lock_guard<std::mutex> lk(g_debug_mu);
-                g_debug_arrays["base.est"] = std::vector<float>(est, est + 12);
-            }
-            debug_put("key.hpcp_raw", c.fa + T.chroma, (size_t)T.Fk * 12, s);
-            debug_put("key.hpcp_smooth", c.fa + T.chroma2, (size_t)T.Fk * 12, s);
-            debug_put("key.energy", c.fa + T.kenergy, T.Fk, s);
-            debug_put("key.weights", c.fa + T.kweights, T.Fk, s);
-            debug_put("key.seg_scores", c.fa + T.seg_scores, (size_t)T.seg_cap * 24, s);
-            debug_put("key.mask_head", c.fa + T.keyspec, (size_t)std::min<uint32_t>(T.Fk, 64) * dcfg.key_bins, s);
-            debug_put_i("hmm.path", c.ia + T.hmm_path, T.hmm_T, s);
-        }
+    resolve_stage_times(job.stages);
+    if (e != cudaSuccess) {
+        set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " while waiting for a wave");
+        return STRATUM_PROCESSING_ERROR;
     }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, job.ev0, job.ev1);
+    if (wave_ms) *wave_ms += ms;
+    const TrackDev* tracks = static_cast<const TrackDev*>(job.h_tracks.p);
+    const float* oa_host = static_cast<const float*>(job.h_oa.p);
+    const int32_t* ia_host = static_cast<const int32_t*>(job.h_ia.p);
+    for (int i = 0; i < job.nt; ++i)
+        fill_result(tracks[i], oa_host, ia_host, ms / (float)job.nt, job.track_err[i].empty() ? nullptr : job.track_err[i].c_str(), &job.out[job.idx[i]]);
+    if (job.debug_single) debug_dump_wave(c, job);
     return STRATUM_OK;
+}
+
+static void debug_dump_wave(DeviceCtx& c, const WaveJob& job) {
+    cudaStream_t s = c.stream;
+    const DevCfg& dcfg = job.dcfg;
+    const TrackDev& T = static_cast<const TrackDev*>(job.h_tracks.p)[0];
+    if (T.status != 0) return;
+    const HopLayout& H = T.hop[0];
+    const uint32_t F = T.F[0], L = F > 0 ? F - 1 : 0;
+    const uint64_t fm = H.fmax;
+    debug_put("gain", &c.d_tracks[0].gain, 1, s);
+    debug_put("spec512_head", c.fa + H.spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
+    debug_put("onset.spectral_flux", c.fa + H.pair + 0 * fm, L, s);
+    debug_put("frame.hfc", c.fa + H.frame + 2 * fm, F, s);
+    debug_put("frame.energy", c.fa + H.frame + 1 * fm, F, s);
+    debug_put("pair.superflux", c.fa + H.pair + 1 * fm, L, s);
+    debug_put("pair.mel", c.fa + H.pair + 5 * fm, L, s);
+    debug_put_i("onset.energy", c.ia + T.on_energy, T.n_on_energy, s);
+    debug_put_i("onset.spectral", c.ia + T.on_spectral, T.n_on_spectral, s);
+    debug_put_i("onset.hfc", c.ia + T.on_hfc, T.n_on_hfc, s);
+    if (dcfg.hpss_onsets) debug_put_i("onset.hpss", c.ia + T.on_hpss, T.n_on_hpss, s);
+    if (T.hpss_ready) {
+        debug_put("hpss.perc_head", c.fa + T.hop[SLOT_PERC].spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
+        float pe[4] = {T.est[SLOT_PERC].bpm, T.est[SLOT_PERC].confidence, (float)T.est[SLOT_PERC].agreement, (float)T.est[SLOT_PERC].ok};
+        std::lock_guard<std::mutex> lk(g_debug_mu);
+        g_debug_arrays["perc.est"] = std::vector<float>(pe, pe + 4);
+    }
+    const char* vn[5] = {"base.nov.full", "base.nov.low", "base.nov.mid", "base.nov.high", "base.nov.mel"};
+    for (int v = 0; v < 5; ++v) debug_put(vn[v], c.fa + H.nov + (uint64_t)v * fm, L, s);
+    debug_put("base.tg.fft.full", c.fa + H.tgfft, H.fft_cap / 2 + 1, s);
+    debug_put("base.tg.ac.full", c.fa + H.tgac, AC_CAP, s);
+    debug_put("base.cands", c.fa + T.cands[0], (size_t)MAX_CANDS * 4, s);
+    float est[12] = {T.est[0].bpm, T.est[0].confidence, (float)T.est[0].agreement, (float)T.est[0].ok, (float)T.est[0].n_cands,
+                     T.legacy.bpm, T.legacy.confidence, (float)T.legacy.ok, (float)T.escalate, T.est[1].bpm, T.est[2].bpm, 0.0f};
+    {
+        std::lock_guard<std::mutex> lk(g_debug_mu);
+        g_debug_arrays["base.est"] = std::vector<float>(est, est + 12);
+    }
+    debug_put("key.hpcp_raw", c.fa + T.chroma, (size_t)T.Fk * 12, s);
+    debug_put("key.hpcp_smooth", c.fa + T.chroma2, (size_t)T.Fk * 12, s);
+    debug_put("key.energy", c.fa + T.kenergy, T.Fk, s);
+    debug_put("key.weights", c.fa + T.kweights, T.Fk, s);
+    debug_put("key.seg_scores", c.fa + T.seg_scores, (size_t)T.seg_cap * 24, s);
+    if (dcfg.key_compact) debug_put("key.band_head", c.fa + T.kband, (size_t)std::min<uint32_t>(T.Fk, 64) * T.kband_stride, s);
+    else debug_put("key.mask_head", c.fa + T.keyspec, (size_t)std::min<uint32_t>(T.Fk, 64) * dcfg.key_bins, s);
+    debug_put_i("hmm.path", c.ia + T.hmm_path, T.hmm_T, s);
 }
 
 // Footprint (floats) of a track's base work areas.
@@ -1526,22 +1729,17 @@ static uint64_t track_floats(uint64_t n, uint32_t sr, const StratumConfig& cfg) 
     plan_track(fa, oa, ia, T, cfg);
     return align_up(fa.pos, 64) + 64;
 }
-static uint64_t esc_floats(uint64_t n) {
-    TrackDev T{};
-    T.n = n;
-    Bump b;
-    plan_escalation(b, T);
-    return align_up(b.pos, 64);
-}
 
 // Wave packing (host logic, unit-tested through stratum_b200_debug_plan_waves): tracks are taken in order until the wave
 // reaches its sample target or the arena budget.  The target balances the remaining samples over ceil(remaining / cap)
 // waves, so a batch slightly larger than the cap does not end in a tiny (latency-bound) wave.
 struct WaveLimits {
     uint64_t budget_floats;     // float arena budget; raised when a single track alone exceeds it
-    uint32_t wave_max;          // track-count cap
+    uint32_t wave_max;          // track-count cap (<= 65535: a wave's tracks are gridDim.y of most launches)
     uint64_t wave_max_samples;  // sample cap (~0 = none)
 };
+
+constexpr uint32_t WAVE_MAX_TRACKS = 65535;
 
 static void pack_wave(uint32_t& i, uint32_t n_tracks, const uint64_t* lens, const uint32_t* srs, const StratumConfig& cfg, WaveLimits& L, WavePlan& wp) {
     uint64_t used = 0, esc_max = 0, wave_samples = 0, remaining = 0;
@@ -1551,7 +1749,7 @@ static void pack_wave(uint32_t& i, uint32_t n_tracks, const uint64_t* lens, cons
         const uint64_t nw = (remaining + L.wave_max_samples - 1) / L.wave_max_samples;
         wave_target = (remaining + nw - 1) / nw;
     }
-    while (i < n_tracks && wp.idx.size() < L.wave_max) {
+    while (i < n_tracks && wp.idx.size() < std::min(L.wave_max, WAVE_MAX_TRACKS)) {
         if (!wp.idx.empty() && wave_samples + lens[i] / 2 > wave_target) break;
         const uint64_t need = track_floats(lens[i], srs[i], cfg);
         const uint64_t esc = esc_floats(lens[i]);
@@ -1568,68 +1766,135 @@ static void pack_wave(uint32_t& i, uint32_t n_tracks, const uint64_t* lens, cons
     if (used + esc_max > L.budget_floats && wp.idx.size() == 1) L.budget_floats = used + esc_max;  // a single track larger than the budget: let cudaMalloc decide
 }
 
-static int analyze_device(int device_id, const float* d_samples, const uint64_t* offsets, const uint32_t* srs, uint32_t n_tracks, const StratumConfig& cfg,
+// One batch call on one device: waves are queued one ahead of the gather (wave k+1 is planned and its first half queued while
+// wave k runs; the host blocks only for the escalated-track count of the wave it is queueing and for finished results).
+// The caller holds ctx.mu for the whole session.
+struct Session {
+    DeviceCtx& c;
+    const StratumConfig& cfg;
+    DevCfg dcfg;
+    WaveLimits lim{};
+    int cur = 0;  // job slot of the next wave
+    double waves_ms = 0.0;
+    uint32_t n_waves = 0;
+    cudaEvent_t call_a = nullptr, call_b = nullptr;
+    bool opened = false;
+
+    Session(DeviceCtx& ctx, const StratumConfig& cf) : c(ctx), cfg(cf), dcfg(make_devcfg(cf)) {}
+    ~Session() {
+        if (call_a) cudaEventDestroy(call_a);
+        if (call_b) cudaEventDestroy(call_b);
+    }
+
+    int open() {
+        CUDA_OK(cudaSetDevice(c.device));
+        // per-sample-rate tables are built for one configuration; a call with another one starts a fresh set when the
+        // table is getting full (slots are only referenced by the waves of one session, and none is in flight here)
+        if (!c.sr_cfg.empty() && c.sr_host.size() > DeviceCtx::MAX_SR / 2 && memcmp(&c.sr_cfg.back(), &cfg, sizeof cfg) != 0) {
+            c.sr_host.clear();
+            c.sr_cfg.clear();
+        }
+        size_t free_b = 0, total_b = 0;
+        CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+        // budget: what is free now plus what our own arena already holds, minus head room
+        uint64_t budget_floats = (uint64_t)((double)(free_b + c.fa_cap * 4) * 0.90) / 4;
+        // waves of a few hundred tracks already fill the GPU; a larger arena buys nothing and starves the caller (and our
+        // own staging buffers) of memory, so the default is capped at 100 GB
+        double cap_gb = 100.0;
+        if (const char* e = getenv("STRATUM_B200_ARENA_GB")) cap_gb = atof(e);
+        budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(cap_gb * 1e9 / 4));
+        // waves of 128-160 three-minute tracks measured fastest (982-989 tracks/s against 959 in waves of 256, 913 in waves of 64)
+        // (the cap is expressed in samples so that batches of short tracks still fill the device)
+        uint32_t wave_max = WAVE_MAX_TRACKS;
+        uint64_t wave_max_samples = (uint64_t)128 * 7938000;
+        if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) {
+            wave_max = (uint32_t)std::min<long>(std::max(1, atoi(e)), (long)WAVE_MAX_TRACKS);
+            wave_max_samples = ~0ull;
+        }
+        lim = WaveLimits{budget_floats, wave_max, wave_max_samples};
+        CUDA_OK(cudaEventCreate(&call_a));
+        CUDA_OK(cudaEventCreate(&call_b));
+        cudaEventRecord(call_a, c.stream);
+        opened = true;
+        return STRATUM_OK;
+    }
+
+    // Queues the waves of one device-resident group of tracks (track q = d_samples[offs[q] .. offs[q] + lens[q])).  On return the
+    // group's last wave may still be running; every earlier wave of the session has been gathered.  `after_prev` runs once, as soon
+    // as the waves that were in flight at entry are gathered (their sample buffer is free from then on).
+    int submit(const float* d_samples, const uint64_t* offs, const uint64_t* lens, const uint32_t* srs, uint32_t n, StratumResult* out,
+               const std::function<void()>& after_prev) {
+        uint32_t i = 0;
+        bool fired = false;
+        int st = STRATUM_OK;
+        while (i < n && st == STRATUM_OK) {
+            WavePlan wp;
+            {
+                HostSpan span_pack("host_wave_pack");
+                pack_wave(i, n, lens, srs, cfg, lim, wp);
+            }
+            WaveJob& job = c.jobs[cur];
+            WaveJob& prev = c.jobs[cur ^ 1];
+            auto mid = [&]() -> int {
+                const int s2 = wave_end(c, prev, &waves_ms);
+                if (!fired) {
+                    fired = true;
+                    if (after_prev) after_prev();
+                }
+                return s2;
+            };
+            st = wave_begin(c, d_samples, offs, lens, srs, wp, cfg, dcfg, lim.budget_floats, out, job, mid);
+            if (st != STRATUM_OK) {
+                std::string keep = g_last_error;
+                wave_end(c, prev, nullptr);  // a wave_begin that failed before its mid point leaves the previous wave queued
+                wave_end(c, job, nullptr);
+                set_error(keep);
+                break;
+            }
+            ++n_waves;
+            cur ^= 1;
+            if (job.debug_single) st = wave_end(c, job, &waves_ms);  // the debug dumps read the arena: no wave may follow before them
+        }
+        if (!fired && st == STRATUM_OK) {
+            st = wave_end(c, c.jobs[cur ^ 1], &waves_ms);
+            if (after_prev) after_prev();
+        }
+        return st;
+    }
+
+    int drain() {
+        const int s1 = wave_end(c, c.jobs[cur], &waves_ms);
+        const int s2 = wave_end(c, c.jobs[cur ^ 1], &waves_ms);
+        return s1 != STRATUM_OK ? s1 : s2;
+    }
+
+    void close() {  // device time of the whole call, inter-wave gaps included
+        if (!opened) return;
+        cudaEventRecord(call_b, c.stream);
+        cudaEventSynchronize(call_b);
+        float whole_ms = 0.0f;
+        double call_ms = waves_ms;
+        if (cudaEventElapsedTime(&whole_ms, call_a, call_b) == cudaSuccess) call_ms = whole_ms;
+        g_last_call_us.store((uint64_t)(call_ms * 1000.0));
+        g_last_call_waves.store(n_waves);
+    }
+};
+
+static int analyze_device(DeviceCtx* ctx, const float* d_samples, const uint64_t* offsets, const uint32_t* srs, uint32_t n_tracks, const StratumConfig& cfg,
                           StratumResult* out) {
-    int st;
-    DeviceCtx* ctx = get_ctx(device_id, &st);
-    if (!ctx) return st;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CUDA_OK(cudaSetDevice(ctx->device));
-    const DevCfg dcfg = make_devcfg(cfg);
-    // per-sample-rate tables are built for one configuration; a call with another one starts a fresh set when the
-    // table is getting full (slots are only referenced within a call)
-    if (!ctx->sr_cfg.empty() && ctx->sr_host.size() > DeviceCtx::MAX_SR / 2 && memcmp(&ctx->sr_cfg.back(), &cfg, sizeof cfg) != 0) {
-        ctx->sr_host.clear();
-        ctx->sr_cfg.clear();
-    }
-    size_t free_b = 0, total_b = 0;
-    CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-    // budget: what is free now plus what our own arena already holds, minus head room
-    uint64_t budget_floats = (uint64_t)((double)(free_b + ctx->fa_cap * 4) * 0.90) / 4;
-    // waves of a few hundred tracks already fill the GPU; a larger arena buys nothing and starves the caller (and our
-    // own staging buffers) of memory, so the default is capped at 100 GB
-    double cap_gb = 100.0;
-    if (const char* e = getenv("STRATUM_B200_ARENA_GB")) cap_gb = atof(e);
-    budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(cap_gb * 1e9 / 4));
-    // waves of 128-160 three-minute tracks measured fastest (982-989 tracks/s against 959 in waves of 256, 913 in waves of 64)
-    // (the cap is expressed in samples so that batches of short tracks still fill the device)
-    uint32_t wave_max = 1u << 16;
-    uint64_t wave_max_samples = (uint64_t)128 * 7938000;
-    if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) {
-        wave_max = std::max(1, atoi(e));
-        wave_max_samples = ~0ull;
-    }
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    Session S(*ctx, cfg);
+    int st = S.open();
+    if (st != STRATUM_OK) return st;
     std::vector<uint64_t> lens(n_tracks), offs(n_tracks);
     for (uint32_t i = 0; i < n_tracks; ++i) {
         offs[i] = offsets[i];
         lens[i] = offsets[i + 1] - offsets[i];
     }
-    uint32_t i = 0, n_waves = 0;
-    double call_ms = 0.0;
-    cudaEvent_t call_a, call_b;
-    cudaEventCreate(&call_a);
-    cudaEventCreate(&call_b);
-    cudaEventRecord(call_a, ctx->stream);
-    WaveLimits lim{budget_floats, wave_max, wave_max_samples};
-    while (i < n_tracks) {
-        HostSpan span_pack("host_wave_pack");
-        WavePlan wp;
-        pack_wave(i, n_tracks, lens.data(), srs, cfg, lim, wp);
-        budget_floats = lim.budget_floats;
-        span_pack.stop();
-        st = run_wave(*ctx, d_samples, offs.data(), lens.data(), srs, wp, cfg, dcfg, budget_floats, out, &call_ms);
-        if (st != STRATUM_OK) return st;
-        ++n_waves;
-    }
-    cudaEventRecord(call_b, ctx->stream);
-    cudaEventSynchronize(call_b);
-    float whole_ms = 0.0f;
-    if (cudaEventElapsedTime(&whole_ms, call_a, call_b) == cudaSuccess) call_ms = whole_ms;  // includes inter-wave host gaps
-    cudaEventDestroy(call_a);
-    cudaEventDestroy(call_b);
-    g_last_call_us.store((uint64_t)(call_ms * 1000.0));
-    g_last_call_waves.store(n_waves);
-    return STRATUM_OK;
+    st = S.submit(d_samples, offs.data(), lens.data(), srs, n_tracks, out, nullptr);
+    const int st2 = S.drain();
+    S.close();
+    return st != STRATUM_OK ? st : st2;
 }
 
 }  // namespace sb
@@ -1655,14 +1920,16 @@ int32_t stratum_b200_analyze_batch_device(const float* d_samples, const uint64_t
     int st = config_validate(c);
     if (st != STRATUM_OK) return st;
     if (n_tracks == 0) return STRATUM_OK;
-    return analyze_device(device_id, d_samples, offsets, sample_rates, n_tracks, c, out);
+    DeviceCtx* ctx = get_ctx(device_id, &st);
+    if (!ctx) return st;
+    return analyze_device(ctx, d_samples, offsets, sample_rates, n_tracks, c, out);
 }
 
 // Host-buffer batches (f32 samples, or interleaved PCM16 converted on the device): contiguous shards, one host
 // thread per device (examples/analyze_batch.rs:239-326: the only parallelism of the reference is across tracks; the
 // gather is the result array itself).  Each shard is streamed through two device staging buffers: chunk k+1 is
-// uploaded on the copy stream while chunk k is analysed (pinned host memory makes the upload asynchronous; pageable
-// memory still works, without the overlap).
+// uploaded by the device's uploader thread while chunk k is analysed (pinned host memory makes the upload asynchronous;
+// pageable memory still works, without the overlap), and the analysis itself runs one wave ahead of the gather (Session).
 static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels,
                                   uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
     if (!offsets || !sample_rates || !out || (!src && n_tracks && offsets[n_tracks] > 0) || (pcm16 && !channels)) {
@@ -1682,27 +1949,39 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 return STRATUM_INVALID_INPUT;
             }
     const size_t elt = pcm16 ? sizeof(int16_t) : sizeof(float);
-    std::vector<int32_t> devs;
-    if (device_ids && n_devices) devs.assign(device_ids, device_ids + n_devices);
-    else devs.push_back(-1);
-    const uint32_t nd = (uint32_t)devs.size();
+    // device contexts of the call; an id named twice (or -1 next to the current device's id) is one shard, not two
+    std::vector<DeviceCtx*> ctxs;
+    {
+        std::vector<int32_t> devs;
+        if (device_ids && n_devices) devs.assign(device_ids, device_ids + n_devices);
+        else devs.push_back(-1);
+        for (int32_t d : devs) {
+            DeviceCtx* ctx = get_ctx(d, &st);
+            if (!ctx) return st;
+            if (std::find(ctxs.begin(), ctxs.end(), ctx) == ctxs.end()) ctxs.push_back(ctx);
+        }
+    }
+    const uint32_t nd = (uint32_t)ctxs.size();
     std::vector<int> status(nd, STRATUM_OK);
     std::vector<std::string> errs(nd);
     auto work = [&](uint32_t d) {
         const uint32_t a = (uint32_t)((uint64_t)n_tracks * d / nd), b = (uint32_t)((uint64_t)n_tracks * (d + 1) / nd);
         if (a == b) return;
-        int stl;
-        DeviceCtx* ctx = get_ctx(devs[d], &stl);
-        if (!ctx) {
-            status[d] = stl;
-            errs[d] = g_last_error;
-            return;
-        }
-        cudaSetDevice(ctx->device);
+        DeviceCtx* ctx = ctxs[d];
+        auto fail = [&](int code, const std::string& msg) {
+            if (status[d] == STRATUM_OK) {
+                status[d] = code;
+                errs[d] = msg;
+            }
+        };
+        // One call at a time per device: the staging buffers, the conversion buffer, the arenas and the streams belong to the
+        // context, so the whole shard (upload, conversion, analysis) runs under its lock; concurrent callers queue up here.
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(STRATUM_PROCESSING_ERROR, "cudaSetDevice failed");
         // Chunk sizes ramp up: a small first chunk keeps the un-overlapped first upload short, later chunks grow to
         // STRATUM_B200_STAGE_MB of mono f32 (default 3876 MB = 128 three-minute tracks, the most efficient wave size measured:
         // 999 tracks/s device-resident in waves of 128 vs 933 in waves of 64); at least one track per chunk
-        uint64_t chunk_frames = (uint64_t)128 * 7938000;  // = the wave cap of analyze_device: one full-size chunk is one wave
+        uint64_t chunk_frames = (uint64_t)128 * 7938000;  // = the wave cap of a session: one full-size chunk is one wave
         if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_frames = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
         static const bool no_ramp = getenv("STRATUM_B200_STAGE_NO_RAMP") != nullptr;
         struct Chunk {
@@ -1712,11 +1991,12 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
         auto frames_of_track = [&](uint32_t q) { return (offsets[q + 1] - offsets[q]) / (pcm16 ? channels[q] : 1u); };
         std::vector<Chunk> chunks;
         uint64_t max_el = 0, max_fr = 0;
+        uint32_t max_cn = 0;
         uint64_t cur_frames = no_ramp ? chunk_frames : std::max<uint64_t>(chunk_frames / 4, 1u << 16);
         for (uint32_t i = a; i < b;) {
             uint32_t j = i;
             uint64_t fr = 0;
-            while (j < b && (j == i || fr + frames_of_track(j) <= cur_frames)) {
+            while (j < b && j - i < WAVE_MAX_TRACKS && (j == i || fr + frames_of_track(j) <= cur_frames)) {
                 fr += frames_of_track(j);
                 ++j;
             }
@@ -1724,17 +2004,14 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             chunks.push_back(Chunk{i, j, el, fr});
             max_el = std::max(max_el, el);
             max_fr = std::max(max_fr, fr);
+            max_cn = std::max(max_cn, j - i);
             i = j;
             cur_frames = std::min<uint64_t>(chunk_frames, chunks.size() == 1 ? cur_frames * 2 : cur_frames + cur_frames / 2);
         }
         const size_t buf_bytes = (size_t)align_up(max_el * elt + 64, 256);
         {
-            std::lock_guard<std::mutex> lk(ctx->mu);
-            if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
-                status[d] = STRATUM_PROCESSING_ERROR;
-                errs[d] = "copy stream creation failed";
-                return;
-            }
+            if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+                return fail(STRATUM_PROCESSING_ERROR, "copy stream creation failed");
             auto grow = [&](void** p, size_t* cap, size_t need) {
                 if (need <= *cap) return true;
                 if (*p) cudaFree(*p);
@@ -1746,18 +2023,19 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             };
             bool okm = grow((void**)&ctx->d_stage, &ctx->stage_cap, 2 * buf_bytes);
             if (okm && pcm16) okm = grow((void**)&ctx->d_conv, &ctx->conv_cap, (max_fr + 16) * sizeof(float));
-            if (!okm) {
-                status[d] = STRATUM_PROCESSING_ERROR;
-                errs[d] = "staging buffer allocation failed";
-                return;
-            }
+            // per-chunk offset / channel tables of the PCM16 path, two sets (the conversion of chunk k+1 is queued while chunk k runs)
+            const size_t meta_each = (size_t)align_up((size_t)(max_cn + 1) * 16 + (size_t)max_cn * 4 + 64, 256);
+            if (okm && pcm16) okm = grow((void**)&ctx->d_meta, &ctx->meta_cap, 2 * meta_each);
+            if (!okm) return fail(STRATUM_PROCESSING_ERROR, "staging buffer allocation failed");
         }
+        const size_t meta_each = (size_t)align_up((size_t)(max_cn + 1) * 16 + (size_t)max_cn * 4 + 64, 256);
         char* bufs[2] = {reinterpret_cast<char*>(ctx->d_stage), reinterpret_cast<char*>(ctx->d_stage) + buf_bytes};
-        // Uploads run on a helper thread, in pieces of 128 MB with a stream synchronisation after each piece: the analysis of
-        // chunk k issues small host<->device copies of its own (track records, escalation lists) that would otherwise queue
-        // behind a multi-gigabyte transfer on the copy engine and stall the wave until the next chunk has landed (measured: no
-        // overlap at all with 2 GB transfers enqueued in one piece).
-        auto upload = [&](size_t k) -> bool {
+        if (!ctx->uploader) ctx->uploader.reset(new Worker());
+        // Uploads run on the device's uploader thread, in pieces of 128 MB with a stream synchronisation after each piece: the
+        // analysis of chunk k issues small host<->device copies of its own (track records, counts, results) that would otherwise
+        // queue behind a multi-gigabyte transfer on the copy engine and stall the wave until the next chunk has landed (measured:
+        // no overlap at all with 2 GB transfers enqueued in one piece).
+        auto upload = [&, ctx](size_t k) -> bool {
             const Chunk& ch = chunks[k];
             if (cudaSetDevice(ctx->device) != cudaSuccess) return false;
             g_h2d_bytes.fetch_add(ch.elems * elt);
@@ -1769,79 +2047,78 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             }
             return true;
         };
-        bool ok;
-        {
-            HostSpan span_first("host_first_upload");
-            ok = upload(0);
-        }
+        Session S(*ctx, c);
+        int s2 = S.open();
+        if (s2 != STRATUM_OK) return fail(s2, g_last_error);
+        std::future<bool> up = ctx->uploader->post([&] { return upload(0); });
+        bool ok = true;
         for (size_t k = 0; ok && k < chunks.size(); ++k) {
-            // chunk k-1 has been analysed (the call below is synchronous), so its buffer is free for chunk k+1
-            bool up_ok = true;
-            std::thread uploader;
-            if (k + 1 < chunks.size()) uploader = std::thread([&, k] { up_ok = upload(k + 1); });
-            struct Joiner {
-                std::thread& t;
-                ~Joiner() { if (t.joinable()) t.join(); }
-            } joiner{uploader};
-            const Chunk& ch = chunks[k];
-            const uint32_t cn = ch.j - ch.i;
-            std::vector<uint64_t> rel(cn + 1, 0);  // per-track offsets in mono frames inside the chunk
-            for (uint32_t q = 0; q < cn; ++q) rel[q + 1] = rel[q] + frames_of_track(ch.i + q);
-            const float* d_mono = reinterpret_cast<const float*>(bufs[k & 1]);
-            if (pcm16) {
-                // decoder arithmetic on the device: interleaved int16 -> mono f32 (examples/analyze_batch.rs:96-113)
-                std::vector<uint64_t> poff(cn + 1);
-                for (uint32_t q = 0; q <= cn; ++q) poff[q] = offsets[ch.i + q] - offsets[ch.i];
-                uint64_t max_frames = 0;
-                for (uint32_t q = 0; q < cn; ++q) max_frames = std::max(max_frames, rel[q + 1] - rel[q]);
-                // small per-chunk tables live in a context buffer: no cudaMalloc / cudaFree (device-wide syncs) between chunks
-                const size_t meta_need = (size_t)(cn + 1) * 16 + (size_t)cn * 4 + 64;
-                bool okc = true;
-                if (meta_need > ctx->meta_cap) {
-                    if (ctx->d_meta) cudaFree(ctx->d_meta);
-                    ctx->d_meta = nullptr;
-                    ctx->meta_cap = 0;
-                    okc = cudaMalloc(&ctx->d_meta, 2 * meta_need) == cudaSuccess;
-                    if (okc) ctx->meta_cap = 2 * meta_need;
-                }
-                uint64_t* d_poff = reinterpret_cast<uint64_t*>(ctx->d_meta);
-                uint64_t* d_ooff = d_poff + (cn + 1);
-                uint32_t* d_ch = reinterpret_cast<uint32_t*>(d_ooff + (cn + 1));
-                if (okc) {
-                    cudaMemcpyAsync(d_poff, poff.data(), (cn + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-                    cudaMemcpyAsync(d_ooff, rel.data(), (cn + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-                    cudaMemcpyAsync(d_ch, channels + ch.i, cn * 4, cudaMemcpyHostToDevice, ctx->stream);
-                    launch_pcm16_to_mono(ctx->stream, reinterpret_cast<const int16_t*>(bufs[k & 1]), ctx->d_conv, d_poff, d_ooff, d_ch, cn, max_frames);
-                    okc = cudaStreamSynchronize(ctx->stream) == cudaSuccess;  // the offset vectors are stack-owned
-                }
-                if (!okc) {
-                    ok = false;
-                    break;
-                }
-                d_mono = ctx->d_conv;
-            }
-            int s2;
             {
-                HostSpan span_an("host_chunk_analyze");  // wall time of the synchronous analysis call (device time + its host gaps)
-                s2 = analyze_device(ctx->device, d_mono, rel.data(), sample_rates + ch.i, cn, c, out + ch.i);
+                HostSpan span_up(k == 0 ? "host_first_upload" : "host_chunk_wait_upload");  // > 0 later on only when an upload outlasts the analysis beside it
+                ok = up.get();
             }
-            if (s2 != STRATUM_OK) {
-                status[d] = s2;
-                errs[d] = g_last_error;
-                ok = false;
+            if (!ok) {
+                fail(STRATUM_PROCESSING_ERROR, "host to device copy failed");
                 break;
             }
-            {
-                HostSpan span_up("host_chunk_wait_upload");  // > 0 only when the next chunk's upload outlasts this chunk's analysis
-                if (uploader.joinable()) uploader.join();
+            const Chunk& ch = chunks[k];
+            const uint32_t cn = ch.j - ch.i;
+            std::vector<uint64_t> rel(cn + 1, 0), lens(cn);  // per-track offsets in mono frames inside the chunk
+            for (uint32_t q = 0; q < cn; ++q) {
+                lens[q] = frames_of_track(ch.i + q);
+                rel[q + 1] = rel[q] + lens[q];
             }
-            if (!up_ok) ok = false;
+            const float* d_mono = reinterpret_cast<const float*>(bufs[k & 1]);
+            if (pcm16) {
+                // decoder arithmetic on the device: interleaved int16 -> mono f32 (examples/analyze_batch.rs:96-113).  Queued on
+                // the analysis stream, so it runs after the previous chunk's waves have finished with the conversion buffer.
+                char* hm = static_cast<char*>(ctx->h_meta[k & 1].need(meta_each));
+                if (!hm) {
+                    fail(STRATUM_PROCESSING_ERROR, "pinned host allocation failed");
+                    break;
+                }
+                uint64_t* h_poff = reinterpret_cast<uint64_t*>(hm);
+                uint64_t* h_ooff = h_poff + (cn + 1);
+                uint32_t* h_ch = reinterpret_cast<uint32_t*>(h_ooff + (cn + 1));
+                uint64_t max_frames = 0;
+                for (uint32_t q = 0; q <= cn; ++q) {
+                    h_poff[q] = offsets[ch.i + q] - offsets[ch.i];
+                    h_ooff[q] = rel[q];
+                }
+                for (uint32_t q = 0; q < cn; ++q) {
+                    h_ch[q] = channels[ch.i + q];
+                    max_frames = std::max(max_frames, lens[q]);
+                }
+                char* dm = ctx->d_meta + (k & 1) * meta_each;
+                uint64_t* d_poff = reinterpret_cast<uint64_t*>(dm);
+                uint64_t* d_ooff = d_poff + (cn + 1);
+                uint32_t* d_ch = reinterpret_cast<uint32_t*>(d_ooff + (cn + 1));
+                cudaMemcpyAsync(dm, hm, (size_t)(cn + 1) * 16 + (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream);
+                launch_pcm16_to_mono(ctx->stream, reinterpret_cast<const int16_t*>(bufs[k & 1]), ctx->d_conv, d_poff, d_ooff, d_ch, cn, max_frames);
+                d_mono = ctx->d_conv;
+            }
+            bool posted = false;
+            auto after_prev = [&] {  // the previous chunk's waves are gathered: its staging buffer takes chunk k+1
+                if (k + 1 < chunks.size()) {
+                    up = ctx->uploader->post([&, k] { return upload(k + 1); });
+                    posted = true;
+                }
+            };
+            {
+                HostSpan span_an("host_chunk_submit");  // wall time of queueing the chunk (includes gathering the previous one)
+                s2 = S.submit(d_mono, rel.data(), lens.data(), sample_rates + ch.i, cn, out + ch.i, after_prev);
+            }
+            if (s2 != STRATUM_OK) {
+                fail(s2, g_last_error);
+                ok = false;
+                if (posted) up.get();  // the upload lambda refers to this frame
+                break;
+            }
         }
+        s2 = S.drain();
+        if (s2 != STRATUM_OK) fail(s2, g_last_error);
+        S.close();
         cudaStreamSynchronize(ctx->copy_stream);
-        if (!ok && status[d] == STRATUM_OK) {
-            status[d] = STRATUM_PROCESSING_ERROR;
-            errs[d] = "host to device copy failed";
-        }
     };
     if (nd == 1) {
         work(0);
@@ -1865,7 +2142,7 @@ uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* 
     const StratumConfig& c = cfg ? *cfg : def;
     std::vector<uint64_t> lens(n_tracks);
     for (uint32_t q = 0; q < n_tracks; ++q) lens[q] = offsets[q + 1] - offsets[q];
-    WaveLimits lim{(uint64_t)(budget_gb * 1e9 / 4), 1u << 16, (uint64_t)128 * 7938000};
+    WaveLimits lim{(uint64_t)(budget_gb * 1e9 / 4), WAVE_MAX_TRACKS, (uint64_t)128 * 7938000};
     uint32_t i = 0, nw = 0;
     while (i < n_tracks) {
         WavePlan wp;
@@ -2039,6 +2316,20 @@ void stratum_b200_shutdown(void) {
             cudaFree(c->d_stage);
             cudaFree(c->d_conv);
             cudaFree(c->d_meta);
+            cudaFree(c->d_count);
+            c->uploader.reset();
+            for (WaveJob& j : c->jobs) {
+                j.h_tracks.release();
+                j.h_oa.release();
+                j.h_ia.release();
+                j.h_small.release();
+                if (j.ev0) cudaEventDestroy(j.ev0);
+                if (j.ev1) cudaEventDestroy(j.ev1);
+            }
+            c->h_meta[0].release();
+            c->h_meta[1].release();
+            c->h_count.release();
+            if (c->ev_legacy) cudaEventDestroy(c->ev_legacy);
             if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
             cudaStreamDestroy(c->stream);
             if (c->key_stream) cudaStreamDestroy(c->key_stream);
@@ -2070,7 +2361,7 @@ int64_t stratum_b200_stft(const float* samples, uint64_t n, uint32_t frame_size,
     int st;
     DeviceCtx* ctx = get_ctx(-1, &st);
     if (!ctx) return -st;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     cudaSetDevice(ctx->device);
     const uint32_t frames = (uint32_t)((n - frame_size) / hop + 1);
     const uint64_t need = (uint64_t)frames * (frame_size / 2 + 1);
@@ -2101,7 +2392,7 @@ double stratum_b200_fp32_peak_tflops(int32_t device_id) {
     int st;
     DeviceCtx* ctx = get_ctx(device_id, &st);
     if (!ctx) return 0.0;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return 0.0;
     float* d = nullptr;
     if (cudaMalloc(&d, 256) != cudaSuccess) return 0.0;
@@ -2114,7 +2405,7 @@ int32_t stratum_b200_synth_batch(float* d_out, uint32_t n_tracks, uint64_t n_sam
     int st;
     DeviceCtx* ctx = get_ctx(device_id, &st);
     if (!ctx) return st;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CUDA_OK(cudaSetDevice(ctx->device));
     float* d_p = nullptr;
     CUDA_OK(cudaMalloc(&d_p, sizeof(float) * 5 * n_tracks));

@@ -16,7 +16,8 @@
 namespace sb {
 
 constexpr int RING = 32;           // mask ring: supports margin <= 15
-constexpr int HPCP_MAX_PEAKS = 512;  // local maxima in the 100..5000 Hz band (<= (hi-lo+2)/2 = 456 at 44.1 kHz)
+constexpr int HPCP_PEAKS_44K = 512;   // local maxima in the 100..5000 Hz band: <= (hi-lo+2)/2 = 456 at 44.1 kHz, 420 at 48 kHz
+constexpr int HPCP_PEAKS_ANY = 2048;  // any sample rate: a row of the 8192-point key STFT has at most 4097 / 2 local maxima
 constexpr int HPCP_MAX_SEL = 32;     // key_hpcp_peaks_per_frame upper bound accepted by the ABI
 constexpr int HPCP_MAX_HARM = 8;     // key_hpcp_num_harmonics upper bound accepted by the ABI
 
@@ -33,27 +34,63 @@ constexpr int MASK_G = 16;
 // FAST: the default exponent 2 with the mask on — `h*h`, `r*r` and no per-element mode tests.
 // KB: bins per key-spectrogram row when known at compile time (4097 for the default 8192-point key STFT: row offsets become
 // immediates), 0 = cfg.key_bins.
-template <int MG, bool FAST, int KB>
+// COMPACT: the masked rows are read again only by the HPCP peak search (bins [kband_lo, kband_lo + kband_stride)) and through the
+// frame energy sum(y^2) over all bins, so instead of rewriting the 16 KB row in place the kernel writes the band columns into the
+// compact buffer T.kband [Fk x kband_stride] and this CTA's 128-bin share of every frame's energy into T.kepart[blockIdx.x][t]
+// (hpcp_kernel adds the shares in CTA order).  The spectrogram is then read exactly once and 78 % of the mask's stores and of the
+// HPCP kernel's loads disappear.  The energy shares go through a double-buffered shared tile [16 frames x 128 bins] that the four
+// warps fold after each 16-frame group (4 loads + 3 adds + a 5-step shuffle tree per frame), off the per-element chain.
+template <int MG, bool FAST, int KB, bool COMPACT>
 __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
     const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
     __shared__ float ringP[RING][128];
     __shared__ float ringX[MG > 0 ? 1 : RING][128];
+    constexpr int ET_BUFS = (COMPACT && MG > 0) ? 2 : 1;  // the run-time-margin variant already holds two 16 KB rings: one tile, one more barrier
+    __shared__ float et[ET_BUFS][COMPACT ? MASK_G : 1][COMPACT ? 128 : 1];
+    __shared__ float sred[4];
     const TrackDev& T = tr[blockIdx.y];
     const uint32_t nf = T.Fk;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (T.status != 0 || nf == 0 || b >= KBINS) return;
+    const bool valid = b < KBINS;
+    if (T.status != 0 || nf == 0) return;
+    if (!COMPACT && !valid) return;  // the compact variant has CTA barriers in the frame loop: idle threads run it on zeros
     const uint32_t mg = MG > 0 ? (uint32_t)MG : cfg.key_margin;
-    float* K = fa + T.keyspec + b;
+    float* K = fa + T.keyspec + (valid ? b : 0u);
     const int tx = threadIdx.x;
+    const int wid = tx >> 5, lane = tx & 31;
+    const bool inband = COMPACT && valid && b >= T.kband_lo && b < T.kband_lo + T.kband_stride;
+    float* B = fa + T.kband + (inband ? b - T.kband_lo : 0u);
+    const uint32_t bstride = T.kband_stride;
+    float* EP = fa + T.kepart + (uint64_t)blockIdx.x * T.kepart_stride;
     const float p = FAST ? 2.0f : fmaxf(cfg.key_mask_power, 1.0f);
     const bool square = FAST || (p == 2.0f);
     float P = 0.0f;
     ringP[0][tx] = 0.0f;
+    auto ld = [&](uint32_t t) { return (!COMPACT || valid) ? K[(uint64_t)t * KBINS] : 0.0f; };
+    // row >= 0: slot of the energy tile this frame's share goes to (compact groups); row < 0: the tail, folded per frame
+    auto put = [&](uint32_t t, float y, int buf, int row) {
+        if (!COMPACT) {
+            K[(uint64_t)t * KBINS] = y;
+            return;
+        }
+        if (inband) B[(uint64_t)t * bstride] = y;
+        const float e = y * y;
+        if (row >= 0) {
+            et[buf][row][tx] = e;
+        } else {  // CTA-wide fold of one frame (uniform control flow: every thread of the CTA emits the same frames)
+            float v = e;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sred[wid] = v;
+            __syncthreads();
+            if (tx == 0) EP[t] = (sred[0] + sred[1]) + (sred[2] + sred[3]);
+            __syncthreads();
+        }
+    };
     // steady = the window [t - mg, t + mg] lies inside the track: the divisor is the compile-time constant 2*MG + 1 (an IEEE
     // division by a constant needs no reciprocal approximation or range check), no clamping of the window edges
-    auto emit_h = [&](uint32_t t, float h_est, float xt) {
+    auto emit_h = [&](uint32_t t, float h_est, float xt, int buf, int row) {
         if (!FAST && cfg.key_smooth_only) {  // smooth_spectrogram_time alone (extractor.rs:1246-1290, lib.rs:1043-1060)
-            K[(uint64_t)t * KBINS] = h_est;
+            put(t, h_est, buf, row);
             return;
         }
         const float x = fmaxf(xt, 0.0f);
@@ -62,9 +99,9 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
         const float hp = square ? h * h : powf(h, p);
         const float rp = square ? r * r : powf(r, p);
         const float m = hp / (hp + rp + 1e-12f);
-        K[(uint64_t)t * KBINS] = x * m;
+        put(t, x * m, buf, row);
     };
-    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt) {
+    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt, int buf, int row) {
         float h_est;
         if (mg == 0) {
             h_est = xt;
@@ -74,16 +111,17 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
             const float denom = (float)max(en - st, 1u);
             h_est = sum / denom;
         }
-        emit_h(t, h_est, xt);
+        emit_h(t, h_est, xt, buf, row);
     };
     float xp[MASK_G];  // previous group (compile-time margin only)
 #pragma unroll
     for (int q = 0; q < MASK_G; ++q) xp[q] = 0.0f;
     uint32_t i = 0;
+    int buf = 0;
     for (; i + MASK_G <= nf; i += MASK_G) {
         float xs[MASK_G];
 #pragma unroll
-        for (int q = 0; q < MASK_G; ++q) xs[q] = K[(uint64_t)(i + q) * KBINS];
+        for (int q = 0; q < MASK_G; ++q) xs[q] = ld(i + q);
         const bool steady = MG > 0 && i >= 2 * (uint32_t)MG;  // every frame this group emits has its full window (uniform over the CTA)
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) {
@@ -94,29 +132,42 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
                 float xt;
                 if (MG > 0) xt = (q >= MG) ? xs[q >= MG ? q - MG : 0] : xp[q + MASK_G - MG < MASK_G ? q + MASK_G - MG : 0];
                 else xt = ringX[(ii - mg) & (RING - 1)][tx];
-                if (steady) emit_h(ii - MG, (P - ringP[(ii - 2 * MG) & (RING - 1)][tx]) / (float)(2 * MG + 1), xt);
-                else emit(ii - mg, ii + 1, P, xt);
+                if (steady) emit_h(ii - MG, (P - ringP[(ii - 2 * MG) & (RING - 1)][tx]) / (float)(2 * MG + 1), xt, buf, q);
+                else emit(ii - mg, ii + 1, P, xt, buf, q);
             }
             ringP[(ii + 1) & (RING - 1)][tx] = P;
         }
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) xp[q] = xs[q];
+        if (COMPACT) {  // fold the tile: warp w takes rows 4w .. 4w+3 (frames i + row - mg)
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < MASK_G / 4; ++r) {
+                const int row = wid * (MASK_G / 4) + r;
+                float v = (et[buf][row][lane] + et[buf][row][lane + 32]) + (et[buf][row][lane + 64] + et[buf][row][lane + 96]);
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && i + row >= mg) EP[i + row - mg] = v;
+            }
+            if (ET_BUFS == 2) buf ^= 1;  // the next group fills the other tile; this one is rewritten only after the next barrier
+            else __syncthreads();
+        }
     }
     // tail (< 16 frames) and flush: the delayed samples are re-read from rows that are still unmasked
     // (row t is only rewritten by emit(t)), which costs at most 16 + margin scalar loads per thread
     for (; i < nf; ++i) {
-        const float x = K[(uint64_t)i * KBINS];
+        const float x = ld(i);
         P = P + x;
-        if (i >= mg) emit(i - mg, i + 1, P, K[(uint64_t)(i - mg) * KBINS]);
+        if (i >= mg) emit(i - mg, i + 1, P, ld(i - mg), 0, -1);
         ringP[(i + 1) & (RING - 1)][tx] = P;
     }
-    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P, K[(uint64_t)t * KBINS]);
+    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P, ld(t), 0, -1);
 }
 
 // ---- HPCP: one warp per frame ---------------------------------------------------------------------
+template <int MAXP>
 struct HpcpSmem {
-    float mag[HPCP_MAX_PEAKS];
-    uint16_t bin[HPCP_MAX_PEAKS];
+    float mag[MAXP];
+    uint16_t bin[MAXP];
     uint16_t sel[HPCP_MAX_SEL];
     float val[HPCP_MAX_SEL * HPCP_MAX_HARM * 3];
     int8_t tc[HPCP_MAX_SEL * HPCP_MAX_HARM * 3];
@@ -130,8 +181,10 @@ __device__ __forceinline__ float rem_euclid_f(float a, float b) {
 // One band of frame_to_hpcp_tuned_band (extractor.rs:529-680) for the calling warp.  `sel` = the row peaks are picked and ranked
 // on (whitened magnitudes when whitening is on, else the magnitudes), `mag` = the magnitudes that weight the peaks.
 // Returns the L2-normalised profile in lanes 0..11.
+template <int MAXP>
 __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const float* __restrict__ mag, uint32_t lo, uint32_t hi, float fmin, float fmax,
-                                           uint32_t peaks_per_frame, float tuning, float res, HpcpSmem& S, int lane, const DevCfg& cfg) {
+                                           uint32_t peaks_per_frame, float tuning, float res, HpcpSmem<MAXP>& S, int lane, const DevCfg& cfg) {
+    constexpr int HPCP_MAX_PEAKS = MAXP;
     // local maxima in the band, compacted in ascending bin order (extractor.rs:582-606)
     // Eight 32-bin slices at a time: their values are fetched first (eight independent loads in flight instead of three
     // dependent ones per slice), neighbours come from the adjacent lanes / slices by shuffle, then the compare-ballot-compact
@@ -244,8 +297,13 @@ __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const 
             const float spc = rem_euclid_f(semitone, 12.0f);
             const float ppc = rem_euclid_f(roundf(spc), 12.0f);
             const int primary = as_i32(ppc);
-            float dp = 1.0f;
-            for (uint32_t q = 1; q < h; ++q) dp = dp * decay;
+            float dp = 1.0f, da = decay;  // decay.powi(h - 1) as compiler-rt's __powisf2 evaluates it: square-and-multiply
+            for (uint32_t e = h - 1;;) {
+                if (e & 1u) dp = dp * da;
+                e >>= 1;
+                if (e == 0) break;
+                da = da * da;
+            }
             const float hw = dp / (float)h;
             const float contrib = w0 * hw;
 #pragma unroll
@@ -277,33 +335,43 @@ __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const 
     return pc;
 }
 
-__global__ void __launch_bounds__(128) hpcp_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
-                                                   float* fa, DevCfg cfg) {
-    __shared__ HpcpSmem sm[4];
+// MAXP peak slots per frame; WARPS frames per CTA (4 x 512 slots or 2 x 2048 slots of shared memory).
+// cfg.key_compact: the masked band comes from T.kband (mask_kernel<COMPACT>) and the frame energy from the per-CTA shares in T.kepart.
+template <int MAXP, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) hpcp_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
+                                                          float* fa, DevCfg cfg) {
+    __shared__ HpcpSmem<MAXP> sm[WARPS];
     const int t = blockIdx.y;
     const TrackDev& T = tr[t];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t f = blockIdx.x * 4 + w;
+    const uint32_t f = blockIdx.x * WARPS + w;
     if (T.status != 0 || f >= T.Fk || T.beat_sync) return;
-    HpcpSmem& S = sm[w];
+    HpcpSmem<MAXP>& S = sm[w];
     const SrTables& st = srtab[sr_index[t]];
     const uint32_t KBINS = cfg.key_bins;
-    const float* row = fa + T.keyspec + (uint64_t)f * KBINS;
-    const float* sel = cfg.key_whiten ? fa + T.kwhite + (uint64_t)f * T.kwhite_stride : row;
     // frame energy (extractor.rs:1132-1134).  Consumed only through (E/median)^0.5 frame weights, a
-    // tolerance-level quantity, so the 4097-term sum is a warp tree instead of a serial fold.
+    // tolerance-level quantity, so the 4097-term sum is a tree instead of a serial fold.
     float e = 0.0f;
-    for (uint32_t k = lane; k < KBINS; k += 32) {
-        const float x = row[k];
-        e = e + x * x;
+    const float* row;  // indexed by key-STFT bin
+    if (cfg.key_compact) {
+        row = fa + T.kband + (uint64_t)f * T.kband_stride - T.kband_lo;
+        const uint32_t np = (KBINS + 127) / 128;  // CTAs of the mask kernel
+        for (uint32_t k = lane; k < np; k += 32) e = e + fa[T.kepart + (uint64_t)k * T.kepart_stride + f];
+    } else {
+        row = fa + T.keyspec + (uint64_t)f * KBINS;
+        for (uint32_t k = lane; k < KBINS; k += 32) {
+            const float x = row[k];
+            e = e + x * x;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    const float* sel = cfg.key_whiten ? fa + T.kwhite + (uint64_t)f * T.kwhite_stride : row;
     const float res = (float)T.sr / (float)cfg.key_frame;
     const float nyq = (float)T.sr / 2.0f;
-    float pc = hpcp_band(sel, row, st.key_bin_lo, st.key_bin_hi, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), cfg.hpcp_peaks, T.key_tuning, res, S, lane, cfg);
+    float pc = hpcp_band<MAXP>(sel, row, st.key_bin_lo, st.key_bin_hi, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), cfg.hpcp_peaks, T.key_tuning, res, S, lane, cfg);
     if (cfg.key_bass_blend) {  // extractor.rs:1154-1239: (1-w) full + w bass, renormalised
-        const float bass = hpcp_band(sel, row, st.bass_bin_lo, st.bass_bin_hi, st.bass_fmin, st.bass_fmax, min(max(cfg.hpcp_peaks, 1u), 12u), T.key_tuning, res, S,
-                                     lane, cfg);
+        const float bass = hpcp_band<MAXP>(sel, row, st.bass_bin_lo, st.bass_bin_hi, st.bass_fmin, st.bass_fmax, min(max(cfg.hpcp_peaks, 1u), 12u), T.key_tuning, res, S,
+                                           lane, cfg);
         const float bw = clamp_rs(cfg.bass_weight, 0.0f, 1.0f);
         pc = (1.0f - bw) * pc + bw * bass;
         float ss = 0.0f;
@@ -872,9 +940,15 @@ void launch_key_mask(const WaveCtx& c) {
     if (c.max_Fk > 0 && !c.cfg.key_hpss && (c.cfg.key_mask || c.cfg.key_smooth_only)) {  // the median-HPSS mask takes precedence (lib.rs:1011-1030)
         const dim3 g((c.cfg.key_bins + 127) / 128, c.n_tracks);
         const bool fast = !c.cfg.key_smooth_only && fmaxf(c.cfg.key_mask_power, 1.0f) == 2.0f && c.cfg.key_bins == 4097;
-        if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680, 688)
-        else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-        else mask_kernel<0, false, 0><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        if (c.cfg.key_compact) {
+            if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680, 688)
+            else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            else mask_kernel<0, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        } else {
+            if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            else mask_kernel<0, false, 0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+        }
         count_launch("key_mask");
     }
     if (c.max_Fk > 0) launch_key_variants_pre(c);
@@ -883,10 +957,12 @@ void launch_key_mask(const WaveCtx& c) {
 void launch_key_hpcp(const WaveCtx& c) {
     if (c.max_Fk > 0) {
         const dim3 g((c.max_Fk + 3) / 4, c.n_tracks);
+        // HPCP peak slots: 512 cover the 100..5000 Hz band down to 39.2 kHz; lower sample rates put more key-STFT bins into the band
         // which chroma front end a track takes is decided per track (lib.rs:1123-1197): beat-synchronous tracks and plain chroma
         // folding go through chroma_fold_kernel, log-frequency through k_keyvar.cu, everything else through HPCP
         if (c.cfg.key_hpcp && !c.cfg.key_log_freq) {
-            hpcp_kernel<<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+            if (c.max_key_peaks <= (uint32_t)HPCP_PEAKS_44K) hpcp_kernel<HPCP_PEAKS_44K, 4><<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+            else hpcp_kernel<HPCP_PEAKS_ANY, 2><<<dim3((c.max_Fk + 1) / 2, c.n_tracks), 64, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
             count_launch("key_hpcp");
         }
         if (c.cfg.key_beat_sync || (!c.cfg.key_hpcp && !c.cfg.key_log_freq)) {

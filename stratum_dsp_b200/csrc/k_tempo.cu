@@ -564,6 +564,55 @@ __global__ void escalation_gate_kernel(TrackDev* tr, const float* fa, int n_trac
     T.trap_high = trap_high;
 }
 
+// ---- escalation list (lib.rs:412-459): ordered compaction of the gate's flags, on the device ---------------------------
+// list[0 .. count) = indices of the escalated tracks in ascending order, *count_out = count.  The hop-256 / hop-1024 work
+// areas of an escalated track live in arena slots of `slot_stride` floats starting at `slot_base`; the host planned their
+// layouts relative to the slot start (engine.cu: plan_escalation), so the track at list position p only has its offsets moved
+// to slot p mod n_slots.  Replaces a read-back of every track record plus two small copies per escalated track; the host
+// reads one integer.  One CTA; tracks are taken 1024 at a time.
+__global__ void __launch_bounds__(1024) escalation_compact_kernel(TrackDev* tr, int n_tracks, int32_t* list, int32_t* count_out, uint64_t slot_base,
+                                                                  uint64_t slot_stride, uint32_t n_slots) {
+    __shared__ int wcnt[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n_tracks; c0 += 1024) {
+        const int t = c0 + tid;
+        const bool flag = t < n_tracks && tr[t].status == 0 && tr[t].escalate != 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) wcnt[wid] = __popc(m);
+        __syncthreads();
+        int before = base_s;
+        for (int q = 0; q < wid; ++q) before += wcnt[q];
+        if (flag) {
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            list[pos] = t;
+            const uint64_t add = slot_base + (uint64_t)((uint32_t)pos % n_slots) * slot_stride;
+            TrackDev& T = tr[t];
+            for (int h = 1; h <= 2; ++h) {
+                HopLayout& H = T.hop[h];
+                H.spec += add;
+                H.frame += add;
+                H.pair += add;
+                H.nov += add;
+                H.tgfft += add;
+                H.tgac += add;
+                H.tgwork += add;
+                T.cands[h] += add;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int q = 0; q < 32; ++q) tot += wcnt[q];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *count_out = base_s;
+}
+
 // ---- multi-resolution fusion (multi_resolution.rs:407-901): one CTA per escalated track ----------
 __device__ inline float mr_lookup(const TempoCandDev* c, uint32_t n, float bpm, float tol) {  // :282-293
     float best_d = INFINITY, best_s = 0.0f;
@@ -971,6 +1020,11 @@ void launch_tempogram(const WaveCtx& c, int h, const int32_t* d_list, int n_list
 
 void launch_escalation_gate(const WaveCtx& c) {
     escalation_gate_kernel<<<(c.n_tracks + 127) / 128, 128, 0, c.stream>>>(c.tracks, c.fa, c.n_tracks, c.cfg);
+    count_launch("tempogram");
+}
+
+void launch_escalation_compact(const WaveCtx& c, int32_t* d_list, int32_t* d_count, uint64_t slot_base, uint64_t slot_stride, uint32_t n_slots) {
+    escalation_compact_kernel<<<1, 1024, 0, c.stream>>>(c.tracks, c.n_tracks, d_list, d_count, slot_base, slot_stride, n_slots > 0 ? n_slots : 1u);
     count_launch("tempogram");
 }
 

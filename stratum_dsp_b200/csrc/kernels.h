@@ -36,6 +36,7 @@ struct DevCfg {
     int32_t key_mask, key_weighting, key_voting;
     int32_t key_smooth_only;      // harmonic mask off, time smoothing on: the key spectrogram is replaced by its +-margin mean (lib.rs:1043-1060)
     int32_t key_hpcp;             // 0 = plain chroma folding (extractor.rs:393-487)
+    int32_t key_compact;          // the mask writes the HPCP band + per-CTA frame-energy shares instead of rewriting the spectrogram (k_key.cu)
     float chroma_sharpen;         // > 1: sharpen_chroma (chroma/normalization.rs:41-65)
     float key_min_tonal, key_tonal_pow, key_energy_pow;
     uint32_t key_seg_len, key_seg_hop;
@@ -116,6 +117,7 @@ struct WaveCtx {
     uint32_t max_seg_cap;
     uint32_t max_lg_fft;
     uint32_t max_lufs_nb;
+    uint32_t max_key_peaks;  // HPCP peak slots a frame may need: (band bins + 1) / 2 over the wave's sample rates
 };
 
 struct Launcher;  // counts launches + optional stage timing (engine.cu)
@@ -138,6 +140,7 @@ void launch_spectral_onsets_consensus(const WaveCtx& c);
 // k_tempo.cu
 void launch_tempogram(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);
 void launch_escalation_gate(const WaveCtx& c);
+void launch_escalation_compact(const WaveCtx& c, int32_t* d_list, int32_t* d_count, uint64_t slot_base, uint64_t slot_stride, uint32_t n_slots);
 void launch_multires_fusion(const WaveCtx& c, const int32_t* d_list, int n_list);
 void launch_final_bpm(const WaveCtx& c);
 void launch_emit_candidates(const WaveCtx& c);

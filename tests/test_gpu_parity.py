@@ -442,6 +442,10 @@ def test_key_variants_in_a_ragged_batch():
     {"key_segment_len_frames": 512, "key_segment_hop_frames": 128, "key_segment_min_clarity": 0.5},
     {"key_spectrogram_smooth_margin": 6, "key_harmonic_mask_power": 1.5},
     {"key_hpcp_peaks_per_frame": 8, "key_hpcp_num_harmonics": 2, "key_hpcp_harmonic_decay": 0.4, "key_hpcp_mag_power": 0.8},
+    {"key_hpcp_num_harmonics": 8, "key_hpcp_harmonic_decay": 0.83},  # decay.powi(h - 1) beyond h = 4: __powisf2's square-and-multiply roundings
+    {"enable_key_harmonic_mask": 0},  # time smoothing alone through the compact mask path
+    {"enable_key_harmonic_mask": 0, "enable_key_spectrogram_time_smoothing": 0},  # HPCP straight from the STFT rows
+    {"enable_key_hpcp_bass_blend": 1},  # two peak bands in the compact band
     {"tempogram_superflux_max_filter_bins": 2, "tempogram_mel_max_filter_bins": 1, "tempogram_novelty_local_mean_window": 8,
      "tempogram_novelty_smooth_window": 3},
     {"min_bpm": 60.0, "max_bpm": 180.0, "bpm_resolution": 0.5},
@@ -474,3 +478,62 @@ def test_tempogram_candidates_metadata(cfg):
             assert b == e[0] and abs(sc - e[1]) <= 1e-3 * max(abs(e[1]), 1e-6) + 1e-6 and bool(e[4]) == sel
             assert abs(fn - e[2]) < 1e-3 and abs(an - e[3]) < 1e-3
     assert S.analyze_audio(x, SR).metadata.tempogram_candidates is None
+
+
+def test_concurrent_calls_on_one_device_match_serial():
+    # the reference's usage is paths.par_iter().map(analyze_audio) (examples/analyze_batch.rs:260-326): many host threads on one
+    # device.  Calls serialise on the device context; each must still get its own track's result.
+    import threading
+    xs = [synth.render(synth.c2_params(200 + i, (8 + 3 * i) * SR, SR)) for i in range(6)]
+    serial = [S.analyze_audio(x, SR) for x in xs]
+    got = [None] * len(xs)
+    errs = []
+
+    def run(i):
+        try:
+            for _ in range(2):
+                got[i] = S.analyze_audio(xs[i], SR)
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, e))
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(xs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i, (a, b) in enumerate(zip(got, serial)):
+        assert a.bpm == b.bpm and a.key == b.key and a.key_confidence == b.key_confidence and a.grid_stability == b.grid_stability, i
+        assert np.array_equal(a.onsets, b.onsets) and np.array_equal(a.hmm_beat_frames, b.hmm_beat_frames), i
+        assert np.array_equal(a.beat_grid.beats, b.beat_grid.beats), i
+
+
+def test_repeated_device_id_is_one_shard():
+    xs = [synth.render(synth.c2_params(210 + i, 10 * SR, SR)) for i in range(3)]
+    a = S.analyze_batch(xs, SR, devices=[0, 0])
+    b = S.analyze_batch(xs, SR)
+    for x, y in zip(a, b):
+        assert x.bpm == y.bpm and x.key == y.key and np.array_equal(x.onsets, y.onsets)
+
+
+@pytest.mark.parametrize("sr", [22050, 32000, 8000, 96000])
+def test_other_sample_rates_default_key_path(sr):
+    # the reference accepts any sample rate; below 39.2 kHz the 100..5000 Hz HPCP band spans more than 1024 key-STFT bins
+    p = synth.c2_params(220, 14 * sr, sr)
+    p.sample_rate = sr
+    x = synth.render(p)
+    assert_parity(S.analyze_audio(x, sr), O.analyze(x, sr), f"sr={sr}")
+
+
+def test_unsupported_track_fails_alone():
+    # a track the configured key path cannot take (fixed-size band tables) fails with its own NotImplemented error;
+    # the rest of the batch is analysed (examples/analyze_batch.rs:293-322: ItemOut.error)
+    lo = synth.c2_params(230, 10 * 22050, 22050)
+    lo.sample_rate = 22050
+    xs = [synth.render(synth.c2_params(231, 10 * SR, SR)), synth.render(lo), synth.render(synth.c2_params(232, 12 * SR, SR))]
+    cfg = S.AnalysisConfig(enable_key_hpcp=False)
+    res = S.analyze_batch(xs, [SR, 22050, SR], cfg)
+    assert res[1].error is not None and res[1].error.kind == "NotImplemented" and "22050" in res[1].error.message
+    for i in (0, 2):
+        assert res[i].error is None
+        assert_parity(res[i], O.analyze(xs[i], SR, {"enable_key_hpcp": 0}, fast=True), f"track {i}")
