@@ -261,6 +261,10 @@ void stratum_b200_debug_enable(int32_t on);
  * roofline denominator of bench.py (the path is FP32-bound).  0 when no device is usable. */
 double stratum_b200_fp32_peak_tflops(int32_t device_id);
 
+/* Self-check of the range-restricted exact divisions the hot kernels use (csrc/common.cuh) against IEEE division on n random
+ * operand tuples drawn from their documented ranges; mismatches3 = {a/25, hp/(hp+rp+eps), x/rowmax} mismatch counts (all 0). */
+int32_t stratum_b200_debug_check_divisions(uint64_t n, uint32_t seed, uint64_t* mismatches3);
+
 /* Host-side wave planner on its own (no device work): wave index of every track for an arena budget of budget_gb
  * gigabytes; returns the number of waves.  Lets the packing logic be tested without a GPU. */
 uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg, double budget_gb,

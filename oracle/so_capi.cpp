@@ -113,7 +113,7 @@ double so_scalar(void* hp, const char* name) {
     if (!strcmp(name, #f)) return (double)r.f;
     S(bpm) S(bpm_confidence) S(key_is_minor) S(key_index) S(key_confidence) S(key_clarity) S(grid_stability) S(duration_seconds)
     S(sample_rate) S(onset_method_consensus) S(warnings) S(flags) S(multi_res_triggered) S(multi_res_used) S(percussive_triggered)
-    S(percussive_used) S(trim_start) S(trim_end) S(time_sig_beats_per_bar) S(beats_refined)
+    S(percussive_used) S(trim_start) S(trim_end) S(time_sig_beats_per_bar) S(beats_refined) S(key_hashmap_tie)
 #undef S
     return NAN;
 }
@@ -188,6 +188,9 @@ int so_array_names(void* hp, char* buf, int cap) {
     }
     return (int)all.size();
 }
+
+void so_set_fft_variant(int v) { set_fft_variant(v); }
+int so_fft_variant() { return fft_variant(); }
 
 // ---- stage-level entry points -------------------------------------------------------------
 void so_cfft(float* reim, uint64_t m) {  // interleaved re,im; in place

@@ -253,6 +253,7 @@ struct Result {
     std::vector<int32_t> hmm_beat_frames;  // t indices kept by the first HMM pass
     int time_sig_beats_per_bar = 4;
     int beats_refined = 0;  // 1 if the Bayesian per-segment refinement replaced the grid
+    int key_hashmap_tie = 0;  // 1 if the returned key label came out of a weighted vote tied at the top (undetermined in the reference)
     bool has_candidates = false;  // metadata.tempogram_candidates: Option<Vec<TempoCandidateDebug>> (lib.rs:684-697, 740-752)
     std::vector<TempoCand> tempogram_candidates;
 };
@@ -272,6 +273,8 @@ struct Dump {
 struct cpx {
     float re, im;
 };
+void set_fft_variant(int v);  // 0 = SFFT (the parity arithmetic); 1 = float64 rounded once; 2 = f32 radix-2 DIT, no fma (so_fft.cpp)
+int fft_variant();
 void cfft_forward(std::vector<cpx>& x);                         // in place, size power of two
 void rfft_forward(const float* x, size_t n, std::vector<cpx>& X);  // n real (pow2, >=4) -> n/2+1 bins
 
@@ -343,6 +346,7 @@ struct KeyScores {
     float scores[24];
     int key;
     float confidence;
+    int vote_tie = 0;  // 1: the weighted top-3 vote ran with two keys at exactly the best vote (the reference picks by HashMap order, detector.rs:254-275)
 };
 Error detect_key_weighted(const float* chroma, size_t frames, const float* w /*nullable*/, KeyScores& out, int template_set = 0);
 Error detect_key_weighted_mode_heuristic(const float* chroma, size_t frames, const float* w /*nullable*/, int template_set, float third_ratio_margin,

@@ -577,6 +577,11 @@ Error detect_key_weighted(const float* chroma, size_t frames, const float* w, Ke
     int final_key = out.keys[0];
     float final_score = out.scores[0];
     float best_other = out.scores[1];
+    {   // which calls enter the vote with an exact tie (instrumentation for the parity report)
+        const float thr = final_score * 0.95f;
+        const bool use_vote = out.scores[1] >= thr && out.scores[2] >= thr * 0.90f;
+        out.vote_tie = (use_vote && final_score > 0.0f && out.scores[1] / final_score == final_score / final_score) ? 1 : 0;
+    }
     out.key = final_key;
     out.confidence = final_score > 0.0f ? clamp_rs((final_score - best_other) / final_score, 0.0f, 1.0f) : 0.0f;
     return Error{};
@@ -932,6 +937,7 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
     }
     key = ks.key;
     confidence = ks.confidence;
+    r.key_hashmap_tie = (!done && ks.vote_tie) ? 1 : 0;  // segment voting / multi-scale / ensemble rank accumulated scores: no HashMap involved
     float clarity = compute_key_clarity(all_scores, 24);
     r.key_is_minor = key >= 12;
     r.key_index = (uint32_t)(key % 12);

@@ -337,6 +337,12 @@ static int ctx_init(DeviceCtx& c, int device) {
     }
     c.tab.rw2048 = get_tw(c, 2048);  // RW_N[k] = TW_N[k], k <= N/2
     c.tab.rw8192 = get_tw(c, 8192);
+    {   // mirror symmetry of the real-split table (k_stft.cu: stft_key12_kernel reads one entry per bin pair when it holds)
+        const std::vector<float2> rw = make_tw(8192);
+        bool sym = true;
+        for (uint32_t k = 1; k < 2048 && sym; ++k) sym = rw[4096 - k].x == -rw[k].x && rw[4096 - k].y == rw[k].y;
+        c.tab.rw8192_sym = sym ? 1 : 0;
+    }
     c.tab.win2048 = dev_upload(c, make_hann(2048));
     c.tab.win8192 = dev_upload(c, make_hann(8192));
     std::vector<float> mj, mn;
@@ -453,6 +459,8 @@ static void compact_band(uint32_t sr, const StratumConfig& cfg, uint32_t key_fra
 }
 
 static bool key_compact_mode(const StratumConfig& c) {  // see DevCfg::key_compact
+    static const bool off = getenv("STRATUM_B200_KEY_COMPACT") && atoi(getenv("STRATUM_B200_KEY_COMPACT")) == 0;  // A/B switch for measurements
+    if (off) return false;
     const bool mask_runs = !c.enable_key_hpss_harmonic && (c.enable_key_harmonic_mask || (c.enable_key_spectrogram_time_smoothing && c.key_spectrogram_smooth_margin > 0));
     return mask_runs && c.enable_key_hpcp && !c.enable_key_log_frequency && !c.enable_key_beat_synchronous && !c.enable_key_hpcp_whitening &&
            !c.enable_key_tuning_compensation;
@@ -1043,7 +1051,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
         compact_band(T.sr, cfg, kd.key_frame, &T.kband_lo, &T.kband_stride);
         T.kband = fa.take((uint64_t)Fk * T.kband_stride + 32, 32);
         T.kepart_stride = (uint32_t)align_up(Fk + 1, 32);
-        T.kepart = fa.take((uint64_t)((kd.key_bins + 127) / 128) * T.kepart_stride, 32);
+        T.kepart = fa.take((uint64_t)((kd.key_bins + 31) / 32) * T.kepart_stride, 32);  // one row per warp of the mask kernel
     }
     T.chroma = fa.take((uint64_t)Fk * 12 + 12);
     T.chroma2 = fa.take((uint64_t)Fk * 12 + 12);
@@ -2399,6 +2407,23 @@ double stratum_b200_fp32_peak_tflops(int32_t device_id) {
     const double tf = measure_fp32_peak_tflops(ctx->stream, d);
     cudaFree(d);
     return tf;
+}
+
+int32_t stratum_b200_debug_check_divisions(uint64_t n, uint32_t seed, uint64_t* mismatches3) {
+    int st;
+    DeviceCtx* ctx = get_ctx(-1, &st);
+    if (!ctx) return st;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    unsigned long long* d = nullptr;
+    CUDA_OK(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    const int rc = check_divisions(ctx->stream, n, seed, d);
+    unsigned long long h[3] = {~0ull, ~0ull, ~0ull};
+    const cudaError_t e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CUDA_OK(e);
+    for (int i = 0; i < 3; ++i) mismatches3[i] = h[i];
+    return rc == 0 ? STRATUM_OK : STRATUM_PROCESSING_ERROR;
 }
 
 int32_t stratum_b200_synth_batch(float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sample_rate, const float* params5, int32_t device_id) {

@@ -36,39 +36,40 @@ constexpr int MASK_G = 16;
 // immediates), 0 = cfg.key_bins.
 // COMPACT: the masked rows are read again only by the HPCP peak search (bins [kband_lo, kband_lo + kband_stride)) and through the
 // frame energy sum(y^2) over all bins, so instead of rewriting the 16 KB row in place the kernel writes the band columns into the
-// compact buffer T.kband [Fk x kband_stride] and this CTA's 128-bin share of every frame's energy into T.kepart[blockIdx.x][t]
-// (hpcp_kernel adds the shares in CTA order).  The spectrogram is then read exactly once and 78 % of the mask's stores and of the
-// HPCP kernel's loads disappear.  The energy shares go through a double-buffered shared tile [16 frames x 128 bins] that the four
-// warps fold after each 16-frame group (4 loads + 3 adds + a 5-step shuffle tree per frame), off the per-element chain.
+// compact buffer T.kband [Fk x kband_stride] and each WARP's 32-bin share of every frame's energy into T.kepart[warp][t]
+// (hpcp_kernel adds the shares in warp order).  The spectrogram is then read exactly once and 78 % of the mask's stores and of the
+// HPCP kernel's loads disappear.  The shares go through a per-warp shared tile [16 frames x 32 bins (+1 pad)] folded after each
+// 16-frame group: lane l sums 16 bins of frame l mod 16, one shuffle joins the two halves — about 35 instructions per thread and
+// group, off the per-element chain, and no CTA barrier (a first version with a CTA-wide tile and one barrier per group ran 38 %
+// slower than the in-place kernel: the barrier serialises the four warps' load latencies).
 template <int MG, bool FAST, int KB, bool COMPACT>
-__global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
+__global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
     const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
     __shared__ float ringP[RING][128];
     __shared__ float ringX[MG > 0 ? 1 : RING][128];
-    constexpr int ET_BUFS = (COMPACT && MG > 0) ? 2 : 1;  // the run-time-margin variant already holds two 16 KB rings: one tile, one more barrier
-    __shared__ float et[ET_BUFS][COMPACT ? MASK_G : 1][COMPACT ? 128 : 1];
-    __shared__ float sred[4];
+    __shared__ float et[COMPACT ? 4 : 1][COMPACT ? MASK_G : 1][COMPACT ? 33 : 1];
     const TrackDev& T = tr[blockIdx.y];
     const uint32_t nf = T.Fk;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = b < KBINS;
     if (T.status != 0 || nf == 0) return;
-    if (!COMPACT && !valid) return;  // the compact variant has CTA barriers in the frame loop: idle threads run it on zeros
-    const uint32_t mg = MG > 0 ? (uint32_t)MG : cfg.key_margin;
-    float* K = fa + T.keyspec + (valid ? b : 0u);
     const int tx = threadIdx.x;
     const int wid = tx >> 5, lane = tx & 31;
+    if (blockIdx.x * blockDim.x + (uint32_t)wid * 32u >= KBINS) return;  // whole warp past the row
+    if (!COMPACT && !valid) return;  // the compact variant has warp collectives in the frame loop: idle lanes run it on zeros
+    const uint32_t mg = MG > 0 ? (uint32_t)MG : cfg.key_margin;
+    float* K = fa + T.keyspec + (valid ? b : 0u);
     const bool inband = COMPACT && valid && b >= T.kband_lo && b < T.kband_lo + T.kband_stride;
     float* B = fa + T.kband + (inband ? b - T.kband_lo : 0u);
     const uint32_t bstride = T.kband_stride;
-    float* EP = fa + T.kepart + (uint64_t)blockIdx.x * T.kepart_stride;
+    float* EP = fa + T.kepart + (uint64_t)(blockIdx.x * 4 + wid) * T.kepart_stride;  // this warp's share row
     const float p = FAST ? 2.0f : fmaxf(cfg.key_mask_power, 1.0f);
     const bool square = FAST || (p == 2.0f);
     float P = 0.0f;
     ringP[0][tx] = 0.0f;
     auto ld = [&](uint32_t t) { return (!COMPACT || valid) ? K[(uint64_t)t * KBINS] : 0.0f; };
-    // row >= 0: slot of the energy tile this frame's share goes to (compact groups); row < 0: the tail, folded per frame
-    auto put = [&](uint32_t t, float y, int buf, int row) {
+    // row >= 0: slot of the warp's energy tile this frame's share goes to (16-frame groups); row < 0: the tail, folded per frame
+    auto put = [&](uint32_t t, float y, int row) {
         if (!COMPACT) {
             K[(uint64_t)t * KBINS] = y;
             return;
@@ -76,21 +77,18 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
         if (inband) B[(uint64_t)t * bstride] = y;
         const float e = y * y;
         if (row >= 0) {
-            et[buf][row][tx] = e;
-        } else {  // CTA-wide fold of one frame (uniform control flow: every thread of the CTA emits the same frames)
+            et[wid][row][lane] = e;
+        } else {  // warp-wide fold of one frame (uniform control flow: every lane emits the same frames)
             float v = e;
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sred[wid] = v;
-            __syncthreads();
-            if (tx == 0) EP[t] = (sred[0] + sred[1]) + (sred[2] + sred[3]);
-            __syncthreads();
+            if (lane == 0) EP[t] = v;
         }
     };
     // steady = the window [t - mg, t + mg] lies inside the track: the divisor is the compile-time constant 2*MG + 1 (an IEEE
     // division by a constant needs no reciprocal approximation or range check), no clamping of the window edges
-    auto emit_h = [&](uint32_t t, float h_est, float xt, int buf, int row) {
+    auto emit_h = [&](uint32_t t, float h_est, float xt, int row) {
         if (!FAST && cfg.key_smooth_only) {  // smooth_spectrogram_time alone (extractor.rs:1246-1290, lib.rs:1043-1060)
-            put(t, h_est, buf, row);
+            put(t, h_est, row);
             return;
         }
         const float x = fmaxf(xt, 0.0f);
@@ -98,10 +96,12 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
         const float r = fmaxf(x - h, 0.0f);
         const float hp = square ? h * h : powf(h, p);
         const float rp = square ? r * r : powf(r, p);
-        const float m = hp / (hp + rp + 1e-12f);
-        put(t, x * m, buf, row);
+        // FAST: hp, rp are squares of magnitudes (<= 2^40) and the divisor is >= 1e-12, so the quotient is correctly rounded
+        // without the generic division's range check (common.cuh); hp below 2^-100 only occurs below -600 dBFS
+        const float m = FAST ? div_rn_inrange(hp, hp + rp + 1e-12f) : hp / (hp + rp + 1e-12f);
+        put(t, x * m, row);
     };
-    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt, int buf, int row) {
+    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt, int row) {
         float h_est;
         if (mg == 0) {
             h_est = xt;
@@ -111,13 +111,12 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
             const float denom = (float)max(en - st, 1u);
             h_est = sum / denom;
         }
-        emit_h(t, h_est, xt, buf, row);
+        emit_h(t, h_est, xt, row);
     };
     float xp[MASK_G];  // previous group (compile-time margin only)
 #pragma unroll
     for (int q = 0; q < MASK_G; ++q) xp[q] = 0.0f;
     uint32_t i = 0;
-    int buf = 0;
     for (; i + MASK_G <= nf; i += MASK_G) {
         float xs[MASK_G];
 #pragma unroll
@@ -132,24 +131,27 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
                 float xt;
                 if (MG > 0) xt = (q >= MG) ? xs[q >= MG ? q - MG : 0] : xp[q + MASK_G - MG < MASK_G ? q + MASK_G - MG : 0];
                 else xt = ringX[(ii - mg) & (RING - 1)][tx];
-                if (steady) emit_h(ii - MG, (P - ringP[(ii - 2 * MG) & (RING - 1)][tx]) / (float)(2 * MG + 1), xt, buf, q);
-                else emit(ii - mg, ii + 1, P, xt, buf, q);
+                if (steady) {
+                    const float wsum = P - ringP[(ii - 2 * MG) & (RING - 1)][tx];
+                    // FAST (mask on, margin 12): RN(wsum / 25) in three instructions; exact for |wsum| >= 1e-30, and a smaller window sum
+                    // gives h < 1e-31, whose square is zero whichever way the quotient rounds
+                    emit_h(ii - MG, (FAST && MG == 12) ? div_by_25_rn(wsum) : wsum / (float)(2 * MG + 1), xt, q);
+                }
+                else emit(ii - mg, ii + 1, P, xt, q);
             }
             ringP[(ii + 1) & (RING - 1)][tx] = P;
         }
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) xp[q] = xs[q];
-        if (COMPACT) {  // fold the tile: warp w takes rows 4w .. 4w+3 (frames i + row - mg)
-            __syncthreads();
+        if (COMPACT) {  // fold the warp's tile: lane l adds bins 16*(l/16) .. +15 of row l % 16 (frame i + row - mg), halves joined by one shuffle
+            __syncwarp();
+            const int row = lane & (MASK_G - 1), c0 = (lane >> 4) * 16;
+            float v = 0.0f;
 #pragma unroll
-            for (int r = 0; r < MASK_G / 4; ++r) {
-                const int row = wid * (MASK_G / 4) + r;
-                float v = (et[buf][row][lane] + et[buf][row][lane + 32]) + (et[buf][row][lane + 64] + et[buf][row][lane + 96]);
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0 && i + row >= mg) EP[i + row - mg] = v;
-            }
-            if (ET_BUFS == 2) buf ^= 1;  // the next group fills the other tile; this one is rewritten only after the next barrier
-            else __syncthreads();
+            for (int c = 0; c < 16; ++c) v += et[wid][row][c0 + c];
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < MASK_G && i + row >= mg) EP[i + row - mg] = v;
+            __syncwarp();
         }
     }
     // tail (< 16 frames) and flush: the delayed samples are re-read from rows that are still unmasked
@@ -157,10 +159,10 @@ __global__ void __launch_bounds__(128) mask_kernel(const TrackDev* __restrict__ 
     for (; i < nf; ++i) {
         const float x = ld(i);
         P = P + x;
-        if (i >= mg) emit(i - mg, i + 1, P, ld(i - mg), 0, -1);
+        if (i >= mg) emit(i - mg, i + 1, P, ld(i - mg), -1);
         ringP[(i + 1) & (RING - 1)][tx] = P;
     }
-    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P, ld(t), 0, -1);
+    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P, ld(t), -1);
 }
 
 // ---- HPCP: one warp per frame ---------------------------------------------------------------------
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(32 * WARPS) hpcp_kernel(const TrackDev* __rest
     const float* row;  // indexed by key-STFT bin
     if (cfg.key_compact) {
         row = fa + T.kband + (uint64_t)f * T.kband_stride - T.kband_lo;
-        const uint32_t np = (KBINS + 127) / 128;  // CTAs of the mask kernel
+        const uint32_t np = (KBINS + 31) / 32;  // warps of the mask kernel
         for (uint32_t k = lane; k < np; k += 32) e = e + fa[T.kepart + (uint64_t)k * T.kepart_stride + f];
     } else {
         row = fa + T.keyspec + (uint64_t)f * KBINS;

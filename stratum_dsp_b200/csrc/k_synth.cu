@@ -66,6 +66,47 @@ void launch_pcm16_to_mono(cudaStream_t s, const int16_t* d_pcm, float* d_out, co
     count_launch("pcm16");
 }
 
+// ---- self-check of the range-restricted divisions of common.cuh against IEEE division (test instrumentation) ----------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// float with a uniformly random significand and a binary exponent drawn from [elo, ehi]
+__device__ __forceinline__ float rnd_float(uint32_t h, int elo, int ehi) {
+    const uint32_t man = h & 0x7fffffu;
+    const int e = elo + (int)((h >> 23) % (uint32_t)(ehi - elo + 1));
+    return __uint_as_float(((uint32_t)(e + 127) << 23) | man);
+}
+__global__ void division_check_kernel(uint64_t n, uint32_t seed, unsigned long long* bad) {
+    unsigned long long b0 = 0, b1 = 0, b2 = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h1 = mix32((uint32_t)i ^ seed), h2 = mix32(h1 + 0x9e3779b9u + (uint32_t)(i >> 32)), h3 = mix32(h2 ^ 0x85ebca6bu);
+        // div_by_25_rn: any magnitude >= 1e-30, both signs
+        float a = rnd_float(h1, -99, 127);
+        if (h2 & 1u) a = -a;
+        if (__float_as_uint(div_by_25_rn(a)) != __float_as_uint(__fdiv_rn(a, 25.0f))) ++b0;
+        // div_rn_inrange: d in [2^-40, 2^60], a in [2^-60 d, 2 d] (the mask quotient hp / (hp + rp + 1e-12) lies in [0, 1])
+        const float d = rnd_float(h2, -40, 60);
+        const float q = rnd_float(h3, -60, 0);
+        const float num = __fmul_rn(d, q);
+        if (__float_as_uint(div_rn_inrange(num, d)) != __float_as_uint(__fdiv_rn(num, d))) ++b1;
+        // div_by_rcp_rn: frame-constant divisor b with y = RN(1/b), significand not all ones, a in [2^-60 b, b]
+        float bb = rnd_float(h3 ^ h1, -60, 60);
+        if ((__float_as_uint(bb) & 0x7fffffu) == 0x7fffffu) bb = __uint_as_float(__float_as_uint(bb) - 1u);
+        const float aa = __fmul_rn(bb, rnd_float(h1 ^ 0x5bd1e995u, -60, -1));
+        if (__float_as_uint(div_by_rcp_rn(aa, bb, __frcp_rn(bb))) != __float_as_uint(__fdiv_rn(aa, bb))) ++b2;
+    }
+    if (b0) atomicAdd(bad + 0, b0);
+    if (b1) atomicAdd(bad + 1, b1);
+    if (b2) atomicAdd(bad + 2, b2);
+}
+int check_divisions(cudaStream_t s, uint64_t n, uint32_t seed, unsigned long long* d_bad3) {
+    cudaMemsetAsync(d_bad3, 0, 3 * sizeof(unsigned long long), s);
+    division_check_kernel<<<148 * 8, 256, 0, s>>>(n, seed, d_bad3);
+    count_launch("division_check");
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // FP32 FMA microbenchmark for the second roofline denominator (the non-tensor FP32 peak is not in
 // MEASURED_PEAKS.json): 8 independent FMA chains per thread, 2 flops per FMA.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters) {

@@ -47,6 +47,7 @@ def _load(fast: bool = False) -> C.CDLL:
     lib.so_iarray_copy.argtypes = [vp, cp, i64p, C.c_int64]
     lib.so_iarray_copy.restype = C.c_int64
     lib.so_array_names.argtypes = [vp, cp, C.c_int]
+    lib.so_set_fft_variant.argtypes = [C.c_int]
     lib.so_cfft.argtypes = [f32p, C.c_uint64]
     lib.so_rfft.argtypes = [f32p, C.c_uint64, f32p]
     lib.so_stft.argtypes = [f32p, C.c_uint64, C.c_uint64, C.c_uint64, f32p, C.c_uint64]
@@ -91,7 +92,7 @@ def i64ptr(a: np.ndarray):
 
 SCALARS = ["bpm", "bpm_confidence", "key_is_minor", "key_index", "key_confidence", "key_clarity", "grid_stability", "duration_seconds",
            "sample_rate", "onset_method_consensus", "warnings", "flags", "multi_res_triggered", "multi_res_used", "percussive_triggered",
-           "percussive_used", "trim_start", "trim_end", "time_sig_beats_per_bar", "beats_refined"]
+           "percussive_used", "trim_start", "trim_end", "time_sig_beats_per_bar", "beats_refined", "key_hashmap_tie"]
 
 
 class OracleResult:

@@ -214,3 +214,13 @@ def test_wave_planner_balances_and_respects_the_budget():
     assert max(per) <= 1.5 * 128 * T3 and (nw == 1 or min(per) >= 0.3 * max(per))          # no tiny tail wave
     nw, w = _plan([200 * T3])                       # one 10-hour track: still planned (the budget is raised for a single track)
     assert nw == 1
+
+
+def test_division_by_25_is_exact_for_every_float(tmp_path):
+    # tools/check_div_by_const.c: RN(a * RN(1/25)) corrected once (csrc/common.cuh div_by_25_rn) equals a / 25.0f for every finite
+    # float with |a| >= 1e-30 — exhaustive over all 2^32 bit patterns (about 20 s on 8 threads)
+    import subprocess
+    exe = tmp_path / "div25"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", str(exe), str(ROOT / "tools" / "check_div_by_const.c"), "-lm", "-lpthread"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert "mismatches with |a| >= 1e-30: 0" in out, out

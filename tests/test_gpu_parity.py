@@ -537,3 +537,14 @@ def test_unsupported_track_fails_alone():
     for i in (0, 2):
         assert res[i].error is None
         assert_parity(res[i], O.analyze(xs[i], SR, {"enable_key_hpcp": 0}, fast=True), f"track {i}")
+
+
+def test_fast_divisions_match_ieee():
+    # csrc/common.cuh: the per-element divisions of the mask / spectral-flux kernels skip the generic division's range check;
+    # inside their operand ranges they must return the IEEE quotient bit for bit (2^28 random tuples per form)
+    import ctypes as C
+    bad = (C.c_uint64 * 3)()
+    L = S.lib()
+    L.stratum_b200_debug_check_divisions.argtypes = [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+    assert L.stratum_b200_debug_check_divisions(1 << 28, 12345, bad) == 0, S.last_error()
+    assert list(bad) == [0, 0, 0], list(bad)
