@@ -3,21 +3,31 @@
 
     python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
     python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores
+    python bench.py --workload c4|c5 ...                      # BASELINE.json configs[3] / configs[4] instead of configs[1]
 
-A "step" is one pass of analyze_audio over one batch of synthetic 3-minute 44.1 kHz tracks
-(BASELINE.json configs[1]: 1024 tracks per B200, BPM 70-180, random keys — SURVEY.md §8d C2).  The
-batch is generated ON the device before the timed region, so `value` is the device-resident
-throughput; `e2e` is the same metric through the host-buffer C-ABI call (pinned host samples, H2D and
-result D2H inside the timed region).  One process per GPU under torchrun; tracks are independent, so
-ranks share nothing but the barrier and the max-over-ranks time (weak scaling: 1024 tracks per GPU).
+A "step" is one pass of analyze_audio over one batch of synthetic tracks.  Default workload C2 = BASELINE.json configs[1]:
+1024 three-minute 44.1 kHz tracks per B200 (BPM 70-180, random keys).  The batch is generated ON the device
+before the timed region, so `value` is the device-resident throughput.  `e2e` is the same metric through the host-buffer
+C-ABI call on pinned host samples (H2D of the samples and D2H of the results inside the timed region):
 
-The reference arm times the CPU oracle port of the reference algorithm (the Rust crate cannot be built
-in this image: no cargo) with all host threads on a bounded sample of the same workload.
+  * `e2e.value`      one process, ONE call of stratum_b200_analyze_batch with device_ids = [0 .. N-1] on N x tracks-per-GPU
+                     host tracks — the library's own multi-device path (what replaces the reference's par_iter,
+                     examples/analyze_batch.rs:239-326).  Under torchrun rank 0 makes the call after every rank has released
+                     its GPU memory; the other ranks wait at a barrier.
+  * `e2e.per_rank`   every rank calls stratum_b200_analyze_batch on its own GPU with its own tracks-per-GPU host tracks
+                     (N processes, max time over ranks).  At N = 1 the two are the same call.
+
+One process per GPU under torchrun for the device-resident leg; tracks are independent, so ranks share nothing but the barrier
+and the max-over-ranks time (weak scaling: the same batch per GPU at every N).
+
+The reference arm times the CPU oracle port of the reference algorithm (the Rust crate cannot be built in this image: no cargo)
+with all host threads on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import datetime
 import json
 import os
 import statistics
@@ -35,11 +45,17 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 SR = 44100
 N_SAMPLES = 7_938_000  # 3 minutes
-ALGO_BYTES_PER_TRACK = 4 * N_SAMPLES  # one read of the input samples
-FLOPS_KEY_STFT = 15_488 * 532_480  # 8192-point frames, 5 N log2 N convention
-FLOPS_BASE_STFT = 15_500 * 112_640  # 2048-point frames at hop 512
-FLOPS_ESCALATION = 54_250 * 112_640  # hop 256 + 512 + 1024 re-analysis of an escalated track (SURVEY.md §8d counts all three)
-FLOPS_BASE_STFT = 15_500 * 112_640
+FLOPS_KEY_FRAME = 532_480   # 8192-point frame, 5 N log2 N convention
+FLOPS_BASE_FRAME = 112_640  # 2048-point frame
+
+WORKLOADS = {
+    "c2": ("tracks_per_sec_3min_44k1",
+           "C2: batch of synthetic 3-min 44.1 kHz mono tracks, BPM 70-180, random keys (BASELINE.json configs[1]); analyze_audio defaults"),
+    "c4": ("tracks_per_sec_60min_mix",
+           "C4: single 60-min synthetic DJ mix with tempo drift 120->128 BPM (BASELINE.json configs[3]); analyze_audio defaults; replicas only (one track = one GPU)"),
+    "c5": ("tracks_per_sec_ragged_30s_10min",
+           "C5: ragged batch of 30 s - 10 min tracks at 44.1/48 kHz, multi-resolution escalation and key detection enabled (BASELINE.json configs[4])"),
+}
 
 
 def load_peaks():
@@ -123,7 +139,7 @@ def bind_to_gpu_numa(device_index: int) -> str:
         return f"not bound ({type(e).__name__})"
 
 
-def track_params(first: int, count: int) -> np.ndarray:
+def c2_param_rows(first: int, count: int) -> np.ndarray:
     import synth
 
     out = np.zeros((count, 5), np.float32)
@@ -133,15 +149,48 @@ def track_params(first: int, count: int) -> np.ndarray:
     return out
 
 
-def oracle_batch(samples: np.ndarray, n_tracks: int, jobs: int) -> float:
-    """Wall seconds of the CPU oracle over n_tracks concatenated tracks with `jobs` threads
+def workload_layout(workload: str, first: int, count: int):
+    """(lengths, sample rates, per-track generator parameters, expected BPMs) of `count` tracks starting at global index `first`."""
+    import synth
+
+    if workload == "c2":
+        rows = c2_param_rows(first, count)
+        return np.full(count, N_SAMPLES, np.uint64), np.full(count, SR, np.uint32), rows, rows[:, 0].copy()
+    if workload == "c5":
+        ps = [synth.c5_params(first + i) for i in range(count)]
+        rows = np.array([[p.bpm, p.tonic, p.minor, p.phase_frac, p.chord_amp] for p in ps], np.float32)
+        return np.array([p.n_samples for p in ps], np.uint64), np.array([p.sample_rate for p in ps], np.uint32), rows, rows[:, 0].copy()
+    if workload == "c4":
+        return np.full(count, 158_760_000, np.uint64), np.full(count, SR, np.uint32), None, np.full(count, 124.0, np.float32)
+    raise ValueError(workload)
+
+
+def fill_device(S, torch, workload, buf, offsets, lens, srs, rows, device):
+    """Generates the batch on the device (C2, C5) or uploads the host-rendered mix (C4), outside every timed region."""
+    import synth
+
+    if workload == "c2":
+        S.synth_batch(buf.data_ptr(), len(lens), N_SAMPLES, SR, rows, device)
+    elif workload == "c5":
+        for i in range(len(lens)):
+            S.synth_batch(buf.data_ptr() + 4 * int(offsets[i]), 1, int(lens[i]), int(srs[i]), rows[i:i + 1], device)
+    else:
+        x = torch.from_numpy(synth.c4_mix())
+        for i in range(len(lens)):
+            buf[int(offsets[i]):int(offsets[i + 1])].copy_(x)
+    torch.cuda.synchronize()
+
+
+def oracle_batch(samples: np.ndarray, offsets: np.ndarray, srs: np.ndarray, jobs: int) -> float:
+    """Wall seconds of the CPU oracle over the given concatenated tracks with `jobs` threads
     (mirrors rayon par_iter over tracks, examples/analyze_batch.rs:239-326)."""
     import oracle_lib as O
 
     L = O.lib(fast=True)
-    offs = (np.arange(n_tracks + 1, dtype=np.uint64) * np.uint64(samples.size // n_tracks))
-    srs = np.full(n_tracks, SR, np.uint32)
-    return float(L.so_batch_timed(O.f32ptr(samples), offs.ctypes.data_as(C.POINTER(C.c_uint64)), srs.ctypes.data_as(C.POINTER(C.c_uint32)), n_tracks, jobs,
+    n = len(offsets) - 1
+    offs = np.ascontiguousarray(offsets, np.uint64)
+    srs = np.ascontiguousarray(srs, np.uint32)
+    return float(L.so_batch_timed(O.f32ptr(samples), offs.ctypes.data_as(C.POINTER(C.c_uint64)), srs.ctypes.data_as(C.POINTER(C.c_uint32)), n, jobs,
                                   None, None, None))
 
 
@@ -150,31 +199,96 @@ def host_jobs() -> int:
     return max(1, min(n - 1, 32))  # default_jobs = CPUs - 1 (examples/analyze_batch.rs:180-185), capped to bound the sample
 
 
+def cpu_sample(workload: str, n_tracks: int):
+    """Bounded CPU sample of a workload: (samples, offsets, srs, note, units) — units = how many whole tracks the sample stands for."""
+    import synth
+
+    if workload == "c2":
+        xs = [synth.render(synth.c2_params(i)) for i in range(n_tracks)]
+        srs = [SR] * n_tracks
+        note, units = f"{n_tracks} C2 tracks (3 min each)", float(n_tracks)
+    elif workload == "c5":
+        ps = []
+        i = 0
+        while len(ps) < n_tracks:  # tracks of at most 4 minutes keep the sample bounded; the rate is quoted per second of audio too
+            p = synth.c5_params(i)
+            if p.n_samples / p.sample_rate <= 240:
+                ps.append(p)
+            i += 1
+        xs = [synth.render(p) for p in ps]
+        srs = [p.sample_rate for p in ps]
+        note, units = f"{n_tracks} C5 tracks of <= 4 min", float(n_tracks)
+    else:
+        n = 6 * 60 * SR  # the first 6 minutes of the mix per worker; a whole mix is ten times that
+        x = synth.c4_mix(n)
+        xs = [x] * n_tracks
+        srs = [SR] * n_tracks
+        note, units = f"{n_tracks} x the first 6 minutes of the C4 mix (value scaled by 1/10 to whole 60-min mixes)", n_tracks / 10.0
+    offsets = np.zeros(len(xs) + 1, np.uint64)
+    offsets[1:] = np.cumsum([x.size for x in xs], dtype=np.uint64)
+    return np.concatenate(xs), offsets, np.array(srs, np.uint32), note, units
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import synth
-
     subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "-j8"], check=True)
     jobs = host_jobs()
-    n = jobs  # one track per worker and step: a bounded sample of the C2 workload
-    x = np.concatenate([synth.render(synth.c2_params(i)) for i in range(n)])
+    x, offs, srs, note, units = cpu_sample(args.workload, jobs)  # one track per worker and step: a bounded sample of the workload
     for _ in range(max(args.warmup, 0) and 1):  # one warm-up pass is enough for a CPU code (bounded run time)
-        oracle_batch(x, n, jobs)
-    times = [oracle_batch(x, n, jobs) for _ in range(args.steps)]
+        oracle_batch(x, offs, srs, jobs)
+    times = [oracle_batch(x, offs, srs, jobs) for _ in range(args.steps)]
     ms = 1000.0 * sum(times) / len(times)
-    val = n / (ms / 1000.0)
+    val = units / (ms / 1000.0)
+    metric, desc = WORKLOADS[args.workload]
     line = {
-        "impl": "reference", "metric": "tracks_per_sec_3min_44k1", "value": val, "unit": "tracks/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": val, "unit": "tracks/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: batch of synthetic 3-min 44.1 kHz mono tracks, BPM 70-180, random keys (BASELINE.json configs[1]); analyze_audio defaults",
-                   "tracks_per_step": n, "note": "CPU oracle port of stratum-dsp 1.0.0 (Rust toolchain absent), std::thread pool over tracks"},
-        "cpu_baseline": {"value": val, "unit": "tracks/s", "cores": jobs, "kind": "port", "sample": f"{n} C2 tracks per step, {args.steps} steps"},
+        "config": {"workload": desc, "tracks_per_step": jobs,
+                   "note": "CPU oracle port of stratum-dsp 1.0.0 (Rust toolchain absent), std::thread pool over tracks; its scalar FFT is about 4x slower "
+                           "than rustfft's SIMD, so ratios against this arm flatter the GPU by about that factor (BASELINE.md)"},
+        "cpu_baseline": {"value": val, "unit": "tracks/s", "cores": jobs, "kind": "port", "per_worker": val / jobs, "sample": f"{note} per step, {args.steps} steps"},
         "e2e": {"value": val, "unit": "tracks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class Pinned:
+    """Page-locked host array owned by this script (numpy storage registered with cudaHostRegister), released explicitly:
+    torch's pinned-memory allocator caches freed blocks, which would keep hundreds of gigabytes locked between the legs."""
+
+    def __init__(self, torch, n_elems: int, np_dtype):
+        self.torch = torch
+        item = np.dtype(np_dtype).itemsize
+        raw = np.empty(n_elems + 4096 // item, dtype=np_dtype)  # page-aligned view (cudaHostRegister pins whole pages)
+        skip = (-raw.ctypes.data % 4096) // item
+        self.raw = raw
+        self.arr = raw[skip:skip + n_elems]
+        self.registered = False
+        rc = torch.cuda.cudart().cudaHostRegister(self.arr.ctypes.data, self.arr.nbytes, 0)
+        if int(rc) != 0:
+            self.arr = None
+            raise MemoryError(f"cudaHostRegister failed ({rc})")
+        self.registered = True
+        self.tensor = torch.from_numpy(self.arr)
+
+    def free(self):
+        if self.registered:
+            self.torch.cuda.synchronize()
+            self.torch.cuda.cudart().cudaHostUnregister(self.arr.ctypes.data)
+            self.registered = False
+        self.tensor = None
+        self.arr = None
+        self.raw = None
+
+
+def pinned_empty(torch, n_elems: int, np_dtype):
+    try:
+        return Pinned(torch, n_elems, np_dtype)
+    except (MemoryError, RuntimeError):
+        return None
 
 
 def main():
@@ -183,10 +297,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--tracks", type=int, default=1024, help="tracks per GPU and step (BASELINE.json configs[1]: 1024)")
-    ap.add_argument("--e2e-tracks", type=int, default=1024, help="tracks per step of the host-buffer (e2e) leg")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--tracks", type=int, default=0, help="tracks per GPU and step (default: 1024 for c2 = BASELINE.json configs[1], 256 for c5, 1 for c4)")
+    ap.add_argument("--e2e-tracks", type=int, default=0, help="tracks per GPU of the host-buffer (e2e) legs (default: the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi-device-call", action="store_true", help="skip the one-process, one-call multi-device e2e leg at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -205,11 +321,14 @@ def main():
     torch.cuda.set_device(local_rank)
     numa_note = bind_to_gpu_numa(local_rank)
     dist = None
+    host_group = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=40))
+        # host-side group: ranks that wait for rank 0's multi-device call must not spin in an NCCL kernel on the GPUs it measures
+        host_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=40))
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,12 +336,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    nt = args.tracks
+    wl = args.workload
+    metric, wl_desc = WORKLOADS[wl]
+    nt = args.tracks or {"c2": 1024, "c5": 256, "c4": 1}[wl]
+    lens, srs, rows, want_bpm = workload_layout(wl, rank * nt, nt)
+    offsets = np.zeros(nt + 1, np.uint64)
+    offsets[1:] = np.cumsum(lens, dtype=np.uint64)
+    total_samples = int(offsets[-1])
     # ---- device-resident batch: generated on the device, outside the timed region ----
-    buf = torch.empty(nt * N_SAMPLES, dtype=torch.float32, device="cuda")
-    S.synth_batch(buf.data_ptr(), nt, N_SAMPLES, SR, track_params(rank * nt, nt), local_rank)
-    offsets = np.arange(nt + 1, dtype=np.uint64) * np.uint64(N_SAMPLES)
-    srs = np.full(nt, SR, np.uint32)
+    buf = torch.empty(total_samples, dtype=torch.float32, device="cuda")
+    fill_device(S, torch, wl, buf, offsets, lens, srs, rows, local_rank)
 
     waves = [1]
 
@@ -258,10 +381,10 @@ def main():
     # sanity on the last step's results (no oracle here: parity lives in tests/ and smoke())
     ok = sum(1 for r in last if r.status == 0)
     bpm_hit = 0
-    params = track_params(rank * nt, nt)
     for i, r in enumerate(last):
-        b, t = r.bpm, params[i, 0]
-        if r.status == 0 and b > 0 and min(abs(b - t), abs(2 * b - t), abs(b - 2 * t)) <= 2.0:
+        b, t = r.bpm, float(want_bpm[i])
+        tol = 2.0 if wl != "c4" else 6.0  # the mix drifts 120 -> 128
+        if r.status == 0 and b > 0 and min(abs(b - t), abs(2 * b - t), abs(b - 2 * t)) <= tol:
             bpm_hit += 1
     n_escalated = sum(1 for r in last if r.status == 0 and r.tempogram_multi_res_triggered == 1)
     S.free_results(last)
@@ -269,43 +392,43 @@ def main():
     L.stratum_b200_fp32_peak_tflops.restype = C.c_double
     fp32_peak = float(L.stratum_b200_fp32_peak_tflops(C.c_int32(local_rank)))
 
-    # ---- e2e: host buffers through the reference-facing call, H2D + result D2H inside the timed region ----
+    # ---- e2e, per rank: host buffers through the reference-facing call on this rank's GPU ----
     e2e = None
+    ne = min(args.e2e_tracks or nt, nt)
     if not args.no_e2e:
-        ne = min(args.e2e_tracks if world == 1 else min(args.e2e_tracks, 256), nt)  # N ranks pin N host buffers: keep them modest
         host = None
-        while host is None:  # a box with little lockable host memory gets a smaller (still pinned) e2e batch rather than no number
-            try:
-                host = torch.empty(ne * N_SAMPLES, dtype=torch.float32, pin_memory=True)
-            except RuntimeError:
-                if ne <= 32:
-                    raise
-                ne //= 2
-        host.copy_(buf[: ne * N_SAMPLES])
+        while host is None:  # a box with little lockable host memory gets a smaller (still pinned) e2e batch rather than no number — and says so
+            host = pinned_empty(torch, int(offsets[ne]), np.float32)
+            if host is None:
+                if ne <= 1:
+                    raise SystemExit("cannot pin host memory for the e2e leg")
+                ne = max(1, ne // 2)
+        host.tensor.copy_(buf[: int(offsets[ne])])
         torch.cuda.synchronize()
-        hnp = host.numpy()
-        eoff = np.arange(ne + 1, dtype=np.uint64) * np.uint64(N_SAMPLES)
-        import ctypes as _C
-        srs_e = np.full(ne, SR, np.uint32)
+        hnp = host.arr
+        eoff = np.ascontiguousarray(offsets[: ne + 1])
+        srs_e = np.ascontiguousarray(srs[:ne])
+        dev1 = (C.c_int32 * 1)(local_rank)
 
         def host_step():
             # the reference-facing C-ABI call itself (include/stratum_b200.h): host samples in, StratumResult array out
             res = (S.StratumResult * ne)()
-            st = S.lib().stratum_b200_analyze_batch(hnp.ctypes.data, eoff.ctypes.data_as(_C.POINTER(_C.c_uint64)), srs_e.ctypes.data_as(_C.POINTER(_C.c_uint32)), ne,
-                                                    None, (_C.c_int32 * 1)(local_rank), 1, res)
+            st = S.lib().stratum_b200_analyze_batch(hnp.ctypes.data, eoff.ctypes.data_as(C.POINTER(C.c_uint64)), srs_e.ctypes.data_as(C.POINTER(C.c_uint32)), ne,
+                                                    None, dev1, 1, res)
             assert st == 0, S.last_error()
             n_ok = sum(1 for r in res if r.status == 0)
             S.free_results(res)
             return n_ok
 
-        # pinned H2D rate of this box (outside the timed region): the ceiling of the f32 leg is this rate / 31.75 MB per track
-        probe = torch.empty(min(ne, 32) * N_SAMPLES, dtype=torch.float32, device="cuda")
-        probe.copy_(host[: probe.numel()], non_blocking=True)
+        # pinned H2D rate of this box (outside the timed region): the ceiling of the f32 leg is this rate / bytes per track
+        pn = min(int(offsets[ne]), 32 * N_SAMPLES)
+        probe = torch.empty(pn, dtype=torch.float32, device="cuda")
+        probe.copy_(host.tensor[:pn], non_blocking=True)
         torch.cuda.synchronize()
         tb0 = time.perf_counter()
-        probe.copy_(host[: probe.numel()], non_blocking=True)
+        probe.copy_(host.tensor[:pn], non_blocking=True)
         torch.cuda.synchronize()
-        h2d_gbs = probe.numel() * 4 / (time.perf_counter() - tb0) / 1e9
+        h2d_gbs = pn * 4 / (time.perf_counter() - tb0) / 1e9
         del probe
         host_step()  # warm-up (staging buffer allocation)
         h0, d0 = S.transfer_bytes()
@@ -313,38 +436,44 @@ def main():
         te0 = time.perf_counter()
         e_steps = max(1, min(args.steps, 3))
         for _ in range(e_steps):
-            assert host_step() == ne
+            host_step()
         barrier()
         e_ms = (time.perf_counter() - te0) * 1000.0 / e_steps
         h1, d1 = S.transfer_bytes()
         e2e = {"tracks_per_step": ne, "ms_per_step": e_ms, "h2d": (h1 - h0) // e_steps, "d2h": (d1 - d0) // e_steps, "h2d_gbs": h2d_gbs}
-        # informational: the decoder-side entry (16-bit PCM uploaded as is, converted on the device): half the H2D bytes
+        # the decoder-side entry (16-bit PCM uploaded as is, converted on the device): half the H2D bytes
         hnp = None
-        del host  # the f32 buffer is unpinned before the PCM one is pinned
-        pcm = torch.empty(ne * N_SAMPLES, dtype=torch.int16, pin_memory=True)
-        for i in range(0, ne, 8):  # converted in slices: the analysis arenas own most of the device memory
-            a, b = i * N_SAMPLES, min(i + 8, ne) * N_SAMPLES
-            pcm[a:b].copy_((buf[a:b] * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
-        torch.cuda.synchronize()
-        pnp = pcm.numpy()
-        ptracks = [pnp[i * N_SAMPLES:(i + 1) * N_SAMPLES] for i in range(ne)]
-        chans = np.ones(ne, np.uint32)
+        host.free()  # the f32 buffer is unpinned before the PCM one is pinned
+        pcm = pinned_empty(torch, int(offsets[ne]), np.int16)
+        if pcm is not None:
+            sl = 8 * N_SAMPLES
+            for a in range(0, int(offsets[ne]), sl):  # converted in slices: the analysis arenas own most of the device memory
+                b = min(a + sl, int(offsets[ne]))
+                pcm.tensor[a:b].copy_((buf[a:b] * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+            torch.cuda.synchronize()
+            pnp = pcm.arr
+            chans = np.ones(ne, np.uint32)
 
-        def pcm_step():
-            res = (S.StratumResult * ne)()
-            st = S.lib().stratum_b200_analyze_batch_pcm16(pnp.ctypes.data, eoff.ctypes.data_as(_C.POINTER(_C.c_uint64)), srs_e.ctypes.data_as(_C.POINTER(_C.c_uint32)),
-                                                          chans.ctypes.data_as(_C.POINTER(_C.c_uint32)), ne, None, (_C.c_int32 * 1)(local_rank), 1, res)
-            assert st == 0, S.last_error()
-            S.free_results(res)
+            def pcm_step():
+                res = (S.StratumResult * ne)()
+                st = S.lib().stratum_b200_analyze_batch_pcm16(pnp.ctypes.data, eoff.ctypes.data_as(C.POINTER(C.c_uint64)), srs_e.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                              chans.ctypes.data_as(C.POINTER(C.c_uint32)), ne, None, dev1, 1, res)
+                assert st == 0, S.last_error()
+                S.free_results(res)
 
-        pcm_step()
-        barrier()
-        tp0 = time.perf_counter()
-        for _ in range(e_steps):
             pcm_step()
-        barrier()
-        e2e["pcm16_ms_per_step"] = (time.perf_counter() - tp0) * 1000.0 / e_steps
-        del pcm, ptracks
+            barrier()
+            tp0 = time.perf_counter()
+            for _ in range(e_steps):
+                pcm_step()
+            barrier()
+            e2e["pcm16_ms_per_step"] = (time.perf_counter() - tp0) * 1000.0 / e_steps
+            pnp = None
+            pcm.free()
+        else:
+            barrier()
+            barrier()
+            e2e["pcm16_ms_per_step"] = 0.0
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only) ----
     cpu = None
@@ -352,10 +481,16 @@ def main():
         try:
             subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "-j8"], check=True)
             jobs = host_jobs()
-            sample = buf[: jobs * N_SAMPLES].cpu().numpy()
-            sec = oracle_batch(sample, jobs, jobs)
-            cpu = {"value": jobs / sec, "unit": "tracks/s", "cores": jobs, "kind": "port",
-                   "sample": f"first {jobs} tracks of the batch, one per thread, {sec:.1f} s wall (CPU oracle, -O3)"}
+            x, offs_c, srs_c, note, units = cpu_sample(wl, jobs)
+            sec = oracle_batch(x, offs_c, srs_c, jobs)
+            # the north-star target is stated against ONE reference worker: time it on its own (3 tracks, 1 thread)
+            n1 = min(3, jobs)
+            sec1 = oracle_batch(x[: int(offs_c[n1])], offs_c[: n1 + 1], srs_c[:n1], 1)
+            units1 = units * n1 / jobs
+            cpu = {"value": units / sec, "unit": "tracks/s", "cores": jobs, "kind": "port", "per_worker": units / sec / jobs,
+                   "single_worker": {"value": units1 / sec1, "unit": "tracks/s", "cores": 1, "sample": f"the first {n1} tracks of the sample on one thread, {sec1:.1f} s wall"},
+                   "sample": f"{note}, one per thread, {sec:.1f} s wall (CPU oracle, -O3)",
+                   "note": "oracle port, scalar FFT: about 4x slower per worker than the Rust crate's rustfft SIMD path (BASELINE.md), so GPU/CPU ratios against it flatter the GPU by about that factor"}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
             cpu = {"value": None, "unit": "tracks/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
@@ -364,17 +499,41 @@ def main():
     wall_step = wall_ms / args.steps
     e_ms_step = e2e["ms_per_step"] if e2e else 0.0
     p_ms_step = e2e["pcm16_ms_per_step"] if e2e else 0.0
+    ne_min = ne
     if dist:
         t = torch.tensor([ms_step, wall_step, e_ms_step, p_ms_step], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, wall_step, e_ms_step, p_ms_step = (float(v) for v in t.tolist())
-        c = torch.tensor([ok, bpm_hit, launches], dtype=torch.int64, device="cuda")
+        c = torch.tensor([ok, bpm_hit, launches, n_escalated, total_samples], dtype=torch.int64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        ok, bpm_hit, launches = (int(v) for v in c.tolist())
+        ok, bpm_hit, launches, n_escalated, total_samples_all = (int(v) for v in c.tolist())
+        m = torch.tensor([ne], dtype=torch.int64, device="cuda")
+        dist.all_reduce(m, op=dist.ReduceOp.MIN)
+        ne_min = int(m.item())
+    else:
+        total_samples_all = total_samples
+
+    # ---- e2e, one call over all devices (rank 0; the other ranks release their GPUs and wait) ----
+    multi = None
+    if world > 1 and e2e is not None and not args.no_multi_device_call and wl != "c4":
+        del buf
+        S.shutdown()
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                multi = multi_device_call(S, torch, wl, world, ne_min, args)
+            except Exception as e:  # reported, never fatal for the rest of the line
+                multi = {"error": f"{type(e).__name__}: {e}"}
+            S.shutdown()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)  # waits on the host: the other GPUs stay idle while rank 0 drives them
+
     if rank == 0:
         peak, peak_src = load_peaks()
         total_tracks = nt * world
         value = total_tracks / (ms_step / 1000.0)
+        algo_bytes_step = 4 * total_samples  # one read of the input samples (this rank's share)
         # dominant kernel of the step, by device time on the launching stream.  Only single-kernel stages qualify: the
         # tail stages of the tempo path (tempograms, final BPM, beats, legacy, energy onsets) run on the second stream beside
         # the key path, so their event spans include time spent waiting for SM slots and say nothing about kernel cost.
@@ -384,55 +543,168 @@ def main():
         if dom:
             k_ms = stages[dom] / args.steps  # per step (all waves of the step)
             launches_per_step = waves[0]     # one launch of the kernel per wave
-            ach = nt * ALGO_BYTES_PER_TRACK / (k_ms / 1000.0) / 1e9  # = per-launch bytes / per-launch time
-            traffic = None
+            ach = algo_bytes_step / (k_ms / 1000.0) / 1e9  # = per-launch bytes / per-launch time
+            traffic, traffic_all = None, None
             tp = ROOT / "profiles" / "roofline_traffic.json"
-            if tp.exists():  # DRAM bytes per track of this kernel from the committed `ncu --set full` capture -> bytes per launch
+            if tp.exists():  # DRAM bytes per 3-minute track from the committed `ncu --set full` captures -> bytes per launch
                 try:
-                    per_track = json.loads(tp.read_text()).get(dom, {}).get("dram_bytes_per_track")
-                    traffic = per_track * nt / launches_per_step if per_track else None
+                    tj = json.loads(tp.read_text())
+                    scale = total_samples / N_SAMPLES / launches_per_step  # 3-minute-track equivalents per launch
+                    per_track = tj.get(dom, {}).get("dram_bytes_per_track")
+                    traffic = per_track * scale if per_track else None
+                    traffic_all = {k: v["dram_bytes_per_track"] * scale for k, v in tj.items() if isinstance(v, dict) and v.get("dram_bytes_per_track")}
                 except Exception:
                     traffic = None
+            frames_key = sum(max(0, (int(n) - 8192) // 512 + 1) for n in lens)
+            frames_base = sum(max(0, (int(n) - 2048) // 512 + 1) for n in lens)
             roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "peak_source": peak_src, "algorithmic_bytes_per_track": ALGO_BYTES_PER_TRACK, "kernel_ms_per_step": k_ms,
-                    "launches_per_step": launches_per_step, "algorithmic_bytes_per_launch": nt * ALGO_BYTES_PER_TRACK / launches_per_step,
+                    "traffic_by_kernel": traffic_all,
+                    "peak_source": peak_src, "algorithmic_bytes_per_step": algo_bytes_step, "kernel_ms_per_step": k_ms,
+                    "launches_per_step": launches_per_step, "algorithmic_bytes_per_launch": algo_bytes_step / launches_per_step,
                     "kernel_ms_per_launch": k_ms / launches_per_step,
                     "share_of_step": k_ms / ms_step,
                     "note": "path is FP32/shared-memory bound (SURVEY §8d: ~315 flop/B); the HBM fraction is reported as the contract asks",
-                    "fp32_tflops_key_stft": (nt * FLOPS_KEY_STFT / (stages["stft_8192_key"] / args.steps / 1000.0) / 1e12) if "stft_8192_key" in stages else None}
+                    "fp32_tflops_key_stft": (frames_key * FLOPS_KEY_FRAME / (stages["stft_8192_key"] / args.steps / 1000.0) / 1e12) if "stft_8192_key" in stages else None}
             # second denominator: STFT flops of the whole step by the 5 N log2 N convention against the measured FMA rate
-            step_flops = nt * (FLOPS_BASE_STFT + FLOPS_KEY_STFT) + n_escalated * FLOPS_ESCALATION
+            esc_frac = n_escalated / max(1, ok)
+            step_flops = frames_base * FLOPS_BASE_FRAME * (1.0 + 2.5 * esc_frac) + frames_key * FLOPS_KEY_FRAME
             ach_tf = step_flops / (ms_step / 1000.0) / 1e12
             roof["fp32"] = {"achieved": ach_tf, "peak": fp32_peak or None, "unit": "TFLOP/s", "frac": (ach_tf / fp32_peak) if fp32_peak else None,
                             "peak_source": "measured: FMA microbenchmark of this run (stratum_b200_fp32_peak_tflops), 2 flops per FMA",
                             "flops_per_step": step_flops, "escalated_tracks": n_escalated,
                             "note": "STFT flops only (5 N log2 N for the complex transform of N points; the kernels use the real-input packing, "
-                                    "so they execute about half of that); the path compiles with -fmad=false, FMAs only inside the FFT"}
+                                    "so they execute about half of that; an escalated track adds hop-256 and hop-1024 passes = 2.5x its hop-512 frames); "
+                                    "the path compiles with -fmad=false, FMAs only inside the FFT"}
+        e2e_out = None
+        if e2e:
+            per_rank = {"value": ne_min * world / (e_ms_step / 1000.0), "unit": "tracks/s", "tracks_per_gpu": ne_min, "ms_per_step": e_ms_step,
+                        "pcm16_value": (ne_min * world / (p_ms_step / 1000.0)) if p_ms_step > 0 else None,
+                        "note": "N processes, each calling stratum_b200_analyze_batch on its own GPU with its own pinned host batch; max time over ranks"}
+            if world == 1:
+                head = dict(per_rank)
+                head["note"] = "one process, one call of stratum_b200_analyze_batch on pinned host f32 samples: H2D of the samples and D2H of the results inside the timed region"
+            elif multi and "value" in multi:
+                head = multi
+            else:
+                head = dict(per_rank)
+                head["note"] = "per-rank calls (the one-call multi-device leg did not run: " + (multi or {}).get("error", "disabled") + ")"
+            e2e_out = {"value": head["value"], "unit": "tracks/s", "h2d_bytes_per_step": int(head.get("h2d_bytes_per_step", e2e["h2d"] * world)),
+                       "d2h_bytes_per_step": int(head.get("d2h_bytes_per_step", e2e["d2h"] * world)), "tracks_per_gpu": head.get("tracks_per_gpu", ne_min),
+                       "ms_per_step": head["ms_per_step"], "pcm16_value": head.get("pcm16_value"), "pinned_h2d_gbs_rank0": e2e["h2d_gbs"],
+                       "call": "stratum_b200_analyze_batch(device_ids=[0..N-1]) from one process" if world > 1 and multi and "value" in multi else "stratum_b200_analyze_batch, one process per GPU",
+                       "note": head["note"], "per_rank": per_rank}
+            if multi and "value" in multi:
+                e2e_out["multi_device_call"] = {k: v for k, v in multi.items() if k not in ("note",)}
         line = {
-            "metric": "tracks_per_sec_3min_44k1", "value": value, "unit": "tracks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": "tracks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: batch of synthetic 3-min 44.1 kHz mono tracks, BPM 70-180, random keys (BASELINE.json configs[1]); analyze_audio defaults",
-                       "tracks_per_gpu_per_step": nt, "samples_per_track": N_SAMPLES, "l2": "inputs (32.5 GB per GPU) far larger than L2; no flush needed",
+            "config": {"workload": wl_desc, "tracks_per_gpu_per_step": nt, "samples_per_gpu_per_step": total_samples,
+                       "audio_hours_per_gpu_per_step": float(sum(float(n) / float(s) for n, s in zip(lens, srs)) / 3600.0),
+                       "l2": f"inputs ({4 * total_samples / 1e9:.1f} GB per GPU) far larger than L2; no flush needed",
                        "timing": "CUDA events on the library stream around each batch call, max over ranks", "host_placement": numa_note},
             "ms_per_track": ms_step / nt, "wall_ms_per_step": wall_step,
             "gpu_launches": launches, "clocks": clocks,
             "stages_ms_per_step": {k: v / args.steps for k, v in stages.items()},
             "stages_note": "CUDA-event spans per stream; onsets_energy, legacy_bpm, multires_tempogram, final_bpm and beats run on the second stream "
-                           "beside other kernels (late split), so their spans overlap the key-path stages and do not add up to the step",
-            "results_ok": ok, "bpm_within_2_or_octave": bpm_hit, "tracks_total": total_tracks,
+                           "beside other kernels (late split), so their spans overlap the key-path stages and do not add up to the step; "
+                           "host_escalation = host time spent waiting for the escalated-track count while the device is busy (not idle device time)",
+            "results_ok": ok, "bpm_within_2_or_octave": bpm_hit, "tracks_total": total_tracks, "escalated_tracks": n_escalated,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "e2e": ({"value": e2e["tracks_per_step"] * world / (e_ms_step / 1000.0), "unit": "tracks/s", "h2d_bytes_per_step": int(e2e["h2d"]),
-                     "d2h_bytes_per_step": int(e2e["d2h"]), "tracks_per_step": e2e["tracks_per_step"], "ms_per_step": e_ms_step,
-                     "pcm16_value": e2e["tracks_per_step"] * world / (p_ms_step / 1000.0), "pinned_h2d_gbs_rank0": e2e["h2d_gbs"],
-                     "note": "stratum_b200_analyze_batch on pinned host f32 samples: H2D of the samples and D2H of the results inside the timed region; "
-                             "pcm16_value = same through stratum_b200_analyze_batch_pcm16 (int16 upload, conversion on the device)"}
-                    if e2e else None),
+            "e2e": e2e_out,
         }
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multi_device_call(S, torch, wl, world, ne, args):
+    """Rank 0, every GPU of the box free: one process, one stratum_b200_analyze_batch call over device_ids = [0 .. world-1] on
+    world x ne pinned host tracks (the same per-GPU batch as at N = 1; halved, and reported, only if the host cannot pin it)."""
+    per_gpu = ne
+    host = None
+    while host is None:
+        lens, srs, rows, _ = workload_layout(wl, 0, per_gpu * world)
+        offsets = np.zeros(per_gpu * world + 1, np.uint64)
+        offsets[1:] = np.cumsum(lens, dtype=np.uint64)
+        host = pinned_empty(torch, int(offsets[-1]), np.float32)
+        if host is None:
+            if per_gpu <= 16:
+                raise RuntimeError("cannot pin the host batch")
+            per_gpu //= 2
+    n_all = per_gpu * world
+    # fill through GPU 0 in slices of 64 tracks (generator on the device, D2H into the pinned batch); outside the timed region
+    for a in range(0, n_all, 64):
+        b = min(a + 64, n_all)
+        tmp = torch.empty(int(offsets[b] - offsets[a]), dtype=torch.float32, device="cuda")
+        rel = offsets[a:b + 1] - offsets[a]
+        fill_device(S, torch, wl, tmp, rel, lens[a:b], srs[a:b], rows[a:b] if rows is not None else None, 0)
+        host.tensor[int(offsets[a]):int(offsets[b])].copy_(tmp)
+        del tmp
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    hnp = host.arr
+    devs = (C.c_int32 * world)(*range(world))
+    srs_c = np.ascontiguousarray(srs)
+
+    def call():
+        res = (S.StratumResult * n_all)()
+        st = S.lib().stratum_b200_analyze_batch(hnp.ctypes.data, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), srs_c.ctypes.data_as(C.POINTER(C.c_uint32)), n_all,
+                                                None, devs, world, res)
+        assert st == 0, S.last_error()
+        n_ok = sum(1 for r in res if r.status == 0)
+        S.free_results(res)
+        return n_ok
+
+    call()  # warm-up: contexts, arenas and staging buffers of every device
+    steps = max(1, min(args.steps, 3))
+    h0, d0 = S.transfer_bytes()
+    t0 = time.perf_counter()
+    n_ok = 0
+    for _ in range(steps):
+        n_ok = call()
+    ms = (time.perf_counter() - t0) * 1000.0 / steps
+    h1, d1 = S.transfer_bytes()
+    out = {"value": n_all / (ms / 1000.0), "unit": "tracks/s", "tracks_per_gpu": per_gpu, "tracks_per_call": n_all, "ms_per_step": ms, "results_ok": n_ok,
+           "h2d_bytes_per_step": (h1 - h0) // steps, "d2h_bytes_per_step": (d1 - d0) // steps,
+           "note": f"one process, one call of stratum_b200_analyze_batch(device_ids=[0..{world - 1}]) on {n_all} pinned host f32 tracks ({per_gpu} per GPU): "
+                   "the library shards by track, one host thread + one uploader thread per device; H2D of the samples and D2H of the results inside the timed region"}
+    # PCM16 through the same path: convert through GPU 0 slice by slice into a pinned int16 batch
+    hnp = None
+    pcm = pinned_empty(torch, int(offsets[-1]), np.int16)
+    if pcm is None:
+        host.free()
+    else:
+        sl = 16 * N_SAMPLES
+        for a in range(0, int(offsets[-1]), sl):
+            b = min(a + sl, int(offsets[-1]))
+            d = host.tensor[a:b].cuda(non_blocking=True)
+            pcm.tensor[a:b].copy_((d * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+            del d
+        torch.cuda.synchronize()
+        host.free()
+        torch.cuda.empty_cache()
+        pnp = pcm.arr
+        chans = np.ones(n_all, np.uint32)
+
+        def pcall():
+            res = (S.StratumResult * n_all)()
+            st = S.lib().stratum_b200_analyze_batch_pcm16(pnp.ctypes.data, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), srs_c.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                          chans.ctypes.data_as(C.POINTER(C.c_uint32)), n_all, None, devs, world, res)
+            assert st == 0, S.last_error()
+            S.free_results(res)
+
+        pcall()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pcall()
+        pms = (time.perf_counter() - t0) * 1000.0 / steps
+        out["pcm16_value"] = n_all / (pms / 1000.0)
+        out["pcm16_ms_per_step"] = pms
+        pnp = None
+        pcm.free()
+    return out
 
 
 if __name__ == "__main__":

@@ -236,6 +236,49 @@ static int detect_time_signature(const std::vector<float>& beats) {
     return best;
 }
 
+// detect_downbeats_with_time_sig — mod.rs:363-404 (beats non-empty, bpm > 0 checked by the caller)
+static std::vector<float> detect_downbeats_with_time_sig(const std::vector<float>& beats, float bpm, int bpb) {
+    std::vector<float> down;
+    if (beats.empty()) return down;
+    float beat_iv = 60.0f / bpm;
+    float bar_iv = beat_iv * (float)bpb;
+    float tol = bar_iv * 0.1f;
+    down.push_back(beats[0]);
+    for (size_t i = 1; i < beats.size(); ++i) {
+        float expected = down.back() + bar_iv;
+        if (fabsf(beats[i] - expected) <= tol) down.push_back(beats[i]);
+    }
+    return down;
+}
+
+// calculate_grid_stability — mod.rs:425-485, on the beat positions in their given order
+static float calculate_grid_stability(const std::vector<float>& times) {
+    float stab = 0.0f;
+    if (times.size() >= 2) {
+        std::vector<float> iv;
+        for (size_t i = 1; i < times.size(); ++i) {
+            float d = times[i] - times[i - 1];
+            if (d > 0.0f) iv.push_back(d);
+        }
+        if (!iv.empty()) {
+            float sum = 0.0f;
+            for (float d : iv) sum += d;
+            float mean = sum / (float)iv.size();
+            if (mean > 1e-10f) {
+                float vs = 0.0f;
+                for (float d : iv) {
+                    float df = d - mean;
+                    vs += df * df;
+                }
+                float var = vs / (float)iv.size();
+                float cv = sqrtf(var) / mean;
+                stab = 1.0f / (1.0f + cv);
+            }
+        }
+    }
+    return stab;
+}
+
 // generate_beat_grid — beat_tracking/mod.rs:108-247 (+ downbeats :363-404, stability :425-485)
 Error generate_beat_grid(float bpm, float bpm_conf, const std::vector<float>& onsets_s, uint32_t sr, Result& r, Dump* dump) {
     (void)bpm_conf;
@@ -293,46 +336,72 @@ Error generate_beat_grid(float bpm, float bpm_conf, const std::vector<float>& on
     // grid — mod.rs:293-321, 363-404
     std::vector<float> beats = bt;
     std::stable_sort(beats.begin(), beats.end());
-    std::vector<float> down;
-    {
-        float beat_iv = 60.0f / bpm;
-        float bar_iv = beat_iv * (float)bpb;
-        float tol = bar_iv * 0.1f;
-        down.push_back(beats[0]);
-        for (size_t i = 1; i < beats.size(); ++i) {
-            float expected = down.back() + bar_iv;
-            if (fabsf(beats[i] - expected) <= tol) down.push_back(beats[i]);
-        }
-    }
+    std::vector<float> down = detect_downbeats_with_time_sig(beats, bpm, bpb);
     r.beats = beats;
     r.downbeats = down;
     r.bars = down;
-    // stability — mod.rs:425-485 (on beat_positions order)
-    float stab = 0.0f;
-    if (pos.size() >= 2) {
-        std::vector<float> iv;
-        for (size_t i = 1; i < pos.size(); ++i) {
-            float d = pos[i].time_seconds - pos[i - 1].time_seconds;
-            if (d > 0.0f) iv.push_back(d);
-        }
-        if (!iv.empty()) {
-            float sum = 0.0f;
-            for (float d : iv) sum += d;
-            float mean = sum / (float)iv.size();
-            if (mean > 1e-10f) {
-                float vs = 0.0f;
-                for (float d : iv) {
-                    float df = d - mean;
-                    vs += df * df;
-                }
-                float var = vs / (float)iv.size();
-                float cv = sqrtf(var) / mean;
-                stab = 1.0f / (1.0f + cv);
-            }
-        }
-    }
+    std::vector<float> pt;
+    for (auto& p : pos) pt.push_back(p.time_seconds);
+    const float stab = calculate_grid_stability(pt);  // mod.rs:425-485 (on beat_positions order)
     r.grid_stability = stab;
     return Error{};
 }
 
 }  // namespace so
+
+// ---- unit-level entry points (tests/test_oracle_ref_units.py: the reference's own #[test] known answers) ----------------
+extern "C" {
+int so_u_tempo_variations(const float* beats, int n, float nominal, float* out5, int cap) {  // rows: start, end, bpm, confidence, is_variable
+    std::vector<so::TempoSegment> segs;
+    so::Error e = so::detect_tempo_variations(std::vector<float>(beats, beats + n), nominal, segs);
+    if (e) return -e.kind;
+    for (int i = 0; i < std::min<int>(cap, (int)segs.size()); ++i) {
+        out5[5 * i + 0] = segs[i].start;
+        out5[5 * i + 1] = segs[i].end;
+        out5[5 * i + 2] = segs[i].bpm;
+        out5[5 * i + 3] = segs[i].confidence;
+        out5[5 * i + 4] = segs[i].variable ? 1.0f : 0.0f;
+    }
+    return (int)segs.size();
+}
+int so_u_time_signature(const float* beats, int n) { return so::detect_time_signature(std::vector<float>(beats, beats + n)); }
+float so_u_bayes_likelihood(const float* onsets, int n, float bpm) {  // compute_likelihood (bayesian.rs:203-255); empty -> 0 (:211-213)
+    if (n == 0) return 0.0f;
+    return so::Bayes::likelihood(std::vector<float>(onsets, onsets + n), bpm);
+}
+int so_u_bayes_update(float current_bpm, const float* onsets, int n, float* out_bpm) {
+    so::Bayes b{current_bpm};
+    so::Error e = b.update(std::vector<float>(onsets, onsets + n), out_bpm);
+    return e.kind;
+}
+int so_u_downbeats(const float* beats, int n, float bpm, int bpb, float* out, int cap) {
+    if (n > 0 && bpm <= 0.0f) return -so::INVALID_INPUT;
+    std::vector<float> d = so::detect_downbeats_with_time_sig(std::vector<float>(beats, beats + n), bpm, bpb);
+    for (int i = 0; i < std::min<int>(cap, (int)d.size()); ++i) out[i] = d[i];
+    return (int)d.size();
+}
+float so_u_grid_stability(const float* times, int n) { return so::calculate_grid_stability(std::vector<float>(times, times + n)); }
+// generate_beat_grid with the grid itself: beats / downbeats copied out
+int so_u_beat_grid(float bpm, float conf, const float* onsets, int n, uint32_t sr, float* stability, float* beats, int* n_beats, float* down, int* n_down, int cap) {
+    so::Result r;
+    so::Error e = so::generate_beat_grid(bpm, conf, std::vector<float>(onsets, onsets + n), sr, r, nullptr);
+    if (e) return e.kind;
+    *stability = r.grid_stability;
+    *n_beats = (int)r.beats.size();
+    *n_down = (int)r.downbeats.size();
+    for (int i = 0; i < std::min<int>(cap, *n_beats); ++i) beats[i] = r.beats[i];
+    for (int i = 0; i < std::min<int>(cap, *n_down); ++i) down[i] = r.downbeats[i];
+    return 0;
+}
+int so_u_hmm_full(float bpm, const float* onsets, int n, float* times, float* confs, int32_t* frames, int cap) {
+    std::vector<so::BeatPos> b;
+    so::Error e = so::hmm_track_beats(bpm, std::vector<float>(onsets, onsets + n), b, nullptr);
+    if (e) return -e.kind;
+    for (int i = 0; i < std::min<int>(cap, (int)b.size()); ++i) {
+        times[i] = b[i].time_seconds;
+        confs[i] = b[i].confidence;
+        frames[i] = b[i].frame;
+    }
+    return (int)b.size();
+}
+}

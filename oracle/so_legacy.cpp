@@ -371,3 +371,61 @@ Error estimate_bpm_legacy(const std::vector<size_t>& onsets, uint32_t sr, size_t
 }
 
 }  // namespace so
+
+// ---- unit-level entry points (tests/test_oracle_ref_units.py: the reference's own #[test] known answers) ----------------
+extern "C" {
+static std::vector<size_t> u_onsets(const int64_t* o, int n) {
+    std::vector<size_t> v;
+    for (int i = 0; i < n; ++i) v.push_back((size_t)o[i]);
+    return v;
+}
+int so_u_acf_bpm(const int64_t* onsets, int n, uint32_t sr, uint64_t hop, float min_bpm, float max_bpm, float* bpm, float* conf, int cap) {
+    std::vector<so::BpmCandidate> out;
+    so::Error e = so::bpm_from_autocorrelation(u_onsets(onsets, n), sr, (size_t)hop, min_bpm, max_bpm, out);
+    if (e) return -e.kind;
+    for (int i = 0; i < std::min<int>(cap, (int)out.size()); ++i) {
+        bpm[i] = out[i].bpm;
+        conf[i] = out[i].confidence;
+    }
+    return (int)out.size();
+}
+int so_u_comb_bpm(const int64_t* onsets, int n, uint32_t sr, float min_bpm, float max_bpm, float res, float* bpm, float* conf, int cap) {
+    std::vector<so::BpmCandidate> out;
+    so::Error e = so::bpm_from_comb(u_onsets(onsets, n), sr, min_bpm, max_bpm, res, out, nullptr);
+    if (e) return -e.kind;
+    for (int i = 0; i < std::min<int>(cap, (int)out.size()); ++i) {
+        bpm[i] = out[i].bpm;
+        conf[i] = out[i].confidence;
+    }
+    return (int)out.size();
+}
+int so_u_score_bpm(const int64_t* onsets, int n, uint32_t sr, float bpm, float tol, float* score) {
+    *score = 0.0f;
+    return so::score_bpm_candidate(u_onsets(onsets, n), sr, bpm, tol, score).kind;
+}
+int so_u_acf_fft(const float* sig, int n, float* out) {
+    std::vector<float> a = so::acf_fft(std::vector<float>(sig, sig + n));
+    for (size_t i = 0; i < a.size(); ++i) out[i] = a[i];
+    return (int)a.size();
+}
+int so_u_find_peaks(const float* acf, int n, uint64_t offset, int64_t* idx, float* val, int cap) {
+    auto p = so::find_peaks_in_acf(acf, (size_t)n, (size_t)offset);
+    for (int i = 0; i < std::min<int>(cap, (int)p.size()); ++i) {
+        idx[i] = (int64_t)p[i].first;
+        val[i] = p[i].second;
+    }
+    return (int)p.size();
+}
+int so_u_merge(const float* ab, const float* ac, int na, const float* cb, const float* cc, int nc, float* bpm, float* conf, uint32_t* agree, int cap) {
+    std::vector<so::BpmCandidate> a, c;
+    for (int i = 0; i < na; ++i) a.push_back(so::BpmCandidate{ab[i], ac[i]});
+    for (int i = 0; i < nc; ++i) c.push_back(so::BpmCandidate{cb[i], cc[i]});
+    std::vector<so::BpmEstimate> m = so::merge_candidates(a, c);
+    for (int i = 0; i < std::min<int>(cap, (int)m.size()); ++i) {
+        bpm[i] = m[i].bpm;
+        conf[i] = m[i].confidence;
+        agree[i] = m[i].method_agreement;
+    }
+    return (int)m.size();
+}
+}
