@@ -341,6 +341,7 @@ void extract_beat_synchronous_chroma(const Spec& K, uint32_t sr, size_t fft_size
 Spec harmonic_spectrogram_hpss_median_mask(const Spec& K, uint32_t sr, size_t fft_size, float fmin_hz, float fmax_hz, size_t frame_step, size_t time_margin,
                                            size_t freq_margin, float mask_power);
 void smooth_chroma(std::vector<float>& chroma, size_t frames, size_t window);
+void sharpen_chroma(float* ch12, float power);
 struct KeyScores {
     int keys[24];  // 0..11 major, 12..23 minor, in ranked order
     float scores[24];

@@ -444,6 +444,20 @@ Spec harmonic_spectrogram_hpss_median_mask(const Spec& K, uint32_t sr, size_t ff
 }
 
 // smooth_chroma (median) — smoothing.rs:37-94
+// sharpen_chroma — chroma/normalization.rs:41-65: element-wise power, then L2 normalisation (uniform vector when the norm vanishes)
+void sharpen_chroma(float* ch, float power) {
+    float ss = 0.0f;
+    for (int i = 0; i < 12; ++i) {
+        ch[i] = powf(ch[i], power);
+        ss += ch[i] * ch[i];
+    }
+    float norm = sqrtf(ss);
+    if (norm > EPSILON)
+        for (int i = 0; i < 12; ++i) ch[i] /= norm;
+    else
+        for (int i = 0; i < 12; ++i) ch[i] = 1.0f / sqrtf(12.0f);
+}
+
 void smooth_chroma(std::vector<float>& chroma, size_t frames, size_t window) {
     if (frames == 0 || window <= 1) return;
     if (window % 2 == 0) window += 1;
@@ -826,20 +840,8 @@ Error detect_key_path(const float* s, size_t n, uint32_t sr, const Config& c, co
         extract_chroma(*forkey, sr, kfft, c.soft_chroma_mapping, c.soft_mapping_sigma, chroma, energy, tn);
     }
     size_t nf = nf_chroma;
-    if (c.chroma_sharpening_power > 1.0f)  // lib.rs:1200-1208, chroma/normalization.rs:41-65
-        for (size_t t = 0; t < nf; ++t) {
-            float* ch = &chroma[t * 12];
-            float ss = 0.0f;
-            for (int i = 0; i < 12; ++i) {
-                ch[i] = powf(ch[i], c.chroma_sharpening_power);
-                ss += ch[i] * ch[i];
-            }
-            float norm = sqrtf(ss);
-            if (norm > EPSILON)
-                for (int i = 0; i < 12; ++i) ch[i] /= norm;
-            else
-                for (int i = 0; i < 12; ++i) ch[i] = 1.0f / sqrtf(12.0f);
-        }
+    if (c.chroma_sharpening_power > 1.0f)  // lib.rs:1200-1208
+        for (size_t t = 0; t < nf; ++t) sharpen_chroma(&chroma[t * 12], c.chroma_sharpening_power);
     if (dump) {
         dump->f["key.hpcp_raw"] = chroma;
         dump->f["key.energy"] = energy;
