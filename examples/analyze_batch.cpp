@@ -4,8 +4,9 @@
 //   make -C stratum_dsp_b200 example      (g++ -std=c++17 -Iinclude examples/analyze_batch.cpp -Lstratum_dsp_b200/_build -lstratum_b200 ...)
 //   ./analyze_batch [--json] [--devices 0,1,...] a.wav b.wav ...
 //
-// RIFF/WAVE 16-bit PCM files are read with <cstdio> and handed to stratum_b200_analyze_batch_pcm16 undecoded: the int16 -> f32
-// conversion and the mono mixdown of the reference's decoder loop (analyze_batch.rs:96-113) run on the device.  Output as the
+// RIFF/WAVE files (PCM 8/16/24/32 bit, IEEE float 32/64 bit, WAVE_FORMAT_EXTENSIBLE, any channel count) are read with <cstdio> and
+// handed to stratum_b200_analyze_batch_pcm undecoded: the per-format conversion and the mono mixdown of the reference's decoder loop
+// (analyze_batch.rs:70-165) run on the device.  Output as the
 // reference: one JSON object per line with --json (analyze_batch.rs:331-351), else "[i/n] path: BPM=.. Key=..".
 #include <chrono>
 #include <cstdint>
@@ -18,8 +19,8 @@
 #include "stratum_b200.h"
 
 struct Wav {
-    std::vector<int16_t> pcm;  // interleaved
-    uint32_t sr = 0, channels = 0;
+    std::vector<uint8_t> pcm;  // interleaved sample frames as stored in the file
+    uint32_t sr = 0, channels = 0, format = 0;  // StratumPcmFormat
     std::string error;
 };
 
@@ -37,18 +38,28 @@ static Wav read_wav(const char* path) {
     uint16_t fmt = 0, ch = 0, bits = 0;
     while (w.error.empty() && rd(id, 4) && rd(&sz, 4)) {
         if (!std::memcmp(id, "fmt ", 4)) {
-            uint8_t b[16];
-            if (sz < 16 || !rd(b, 16)) { w.error = "bad fmt chunk"; break; }
+            uint8_t b[40] = {};
+            const size_t take = sz < 40 ? sz : 40;
+            if (sz < 16 || !rd(b, take)) { w.error = "bad fmt chunk"; break; }
             std::memcpy(&fmt, b, 2);
             std::memcpy(&ch, b + 2, 2);
             std::memcpy(&w.sr, b + 4, 4);
             std::memcpy(&bits, b + 14, 2);
-            std::fseek(f, (long)(sz - 16 + (sz & 1)), SEEK_CUR);
+            if (fmt == 0xFFFE && take >= 26) std::memcpy(&fmt, b + 24, 2);  // WAVE_FORMAT_EXTENSIBLE: the sub-format GUID starts with the real tag
+            std::fseek(f, (long)(sz - take + (sz & 1)), SEEK_CUR);
         } else if (!std::memcmp(id, "data", 4)) {
-            if ((fmt != 1 && fmt != 0xFFFE) || bits != 16 || ch == 0) { w.error = "unsupported format (16-bit PCM only)"; break; }
+            if (fmt == 1 && bits == 8) w.format = STRATUM_PCM_U8;
+            else if (fmt == 1 && bits == 16) w.format = STRATUM_PCM_S16;
+            else if (fmt == 1 && bits == 24) w.format = STRATUM_PCM_S24;
+            else if (fmt == 1 && bits == 32) w.format = STRATUM_PCM_S32;
+            else if (fmt == 3 && bits == 32) w.format = STRATUM_PCM_F32;
+            else if (fmt == 3 && bits == 64) w.format = STRATUM_PCM_F64;
+            if (w.format == 0 || ch == 0) { w.error = "Unsupported sample format"; break; }
             w.channels = ch;
-            w.pcm.resize(sz / 2);
-            if (!rd(w.pcm.data(), (size_t)(sz / 2) * 2)) w.error = "truncated data chunk";
+            const size_t frame = (size_t)(bits / 8) * ch;
+            w.pcm.resize(sz);
+            const size_t got = std::fread(w.pcm.data(), 1, sz, f);  // a streamed file may carry a bogus length: keep what is there
+            w.pcm.resize(got / frame * frame);
             break;
         } else {
             std::fseek(f, (long)(sz + (sz & 1)), SEEK_CUR);
@@ -85,23 +96,24 @@ int main(int argc, char** argv) {
     std::vector<Wav> wavs;
     for (const char* p : paths) wavs.push_back(read_wav(p));
     // tracks that decoded, concatenated: the batch surface takes one buffer + offsets (include/stratum_b200.h)
-    std::vector<int16_t> cat;
-    std::vector<uint64_t> offsets(1, 0);
-    std::vector<uint32_t> srs, chans, index;
+    std::vector<uint8_t> cat;
+    std::vector<uint64_t> offsets(1, 0);  // byte offsets
+    std::vector<uint32_t> srs, chans, fmts, index;
     for (size_t i = 0; i < wavs.size(); ++i)
         if (wavs[i].error.empty()) {
             cat.insert(cat.end(), wavs[i].pcm.begin(), wavs[i].pcm.end());
             offsets.push_back(cat.size());
             srs.push_back(wavs[i].sr);
             chans.push_back(wavs[i].channels);
+            fmts.push_back(wavs[i].format);
             index.push_back((uint32_t)i);
         }
     std::vector<StratumResult> res(index.size());
     if (!index.empty()) {
         StratumConfig cfg;
         stratum_b200_config_default(&cfg);
-        const int32_t st = stratum_b200_analyze_batch_pcm16(cat.data(), offsets.data(), srs.data(), chans.data(), (uint32_t)index.size(), &cfg,
-                                                            devices.empty() ? nullptr : devices.data(), (uint32_t)devices.size(), res.data());
+        const int32_t st = stratum_b200_analyze_batch_pcm(cat.data(), offsets.data(), srs.data(), chans.data(), fmts.data(), (uint32_t)index.size(), &cfg,
+                                                          devices.empty() ? nullptr : devices.data(), (uint32_t)devices.size(), res.data());
         if (st != STRATUM_OK) {
             char msg[512];
             stratum_b200_last_error(msg, sizeof msg);

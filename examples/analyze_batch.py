@@ -5,9 +5,9 @@
 
 Same output as the reference: one JSON object per line with --json (same keys, same number formatting,
 errors as {"file":..,"error":..}), otherwise the "[i/n] path: BPM=.. Key=.." lines; summary on stderr.
-The reference decodes with symphonia (out of scope here: SURVEY §8f n4); this tool reads RIFF/WAVE PCM with the
-standard library and hands 16-bit PCM to the device undecoded (the int16 -> f32 conversion and the mono mixdown of
-examples/analyze_batch.rs:96-113 run on the GPU).  `--jobs` is accepted and ignored: parallelism is across the
+The reference decodes with symphonia; this tool reads the RIFF/WAVE container itself (PCM 8/16/24/32 bit, IEEE float 32/64 bit,
+WAVE_FORMAT_EXTENSIBLE, any channel count) and hands the sample bytes to the device undecoded: the per-format conversion and the
+mono mixdown of examples/analyze_batch.rs:70-165 run on the GPU (compressed formats need a decoder library on the caller's side).  `--jobs` is accepted and ignored: parallelism is across the
 tracks of the batch on the device(s).
 """
 from __future__ import annotations
@@ -15,23 +15,12 @@ from __future__ import annotations
 import json
 import sys
 import time
-import wave
 from pathlib import Path
 
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import stratum_dsp_b200 as S  # noqa: E402
-
-
-def read_wav_pcm16(path: str):
-    with wave.open(path, "rb") as w:
-        ch, width, sr, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
-        raw = w.readframes(n)
-    if width != 2:
-        raise ValueError(f"unsupported sample width {8 * width} bit (16-bit PCM only)")
-    x = np.frombuffer(raw, dtype="<i2")
-    return (x.reshape(-1, ch) if ch > 1 else x), sr
 
 
 def _display(e) -> str:
@@ -71,16 +60,14 @@ def main(argv):
         return 2
     print(f"Batch: {len(paths)} files, devices={devices or 'current'}", file=sys.stderr)
     t0 = time.perf_counter()
-    tracks, srs, idx, errors = [], [], [], {}
+    tracks, idx, errors = [], [], {}
     for i, p in enumerate(paths):
         try:
-            x, sr = read_wav_pcm16(p)
-            tracks.append(x)
-            srs.append(sr)
+            tracks.append(S.read_wav(p))
             idx.append(i)
         except Exception as e:  # decode failure -> ItemOut.error, the batch goes on
             errors[i] = str(e)
-    results = dict(zip(idx, S.analyze_batch_pcm16(tracks, srs, devices=devices))) if tracks else {}
+    results = dict(zip(idx, S.analyze_batch_pcm(tracks, devices=devices))) if tracks else {}
     times = []
     for i, p in enumerate(paths):
         r = results.get(i)

@@ -207,6 +207,24 @@ int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets
 int32_t stratum_b200_analyze_batch_pcm16(const int16_t* pcm, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels,
                                          uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out);
 
+/* General decoder-side entry: every sample format the reference's decoder loop converts (examples/analyze_batch.rs:70-165).
+ * Track i is interleaved PCM in formats[i] (StratumPcmFormat) with channels[i] channels at pcm[byte_offsets[i] .. byte_offsets[i+1])
+ * (BYTE offsets; a whole number of frames per track; little-endian; 24-bit samples packed in 3 bytes).  Conversion and mixdown run on
+ * the device with the reference's arithmetic: u8 (s - 128) / 128, s16 s / 32768, s24 s / 8388608, s32 s as f32 / 2147483648, f32 as
+ * is, f64 as f32; channels summed left to right in f32 from 0.0 and divided by the channel count.  Compressed formats stay on the
+ * caller's side (a decoder library's job); what it hands over is PCM in one of these layouts. */
+typedef enum StratumPcmFormat {
+    STRATUM_PCM_U8 = 1,
+    STRATUM_PCM_S16 = 2,
+    STRATUM_PCM_S24 = 3,
+    STRATUM_PCM_S32 = 4,
+    STRATUM_PCM_F32 = 5,
+    STRATUM_PCM_F64 = 6
+} StratumPcmFormat;
+int32_t stratum_b200_analyze_batch_pcm(const void* pcm, const uint64_t* byte_offsets, const uint32_t* sample_rates, const uint32_t* channels,
+                                       const uint32_t* formats, uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices,
+                                       StratumResult* out);
+
 /* Same, with `samples` already resident in the memory of device `device_id` (single device). */
 int32_t stratum_b200_analyze_batch_device(const float* d_samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks,
                                           const StratumConfig* cfg, int32_t device_id, StratumResult* out);

@@ -480,6 +480,93 @@ def analyze_batch_pcm16(tracks: Sequence, sample_rates: int | Iterable[int], con
     return _collect(res, n)
 
 
+PCM_U8, PCM_S16, PCM_S24, PCM_S32, PCM_F32, PCM_F64 = 1, 2, 3, 4, 5, 6  # StratumPcmFormat
+_PCM_BYTES = {PCM_U8: 1, PCM_S16: 2, PCM_S24: 3, PCM_S32: 4, PCM_F32: 4, PCM_F64: 8}
+
+
+@dataclass
+class PcmTrack:
+    """Undecoded interleaved PCM of one track: ``data`` = the bytes of the sample frames (little-endian, 24-bit packed)."""
+
+    data: np.ndarray  # uint8
+    fmt: int          # PCM_*
+    channels: int
+    sample_rate: int
+
+    @property
+    def frames(self) -> int:
+        return self.data.size // (_PCM_BYTES[self.fmt] * self.channels)
+
+
+def read_wav(path) -> PcmTrack:
+    """RIFF/WAVE container -> PcmTrack without touching the samples: WAVE_FORMAT_PCM (8/16/24/32 bit), WAVE_FORMAT_IEEE_FLOAT
+    (32/64 bit) and WAVE_FORMAT_EXTENSIBLE with a PCM or IEEE-float sub-format, any channel count (the formats symphonia's WAV
+    reader hands to the reference's decoder loop, examples/analyze_batch.rs:30-178).  Conversion and mixdown happen on the device."""
+    import struct
+
+    raw = np.fromfile(str(path), dtype=np.uint8)
+    b = raw.tobytes() if raw.size < (1 << 16) else None
+    hdr = bytes(raw[:12])
+    if len(hdr) < 12 or hdr[:4] != b"RIFF" or hdr[8:12] != b"WAVE":
+        raise ValueError("not a RIFF/WAVE file")
+    pos, fmt, data = 12, None, None
+    while pos + 8 <= raw.size:
+        cid = bytes(raw[pos:pos + 4])
+        (size,) = struct.unpack("<I", bytes(raw[pos + 4:pos + 8]))
+        body = pos + 8
+        if cid == b"fmt ":
+            f = bytes(raw[body:body + min(size, 40)])
+            tag, ch, sr, _br, _align, bits = struct.unpack("<HHIIHH", f[:16])
+            if tag == 0xFFFE and len(f) >= 40:  # WAVE_FORMAT_EXTENSIBLE: the sub-format GUID starts with the real tag
+                (tag,) = struct.unpack("<H", f[24:26])
+            fmt = (tag, ch, sr, bits)
+        elif cid == b"data":
+            end = min(body + size, raw.size)  # a streamed file may carry a bogus length
+            data = raw[body:end]
+            if fmt is not None:
+                break
+        pos = body + size + (size & 1)
+    del b
+    if fmt is None or data is None:
+        raise ValueError("WAVE file without fmt/data chunk")
+    tag, ch, sr, bits = fmt
+    if tag == 1 and bits in (8, 16, 24, 32):
+        pf = {8: PCM_U8, 16: PCM_S16, 24: PCM_S24, 32: PCM_S32}[bits]
+    elif tag == 3 and bits in (32, 64):
+        pf = PCM_F32 if bits == 32 else PCM_F64
+    else:
+        raise ValueError(f"Unsupported sample format (format tag {tag}, {bits} bit)")
+    if ch == 0:
+        raise ValueError("WAVE file with zero channels")
+    frame = _PCM_BYTES[pf] * ch
+    return PcmTrack(np.ascontiguousarray(data[: data.size // frame * frame]), pf, ch, sr)
+
+
+def analyze_batch_pcm(tracks: Sequence[PcmTrack], config: AnalysisConfig | None = None, devices: Sequence[int] | None = None) -> list:
+    """stratum_b200_analyze_batch_pcm: undecoded PCM tracks of any supported format / channel count in one call."""
+    n = len(tracks)
+    if n == 0:
+        return []
+    flat = [np.ascontiguousarray(t.data, dtype=np.uint8).reshape(-1) for t in tracks]
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum([a.size for a in flat], dtype=np.uint64)
+    cat = np.concatenate(flat) if n > 1 else flat[0]
+    srs = np.ascontiguousarray([t.sample_rate for t in tracks], dtype=np.uint32)
+    chans = np.ascontiguousarray([t.channels for t in tracks], dtype=np.uint32)
+    fmts = np.ascontiguousarray([t.fmt for t in tracks], dtype=np.uint32)
+    res = (StratumResult * n)()
+    dev = (C.c_int32 * len(devices))(*devices) if devices else None
+    L = lib()
+    L.stratum_b200_analyze_batch_pcm.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(_u), C.POINTER(_u), C.POINTER(_u), C.c_uint32, C.c_void_p,
+                                                 C.POINTER(C.c_int32), C.c_uint32, C.POINTER(StratumResult)]
+    cfgp = C.cast(C.byref(config._c), C.c_void_p) if config is not None else None
+    st = L.stratum_b200_analyze_batch_pcm(cat.ctypes.data if cat.size else None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), srs.ctypes.data_as(C.POINTER(_u)),
+                                          chans.ctypes.data_as(C.POINTER(_u)), fmts.ctypes.data_as(C.POINTER(_u)), n, cfgp, dev, len(devices) if devices else 0, res)
+    if st != OK:
+        _fail(st, res, n)
+    return _collect(res, n)
+
+
 def analyze_batch_device(d_samples_ptr: int, offsets: np.ndarray, sample_rates: Sequence[int], config: AnalysisConfig | None = None,
                          device: int = -1, convert: bool = True):
     """Batch already resident in device memory (``d_samples_ptr`` = device address of the concatenated f32

@@ -1938,9 +1938,24 @@ int32_t stratum_b200_analyze_batch_device(const float* d_samples, const uint64_t
 // gather is the result array itself).  Each shard is streamed through two device staging buffers: chunk k+1 is
 // uploaded by the device's uploader thread while chunk k is analysed (pinned host memory makes the upload asynchronous;
 // pageable memory still works, without the overlap), and the analysis itself runs one wave ahead of the gather (Session).
-static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels,
+static uint32_t pcm_bytes_per_sample(uint32_t fmt) {
+    switch (fmt) {
+        case STRATUM_PCM_U8: return 1;
+        case STRATUM_PCM_S16: return 2;
+        case STRATUM_PCM_S24: return 3;
+        case STRATUM_PCM_S32: return 4;
+        case STRATUM_PCM_F32: return 4;
+        case STRATUM_PCM_F64: return 8;
+        default: return 0;
+    }
+}
+
+// boff: byte offsets of the tracks inside src (n_tracks + 1).  formats == nullptr: mono f32 samples analysed straight from the staging
+// buffer; otherwise interleaved PCM in the given per-track format and channel count, converted and mixed down on the device.
+static int32_t analyze_host_batch(const void* src, const uint64_t* boff, const uint32_t* sample_rates, const uint32_t* channels, const uint32_t* formats,
                                   uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
-    if (!offsets || !sample_rates || !out || (!src && n_tracks && offsets[n_tracks] > 0) || (pcm16 && !channels)) {
+    const bool pcm = formats != nullptr;
+    if (!boff || !sample_rates || !out || (!src && n_tracks && boff[n_tracks] > 0) || (pcm && !channels)) {
         set_error("null argument");
         return STRATUM_INVALID_INPUT;
     }
@@ -1950,13 +1965,22 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
     int st = config_validate(c);
     if (st != STRATUM_OK) return st;
     if (n_tracks == 0) return STRATUM_OK;
-    if (pcm16)
-        for (uint32_t i = 0; i < n_tracks; ++i)
-            if (channels[i] == 0 || channels[i] > 64 || (offsets[i + 1] - offsets[i]) % channels[i] != 0) {
-                set_error("PCM16 track length is not a multiple of its channel count (or channels outside 1..64)");
+    std::vector<uint32_t> bpf(n_tracks, 4);  // bytes per mono frame
+    if (pcm)
+        for (uint32_t i = 0; i < n_tracks; ++i) {
+            const uint32_t bps = pcm_bytes_per_sample(formats[i]);
+            if (bps == 0) {
+                set_error("unknown PCM sample format (STRATUM_PCM_*)");
                 return STRATUM_INVALID_INPUT;
             }
-    const size_t elt = pcm16 ? sizeof(int16_t) : sizeof(float);
+            if (channels[i] == 0 || channels[i] > 64 || (boff[i + 1] - boff[i]) % ((uint64_t)bps * channels[i]) != 0) {
+                set_error("PCM track length is not a whole number of frames (or channels outside 1..64)");
+                return STRATUM_INVALID_INPUT;
+            }
+            bpf[i] = bps * channels[i];
+        }
+    const uint64_t* offsets = boff;
+    const size_t elt = 1;  // offsets are in bytes
     // device contexts of the call; an id named twice (or -1 next to the current device's id) is one shard, not two
     std::vector<DeviceCtx*> ctxs;
     {
@@ -1996,7 +2020,7 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
             uint32_t i, j;
             uint64_t elems, frames;
         };
-        auto frames_of_track = [&](uint32_t q) { return (offsets[q + 1] - offsets[q]) / (pcm16 ? channels[q] : 1u); };
+        auto frames_of_track = [&](uint32_t q) { return (offsets[q + 1] - offsets[q]) / bpf[q]; };
         std::vector<Chunk> chunks;
         uint64_t max_el = 0, max_fr = 0;
         uint32_t max_cn = 0;
@@ -2030,13 +2054,13 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 return true;
             };
             bool okm = grow((void**)&ctx->d_stage, &ctx->stage_cap, 2 * buf_bytes);
-            if (okm && pcm16) okm = grow((void**)&ctx->d_conv, &ctx->conv_cap, (max_fr + 16) * sizeof(float));
+            if (okm && pcm) okm = grow((void**)&ctx->d_conv, &ctx->conv_cap, (max_fr + 16) * sizeof(float));
             // per-chunk offset / channel tables of the PCM16 path, two sets (the conversion of chunk k+1 is queued while chunk k runs)
-            const size_t meta_each = (size_t)align_up((size_t)(max_cn + 1) * 16 + (size_t)max_cn * 4 + 64, 256);
-            if (okm && pcm16) okm = grow((void**)&ctx->d_meta, &ctx->meta_cap, 2 * meta_each);
+            const size_t meta_each = (size_t)align_up((size_t)(max_cn + 1) * 16 + (size_t)max_cn * 8 + 64, 256);
+            if (okm && pcm) okm = grow((void**)&ctx->d_meta, &ctx->meta_cap, 2 * meta_each);
             if (!okm) return fail(STRATUM_PROCESSING_ERROR, "staging buffer allocation failed");
         }
-        const size_t meta_each = (size_t)align_up((size_t)(max_cn + 1) * 16 + (size_t)max_cn * 4 + 64, 256);
+        const size_t meta_each = (size_t)align_up((size_t)(max_cn + 1) * 16 + (size_t)max_cn * 8 + 64, 256);
         char* bufs[2] = {reinterpret_cast<char*>(ctx->d_stage), reinterpret_cast<char*>(ctx->d_stage) + buf_bytes};
         if (!ctx->uploader) ctx->uploader.reset(new Worker());
         // Uploads run on the device's uploader thread, in pieces of 128 MB with a stream synchronisation after each piece: the
@@ -2077,8 +2101,8 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 rel[q + 1] = rel[q] + lens[q];
             }
             const float* d_mono = reinterpret_cast<const float*>(bufs[k & 1]);
-            if (pcm16) {
-                // decoder arithmetic on the device: interleaved int16 -> mono f32 (examples/analyze_batch.rs:96-113).  Queued on
+            if (pcm) {
+                // decoder arithmetic on the device: interleaved PCM -> mono f32 (examples/analyze_batch.rs:70-165).  Queued on
                 // the analysis stream, so it runs after the previous chunk's waves have finished with the conversion buffer.
                 char* hm = static_cast<char*>(ctx->h_meta[k & 1].need(meta_each));
                 if (!hm) {
@@ -2088,6 +2112,7 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 uint64_t* h_poff = reinterpret_cast<uint64_t*>(hm);
                 uint64_t* h_ooff = h_poff + (cn + 1);
                 uint32_t* h_ch = reinterpret_cast<uint32_t*>(h_ooff + (cn + 1));
+                uint32_t* h_fmt = h_ch + cn;
                 uint64_t max_frames = 0;
                 for (uint32_t q = 0; q <= cn; ++q) {
                     h_poff[q] = offsets[ch.i + q] - offsets[ch.i];
@@ -2095,14 +2120,16 @@ static int32_t analyze_host_batch(const void* src, bool pcm16, const uint64_t* o
                 }
                 for (uint32_t q = 0; q < cn; ++q) {
                     h_ch[q] = channels[ch.i + q];
+                    h_fmt[q] = formats[ch.i + q];
                     max_frames = std::max(max_frames, lens[q]);
                 }
                 char* dm = ctx->d_meta + (k & 1) * meta_each;
                 uint64_t* d_poff = reinterpret_cast<uint64_t*>(dm);
                 uint64_t* d_ooff = d_poff + (cn + 1);
                 uint32_t* d_ch = reinterpret_cast<uint32_t*>(d_ooff + (cn + 1));
-                cudaMemcpyAsync(dm, hm, (size_t)(cn + 1) * 16 + (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream);
-                launch_pcm16_to_mono(ctx->stream, reinterpret_cast<const int16_t*>(bufs[k & 1]), ctx->d_conv, d_poff, d_ooff, d_ch, cn, max_frames);
+                uint32_t* d_fmt = d_ch + cn;
+                cudaMemcpyAsync(dm, hm, (size_t)(cn + 1) * 16 + (size_t)cn * 8, cudaMemcpyHostToDevice, ctx->stream);
+                launch_pcm_to_mono(ctx->stream, bufs[k & 1], ctx->d_conv, d_poff, d_ooff, d_ch, d_fmt, cn, max_frames);
                 d_mono = ctx->d_conv;
             }
             bool posted = false;
@@ -2161,14 +2188,37 @@ uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* 
     return nw;
 }
 
+static std::vector<uint64_t> scaled_offsets(const uint64_t* offsets, uint32_t n, uint64_t elt) {
+    std::vector<uint64_t> b((size_t)n + 1, 0);
+    if (offsets)
+        for (uint32_t i = 0; i <= n; ++i) b[i] = offsets[i] * elt;
+    return b;
+}
+
 int32_t stratum_b200_analyze_batch(const float* samples, const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg,
                                    const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
-    return analyze_host_batch(samples, false, offsets, sample_rates, nullptr, n_tracks, cfg, device_ids, n_devices, out);
+    const std::vector<uint64_t> b = scaled_offsets(offsets, n_tracks, sizeof(float));
+    return analyze_host_batch(samples, offsets ? b.data() : nullptr, sample_rates, nullptr, nullptr, n_tracks, cfg, device_ids, n_devices, out);
 }
 
 int32_t stratum_b200_analyze_batch_pcm16(const int16_t* pcm, const uint64_t* offsets, const uint32_t* sample_rates, const uint32_t* channels, uint32_t n_tracks,
                                          const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
-    return analyze_host_batch(pcm, true, offsets, sample_rates, channels, n_tracks, cfg, device_ids, n_devices, out);
+    const std::vector<uint64_t> b = scaled_offsets(offsets, n_tracks, sizeof(int16_t));
+    const std::vector<uint32_t> fmt(n_tracks, (uint32_t)STRATUM_PCM_S16);
+    if (!channels) {
+        set_error("null argument");
+        return STRATUM_INVALID_INPUT;
+    }
+    return analyze_host_batch(pcm, offsets ? b.data() : nullptr, sample_rates, channels, fmt.data(), n_tracks, cfg, device_ids, n_devices, out);
+}
+
+int32_t stratum_b200_analyze_batch_pcm(const void* pcm, const uint64_t* byte_offsets, const uint32_t* sample_rates, const uint32_t* channels, const uint32_t* formats,
+                                       uint32_t n_tracks, const StratumConfig* cfg, const int32_t* device_ids, uint32_t n_devices, StratumResult* out) {
+    if (!formats || !channels) {
+        set_error("null argument");
+        return STRATUM_INVALID_INPUT;
+    }
+    return analyze_host_batch(pcm, byte_offsets, sample_rates, channels, formats, n_tracks, cfg, device_ids, n_devices, out);
 }
 
 int32_t stratum_b200_analyze_audio(const float* samples, uint64_t n_samples, uint32_t sample_rate, const StratumConfig* cfg, StratumResult* out) {

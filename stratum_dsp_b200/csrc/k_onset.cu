@@ -6,6 +6,8 @@
 //
 // Every sum that feeds a comparison is accumulated in the reference's order (bin 0 upward, one
 // rounded multiply and one rounded add per term), one thread per frame / frame pair.
+#include <algorithm>
+
 #include "framed.cuh"
 #include "kernels.h"
 
@@ -163,9 +165,15 @@ struct ParSmem {
     float mel[2][MEL_MAX];
 };
 
+// K4: the SuperFlux radius is the default 4 (config.rs:634) — the pair pass then gives every lane four CONSECUTIVE bins: the twelve
+// previous-frame values their windows cover come from three 16-byte shared loads and the four 9-tap maxima share the maximum of the
+// six values common to all windows (17 FMNMX for four bins instead of 36 loads + 36 FMNMX, and a quarter of the shared-memory
+// instructions: ncu had the L1/shared pipe at 73 % on the lane-strided version).  Sums are warp trees either way (tolerance-level
+// consumers), so only their association changes.
+template <bool K4>
 __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, const SrTables* srtab,
                                                        const int32_t* sr_index, int h, float* fa, DevCfg cfg) {
-    __shared__ ParSmem sm[4];
+    __shared__ __align__(16) ParSmem sm[4];
     const int t = list ? list[blockIdx.y] : blockIdx.y;
     const TrackDev& T = tr[t];
     const uint32_t F = T.F[h];
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
     float* fr = fa + HL.frame;
     float* pr = fa + HL.pair;
     const uint64_t fm = HL.fmax;
-    const int K = (int)min(max(cfg.sf_k, 1u), (uint32_t)HALO);
+    const int K = K4 ? 4 : (int)min(max(cfg.sf_k, 1u), (uint32_t)HALO);
     const int MK = (int)max(cfg.mel_k, 1u);
     const int nm = (int)st.n_mels;
     const int e0 = (int)st.b0, e1 = (int)st.b_low, e2 = (int)st.b_mid, e3 = (int)st.b_hi;
@@ -197,41 +205,97 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
         // per-band accumulators are selected with predicates, never indexed: a run-time index would put the arrays in local
         // memory and chain every iteration through a store -> load round trip (27 % of the kernel's stall samples in ncu)
         float Eb[3] = {0.0f, 0.0f, 0.0f}, Hb[3] = {0.0f, 0.0f, 0.0f};
-        for (int b = lane; b < 1025; b += 32) {
-            const float x = row[b];
-            Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
-            if (emit && b >= e0 && b < e3) {
+        // A 32-bin slice that lies inside one band (all but the three slices holding a band edge) adds into a running pair that is
+        // folded into its band's accumulators when the band changes: two adds per bin instead of six predicated ones.
+        float ea = 0.0f, ha = 0.0f;
+        int aband = -1;
+        auto fold = [&]() {
+            Eb[0] += aband == 0 ? ea : 0.0f;
+            Hb[0] += aband == 0 ? ha : 0.0f;
+            Eb[1] += aband == 1 ? ea : 0.0f;
+            Hb[1] += aband == 1 ? ha : 0.0f;
+            Eb[2] += aband == 2 ? ea : 0.0f;
+            Hb[2] += aband == 2 ? ha : 0.0f;
+            ea = ha = 0.0f;
+        };
+        for (int b0 = 0; b0 < 1025; b0 += 32) {
+            const int b = b0 + lane;
+            const bool in = b < 1025;
+            const float x = in ? row[b] : 0.0f;
+            if (in) Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
+            if (!emit) continue;
+            const int lo = b0, hi = min(b0 + 31, 1024);  // slice range (warp-uniform)
+            int sband = -2;  // -2: slice touches no band at all; -1: mixed
+            if (hi >= e0 && lo < e3) sband = (lo >= e0 && hi < e1) ? 0 : ((lo >= e1 && hi < e2) ? 1 : ((lo >= e2 && hi < e3) ? 2 : -1));
+            if (sband >= 0) {
+                if (sband != aband) {
+                    fold();
+                    aband = sband;
+                }
+                ea += x * x;
+                ha += (float)b * x * x;
+            } else if (sband == -1 && in && b >= e0 && b < e3) {
                 const float xx = x * x, kx = (float)b * x * x;
-                const bool b0 = b < e1, b1 = !b0 && b < e2, b2 = !b0 && !b1;
-                Eb[0] += b0 ? xx : 0.0f;
-                Hb[0] += b0 ? kx : 0.0f;
-                Eb[1] += b1 ? xx : 0.0f;
-                Hb[1] += b1 ? kx : 0.0f;
-                Eb[2] += b2 ? xx : 0.0f;
-                Hb[2] += b2 ? kx : 0.0f;
+                const bool q0 = b < e1, q1 = !q0 && b < e2, q2 = !q0 && !q1;
+                Eb[0] += q0 ? xx : 0.0f;
+                Hb[0] += q0 ? kx : 0.0f;
+                Eb[1] += q1 ? xx : 0.0f;
+                Hb[1] += q1 ? kx : 0.0f;
+                Eb[2] += q2 ? xx : 0.0f;
+                Hb[2] += q2 ? kx : 0.0f;
             }
         }
+        fold();
         __syncwarp();
         float sf = 0.0f, sfb[3] = {0.0f, 0.0f, 0.0f};
+        // one bin of the pair pass: pm = max of the previous frame's 2K+1 window around b (novelty.rs:360-420), lc = this frame's value
+        auto pair_bin = [&](int b, float pm, float lc) {
+            const float d = fmaxf(lc - pm, 0.0f);
+            sf += d * d;
+            if (b >= e0 && b < e3) {
+                const int band = b < e1 ? 0 : (b < e2 ? 1 : 2);
+                const int lo = band == 0 ? e0 : (band == 1 ? e1 : e2), hi = band == 0 ? e1 : (band == 1 ? e2 : e3);
+                float pmb = pm;
+                if (b - K < lo || b + K >= hi) {  // window clipped to the band (novelty.rs:432-441)
+                    pmb = 0.0f;
+                    for (int j = max(b - K, lo); j < min(b + K + 1, hi); ++j) pmb = fmaxf(pmb, Lp[j]);
+                }
+                const float db = fmaxf(lc - pmb, 0.0f), dd = db * db;
+                sfb[0] += band == 0 ? dd : 0.0f;
+                sfb[1] += band == 1 ? dd : 0.0f;
+                sfb[2] += band == 2 ? dd : 0.0f;
+            }
+        };
         if (pair) {
-            for (int b = lane; b < 1025; b += 32) {
-                float pm = 0.0f;
-                for (int j = -K; j <= K; ++j) pm = fmaxf(pm, Lp[b + j]);
-                const float lc = Lc[b];
-                const float d = fmaxf(lc - pm, 0.0f);
-                sf += d * d;
-                if (b >= e0 && b < e3) {
-                    const int band = b < e1 ? 0 : (b < e2 ? 1 : 2);
-                    const int lo = band == 0 ? e0 : (band == 1 ? e1 : e2), hi = band == 0 ? e1 : (band == 1 ? e2 : e3);
-                    float pmb = pm;
-                    if (b - K < lo || b + K >= hi) {  // window clipped to the band (novelty.rs:432-441)
-                        pmb = 0.0f;
-                        for (int j = max(b - K, lo); j < min(b + K + 1, hi); ++j) pmb = fmaxf(pmb, Lp[j]);
-                    }
-                    const float db = fmaxf(lc - pmb, 0.0f), dd = db * db;
-                    sfb[0] += band == 0 ? dd : 0.0f;
-                    sfb[1] += band == 1 ? dd : 0.0f;
-                    sfb[2] += band == 2 ? dd : 0.0f;
+            if (K4) {
+#pragma unroll 2
+                for (int g = 0; g < 8; ++g) {
+                    const int b0 = 4 * lane + 128 * g;  // bins b0 .. b0+3 (<= 1023); windows cover Lp[b0-4 .. b0+7]
+                    const float4 va = *reinterpret_cast<const float4*>(Lp + b0 - 4);
+                    const float4 vb = *reinterpret_cast<const float4*>(Lp + b0);
+                    const float4 vc = *reinterpret_cast<const float4*>(Lp + b0 + 4);
+                    const float4 lc4 = *reinterpret_cast<const float4*>(Lc + b0);
+                    // v[0..11] = va.xyzw vb.xyzw vc.xyzw; window of bin b0+j = v[j .. j+8]; common core v[3..8]
+                    const float core = fmaxf(fmaxf(fmaxf(va.w, vb.x), fmaxf(vb.y, vb.z)), fmaxf(vb.w, vc.x));
+                    const float m0 = fmaxf(fmaxf(core, va.x), fmaxf(va.y, va.z));
+                    const float m1 = fmaxf(fmaxf(core, va.y), fmaxf(va.z, vc.y));
+                    const float m2 = fmaxf(fmaxf(core, va.z), fmaxf(vc.y, vc.z));
+                    const float m3 = fmaxf(fmaxf(core, vc.y), fmaxf(vc.z, vc.w));
+                    pair_bin(b0, fmaxf(m0, 0.0f), lc4.x);
+                    pair_bin(b0 + 1, fmaxf(m1, 0.0f), lc4.y);
+                    pair_bin(b0 + 2, fmaxf(m2, 0.0f), lc4.z);
+                    pair_bin(b0 + 3, fmaxf(m3, 0.0f), lc4.w);
+                }
+                if (lane == 0) {  // bin 1024
+                    float pm = 0.0f;
+                    for (int j = -4; j <= 4; ++j) pm = fmaxf(pm, Lp[1024 + j]);
+                    pair_bin(1024, pm, Lc[1024]);
+                }
+            } else {
+                for (int b = lane; b < 1025; b += 32) {
+                    float pm = 0.0f;
+                    for (int j = -K; j <= K; ++j) pm = fmaxf(pm, Lp[b + j]);
+                    pair_bin(b, pm, Lc[b]);
                 }
             }
         }
@@ -501,7 +565,8 @@ void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_
     dim3 grid((c.max_F[h] + 127) / 128, n_list);
     seq_feat_kernel<<<dim3((c.max_F[h] + 123) / 124, n_list), 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
     count_launch("spec_features");
-    par_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
+    if (std::min(std::max(c.cfg.sf_k, 1u), (uint32_t)HALO) == 4u) par_feat_kernel<true><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
+    else par_feat_kernel<false><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
     count_launch("spec_features");
 }
 

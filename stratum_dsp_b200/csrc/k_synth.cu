@@ -37,33 +37,71 @@ __global__ void __launch_bounds__(256) synth_kernel(float* __restrict__ out, uin
     }
 }
 
-// Interleaved PCM16 -> mono f32, the reference's decoder arithmetic (examples/analyze_batch.rs:96-113):
-// `s as f32 / 32768.0` per channel, summed left to right in f32 from 0.0, divided by the channel count.
-__global__ void __launch_bounds__(256) pcm16_to_mono_kernel(const int16_t* __restrict__ pcm, float* __restrict__ out, const uint64_t* __restrict__ pcm_off,
-                                                            const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ channels) {
+// Interleaved PCM -> mono f32 with the reference decoder's arithmetic (examples/analyze_batch.rs:70-165): every channel sample is
+// converted on its own (u8: (s - 128) / 128; s16: s / 32768; s24: s / 8388608; s32: s as f32 / 2147483648; f32: as is; f64: as f32),
+// the channel values are summed left to right in f32 starting from 0.0 and divided by the channel count.  The integer scalings are
+// divisions by powers of two, i.e. exact multiplications; the mean over the channels is a true division unless the count is 1.
+// One grid row per track; formats and channel counts are per track (STRATUM_PCM_*).
+__device__ __forceinline__ float pcm_sample(const unsigned char* __restrict__ p, uint64_t idx, uint32_t fmt) {
+    switch (fmt) {
+        case STRATUM_PCM_U8: return __fmul_rn(__fsub_rn((float)p[idx], 128.0f), 0.0078125f);
+        case STRATUM_PCM_S16: {
+            const unsigned char* q = p + 2 * idx;
+            const int16_t v = (int16_t)((uint16_t)q[0] | ((uint16_t)q[1] << 8));
+            return __fmul_rn((float)v, 3.0517578125e-05f);
+        }
+        case STRATUM_PCM_S24: {
+            const unsigned char* q = p + 3 * idx;
+            int32_t v = (int32_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16));
+            v = (v << 8) >> 8;  // sign-extend 24 -> 32
+            return __fmul_rn((float)v, 1.1920928955078125e-07f);
+        }
+        case STRATUM_PCM_S32: {
+            const unsigned char* q = p + 4 * idx;
+            const int32_t v = (int32_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+            return __fmul_rn((float)v, 4.656612873077393e-10f);
+        }
+        case STRATUM_PCM_F32: {
+            const unsigned char* q = p + 4 * idx;
+            return __uint_as_float((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24));
+        }
+        default: {  // STRATUM_PCM_F64
+            const unsigned char* q = p + 8 * idx;
+            unsigned long long u = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) u |= (unsigned long long)q[k] << (8 * k);
+            return (float)__longlong_as_double((long long)u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pcm_to_mono_kernel(const unsigned char* __restrict__ pcm, float* __restrict__ out, const uint64_t* __restrict__ byte_off,
+                                                          const uint64_t* __restrict__ out_off, const uint32_t* __restrict__ channels,
+                                                          const uint32_t* __restrict__ formats) {
     const uint32_t trk = blockIdx.y;
-    const uint32_t C = channels[trk];
+    const uint32_t C = channels[trk], fmt = formats[trk];
     const uint64_t frames = out_off[trk + 1] - out_off[trk];
-    const int16_t* p = pcm + pcm_off[trk];
+    const unsigned char* p = pcm + byte_off[trk];
     float* o = out + out_off[trk];
+    const bool s16_aligned = fmt == STRATUM_PCM_S16 && (reinterpret_cast<uintptr_t>(p) & 1u) == 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < frames; i += (uint64_t)gridDim.x * blockDim.x) {
         if (C == 1) {
-            o[i] = __fdiv_rn((float)p[i], 32768.0f);
+            o[i] = s16_aligned ? __fmul_rn((float)reinterpret_cast<const int16_t*>(p)[i], 3.0517578125e-05f) : pcm_sample(p, i, fmt);
         } else {
             float acc = 0.0f;
-            for (uint32_t ch = 0; ch < C; ++ch) acc = __fadd_rn(acc, __fdiv_rn((float)p[i * C + ch], 32768.0f));
+            for (uint32_t ch = 0; ch < C; ++ch) acc = __fadd_rn(acc, pcm_sample(p, i * C + ch, fmt));
             o[i] = __fdiv_rn(acc, (float)C);
         }
     }
 }
 
-void launch_pcm16_to_mono(cudaStream_t s, const int16_t* d_pcm, float* d_out, const uint64_t* d_pcm_off, const uint64_t* d_out_off, const uint32_t* d_channels,
-                          uint32_t n_tracks, uint64_t max_frames) {
+void launch_pcm_to_mono(cudaStream_t s, const void* d_pcm, float* d_out, const uint64_t* d_byte_off, const uint64_t* d_out_off, const uint32_t* d_channels,
+                        const uint32_t* d_formats, uint32_t n_tracks, uint64_t max_frames) {
     if (n_tracks == 0 || max_frames == 0) return;
     unsigned gx = (unsigned)((max_frames + 256 * 8 - 1) / (256 * 8));
     if (gx > 8192) gx = 8192;
-    pcm16_to_mono_kernel<<<dim3(gx, n_tracks), 256, 0, s>>>(d_pcm, d_out, d_pcm_off, d_out_off, d_channels);
-    count_launch("pcm16");
+    pcm_to_mono_kernel<<<dim3(gx, n_tracks), 256, 0, s>>>(static_cast<const unsigned char*>(d_pcm), d_out, d_byte_off, d_out_off, d_channels, d_formats);
+    count_launch("pcm");
 }
 
 // ---- self-check of the range-restricted divisions of common.cuh against IEEE division (test instrumentation) ----------------

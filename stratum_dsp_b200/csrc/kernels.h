@@ -160,8 +160,8 @@ void launch_key_vote(const WaveCtx& c);
 void launch_key_variants_pre(const WaveCtx& c);  // k_keyvar.cu: median-HPSS mask, tuning estimate, whitening, per-track fold tables
 void launch_key_chroma_variants(const WaveCtx& c);  // k_keyvar.cu: log-frequency chroma, beat-synchronous chroma
 // k_synth.cu
-void launch_pcm16_to_mono(cudaStream_t s, const int16_t* d_pcm, float* d_out, const uint64_t* d_pcm_off, const uint64_t* d_out_off, const uint32_t* d_channels,
-                          uint32_t n_tracks, uint64_t max_frames);
+void launch_pcm_to_mono(cudaStream_t s, const void* d_pcm, float* d_out, const uint64_t* d_byte_off, const uint64_t* d_out_off, const uint32_t* d_channels,
+                        const uint32_t* d_formats, uint32_t n_tracks, uint64_t max_frames);
 int check_divisions(cudaStream_t s, uint64_t n, uint32_t seed, unsigned long long* d_bad3);  // common.cuh divisions vs IEEE division (test instrumentation)
 double measure_fp32_peak_tflops(cudaStream_t s, float* d_scratch);  // FMA microbenchmark (bench instrumentation)
 void launch_synth(cudaStream_t s, float* d_out, uint32_t n_tracks, uint64_t n_samples, uint32_t sr, const float* d_params5);

@@ -224,3 +224,28 @@ def test_division_by_25_is_exact_for_every_float(tmp_path):
     subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", str(exe), str(ROOT / "tools" / "check_div_by_const.c"), "-lm", "-lpthread"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
     assert "mismatches with |a| >= 1e-30: 0" in out, out
+
+
+@pytest.mark.parametrize("fmt,ext,ch", [("s16", False, 1), ("s24", False, 2), ("s32", True, 6), ("u8", False, 1), ("f32", True, 2), ("f64", False, 3)])
+def test_wav_container_reader(tmp_path, fmt, ext, ch):
+    # host half of the decoder-side entry: the RIFF/WAVE container is parsed without touching the samples (stratum_dsp_b200.read_wav)
+    import wavgen
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((1234, ch)) * 0.2).squeeze()
+    p = tmp_path / "t.wav"
+    p.write_bytes(wavgen.wav_bytes(x, 48000, fmt, extensible=ext, extra_chunk=True))
+    t = S.read_wav(p)
+    want = {"u8": S.PCM_U8, "s16": S.PCM_S16, "s24": S.PCM_S24, "s32": S.PCM_S32, "f32": S.PCM_F32, "f64": S.PCM_F64}[fmt]
+    assert (t.fmt, t.channels, t.sample_rate, t.frames) == (want, ch, 48000, 1234)
+    assert t.data.tobytes() == wavgen.encode(x, fmt)
+
+
+def test_wav_container_reader_rejects_other_formats(tmp_path):
+    import struct
+    p = tmp_path / "bad.wav"
+    p.write_bytes(b"RIFF" + struct.pack("<I", 36) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 0x55, 2, 44100, 0, 0, 0) + b"data" + struct.pack("<I", 0))
+    with pytest.raises(ValueError, match="Unsupported sample format"):
+        S.read_wav(p)
+    p.write_bytes(b"OggS....")
+    with pytest.raises(ValueError):
+        S.read_wav(p)

@@ -548,3 +548,31 @@ def test_fast_divisions_match_ieee():
     L.stratum_b200_debug_check_divisions.argtypes = [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
     assert L.stratum_b200_debug_check_divisions(1 << 28, 12345, bad) == 0, S.last_error()
     assert list(bad) == [0, 0, 0], list(bad)
+
+
+def test_pcm_formats_match_reference_decoder_arithmetic(tmp_path):
+    # every sample format of the reference's decoder loop (examples/analyze_batch.rs:70-165), converted and mixed
+    # down on the device from the file's own bytes; mixed formats, channel counts and sample rates in one call
+    import wavgen
+    cases = [("s24", 2, SR, False), ("f32", 1, 48000, True), ("s32", 6, SR, True), ("u8", 1, SR, False), ("f64", 2, 48000, False), ("s16", 3, SR, True)]
+    tracks, want = [], []
+    for i, (fmt, ch, sr, ext) in enumerate(cases):
+        p = synth.c2_params(300 + i, 11 * sr, sr)
+        p.sample_rate = sr
+        mono = synth.render(p).astype(np.float64) * 0.8
+        x = mono if ch == 1 else np.stack([mono * (1.0 - 0.1 * c) for c in range(ch)], axis=1)
+        path = tmp_path / f"{fmt}_{ch}.wav"
+        path.write_bytes(wavgen.wav_bytes(x, sr, fmt, extensible=ext, extra_chunk=bool(i & 1)))
+        t = S.read_wav(path)
+        tracks.append(t)
+        want.append((wavgen.decode_reference(t.data.tobytes(), fmt, ch), sr, f"{fmt} x{ch}"))
+    res = S.analyze_batch_pcm(tracks)
+    for g, (x, sr, label) in zip(res, want):
+        assert_parity(g, O.analyze(x, sr), label)
+    # the CPU-decoded samples through the f32 entry give the same bits as the device-side conversion
+    same = S.analyze_audio(want[0][0], want[0][1])
+    assert same.bpm == res[0].bpm and np.array_equal(same.onsets, res[0].onsets) and same.key_clarity == res[0].key_clarity
+    # a track that is not a whole number of frames is an argument error
+    bad = S.PcmTrack(np.zeros(7, np.uint8), S.PCM_S24, 2, SR)
+    with pytest.raises(S.AnalysisError):
+        S.analyze_batch_pcm([bad])

@@ -8,7 +8,7 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import stratum_dsp_b200 as S  # noqa: E402
-from bench import N_SAMPLES, SR, track_params  # noqa: E402
+from bench import N_SAMPLES, SR, c2_param_rows as track_params  # noqa: E402
 
 nt = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
