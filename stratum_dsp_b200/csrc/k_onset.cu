@@ -205,36 +205,20 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
         // per-band accumulators are selected with predicates, never indexed: a run-time index would put the arrays in local
         // memory and chain every iteration through a store -> load round trip (27 % of the kernel's stall samples in ncu)
         float Eb[3] = {0.0f, 0.0f, 0.0f}, Hb[3] = {0.0f, 0.0f, 0.0f};
-        // A 32-bin slice that lies inside one band (all but the three slices holding a band edge) adds into a running pair that is
-        // folded into its band's accumulators when the band changes: two adds per bin instead of six predicated ones.
-        float ea = 0.0f, ha = 0.0f;
-        int aband = -1;
-        auto fold = [&]() {
-            Eb[0] += aband == 0 ? ea : 0.0f;
-            Hb[0] += aband == 0 ? ha : 0.0f;
-            Eb[1] += aband == 1 ? ea : 0.0f;
-            Hb[1] += aband == 1 ? ha : 0.0f;
-            Eb[2] += aband == 2 ? ea : 0.0f;
-            Hb[2] += aband == 2 ? ha : 0.0f;
-            ea = ha = 0.0f;
-        };
+        // the row is fetched four 32-bin slices ahead (read-only path: the loads may pass the shared-memory stores of the slices in
+        // front of them): ncu had this loop waiting on one global load per slice (long-scoreboard 7.1 warps per issue, issue 47 %)
+        float xq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xq[u] = __ldg(row + 32 * u + lane);
+#pragma unroll 4
         for (int b0 = 0; b0 < 1025; b0 += 32) {
             const int b = b0 + lane;
             const bool in = b < 1025;
-            const float x = in ? row[b] : 0.0f;
+            const int u = (b0 >> 5) & 3;
+            const float x = in ? xq[u] : 0.0f;
+            if (b + 128 < 1025) xq[u] = __ldg(row + b + 128);
             if (in) Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
-            if (!emit) continue;
-            const int lo = b0, hi = min(b0 + 31, 1024);  // slice range (warp-uniform)
-            int sband = -2;  // -2: slice touches no band at all; -1: mixed
-            if (hi >= e0 && lo < e3) sband = (lo >= e0 && hi < e1) ? 0 : ((lo >= e1 && hi < e2) ? 1 : ((lo >= e2 && hi < e3) ? 2 : -1));
-            if (sband >= 0) {
-                if (sband != aband) {
-                    fold();
-                    aband = sband;
-                }
-                ea += x * x;
-                ha += (float)b * x * x;
-            } else if (sband == -1 && in && b >= e0 && b < e3) {
+            if (emit && in && b >= e0 && b < e3) {
                 const float xx = x * x, kx = (float)b * x * x;
                 const bool q0 = b < e1, q1 = !q0 && b < e2, q2 = !q0 && !q1;
                 Eb[0] += q0 ? xx : 0.0f;
@@ -245,7 +229,6 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
                 Hb[2] += q2 ? kx : 0.0f;
             }
         }
-        fold();
         __syncwarp();
         float sf = 0.0f, sfb[3] = {0.0f, 0.0f, 0.0f};
         // one bin of the pair pass: pm = max of the previous frame's 2K+1 window around b (novelty.rs:360-420), lc = this frame's value
