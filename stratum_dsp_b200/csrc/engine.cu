@@ -965,6 +965,7 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.key_frame = c.enable_key_stft_override ? std::max<uint32_t>(c.key_stft_frame_size, 256) : c.frame_size;  // lib.rs:984-995
     d.key_hop = c.enable_key_stft_override ? std::max<uint32_t>(c.key_stft_hop_size, 1) : c.hop_size;
     d.key_bins = d.key_frame / 2 + 1;
+    d.key_stride = key_compact_mode(c) ? (d.key_bins + 7) / 8 * 8 : d.key_bins;  // compact mode: only the STFT writes and the mask reads these rows
     d.key_mode = c.enable_key_ensemble ? KEY_ROWS_ENSEMBLE : (c.enable_key_multi_scale ? KEY_ROWS_MULTI_SCALE : KEY_ROWS_VOTE);
     d.key_template_set = c.key_template_set;
     d.key_edge_trim = c.enable_key_edge_trim;
@@ -1045,7 +1046,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.sil_rms = fa.take(Fsil + 1);
     T.erms = fa.take(F512 + 2);
     T.scratch = fa.take((uint64_t)12 * T.fall);
-    T.keyspec = fa.take((uint64_t)Fk * kd.key_bins + 8);
+    T.keyspec = fa.take((uint64_t)Fk * kd.key_stride + 8, 32);
     T.keymask = T.keyspec;  // the mask is applied in place (or, key_compact: only its HPCP band is kept, in kband)
     if (kd.key_compact) {
         compact_band(T.sr, cfg, kd.key_frame, &T.kband_lo, &T.kband_stride);
@@ -1507,7 +1508,7 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
             cudaMemcpyAsync(&T, c.d_tracks, sizeof(TrackDev), cudaMemcpyDeviceToHost, ks);
             cudaStreamSynchronize(ks);
             const uint32_t nk = std::min<uint32_t>(T.Fk, 64);
-            debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * dcfg.key_bins, ks);
+            debug_put("key.spec_head", c.fa + T.keyspec, (size_t)nk * dcfg.key_stride, ks);  // rows of key_stride floats
         }
         { StageTimer t(ks, "key_mask"); launch_key_mask(wk); }
         { StageTimer t(ks, "key_hpcp"); launch_key_hpcp(wk); }

@@ -45,6 +45,9 @@ constexpr int MASK_G = 16;
 template <int MG, bool FAST, int KB, bool COMPACT>
 __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
     const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
+    // floats per spectrogram row: the compact variant's input rows are padded to a 32-byte sector by the STFT (DevCfg::key_stride), so a
+    // warp's 128-byte load is four aligned sectors instead of five (ncu: 309 MB read per track for 254 MB of rows before the padding)
+    const uint32_t KSTRIDE = COMPACT ? (KB ? (uint32_t)((KB + 7) / 8 * 8) : cfg.key_stride) : KBINS;
     __shared__ float ringP[RING][128];
     __shared__ float ringX[MG > 0 ? 1 : RING][128];
     __shared__ float et[COMPACT ? 4 : 1][COMPACT ? MASK_G : 1][COMPACT ? 33 : 1];
@@ -67,11 +70,11 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
     const bool square = FAST || (p == 2.0f);
     float P = 0.0f;
     ringP[0][tx] = 0.0f;
-    auto ld = [&](uint32_t t) { return (!COMPACT || valid) ? K[(uint64_t)t * KBINS] : 0.0f; };
+    auto ld = [&](uint32_t t) { return (!COMPACT || valid) ? K[(uint64_t)t * KSTRIDE] : 0.0f; };
     // row >= 0: slot of the warp's energy tile this frame's share goes to (16-frame groups); row < 0: the tail, folded per frame
     auto put = [&](uint32_t t, float y, int row) {
         if (!COMPACT) {
-            K[(uint64_t)t * KBINS] = y;
+            K[(uint64_t)t * KSTRIDE] = y;
             return;
         }
         if (inband) B[(uint64_t)t * bstride] = y;

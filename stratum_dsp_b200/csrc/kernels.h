@@ -31,6 +31,7 @@ struct DevCfg {
     float lg_pmin, lg_pmax, lg_smin, lg_smax, lg_mp, lg_ms, lg_me;
     // key
     uint32_t key_frame, key_hop, key_bins;  // key STFT geometry (lib.rs:984-995): override values or frame_size / hop_size; bins = frame/2 + 1
+    uint32_t key_stride;          // floats per key-spectrogram row: key_bins, or (key_compact) rounded up to a 32-byte sector so that row loads are sector-aligned
     uint32_t key_margin;
     float key_mask_power;
     int32_t key_mask, key_weighting, key_voting;
