@@ -593,6 +593,9 @@ def main():
                        "ms_per_step": head["ms_per_step"], "pcm16_value": head.get("pcm16_value"), "pinned_h2d_gbs_rank0": e2e["h2d_gbs"],
                        "call": "stratum_b200_analyze_batch(device_ids=[0..N-1]) from one process" if world > 1 and multi and "value" in multi else "stratum_b200_analyze_batch, one process per GPU",
                        "note": head["note"], "per_rank": per_rank}
+            e2e_out["h2d_gbs_aggregate"] = e2e_out["h2d_bytes_per_step"] / (e2e_out["ms_per_step"] / 1000.0) / 1e9
+            e2e_out["h2d_note"] = ("pinned_h2d_gbs_rank0 is a plain pinned torch copy timed while every rank does the same: times N it is the host's aggregate "
+                                   "host-to-device rate, the ceiling of the f32 leg (31.75 MB per track); pcm16_value moves half the bytes")
             if multi and "value" in multi:
                 e2e_out["multi_device_call"] = {k: v for k, v in multi.items() if k not in ("note",)}
         line = {

@@ -2025,7 +2025,13 @@ static int32_t analyze_host_batch(const void* src, const uint64_t* boff, const u
         std::vector<Chunk> chunks;
         uint64_t max_el = 0, max_fr = 0;
         uint32_t max_cn = 0;
-        uint64_t cur_frames = no_ramp ? chunk_frames : std::max<uint64_t>(chunk_frames / 4, 1u << 16);
+        // ramp: "a,b" = first chunk a/8 of a full chunk, growth by b/8 of a full chunk per step (default 2,2: 1/4, 1/2, 3/4, 1 ...)
+        static const char* ramp_env = getenv("STRATUM_B200_STAGE_RAMP");
+        int ramp_first = 2, ramp_step = 2;
+        if (ramp_env) sscanf(ramp_env, "%d,%d", &ramp_first, &ramp_step);
+        ramp_first = std::min(std::max(ramp_first, 1), 8);
+        ramp_step = std::min(std::max(ramp_step, 1), 8);
+        uint64_t cur_frames = no_ramp ? chunk_frames : std::max<uint64_t>(chunk_frames * ramp_first / 8, 1u << 16);
         for (uint32_t i = a; i < b;) {
             uint32_t j = i;
             uint64_t fr = 0;
@@ -2039,7 +2045,7 @@ static int32_t analyze_host_batch(const void* src, const uint64_t* boff, const u
             max_fr = std::max(max_fr, fr);
             max_cn = std::max(max_cn, j - i);
             i = j;
-            cur_frames = std::min<uint64_t>(chunk_frames, chunks.size() == 1 ? cur_frames * 2 : cur_frames + cur_frames / 2);
+            cur_frames = std::min<uint64_t>(chunk_frames, cur_frames + chunk_frames * ramp_step / 8);
         }
         const size_t buf_bytes = (size_t)align_up(max_el * elt + 64, 256);
         {
