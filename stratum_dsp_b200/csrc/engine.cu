@@ -456,6 +456,9 @@ static void compact_band(uint32_t sr, const StratumConfig& cfg, uint32_t key_fra
     const uint32_t end = std::min(hi + 2, key_bins);  // one past the last column read
     *lo_out = first;
     *stride_out = (uint32_t)align_up(end - first, 32);
+    // one stride for every sample rate whose band fits (>= 39.2 kHz with 8192-point key frames): mask_kernel<.., BS = 960> then addresses
+    // the band rows with immediates; 44.1 kHz needs 960 anyway, 48 kHz would need 864
+    if (key_frame == 8192 && *stride_out <= 960) *stride_out = 960;
 }
 
 static bool key_compact_mode(const StratumConfig& c) {  // see DevCfg::key_compact
@@ -554,6 +557,42 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
     mel_off.resize(42, mel_off.back());
     if (mel_bin.empty()) { mel_bin.push_back(0); mel_w.push_back(0.0f); }
     st.variant_mask = vm;
+    // Mel fold schedule for par_feat_kernel: the bands' entry lists cut into at most 64 chunks of near-equal length (two per lane), a
+    // band's chunks consecutive in `pos` order so that one lane per band can add their partial sums in order afterwards.  Layout:
+    // [0..64) first entry, [64..128) end entry, [128..192) position of the chunk's partial sum, [192..233) first position of each band.
+    {
+        std::vector<int32_t> ck(256, 0);
+        const uint32_t nm = st.n_mels;
+        uint32_t C = 1;
+        for (;; ++C) {
+            uint32_t k = 0;
+            for (uint32_t m = 0; m < nm; ++m) k += ((uint32_t)(mel_off[m + 1] - mel_off[m]) + C - 1) / C;
+            if (k <= 64) break;
+        }
+        struct Chunk { int32_t a, e, pos; };
+        std::vector<Chunk> chunks;
+        int32_t pos = 0;
+        for (uint32_t m = 0; m < nm; ++m) {
+            ck[192 + m] = pos;
+            const uint32_t n = (uint32_t)(mel_off[m + 1] - mel_off[m]);
+            const uint32_t k = (n + C - 1) / C;
+            int32_t a = mel_off[m];
+            for (uint32_t j = 0; j < k; ++j) {
+                const int32_t len = (int32_t)(n / k + (j < n % k ? 1 : 0));
+                chunks.push_back({a, a + len, pos++});
+                a += len;
+            }
+        }
+        for (uint32_t m = nm; m <= 40; ++m) ck[192 + m] = pos;
+        std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.e - x.a > y.e - y.a; });
+        for (size_t i = 0; i < 64; ++i) {
+            const Chunk ch = i < chunks.size() ? chunks[i] : Chunk{0, 0, (int32_t)std::min<size_t>(i, 63)};  // idle slots write a partial nobody reads (positions >= the chunk count)
+            ck[i] = ch.a;
+            ck[64 + i] = ch.e;
+            ck[128 + i] = ch.pos;
+        }
+        st.mel_chunks = dev_upload(c, ck);
+    }
     st.mel_off = dev_upload(c, mel_off);
     st.mel_bin = dev_upload(c, mel_bin);
     st.mel_w = dev_upload(c, mel_w);
@@ -1338,6 +1377,7 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
     w.tab = c.tab;
     w.cfg = dcfg;
     w.max_key_peaks = 1;
+    bool kband_seen = false;
     const bool mr_on = dcfg.mr_enabled && !dcfg.force_legacy;
     for (int i = 0; i < nt; ++i) {
         TrackDev& T = tracks[i];
@@ -1370,6 +1410,8 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
             T.sr = T.sr ? T.sr : 1;
         }
         plan_track(fa, oa, ia, T, cfg);
+        if (T.status == 0 && T.kband_stride != w.kband_stride_common) w.kband_stride_common = kband_seen ? 0u : T.kband_stride;
+        if (T.status == 0) kband_seen = true;
         T.hop[0].tgtw = get_tw(c, T.hop[0].fft_cap);
         if (dcfg.hpss_onsets || dcfg.perc_fallback) T.hop[SLOT_PERC].tgtw = get_tw(c, T.hop[SLOT_PERC].fft_cap);
         T.lg_tw = get_tw(c, T.lg_fft);

@@ -10,6 +10,8 @@
 // HBM traffic per key frame: the 4097-bin magnitude row is written once by the STFT, read + rewritten
 // in place by the mask and read once by the HPCP kernel (4 x 16 KB); everything after that is 12 floats
 // per frame.
+#include <type_traits>
+
 #include "framed.cuh"
 #include "key_rows.cuh"
 
@@ -42,7 +44,12 @@ constexpr int MASK_G = 16;
 // 16-frame group: lane l sums 16 bins of frame l mod 16, one shuffle joins the two halves — about 35 instructions per thread and
 // group, off the per-element chain, and no CTA barrier (a first version with a CTA-wide tile and one barrier per group ran 38 %
 // slower than the in-place kernel: the barrier serialises the four warps' load latencies).
-template <int MG, bool FAST, int KB, bool COMPACT>
+// BS: floats per row of the compact band when known at compile time (960 covers the 100..5000 Hz band of the 8192-point key STFT at every
+// sample rate >= 39.2 kHz: the band stores become base + immediate instead of a 64-bit multiply-add per element), 0 = T.kband_stride.
+// Two 16-frame groups per loop trip: the prefix ring has 32 slots, so with the trip starting at a multiple of 32 every ring index of the
+// steady state is a compile-time constant (ncu/SASS of the one-group loop: five uniform-datapath instructions per element rebuilding
+// (ii & 31) * 512 offsets, six for the band store's address — 37 instructions per element, 24 of them arithmetic).
+template <int MG, bool FAST, int KB, bool COMPACT, int BS = 0>
 __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
     const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
     // floats per spectrogram row: the compact variant's input rows are padded to a 32-byte sector by the STFT (DevCfg::key_stride), so a
@@ -64,20 +71,24 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
     float* K = fa + T.keyspec + (valid ? b : 0u);
     const bool inband = COMPACT && valid && b >= T.kband_lo && b < T.kband_lo + T.kband_stride;
     float* B = fa + T.kband + (inband ? b - T.kband_lo : 0u);
-    const uint32_t bstride = T.kband_stride;
+    const uint32_t bstride = BS ? (uint32_t)BS : T.kband_stride;
     float* EP = fa + T.kepart + (uint64_t)(blockIdx.x * 4 + wid) * T.kepart_stride;  // this warp's share row
     const float p = FAST ? 2.0f : fmaxf(cfg.key_mask_power, 1.0f);
     const bool square = FAST || (p == 2.0f);
     float P = 0.0f;
     ringP[0][tx] = 0.0f;
     auto ld = [&](uint32_t t) { return (!COMPACT || valid) ? K[(uint64_t)t * KSTRIDE] : 0.0f; };
+    // where frame t's masked value goes: its column of the compact band, or the spectrogram row itself (in place)
+    const uint32_t dstride = COMPACT ? bstride : KSTRIDE;
+    float* const D = COMPACT ? B : K;
+    auto dst_of = [&](uint32_t t) { return D + (uint64_t)t * dstride; };
     // row >= 0: slot of the warp's energy tile this frame's share goes to (16-frame groups); row < 0: the tail, folded per frame
-    auto put = [&](uint32_t t, float y, int row) {
+    auto put = [&](uint32_t t, float* dst, float y, int row) {
         if (!COMPACT) {
-            K[(uint64_t)t * KSTRIDE] = y;
+            *dst = y;
             return;
         }
-        if (inband) B[(uint64_t)t * bstride] = y;
+        if (inband) *dst = y;
         const float e = y * y;
         if (row >= 0) {
             et[wid][row][lane] = e;
@@ -89,9 +100,9 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
     };
     // steady = the window [t - mg, t + mg] lies inside the track: the divisor is the compile-time constant 2*MG + 1 (an IEEE
     // division by a constant needs no reciprocal approximation or range check), no clamping of the window edges
-    auto emit_h = [&](uint32_t t, float h_est, float xt, int row) {
+    auto emit_h = [&](uint32_t t, float* dst, float h_est, float xt, int row) {
         if (!FAST && cfg.key_smooth_only) {  // smooth_spectrogram_time alone (extractor.rs:1246-1290, lib.rs:1043-1060)
-            put(t, h_est, row);
+            put(t, dst, h_est, row);
             return;
         }
         const float x = fmaxf(xt, 0.0f);
@@ -102,9 +113,9 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
         // FAST: hp, rp are squares of magnitudes (<= 2^40) and the divisor is >= 1e-12, so the quotient is correctly rounded
         // without the generic division's range check (common.cuh); hp below 2^-100 only occurs below -600 dBFS
         const float m = FAST ? div_rn_inrange(hp, hp + rp + 1e-12f) : hp / (hp + rp + 1e-12f);
-        put(t, x * m, row);
+        put(t, dst, x * m, row);
     };
-    auto emit = [&](uint32_t t, uint32_t en, float Pen, float xt, int row) {
+    auto emit = [&](uint32_t t, float* dst, uint32_t en, float Pen, float xt, int row) {
         float h_est;
         if (mg == 0) {
             h_est = xt;
@@ -114,35 +125,42 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
             const float denom = (float)max(en - st, 1u);
             h_est = sum / denom;
         }
-        emit_h(t, h_est, xt, row);
+        emit_h(t, dst, h_est, xt, row);
     };
     float xp[MASK_G];  // previous group (compile-time margin only)
 #pragma unroll
     for (int q = 0; q < MASK_G; ++q) xp[q] = 0.0f;
-    uint32_t i = 0;
-    for (; i + MASK_G <= nf; i += MASK_G) {
+    // one 16-frame group starting at frame i; PH = i mod 32 (0 or 16) as a type, so ring slots are constants
+    // STEADY (a type as well, so the two code paths are separate loops and not a branch per element): every frame the group emits has
+    // its full window, i >= 2 * MG
+    auto group = [&](uint32_t i, auto ph, auto st) {
+        constexpr int PH = decltype(ph)::value;
+        constexpr bool steady = MG > 0 && decltype(st)::value;
         float xs[MASK_G];
+        // one 64-bit address per group for the loads and one for the stores; the 16 frames are immediates off them when the strides
+        // are compile-time constants (KB, BS)
+        const float* kp = K + (uint64_t)i * KSTRIDE;
+        float* dp = D + ((int64_t)i - (int64_t)mg) * (int64_t)dstride;  // frame i - mg; only dereferenced for frames >= 0
 #pragma unroll
-        for (int q = 0; q < MASK_G; ++q) xs[q] = ld(i + q);
-        const bool steady = MG > 0 && i >= 2 * (uint32_t)MG;  // every frame this group emits has its full window (uniform over the CTA)
+        for (int q = 0; q < MASK_G; ++q) xs[q] = (!COMPACT || valid) ? kp[(uint32_t)q * KSTRIDE] : 0.0f;
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) {
             const uint32_t ii = i + q;
-            if (MG == 0) ringX[ii & (RING - 1)][tx] = xs[q];
+            if (MG == 0) ringX[(PH + q) & (RING - 1)][tx] = xs[q];
             P = P + xs[q];
-            if (ii >= mg) {  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
+            if (steady || ii >= mg) {  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
                 float xt;
                 if (MG > 0) xt = (q >= MG) ? xs[q >= MG ? q - MG : 0] : xp[q + MASK_G - MG < MASK_G ? q + MASK_G - MG : 0];
                 else xt = ringX[(ii - mg) & (RING - 1)][tx];
                 if (steady) {
-                    const float wsum = P - ringP[(ii - 2 * MG) & (RING - 1)][tx];
+                    const float wsum = P - ringP[(PH + q + 2 * RING - 2 * MG) & (RING - 1)][tx];
                     // FAST (mask on, margin 12): RN(wsum / 25) in three instructions; exact for |wsum| >= 1e-30, and a smaller window sum
                     // gives h < 1e-31, whose square is zero whichever way the quotient rounds
-                    emit_h(ii - MG, (FAST && MG == 12) ? div_by_25_rn(wsum) : wsum / (float)(2 * MG + 1), xt, q);
+                    emit_h(ii - MG, dp + (uint32_t)q * dstride, (FAST && MG == 12) ? div_by_25_rn(wsum) : wsum / (float)(2 * MG + 1), xt, q);
                 }
-                else emit(ii - mg, ii + 1, P, xt, q);
+                else emit(ii - mg, dp + (uint32_t)q * dstride, ii + 1, P, xt, q);
             }
-            ringP[(ii + 1) & (RING - 1)][tx] = P;
+            ringP[(PH + q + 1) & (RING - 1)][tx] = P;
         }
 #pragma unroll
         for (int q = 0; q < MASK_G; ++q) xp[q] = xs[q];
@@ -153,29 +171,51 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
 #pragma unroll
             for (int c = 0; c < 16; ++c) v += et[wid][row][c0 + c];
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < MASK_G && i + row >= mg) EP[i + row - mg] = v;
+            if (lane < MASK_G && (steady || i + row >= mg)) EP[i + row - mg] = v;
             __syncwarp();
         }
+    };
+    static_assert(RING == 2 * MASK_G, "two groups per ring revolution");
+    static_assert(MG == 0 || 2 * MG <= 2 * MASK_G, "the first ring revolution is the only one with clipped windows");
+    using PH0 = std::integral_constant<int, 0>;
+    using PH1 = std::integral_constant<int, MASK_G>;
+    uint32_t i = 0;
+    if (2 * MASK_G <= nf) {  // first revolution: windows clipped at the track start
+        group(0, PH0{}, std::false_type{});
+        group(MASK_G, PH1{}, std::false_type{});
+        i = 2 * MASK_G;
+    }
+    for (; i + 2 * MASK_G <= nf; i += 2 * MASK_G) {
+        group(i, PH0{}, std::true_type{});
+        group(i + MASK_G, PH1{}, std::true_type{});
+    }
+    if (i + MASK_G <= nf) {
+        if (i == 0) group(i, PH0{}, std::false_type{});
+        else group(i, PH0{}, std::true_type{});
+        i += MASK_G;
     }
     // tail (< 16 frames) and flush: the delayed samples are re-read from rows that are still unmasked
     // (row t is only rewritten by emit(t)), which costs at most 16 + margin scalar loads per thread
     for (; i < nf; ++i) {
         const float x = ld(i);
         P = P + x;
-        if (i >= mg) emit(i - mg, i + 1, P, ld(i - mg), -1);
+        if (i >= mg) emit(i - mg, dst_of(i - mg), i + 1, P, ld(i - mg), -1);
         ringP[(i + 1) & (RING - 1)][tx] = P;
     }
-    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, nf, P, ld(t), -1);
+    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, dst_of(t), nf, P, ld(t), -1);
 }
 
 // ---- HPCP: one warp per frame ---------------------------------------------------------------------
-template <int MAXP>
+// MAXI: (peak, harmonic) items per frame the instantiation has room for (the defaults need 24 x 4 = 96)
+template <int MAXP, int MAXI = HPCP_MAX_SEL * HPCP_MAX_HARM>
 struct HpcpSmem {
     float mag[MAXP];
     uint16_t bin[MAXP];
     uint16_t sel[HPCP_MAX_SEL];
-    float val[HPCP_MAX_SEL * HPCP_MAX_HARM * 3];
-    int8_t tc[HPCP_MAX_SEL * HPCP_MAX_HARM * 3];
+    // per (peak, harmonic) item: val[4 it + s], s = 1..3 = its contributions to the pitch classes primary - 1, primary, primary + 1
+    // (slot 0 = 0.0f), and map[it] = twelve 2-bit slot numbers, class c at bits 2c (0 = no contribution)
+    __align__(16) float val[MAXI * 4];
+    __align__(16) uint32_t map[MAXI];
 };
 
 __device__ __forceinline__ float rem_euclid_f(float a, float b) {
@@ -186,9 +226,9 @@ __device__ __forceinline__ float rem_euclid_f(float a, float b) {
 // One band of frame_to_hpcp_tuned_band (extractor.rs:529-680) for the calling warp.  `sel` = the row peaks are picked and ranked
 // on (whitened magnitudes when whitening is on, else the magnitudes), `mag` = the magnitudes that weight the peaks.
 // Returns the L2-normalised profile in lanes 0..11.
-template <int MAXP>
+template <int MAXP, int MAXI>
 __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const float* __restrict__ mag, uint32_t lo, uint32_t hi, float fmin, float fmax,
-                                           uint32_t peaks_per_frame, float tuning, float res, HpcpSmem<MAXP>& S, int lane, const DevCfg& cfg) {
+                                           uint32_t peaks_per_frame, float tuning, float res, HpcpSmem<MAXP, MAXI>& S, int lane, const DevCfg& cfg) {
     constexpr int HPCP_MAX_PEAKS = MAXP;
     // local maxima in the band, compacted in ascending bin order (extractor.rs:582-606)
     // Eight 32-bin slices at a time: their values are fetched first (eight independent loads in flight instead of three
@@ -245,12 +285,21 @@ __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const 
                 const uint32_t i = q * 32 + lane;
                 e[q] = i < np ? __float_as_uint(S.mag[i]) : 0u;  // peaks are strictly positive, 0 never counts
             }
+            // Early exit: as soon as exactly K values are >= cand the survivors are known (everything >= cand) whatever the lower bits of
+            // the K-th value are, so the search stops with thr = cand - 1 ("> thr" == ">= cand", and values equal to thr are then
+            // offered as ties with need = 0).  The K-th and (K+1)-th largest peaks of a spectrum row rarely share more than the exponent
+            // and a few mantissa bits: about a dozen rounds instead of 31, same selection.
             for (int bit = 30; bit >= 0; --bit) {
                 const uint32_t cand = thr | (1u << bit);
                 uint32_t c = 0;
 #pragma unroll
                 for (int q = 0; q < HPCP_MAX_PEAKS / 32; ++q) c += e[q] >= cand;
-                if (__reduce_add_sync(0xffffffffu, c) >= K) thr = cand;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c == K) {
+                    thr = cand - 1u;
+                    break;
+                }
+                if (c > K) thr = cand;
             }
             uint32_t gt = 0;
 #pragma unroll
@@ -291,11 +340,11 @@ __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const 
             const float mg = fmaxf(mag[bin], 0.0f);  // the original magnitude weights the peak even when whitening picked it (:628-637)
             const float w0 = (pw == 0.5f) ? sqrtf(mg) : powf(mg, pw);
             const float fh = f0 * (float)h;
-            int8_t* tcs = S.tc + it * 3;
-            float* vals = S.val + it * 3;
+            float* vals = S.val + it * 4;
+            vals[0] = 0.0f;
             // `break` at fh > fmax and `continue` at fh < fmin both leave this (peak, h) without a contribution
             if (!(f0 > 0.0f) || !(w0 > 0.0f) || fh > fmax || fh < fmin) {
-                tcs[0] = tcs[1] = tcs[2] = -1;
+                S.map[it] = 0u;
                 continue;
             }
             const float semitone = 12.0f * log2f(fh / 440.0f) + 57.0f - tuning;
@@ -311,21 +360,34 @@ __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const 
             }
             const float hw = dp / (float)h;
             const float contrib = w0 * hw;
+            uint32_t map = 0u;
 #pragma unroll
             for (int off = -1; off <= 1; ++off) {
                 const int tc = ((primary + off) % 12 + 12) % 12;
                 float dist = fabsf(spc - (float)tc);
                 dist = fminf(dist, 12.0f - dist);
                 const float wgt = expf(-dist * dist / (2.0f * sigma * sigma));
-                tcs[off + 1] = (int8_t)tc;
-                vals[off + 1] = contrib * wgt;
+                map |= (uint32_t)(off + 2) << (2 * tc);  // the three classes are distinct
+                vals[off + 2] = contrib * wgt;
             }
+            S.map[it] = map;
         }
+        const uint32_t items4 = (items + 3u) & ~3u;
+        if (lane < items4 - items) S.map[items + lane] = 0u, S.val[4 * (items + lane)] = 0.0f;  // pad to whole groups of four
         __syncwarp();
+        // Pitch-class fold, lane = class: contributions in (peak, harmonic, offset) order like the reference (extractor.rs:640-664).  An item
+        // touches a class at most once, so the lane takes its slot number from the item's map and adds that slot — slot 0 holds 0.0f, and
+        // x + 0.0f == x for the non-negative sums here — instead of scanning all 3 x items (class, value) entries.
         if (lane < 12) {
-            const uint32_t ne = items * 3;
-            for (uint32_t q = 0; q < ne; ++q)
-                if (S.tc[q] == lane) pc = pc + S.val[q];
+            const int sh = 2 * lane;
+            for (uint32_t it = 0; it < items4; it += 4) {
+                const uint4 m = *reinterpret_cast<const uint4*>(S.map + it);
+                const float* v = S.val + 4 * it;
+                pc = pc + v[(m.x >> sh) & 3u];
+                pc = pc + v[4 + ((m.y >> sh) & 3u)];
+                pc = pc + v[8 + ((m.z >> sh) & 3u)];
+                pc = pc + v[12 + ((m.w >> sh) & 3u)];
+            }
         }
         // L2 normalise with the reference's sequential sum of squares (extractor.rs:668-677)
         float ss = 0.0f;
@@ -342,16 +404,16 @@ __device__ __forceinline__ float hpcp_band(const float* __restrict__ sel, const 
 
 // MAXP peak slots per frame; WARPS frames per CTA (4 x 512 slots or 2 x 2048 slots of shared memory).
 // cfg.key_compact: the masked band comes from T.kband (mask_kernel<COMPACT>) and the frame energy from the per-CTA shares in T.kepart.
-template <int MAXP, int WARPS>
+template <int MAXP, int WARPS, int MAXI = HPCP_MAX_SEL * HPCP_MAX_HARM>
 __global__ void __launch_bounds__(32 * WARPS) hpcp_kernel(const TrackDev* __restrict__ tr, const SrTables* __restrict__ srtab, const int32_t* __restrict__ sr_index,
                                                           float* fa, DevCfg cfg) {
-    __shared__ HpcpSmem<MAXP> sm[WARPS];
+    __shared__ HpcpSmem<MAXP, MAXI> sm[WARPS];
     const int t = blockIdx.y;
     const TrackDev& T = tr[t];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t f = blockIdx.x * WARPS + w;
     if (T.status != 0 || f >= T.Fk || T.beat_sync) return;
-    HpcpSmem<MAXP>& S = sm[w];
+    HpcpSmem<MAXP, MAXI>& S = sm[w];
     const SrTables& st = srtab[sr_index[t]];
     const uint32_t KBINS = cfg.key_bins;
     // frame energy (extractor.rs:1132-1134).  Consumed only through (E/median)^0.5 frame weights, a
@@ -373,9 +435,9 @@ __global__ void __launch_bounds__(32 * WARPS) hpcp_kernel(const TrackDev* __rest
     const float* sel = cfg.key_whiten ? fa + T.kwhite + (uint64_t)f * T.kwhite_stride : row;
     const float res = (float)T.sr / (float)cfg.key_frame;
     const float nyq = (float)T.sr / 2.0f;
-    float pc = hpcp_band<MAXP>(sel, row, st.key_bin_lo, st.key_bin_hi, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), cfg.hpcp_peaks, T.key_tuning, res, S, lane, cfg);
+    float pc = hpcp_band<MAXP, MAXI>(sel, row, st.key_bin_lo, st.key_bin_hi, fmaxf(100.0f, 20.0f), fminf(5000.0f, nyq), cfg.hpcp_peaks, T.key_tuning, res, S, lane, cfg);
     if (cfg.key_bass_blend) {  // extractor.rs:1154-1239: (1-w) full + w bass, renormalised
-        const float bass = hpcp_band<MAXP>(sel, row, st.bass_bin_lo, st.bass_bin_hi, st.bass_fmin, st.bass_fmax, min(max(cfg.hpcp_peaks, 1u), 12u), T.key_tuning, res, S,
+        const float bass = hpcp_band<MAXP, MAXI>(sel, row, st.bass_bin_lo, st.bass_bin_hi, st.bass_fmin, st.bass_fmax, min(max(cfg.hpcp_peaks, 1u), 12u), T.key_tuning, res, S,
                                            lane, cfg);
         const float bw = clamp_rs(cfg.bass_weight, 0.0f, 1.0f);
         pc = (1.0f - bw) * pc + bw * bass;
@@ -946,7 +1008,8 @@ void launch_key_mask(const WaveCtx& c) {
         const dim3 g((c.cfg.key_bins + 127) / 128, c.n_tracks);
         const bool fast = !c.cfg.key_smooth_only && fmaxf(c.cfg.key_mask_power, 1.0f) == 2.0f && c.cfg.key_bins == 4097;
         if (c.cfg.key_compact) {
-            if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680, 688)
+            if (c.cfg.key_margin == 12 && fast && c.kband_stride_common == 960) mask_kernel<12, true, 4097, true, 960><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680, 688) at >= 39.2 kHz
+            else if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
             else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
             else mask_kernel<0, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
         } else {
@@ -966,7 +1029,9 @@ void launch_key_hpcp(const WaveCtx& c) {
         // which chroma front end a track takes is decided per track (lib.rs:1123-1197): beat-synchronous tracks and plain chroma
         // folding go through chroma_fold_kernel, log-frequency through k_keyvar.cu, everything else through HPCP
         if (c.cfg.key_hpcp && !c.cfg.key_log_freq) {
-            if (c.max_key_peaks <= (uint32_t)HPCP_PEAKS_44K) hpcp_kernel<HPCP_PEAKS_44K, 4><<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+            const uint32_t max_items = std::min(std::max(c.cfg.hpcp_peaks, 1u), (uint32_t)HPCP_MAX_SEL) * std::min(std::max(c.cfg.hpcp_harm, 1u), (uint32_t)HPCP_MAX_HARM);
+            if (c.max_key_peaks <= (uint32_t)HPCP_PEAKS_44K && max_items <= 128) hpcp_kernel<HPCP_PEAKS_44K, 4, 128><<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
+            else if (c.max_key_peaks <= (uint32_t)HPCP_PEAKS_44K) hpcp_kernel<HPCP_PEAKS_44K, 4><<<g, 128, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
             else hpcp_kernel<HPCP_PEAKS_ANY, 2><<<dim3((c.max_Fk + 1) / 2, c.n_tracks), 64, 0, c.stream>>>(c.tracks, c.srtab, c.sr_index, c.fa, c.cfg);
             count_launch("key_hpcp");
         }

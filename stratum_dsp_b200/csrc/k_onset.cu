@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const
 struct ParSmem {
     float L[2][1025 + 2 * HALO + 7];
     float mel[2][MEL_MAX];
+    float part[64];  // partial sums of the mel fold's chunks
 };
 
 // K4: the SuperFlux radius is the default 4 (config.rs:634) — the pair pass then gives every lane four CONSECUTIVE bins: the twelve
@@ -206,27 +207,33 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
         // memory and chain every iteration through a store -> load round trip (27 % of the kernel's stall samples in ncu)
         float Eb[3] = {0.0f, 0.0f, 0.0f}, Hb[3] = {0.0f, 0.0f, 0.0f};
         // the row is fetched four 32-bin slices ahead (read-only path: the loads may pass the shared-memory stores of the slices in
-        // front of them): ncu had this loop waiting on one global load per slice (long-scoreboard 7.1 warps per issue, issue 47 %)
-        float xq[4];
+        // front of them): ncu had this loop waiting on one global load per slice (long-scoreboard 7.1 warps per issue, issue 47 %).
+        // Measured and rejected (round 2, r02s): walking the row band by band with one unpredicated accumulator pair per band, or slice
+        // by slice with test-free code for slices inside one band — 25-35 % fewer instructions in this loop, 9-22 % SLOWER: the warp is
+        // bound by the dependent chain of the logarithm at 6 warps per scheduler, and the four interleaved slices of this form are what
+        // gives it instruction-level parallelism.
+        {
+            float xq[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xq[u] = __ldg(row + 32 * u + lane);
+            for (int u = 0; u < 4; ++u) xq[u] = __ldg(row + 32 * u + lane);
 #pragma unroll 4
-        for (int b0 = 0; b0 < 1025; b0 += 32) {
-            const int b = b0 + lane;
-            const bool in = b < 1025;
-            const int u = (b0 >> 5) & 3;
-            const float x = in ? xq[u] : 0.0f;
-            if (b + 128 < 1025) xq[u] = __ldg(row + b + 128);
-            if (in) Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
-            if (emit && in && b >= e0 && b < e3) {
-                const float xx = x * x, kx = (float)b * x * x;
-                const bool q0 = b < e1, q1 = !q0 && b < e2, q2 = !q0 && !q1;
-                Eb[0] += q0 ? xx : 0.0f;
-                Hb[0] += q0 ? kx : 0.0f;
-                Eb[1] += q1 ? xx : 0.0f;
-                Hb[1] += q1 ? kx : 0.0f;
-                Eb[2] += q2 ? xx : 0.0f;
-                Hb[2] += q2 ? kx : 0.0f;
+            for (int b0 = 0; b0 < 1025; b0 += 32) {
+                const int b = b0 + lane;
+                const bool in = b < 1025;
+                const int u = (b0 >> 5) & 3;
+                const float x = in ? xq[u] : 0.0f;
+                if (b + 128 < 1025) xq[u] = __ldg(row + b + 128);
+                if (in) Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
+                if (emit && in && b >= e0 && b < e3) {
+                    const float xx = x * x, kx = (float)b * x * x;
+                    const bool q0 = b < e1, q1 = !q0 && b < e2, q2 = !q0 && !q1;
+                    Eb[0] += q0 ? xx : 0.0f;
+                    Hb[0] += q0 ? kx : 0.0f;
+                    Eb[1] += q1 ? xx : 0.0f;
+                    Hb[1] += q1 ? kx : 0.0f;
+                    Eb[2] += q2 ? xx : 0.0f;
+                    Hb[2] += q2 ? kx : 0.0f;
+                }
             }
         }
         __syncwarp();
@@ -282,14 +289,30 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
                 }
             }
         }
-        // mel bands: lane m folds its triangle in ascending-bin order (novelty.rs:172-189)
+        // mel bands (novelty.rs:172-189): the bands' entry lists are cut into 64 chunks of near-equal length (engine.cu), every lane folds two
+        // of them in ascending-bin order, then lane m adds the partial sums of band m in order.  One lane per band walked the widest triangle
+        // of each round of 32 bands with the other lanes idle (17 % of the kernel's stall samples, ncu r02q; the chunked fold measured 3 % off the
+        // kernel); the mel curve only reaches the BPM through tolerance-level novelty values, so the association of the sum is free.
         float* Mc = S.mel[cur];
         const float* Mp = S.mel[cur ^ 1];
-        for (int m = lane; m < nm; m += 32) {
-            float acc = 0.0f;
-            const int a = st.mel_off[m], e = st.mel_off[m + 1];
-            for (int q = a; q < e; ++q) acc = __fadd_rn(acc, __fmul_rn(Lc[st.mel_bin[q]], st.mel_w[q]));
-            Mc[m] = acc;
+        if (nm > 0) {
+            const int32_t* ck = st.mel_chunks;
+            const int32_t* mbin = st.mel_bin;
+            const float* mw = st.mel_w;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int slot = 32 * r + lane;
+                const int a = __ldg(ck + slot), e = __ldg(ck + 64 + slot);
+                float acc = 0.0f;
+                for (int q = a; q < e; ++q) acc = __fadd_rn(acc, __fmul_rn(Lc[__ldg(mbin + q)], __ldg(mw + q)));
+                S.part[__ldg(ck + 128 + slot)] = acc;
+            }
+            __syncwarp();
+            for (int m = lane; m < nm; m += 32) {
+                float acc = 0.0f;
+                for (int j = __ldg(ck + 192 + m); j < __ldg(ck + 193 + m); ++j) acc = __fadd_rn(acc, S.part[j]);
+                Mc[m] = acc;
+            }
         }
         __syncwarp();
         float ms = 0.0f;

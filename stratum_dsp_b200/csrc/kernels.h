@@ -79,6 +79,7 @@ struct SrTables {
     const int32_t* mel_off;           // [n_mels + 1] entry ranges per mel band
     const int32_t* mel_bin;           // flat entries in ascending-bin order per band (centre bin twice: rising and falling slope)
     const float* mel_w;
+    const int32_t* mel_chunks;        // fold schedule of par_feat_kernel (engine.cu: sr_slot): 64 chunks (first, end, position) + 41 band starts
     uint32_t key_bin_lo, key_bin_hi;  // HPCP peak search range in the key STFT (extractor.rs:584-591)
     uint32_t fold_lo, fold_hi;        // chroma-folding bin range (extractor.rs:407-417); lo > hi = empty
     const int32_t* fold_off;          // [13] entry ranges per pitch class
@@ -119,6 +120,7 @@ struct WaveCtx {
     uint32_t max_lg_fft;
     uint32_t max_lufs_nb;
     uint32_t max_key_peaks;  // HPCP peak slots a frame may need: (band bins + 1) / 2 over the wave's sample rates
+    uint32_t kband_stride_common;  // row stride of the compact key band when every live track of the wave has the same one, else 0
 };
 
 struct Launcher;  // counts launches + optional stage timing (engine.cu)
