@@ -127,73 +127,102 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
         }
         emit_h(t, dst, h_est, xt, row);
     };
-    float xp[MASK_G];  // previous group (compile-time margin only)
+    // The main part of the track (whole 16-frame groups) runs as half-steps of 8 frames over four register arrays in rotating roles:
+    // step k consumes h[k & 3] (frames 8k .. 8k+7), takes its delayed samples x[t - MG] from the two arrays before it, and starts the
+    // loads of step k + 1 into the fourth BEFORE it computes — so every load has a whole half-step of arithmetic (~240 instructions per
+    // warp, times the other resident warps) to land, with the same 32 sample registers the one-group form used for "this group" and
+    // "previous group".  (r02q/r02r: with the loads issued at the top of the group that consumes them the kernel sat on the long
+    // scoreboard for 22 % of its samples, and 19 % fewer instructions did not move its run time.)  R = k & 3 and STEADY are types:
+    // four steps per loop trip make every prefix-ring slot a compile-time constant, and the clipped-window code of the first ring
+    // revolution stays out of the steady loop.
+    constexpr int H = 8;
+    static_assert(RING == 4 * H && MASK_G == 2 * H, "four half-steps per ring revolution, two per energy tile");
+    static_assert(MG == 0 || (MG > H && MG <= 2 * H), "delayed samples come from the two previous half-steps");
+    float h[4][H];
 #pragma unroll
-    for (int q = 0; q < MASK_G; ++q) xp[q] = 0.0f;
-    // one 16-frame group starting at frame i; PH = i mod 32 (0 or 16) as a type, so ring slots are constants
-    // STEADY (a type as well, so the two code paths are separate loops and not a branch per element): every frame the group emits has
-    // its full window, i >= 2 * MG
-    auto group = [&](uint32_t i, auto ph, auto st) {
-        constexpr int PH = decltype(ph)::value;
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < H; ++q) h[r][q] = 0.0f;
+    const uint32_t n_half = 2 * (nf / MASK_G);
+    const float* kp = K;                                  // row 8k of this thread's column
+    float* dp = D - (int64_t)mg * (int64_t)dstride;       // destination of frame 8k - mg; only dereferenced for frames >= 0
+    auto fetch = [&](float (&dst)[H], const float* from) {
+#pragma unroll
+        for (int q = 0; q < H; ++q) dst[q] = (!COMPACT || valid) ? from[(uint32_t)q * KSTRIDE] : 0.0f;
+    };
+    auto step = [&](uint32_t k, auto r_t, auto st) {
+        constexpr int R = decltype(r_t)::value;
         constexpr bool steady = MG > 0 && decltype(st)::value;
-        float xs[MASK_G];
-        // one 64-bit address per group for the loads and one for the stores; the 16 frames are immediates off them when the strides
-        // are compile-time constants (KB, BS)
-        const float* kp = K + (uint64_t)i * KSTRIDE;
-        float* dp = D + ((int64_t)i - (int64_t)mg) * (int64_t)dstride;  // frame i - mg; only dereferenced for frames >= 0
+        const uint32_t i = k * H;
+        if (k + 1 < n_half) fetch(h[(R + 1) & 3], kp + (uint64_t)H * KSTRIDE);
+        const float(&cur)[H] = h[R];
+        const float(&p1)[H] = h[(R + 3) & 3];
+        const float(&p2)[H] = h[(R + 2) & 3];
 #pragma unroll
-        for (int q = 0; q < MASK_G; ++q) xs[q] = (!COMPACT || valid) ? kp[(uint32_t)q * KSTRIDE] : 0.0f;
-#pragma unroll
-        for (int q = 0; q < MASK_G; ++q) {
+        for (int q = 0; q < H; ++q) {
             const uint32_t ii = i + q;
-            if (MG == 0) ringX[(PH + q) & (RING - 1)][tx] = xs[q];
-            P = P + xs[q];
+            constexpr int PH = R * H;
+            const int row = (R & 1) * H + q;  // slot of the warp's 16-frame energy tile
+            if (MG == 0) ringX[(PH + q) & (RING - 1)][tx] = cur[q];
+            P = P + cur[q];
             if (steady || ii >= mg) {  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
                 float xt;
-                if (MG > 0) xt = (q >= MG) ? xs[q >= MG ? q - MG : 0] : xp[q + MASK_G - MG < MASK_G ? q + MASK_G - MG : 0];
+                if (MG > 0) xt = (q + 2 * H - MG < H) ? p2[(q + 2 * H - MG) & (H - 1)] : p1[(q + H - MG) & (H - 1)];  // x[8k + q - MG]
                 else xt = ringX[(ii - mg) & (RING - 1)][tx];
                 if (steady) {
                     const float wsum = P - ringP[(PH + q + 2 * RING - 2 * MG) & (RING - 1)][tx];
                     // FAST (mask on, margin 12): RN(wsum / 25) in three instructions; exact for |wsum| >= 1e-30, and a smaller window sum
                     // gives h < 1e-31, whose square is zero whichever way the quotient rounds
-                    emit_h(ii - MG, dp + (uint32_t)q * dstride, (FAST && MG == 12) ? div_by_25_rn(wsum) : wsum / (float)(2 * MG + 1), xt, q);
+                    emit_h(ii - MG, dp + (uint32_t)q * dstride, (FAST && MG == 12) ? div_by_25_rn(wsum) : wsum / (float)(2 * MG + 1), xt, row);
                 }
-                else emit(ii - mg, dp + (uint32_t)q * dstride, ii + 1, P, xt, q);
+                else emit(ii - mg, dp + (uint32_t)q * dstride, ii + 1, P, xt, row);
             }
             ringP[(PH + q + 1) & (RING - 1)][tx] = P;
         }
-#pragma unroll
-        for (int q = 0; q < MASK_G; ++q) xp[q] = xs[q];
-        if (COMPACT) {  // fold the warp's tile: lane l adds bins 16*(l/16) .. +15 of row l % 16 (frame i + row - mg), halves joined by one shuffle
+        kp += (uint64_t)H * KSTRIDE;
+        dp += (uint64_t)H * dstride;
+        if (COMPACT && (R & 1)) {  // fold the warp's tile: lane l adds bins 16*(l/16) .. +15 of row l % 16 (frame i16 + row - mg), halves joined by one shuffle
+            const uint32_t i16 = i - H;
             __syncwarp();
             const int row = lane & (MASK_G - 1), c0 = (lane >> 4) * 16;
             float v = 0.0f;
 #pragma unroll
             for (int c = 0; c < 16; ++c) v += et[wid][row][c0 + c];
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < MASK_G && (steady || i + row >= mg)) EP[i + row - mg] = v;
+            if (lane < MASK_G && (steady || i16 + row >= mg)) EP[i16 + row - mg] = v;
             __syncwarp();
         }
     };
-    static_assert(RING == 2 * MASK_G, "two groups per ring revolution");
-    static_assert(MG == 0 || 2 * MG <= 2 * MASK_G, "the first ring revolution is the only one with clipped windows");
-    using PH0 = std::integral_constant<int, 0>;
-    using PH1 = std::integral_constant<int, MASK_G>;
-    uint32_t i = 0;
-    if (2 * MASK_G <= nf) {  // first revolution: windows clipped at the track start
-        group(0, PH0{}, std::false_type{});
-        group(MASK_G, PH1{}, std::false_type{});
-        i = 2 * MASK_G;
+    using R0 = std::integral_constant<int, 0>;
+    using R1 = std::integral_constant<int, 1>;
+    using R2 = std::integral_constant<int, 2>;
+    using R3 = std::integral_constant<int, 3>;
+    uint32_t k = 0;
+    if (n_half > 0) fetch(h[0], kp);
+    if (n_half >= 4) {  // first ring revolution: windows clipped at the track start
+        step(0, R0{}, std::false_type{});
+        step(1, R1{}, std::false_type{});
+        step(2, R2{}, std::false_type{});
+        step(3, R3{}, std::false_type{});
+        k = 4;
     }
-    for (; i + 2 * MASK_G <= nf; i += 2 * MASK_G) {
-        group(i, PH0{}, std::true_type{});
-        group(i + MASK_G, PH1{}, std::true_type{});
+    for (; k + 4 <= n_half; k += 4) {
+        step(k, R0{}, std::true_type{});
+        step(k + 1, R1{}, std::true_type{});
+        step(k + 2, R2{}, std::true_type{});
+        step(k + 3, R3{}, std::true_type{});
     }
-    if (i + MASK_G <= nf) {
-        if (i == 0) group(i, PH0{}, std::false_type{});
-        else group(i, PH0{}, std::true_type{});
-        i += MASK_G;
+    if (k + 2 <= n_half) {  // one more group of 16
+        if (k == 0) {
+            step(k, R0{}, std::false_type{});
+            step(k + 1, R1{}, std::false_type{});
+        } else {
+            step(k, R0{}, std::true_type{});
+            step(k + 1, R1{}, std::true_type{});
+        }
+        k += 2;
     }
+    uint32_t i = k * H;
     // tail (< 16 frames) and flush: the delayed samples are re-read from rows that are still unmasked
     // (row t is only rewritten by emit(t)), which costs at most 16 + margin scalar loads per thread
     for (; i < nf; ++i) {
