@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
 // ---- consensus vote + caller policy ------------------------------------------------------------
 // One CTA per track.  Fast path (lists fit in shared memory): parallel 3-way merge by rank (binary searches,
 // method order 0,1,2 on equal samples like the reference's stable sort), gap flags, block scan -> cluster ids,
-// one thread per cluster for the integer mean / vote mask, block scan -> compaction.  Clusters are separated by
+// one thread per cluster for the integer mean / vote mask, block scan -> compaction (work arrays in global memory beyond CONS_MAX onsets).  Clusters are separated by
 // more than `tol` samples, so their centres are strictly increasing and the reference's sort + dedup
 // (lib.rs:266-271) is the identity.  Slow path (very long tracks): the same logic run serially by thread 0.
 constexpr uint32_t CONS_MAX = 12288;  // onsets (all three lists) handled by the fast path (a 3-minute track has ~5 000)
@@ -407,7 +407,7 @@ __device__ __forceinline__ uint32_t count_less(const int32_t* a, uint32_t n, int
     return lo;
 }
 
-__global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* ia, int n_tracks, DevCfg cfg) {
+__global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* ia, float* fa, int n_tracks, DevCfg cfg) {
     extern __shared__ int32_t cs[];
     __shared__ uint32_t sc[34];
     __shared__ uint32_t s_strong;
@@ -433,12 +433,18 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
         return;
     }
     const uint32_t tol = as_u32(__fmul_rn(__fdiv_rn((float)cfg.consensus_tol_ms, 1000.0f), (float)T.sr));  // consensus.rs:149
-    if (total <= CONS_MAX) {
-        int32_t* in = cs;                            // [total] the three lists back to back; dead after the merge ...
-        int32_t* starts = cs;                        // ... and reused as [clusters + 1] first merged index of each cluster
-        int32_t* merged = cs + CONS_MAX + 2;         // [total]
-        int32_t* centre = cs + 2 * CONS_MAX + 2;     // [clusters] centre; bit 31 marks "voted by >= 2 methods"
-        uint8_t* meth = reinterpret_cast<uint8_t*>(cs + 3 * CONS_MAX + 2);  // [total]
+    // Work arrays: shared memory up to CONS_MAX onsets, else the track's float scratch area in global memory (12 x the largest frame count
+    // words; the flux curves it held are dead once the detectors' onset lists exist, and the novelty kernels rewrite it later) — a
+    // 60-minute mix has ~32 000 onsets, and the serial fallback below took 41 ms of its 140 ms on one thread (profiles/r02d_bench_c4).
+    const bool in_smem = total <= CONS_MAX;
+    const uint64_t cap = in_smem ? CONS_MAX : total;
+    if (in_smem || (13 * cap) / 4 + 8 <= (uint64_t)12 * T.fall) {
+        int32_t* base = in_smem ? cs : reinterpret_cast<int32_t*>(fa + T.scratch);
+        int32_t* in = base;                          // [total] the three lists back to back; dead after the merge ...
+        int32_t* starts = base;                      // ... and reused as [clusters + 1] first merged index of each cluster
+        int32_t* merged = base + cap + 2;            // [total]
+        int32_t* centre = base + 2 * cap + 2;        // [clusters] centre; bit 31 marks "voted by >= 2 methods"
+        uint8_t* meth = reinterpret_cast<uint8_t*>(base + 3 * cap + 2);  // [total]
         for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) in[i] = G0[i];
         for (uint32_t i = threadIdx.x; i < n1; i += blockDim.x) in[n0 + i] = G1[i];
         for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) in[n0 + n1 + i] = G2[i];
@@ -590,7 +596,7 @@ void launch_spectral_onsets_consensus(const WaveCtx& c) {
             attr_dev[dev & 63] = true;
         }
     }
-    consensus_kernel<<<c.n_tracks, 256, CONS_SMEM, c.stream>>>(c.tracks, c.ia, c.n_tracks, c.cfg);
+    consensus_kernel<<<c.n_tracks, 256, CONS_SMEM, c.stream>>>(c.tracks, c.ia, c.fa, c.n_tracks, c.cfg);
     count_launch("onsets");
 }
 
