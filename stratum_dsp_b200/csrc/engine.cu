@@ -1090,6 +1090,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     if (kd.key_compact) {
         compact_band(T.sr, cfg, kd.key_frame, &T.kband_lo, &T.kband_stride);
         T.kband = fa.take((uint64_t)Fk * T.kband_stride + 32, 32);
+        T.kprefix = fa.take((uint64_t)MASK_SEG_MAX * kd.key_stride, 32);
         T.kepart_stride = (uint32_t)align_up(Fk + 1, 32);
         T.kepart = fa.take((uint64_t)((kd.key_bins + 31) / 32) * T.kepart_stride, 32);  // one row per warp of the mask kernel
     }

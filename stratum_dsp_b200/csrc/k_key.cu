@@ -49,8 +49,13 @@ constexpr int MASK_G = 16;
 // Two 16-frame groups per loop trip: the prefix ring has 32 slots, so with the trip starting at a multiple of 32 every ring index of the
 // steady state is a compile-time constant (ncu/SASS of the one-group loop: five uniform-datapath instructions per element rebuilding
 // (ii & 31) * 512 offsets, six for the band store's address — 37 instructions per element, 24 of them arithmetic).
+// seg_len > 0 (COMPACT only, a multiple of 32): the track is cut into floor(Fk / seg_len) time segments, one per blockIdx.z, for waves with
+// too few tracks to fill the device (a single 60-minute mix is 33 CTAs walking 310 000 frames each: 36 ms on 3 % of the warps).  Segment z
+// starts from the exact prefix of the frames before z * seg_len (mask_prefix_kernel: the same serial additions, nothing else), consumes
+// frames [z * seg_len, (z + 1) * seg_len + 32) and emits every frame whose window it has seen in full — the 20 frames two neighbouring
+// segments both emit get bit-identical values.  Only the last segment runs the tail and the flush.
 template <int MG, bool FAST, int KB, bool COMPACT, int BS = 0>
-__global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg) {
+__global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg, uint32_t seg_len) {
     const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
     // floats per spectrogram row: the compact variant's input rows are padded to a 32-byte sector by the STFT (DevCfg::key_stride), so a
     // warp's 128-byte load is four aligned sectors instead of five (ncu: 309 MB read per track for 254 MB of rows before the padding)
@@ -75,8 +80,15 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
     float* EP = fa + T.kepart + (uint64_t)(blockIdx.x * 4 + wid) * T.kepart_stride;  // this warp's share row
     const float p = FAST ? 2.0f : fmaxf(cfg.key_mask_power, 1.0f);
     const bool square = FAST || (p == 2.0f);
-    float P = 0.0f;
-    ringP[0][tx] = 0.0f;
+    const uint32_t z = COMPACT ? blockIdx.z : 0u;
+    const uint32_t nz = (COMPACT && seg_len) ? max(1u, nf / seg_len) : 1u;
+    if (z >= nz) return;
+    const uint32_t c0 = z * seg_len;                                    // first frame consumed (a multiple of the ring length)
+    const bool last = z + 1 == nz;
+    const uint32_t c1 = last ? nf : c0 + seg_len + RING;                // one past the last frame consumed
+    const uint32_t emit_from = z ? c0 + 2 * mg : mg;                    // frame t = ii - mg is emitted for consumed frames ii >= emit_from
+    float P = (z && valid) ? fa[T.kprefix + (uint64_t)(z - 1) * KSTRIDE + b] : 0.0f;  // prefix[c0]
+    ringP[0][tx] = P;
     auto ld = [&](uint32_t t) { return (!COMPACT || valid) ? K[(uint64_t)t * KSTRIDE] : 0.0f; };
     // where frame t's masked value goes: its column of the compact band, or the spectrogram row itself (in place)
     const uint32_t dstride = COMPACT ? bstride : KSTRIDE;
@@ -143,9 +155,9 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int q = 0; q < H; ++q) h[r][q] = 0.0f;
-    const uint32_t n_half = 2 * (nf / MASK_G);
-    const float* kp = K;                                  // row 8k of this thread's column
-    float* dp = D - (int64_t)mg * (int64_t)dstride;       // destination of frame 8k - mg; only dereferenced for frames >= 0
+    const uint32_t k0 = c0 / H, k_end = k0 + 2 * ((c1 - c0) / MASK_G);
+    const float* kp = K + (uint64_t)c0 * KSTRIDE;                              // row 8k of this thread's column
+    float* dp = D + ((int64_t)c0 - (int64_t)mg) * (int64_t)dstride;            // destination of frame 8k - mg; only dereferenced for emitted frames
     auto fetch = [&](float (&dst)[H], const float* from) {
 #pragma unroll
         for (int q = 0; q < H; ++q) dst[q] = (!COMPACT || valid) ? from[(uint32_t)q * KSTRIDE] : 0.0f;
@@ -154,7 +166,7 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
         constexpr int R = decltype(r_t)::value;
         constexpr bool steady = MG > 0 && decltype(st)::value;
         const uint32_t i = k * H;
-        if (k + 1 < n_half) fetch(h[(R + 1) & 3], kp + (uint64_t)H * KSTRIDE);
+        if (k + 1 < k_end) fetch(h[(R + 1) & 3], kp + (uint64_t)H * KSTRIDE);
         const float(&cur)[H] = h[R];
         const float(&p1)[H] = h[(R + 3) & 3];
         const float(&p2)[H] = h[(R + 2) & 3];
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
             const int row = (R & 1) * H + q;  // slot of the warp's 16-frame energy tile
             if (MG == 0) ringX[(PH + q) & (RING - 1)][tx] = cur[q];
             P = P + cur[q];
-            if (steady || ii >= mg) {  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
+            if (steady || ii >= emit_from) {  // prefix[t - mg] was written 2*mg+1 steps ago: still in the ring
                 float xt;
                 if (MG > 0) xt = (q + 2 * H - MG < H) ? p2[(q + 2 * H - MG) & (H - 1)] : p1[(q + H - MG) & (H - 1)];  // x[8k + q - MG]
                 else xt = ringX[(ii - mg) & (RING - 1)][tx];
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
 #pragma unroll
             for (int c = 0; c < 16; ++c) v += et[wid][row][c0 + c];
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < MASK_G && (steady || i16 + row >= mg)) EP[i16 + row - mg] = v;
+            if (lane < MASK_G && (steady || i16 + row >= emit_from)) EP[i16 + row - mg] = v;
             __syncwarp();
         }
     };
@@ -197,23 +209,23 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
     using R1 = std::integral_constant<int, 1>;
     using R2 = std::integral_constant<int, 2>;
     using R3 = std::integral_constant<int, 3>;
-    uint32_t k = 0;
-    if (n_half > 0) fetch(h[0], kp);
-    if (n_half >= 4) {  // first ring revolution: windows clipped at the track start
-        step(0, R0{}, std::false_type{});
-        step(1, R1{}, std::false_type{});
-        step(2, R2{}, std::false_type{});
-        step(3, R3{}, std::false_type{});
-        k = 4;
+    uint32_t k = k0;
+    if (k_end > k0) fetch(h[0], kp);
+    if (k_end - k0 >= 4) {  // first ring revolution: windows clipped at the track start / frames before the segment's first full window
+        step(k, R0{}, std::false_type{});
+        step(k + 1, R1{}, std::false_type{});
+        step(k + 2, R2{}, std::false_type{});
+        step(k + 3, R3{}, std::false_type{});
+        k += 4;
     }
-    for (; k + 4 <= n_half; k += 4) {
+    for (; k + 4 <= k_end; k += 4) {
         step(k, R0{}, std::true_type{});
         step(k + 1, R1{}, std::true_type{});
         step(k + 2, R2{}, std::true_type{});
         step(k + 3, R3{}, std::true_type{});
     }
-    if (k + 2 <= n_half) {  // one more group of 16
-        if (k == 0) {
+    if (k + 2 <= k_end) {  // one more group of 16
+        if (k == k0) {
             step(k, R0{}, std::false_type{});
             step(k + 1, R1{}, std::false_type{});
         } else {
@@ -222,16 +234,64 @@ __global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict
         }
         k += 2;
     }
+    if (!last) return;
     uint32_t i = k * H;
     // tail (< 16 frames) and flush: the delayed samples are re-read from rows that are still unmasked
     // (row t is only rewritten by emit(t)), which costs at most 16 + margin scalar loads per thread
     for (; i < nf; ++i) {
         const float x = ld(i);
         P = P + x;
-        if (i >= mg) emit(i - mg, dst_of(i - mg), i + 1, P, ld(i - mg), -1);
+        if (i >= emit_from) emit(i - mg, dst_of(i - mg), i + 1, P, ld(i - mg), -1);
         ringP[(i + 1) & (RING - 1)][tx] = P;
     }
-    for (uint32_t t = nf > mg ? nf - mg : 0; t < nf; ++t) emit(t, dst_of(t), nf, P, ld(t), -1);
+    for (uint32_t t = max(nf > mg ? nf - mg : 0u, z ? c0 + mg : 0u); t < nf; ++t) emit(t, dst_of(t), nf, P, ld(t), -1);
+}
+
+// Exact prefixes at the segment starts of a time-segmented mask launch: prefix[z - 1][bin] = the serial f32 sum of the bin's magnitudes
+// over frames [0, z * seg_len), z = 1 .. nz - 1 — the additions of the mask's own scan and nothing else, so a segment that starts from it
+// continues the reference's rounding sequence (extractor.rs:1274-1279).  A pure dependent add chain per thread; the rows are fetched 48
+// frames ahead (three register batches of 16 in flight) because with one warp per scheduler nothing else hides the memory latency.
+template <int KB>
+__global__ void __launch_bounds__(128) mask_prefix_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg, uint32_t seg_len) {
+    const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
+    const uint32_t KSTRIDE = KB ? (uint32_t)((KB + 7) / 8 * 8) : cfg.key_stride;
+    const TrackDev& T = tr[blockIdx.y];
+    const uint32_t nf = T.Fk;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (T.status != 0 || b >= KBINS || seg_len == 0) return;
+    const uint32_t nz = max(1u, nf / seg_len);
+    if (nz < 2) return;
+    const float* K = fa + T.keyspec + b;
+    float* out = fa + T.kprefix + b;
+    const uint32_t per_seg = seg_len / 16;          // seg_len is a multiple of 32
+    const uint32_t n_batches = (nz - 1) * per_seg;
+    float a[4][16];
+    auto fetch = [&](float (&dst)[16], uint32_t batch) {
+        const float* p = K + (uint64_t)batch * 16 * KSTRIDE;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) dst[q] = p[(uint32_t)q * KSTRIDE];
+    };
+    fetch(a[0], 0);
+    if (n_batches > 1) fetch(a[1], 1);
+    if (n_batches > 2) fetch(a[2], 2);
+    float P = 0.0f;
+    auto consume = [&](uint32_t j, auto r_t) {
+        constexpr int R = decltype(r_t)::value;
+        if (j + 3 < n_batches) fetch(a[(R + 3) & 3], j + 3);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) P = P + a[R][q];
+        if ((j + 1) % per_seg == 0) out[(uint64_t)((j + 1) / per_seg - 1) * KSTRIDE] = P;
+    };
+    uint32_t j = 0;
+    for (; j + 4 <= n_batches; j += 4) {
+        consume(j, std::integral_constant<int, 0>{});
+        consume(j + 1, std::integral_constant<int, 1>{});
+        consume(j + 2, std::integral_constant<int, 2>{});
+        consume(j + 3, std::integral_constant<int, 3>{});
+    }
+    if (j < n_batches) consume(j++, std::integral_constant<int, 0>{});
+    if (j < n_batches) consume(j++, std::integral_constant<int, 1>{});
+    if (j < n_batches) consume(j++, std::integral_constant<int, 2>{});
 }
 
 // ---- HPCP: one warp per frame ---------------------------------------------------------------------
@@ -1034,17 +1094,31 @@ __global__ void key_vote_kernel(TrackDev* tr, const float* fa, int n_tracks, Dev
 
 void launch_key_mask(const WaveCtx& c) {
     if (c.max_Fk > 0 && !c.cfg.key_hpss && (c.cfg.key_mask || c.cfg.key_smooth_only)) {  // the median-HPSS mask takes precedence (lib.rs:1011-1030)
-        const dim3 g((c.cfg.key_bins + 127) / 128, c.n_tracks);
+        dim3 g((c.cfg.key_bins + 127) / 128, c.n_tracks);
         const bool fast = !c.cfg.key_smooth_only && fmaxf(c.cfg.key_mask_power, 1.0f) == 2.0f && c.cfg.key_bins == 4097;
+        // Few long tracks: cut the time axis so that the launch has about four CTAs per SM (see mask_kernel); segments of at least 2048
+        // frames, at most MASK_SEG_MAX per track (the prefix rows planned in engine.cu).
+        uint32_t seg_len = 0;
+        if (c.cfg.key_compact && c.cfg.key_margin == 12 && fast && c.max_Fk >= 8192 && g.x * g.y < 300) {
+            const uint32_t want = std::min<uint32_t>(MASK_SEG_MAX, 592u / (g.x * g.y));
+            seg_len = std::max<uint32_t>(2048u, ((c.max_Fk / std::max(want, 1u)) + 31u) & ~31u);
+            const uint32_t nseg = std::max(1u, c.max_Fk / seg_len);
+            if (nseg < 2) seg_len = 0;
+            else {
+                g.z = nseg;
+                mask_prefix_kernel<4097><<<dim3(g.x, g.y), 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, seg_len);
+                count_launch("key_mask");
+            }
+        }
         if (c.cfg.key_compact) {
-            if (c.cfg.key_margin == 12 && fast && c.kband_stride_common == 960) mask_kernel<12, true, 4097, true, 960><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);  // defaults (config.rs:669, 680, 688) at >= 39.2 kHz
-            else if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-            else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-            else mask_kernel<0, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            if (c.cfg.key_margin == 12 && fast && c.kband_stride_common == 960) mask_kernel<12, true, 4097, true, 960><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, seg_len);  // defaults (config.rs:669, 680, 688) at >= 39.2 kHz
+            else if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, seg_len);
+            else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, 0u);
+            else mask_kernel<0, false, 0, true><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, 0u);
         } else {
-            if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-            else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
-            else mask_kernel<0, false, 0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg);
+            if (c.cfg.key_margin == 12 && fast) mask_kernel<12, true, 4097, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, 0u);
+            else if (c.cfg.key_margin == 12) mask_kernel<12, false, 0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, 0u);
+            else mask_kernel<0, false, 0, false><<<g, 128, 0, c.stream>>>(c.tracks, c.fa, c.cfg, 0u);
         }
         count_launch("key_mask");
     }
