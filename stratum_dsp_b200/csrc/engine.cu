@@ -343,6 +343,12 @@ static int ctx_init(DeviceCtx& c, int device) {
         for (uint32_t k = 1; k < 2048 && sym; ++k) sym = rw[4096 - k].x == -rw[k].x && rw[4096 - k].y == rw[k].y;
         c.tab.rw8192_sym = sym ? 1 : 0;
     }
+    {
+        const std::vector<float2> rw = make_tw(2048);
+        bool sym = true;
+        for (uint32_t k = 1; k < 512 && sym; ++k) sym = rw[1024 - k].x == -rw[k].x && rw[1024 - k].y == rw[k].y;
+        c.tab.rw2048_sym = sym ? 1 : 0;
+    }
     c.tab.win2048 = dev_upload(c, make_hann(2048));
     c.tab.win8192 = dev_upload(c, make_hann(8192));
     std::vector<float> mj, mn;

@@ -190,6 +190,26 @@ def test_stage_intermediates_single_track():
         S.debug_enable(False)
 
 
+def test_time_segmented_mask_is_bit_identical():
+    # A wave with few long tracks cuts the harmonic mask's time axis into segments that start from exact prefixes (k_key.cu: mask_kernel
+    # seg_len, mask_prefix_kernel); a wave with many tracks walks every bin in one piece.  Same track, both ways: every chroma value, frame
+    # energy and key weight must be bit-identical (reference: extractor.rs:1246-1349, a sequential f32 prefix per bin).
+    x = synth.render(synth.c2_params(3, 100 * SR, SR))  # 8 598 key frames: segmented when analysed alone
+    fill = [synth.render(synth.c2_params(40 + i, 4 * SR, SR)) for i in range(11)]
+    S.debug_enable(True)
+    try:
+        names = ("key.hpcp_raw", "key.energy", "key.weights", "key.band_head")
+        S.analyze_audio(x, SR)
+        alone = {nm: S.debug_array(nm).copy() for nm in names}
+        S.analyze_batch([x] + fill, SR)
+        batch = {nm: S.debug_array(nm).copy() for nm in names}
+    finally:
+        S.debug_enable(False)
+    assert alone["key.hpcp_raw"].size == batch["key.hpcp_raw"].size > 8000 * 12  # the dumped track of the batch is the long one
+    for nm in names:
+        assert np.array_equal(alone[nm], batch[nm]), nm
+
+
 def test_device_resident_batch_and_synth():
     torch = pytest.importorskip("torch")
     n, nt = 20 * SR, 4

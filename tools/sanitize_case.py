@@ -27,5 +27,11 @@ for cfg in (None, S.AnalysisConfig(normalization=S.NORM_RMS), S.AnalysisConfig(n
 pcm = [np.clip(np.round(t * 32767), -32768, 32767).astype(np.int16) for t in tracks[:2]]
 print([round(r.bpm, 2) for r in S.analyze_batch_pcm16(pcm, srs[:2])])
 print(S.stft(tracks[0][: 3 * SR], 8192, 512).shape, S.stft(tracks[0][: 2 * SR], 2048, 256).shape)
+# one long track per call: the time-segmented mask (Fk >= 8192 with a handful of tracks) and, at 25 minutes, the consensus vote's
+# global-memory work arrays (more than 12 288 onsets)
+for secs in (120, 25 * 60):
+    p = synth.TrackParams(126.0, 5, 0, 0.2, 0.1, SR, secs * SR)
+    r = S.analyze_audio(synth.render(p), SR)
+    print(secs, round(r.bpm, 2), r.key.name(), len(r.onsets) if hasattr(r, "onsets") else None)
 S.shutdown()
 print("done")
