@@ -1798,6 +1798,7 @@ struct WaveLimits {
 };
 
 constexpr uint32_t WAVE_MAX_TRACKS = 65535;
+constexpr uint64_t WAVE_CAP_SAMPLES = (uint64_t)208 * 7938000;  // device-resident wave cap: 208 three-minute tracks (see Session::open)
 
 static void pack_wave(uint32_t& i, uint32_t n_tracks, const uint64_t* lens, const uint32_t* srs, const StratumConfig& cfg, WaveLimits& L, WavePlan& wp) {
     uint64_t used = 0, esc_max = 0, wave_samples = 0, remaining = 0;
@@ -1861,10 +1862,11 @@ struct Session {
         double cap_gb = 100.0;
         if (const char* e = getenv("STRATUM_B200_ARENA_GB")) cap_gb = atof(e);
         budget_floats = std::min<uint64_t>(budget_floats, (uint64_t)(cap_gb * 1e9 / 4));
-        // waves of 128-160 three-minute tracks measured fastest (982-989 tracks/s against 959 in waves of 256, 913 in waves of 64)
-        // (the cap is expressed in samples so that batches of short tracks still fill the device)
+        // wave size (three-minute tracks), device-resident batch of 1024, round 2 kernels (r02p): 103 -> 1322 tracks/s, 128 -> 1338, 171 -> 1355,
+        // 205 -> 1355, 256 -> 1358; round 1 had 128-160 fastest.  The cap is expressed in samples so that batches of short tracks still
+        // fill the device; 208 cuts the 1024-track batch into five even waves.  (Host batches are cut by the upload chunks instead: 128.)
         uint32_t wave_max = WAVE_MAX_TRACKS;
-        uint64_t wave_max_samples = (uint64_t)128 * 7938000;
+        uint64_t wave_max_samples = WAVE_CAP_SAMPLES;
         if (const char* e = getenv("STRATUM_B200_WAVE_MAX_TRACKS")) {
             wave_max = (uint32_t)std::min<long>(std::max(1, atoi(e)), (long)WAVE_MAX_TRACKS);
             wave_max_samples = ~0ull;
@@ -2233,7 +2235,7 @@ uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* 
     const StratumConfig& c = cfg ? *cfg : def;
     std::vector<uint64_t> lens(n_tracks);
     for (uint32_t q = 0; q < n_tracks; ++q) lens[q] = offsets[q + 1] - offsets[q];
-    WaveLimits lim{(uint64_t)(budget_gb * 1e9 / 4), WAVE_MAX_TRACKS, (uint64_t)128 * 7938000};
+    WaveLimits lim{(uint64_t)(budget_gb * 1e9 / 4), WAVE_MAX_TRACKS, WAVE_CAP_SAMPLES};
     uint32_t i = 0, nw = 0;
     while (i < n_tracks) {
         WavePlan wp;

@@ -196,14 +196,14 @@ def _plan(lens, srs=None, budget_gb=100.0, cfg=None):
 
 def test_wave_planner_balances_and_respects_the_budget():
     T3 = 7_938_000  # 3 minutes at 44.1 kHz
-    nw, w = _plan([T3] * 1024)
-    assert nw == 8 and np.bincount(w).tolist() == [128] * 8
-    nw, w = _plan([T3] * 135)                       # a little over one full wave: two balanced waves, not 128 + 7
-    assert nw == 2 and sorted(np.bincount(w).tolist()) == [67, 68]
+    nw, w = _plan([T3] * 1024)                      # wave cap = 208 three-minute tracks: five even waves
+    assert nw == 5 and sorted(np.bincount(w).tolist()) == [204, 205, 205, 205, 205]
+    nw, w = _plan([T3] * 215)                       # a little over one full wave: two balanced waves, not 208 + 7
+    assert nw == 2 and sorted(np.bincount(w).tolist()) == [107, 108]
     nw, w = _plan([T3] * 64)
     assert nw == 1
     nw, w = _plan([T3 // 6] * 3000)                 # short tracks: the cap is in samples, not in tracks
-    assert nw == 4 and np.bincount(w).min() >= 700
+    assert nw == 3 and np.bincount(w).min() >= 900
     nw, w = _plan([T3] * 200, budget_gb=10.0)       # a 10 GB arena holds ~25 three-minute tracks with their escalation room
     assert nw >= 8 and np.bincount(w).max() <= 32 and np.all(np.diff(w) >= 0)
     rng = np.random.RandomState(3)
@@ -211,7 +211,7 @@ def test_wave_planner_balances_and_respects_the_budget():
     nw, w = _plan(lens, srs=[44100, 48000] * 128)
     assert np.all(np.diff(w) >= 0) and w[0] == 0 and w[-1] == nw - 1                       # contiguous, in order, every track placed
     per = [int(lens[w == k].sum()) for k in range(nw)]
-    assert max(per) <= 1.5 * 128 * T3 and (nw == 1 or min(per) >= 0.3 * max(per))          # no tiny tail wave
+    assert max(per) <= 1.5 * 208 * T3 and (nw == 1 or min(per) >= 0.3 * max(per))          # no tiny tail wave
     nw, w = _plan([200 * T3])                       # one 10-hour track: still planned (the budget is raised for a single track)
     assert nw == 1
 
