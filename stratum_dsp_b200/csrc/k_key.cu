@@ -54,8 +54,10 @@ constexpr int MASK_G = 16;
 // starts from the exact prefix of the frames before z * seg_len (mask_prefix_kernel: the same serial additions, nothing else), consumes
 // frames [z * seg_len, (z + 1) * seg_len + 32) and emits every frame whose window it has seen in full — the 20 frames two neighbouring
 // segments both emit get bit-identical values.  Only the last segment runs the tail and the flush.
+// Seven CTAs per SM (72 registers): under the nine-CTA cap of 56 registers the compiler could not overlap the dependent chains of
+// neighbouring frames; per 512 tracks (r02D-r02G) 9 CTAs 53.5 ms, 8 CTAs 51.9, 7 CTAs 41.1, 6 CTAs 43.5, 5 CTAs 48.2.
 template <int MG, bool FAST, int KB, bool COMPACT, int BS = 0>
-__global__ void __launch_bounds__(128, 9) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg, uint32_t seg_len) {
+__global__ void __launch_bounds__(128, 7) mask_kernel(const TrackDev* __restrict__ tr, float* fa, DevCfg cfg, uint32_t seg_len) {
     const uint32_t KBINS = KB ? (uint32_t)KB : cfg.key_bins;
     // floats per spectrogram row: the compact variant's input rows are padded to a 32-byte sector by the STFT (DevCfg::key_stride), so a
     // warp's 128-byte load is four aligned sectors instead of five (ncu: 309 MB read per track for 254 MB of rows before the padding)
