@@ -213,16 +213,17 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
         // bound by the dependent chain of the logarithm at 6 warps per scheduler, and the four interleaved slices of this form are what
         // gives it instruction-level parallelism.
         {
-            float xq[4];
+            constexpr int PF = 8;  // slices in flight (8 measured 4 % faster than 4: r02H)
+            float xq[PF];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) xq[u] = __ldg(row + 32 * u + lane);
-#pragma unroll 4
+            for (int u = 0; u < PF; ++u) xq[u] = __ldg(row + 32 * u + lane);
+#pragma unroll PF
             for (int b0 = 0; b0 < 1025; b0 += 32) {
                 const int b = b0 + lane;
                 const bool in = b < 1025;
-                const int u = (b0 >> 5) & 3;
+                const int u = (b0 >> 5) & (PF - 1);
                 const float x = in ? xq[u] : 0.0f;
-                if (b + 128 < 1025) xq[u] = __ldg(row + b + 128);
+                if (b + 32 * PF < 1025) xq[u] = __ldg(row + b + 32 * PF);
                 if (in) Lc[b] = logf(1.0f + fmaxf(x, 0.0f));  // novelty.rs:354
                 if (emit && in && b >= e0 && b < e3) {
                     const float xx = x * x, kx = (float)b * x * x;
