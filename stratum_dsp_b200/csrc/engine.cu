@@ -217,6 +217,7 @@ struct DeviceCtx {
     Tables tab{};
     std::vector<void*> owned;                 // table allocations
     std::map<uint32_t, float2*> tw_tables;    // size -> TW table (Stockham twiddles, oracle/so_fft.cpp)
+    std::map<uint32_t, const float*> hann_tables;  // frame size -> Hann window of the generic STFT
     std::vector<SrTables> sr_host;
     std::vector<StratumConfig> sr_cfg;        // configuration each sr_host entry was built for (the tables depend on it)
     SrTables* d_srtab = nullptr;
@@ -320,6 +321,18 @@ static const float2* get_tw(DeviceCtx& c, uint32_t M) {
     float2* p = dev_upload(c, make_tw(M));
     c.tw_tables[M] = p;
     return p;
+}
+
+// tables of the generic STFT for frame size n (a power of two); win == nullptr on allocation failure
+static GenStft get_gen_stft(DeviceCtx& c, uint32_t n) {
+    GenStft g{};
+    auto it = c.hann_tables.find(n);
+    if (it == c.hann_tables.end()) it = c.hann_tables.emplace(n, dev_upload(c, make_hann(n))).first;
+    g.win = it->second;
+    g.tw = get_tw(c, n / 2);
+    g.rw = get_tw(c, n);
+    g.n = (g.win && g.tw && g.rw) ? n : 0;
+    return g;
 }
 
 static int ctx_init(DeviceCtx& c, int device) {
@@ -896,8 +909,10 @@ static int config_validate(const StratumConfig& c) {
     if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
     if (c.emit_tempogram_candidates && c.tempogram_candidates_top_n > 200) return ni("tempogram_candidates_top_n > 200");
     if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
-    if (c.enable_key_stft_override && std::max<uint32_t>(c.key_stft_frame_size, 256) != 8192 && std::max<uint32_t>(c.key_stft_frame_size, 256) != 2048)
-        return ni("key_stft_frame_size other than 2048 or 8192");
+    if (c.enable_key_stft_override) {  // any power of two from 256 (lib.rs:986 clamps below) to 8192; 2048 and 8192 have fused kernels
+        const uint32_t kf = std::max<uint32_t>(c.key_stft_frame_size, 256);
+        if ((kf & (kf - 1)) != 0 || kf > 8192) return ni("key_stft_frame_size that is not a power of two between 256 and 8192");
+    }
     if (c.key_spectrogram_smooth_margin > 15) return ni("key_spectrogram_smooth_margin > 15");
     if (c.key_hpcp_peaks_per_frame > 32) return ni("key_hpcp_peaks_per_frame > 32");
     if (c.key_hpcp_num_harmonics > 8) return ni("key_hpcp_num_harmonics > 8");
@@ -1384,6 +1399,13 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
     w.tab = c.tab;
     w.cfg = dcfg;
     w.max_key_peaks = 1;
+    if (dcfg.key_frame != 2048 && dcfg.key_frame != 8192) {
+        w.gen_key = get_gen_stft(c, dcfg.key_frame);
+        if (w.gen_key.n == 0) {
+            set_error("table allocation failed");
+            return STRATUM_PROCESSING_ERROR;
+        }
+    }
     bool kband_seen = false;
     const bool mr_on = dcfg.mr_enabled && !dcfg.force_legacy;
     for (int i = 0; i < nt; ++i) {
@@ -2465,8 +2487,8 @@ size_t stratum_b200_sizeof(int32_t which) {
 }
 
 int64_t stratum_b200_stft(const float* samples, uint64_t n, uint32_t frame_size, uint32_t hop, float gain, float* out, uint64_t out_cap) {
-    if (frame_size != 2048 && frame_size != 8192) {
-        set_error("frame_size must be 2048 or 8192");
+    if (frame_size < 64 || frame_size > 16384 || (frame_size & (frame_size - 1)) != 0) {
+        set_error("frame_size must be a power of two between 64 and 16384");
         return -STRATUM_NOT_IMPLEMENTED;
     }
     if (hop == 0 || !samples || !out) {
@@ -2492,7 +2514,17 @@ int64_t stratum_b200_stft(const float* samples, uint64_t n, uint32_t frame_size,
         return -STRATUM_PROCESSING_ERROR;
     }
     cudaMemcpyAsync(d_in, samples, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    launch_stft_raw(ctx->stream, d_in, n, frame_size, hop, gain, ctx->tab, d_out, frames);
+    GenStft gen{};
+    if (frame_size != 2048 && frame_size != 8192) {
+        gen = get_gen_stft(*ctx, frame_size);
+        if (gen.n == 0) {
+            cudaFree(d_in);
+            cudaFree(d_out);
+            set_error("table allocation failed");
+            return -STRATUM_PROCESSING_ERROR;
+        }
+    }
+    launch_stft_raw(ctx->stream, d_in, n, frame_size, hop, gain, ctx->tab, d_out, frames, &gen);
     cudaMemcpyAsync(out, d_out, need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     const cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_in);

@@ -100,6 +100,14 @@ struct SrTables {
     uint32_t lufs_block;              // (sr * 0.4) as usize, normalization.rs:198
 };
 
+// Tables of the generic STFT (k_stft.cu: stft_any_kernel) for one frame size N = 2^m: Hann window, TW_{N/2} and the real-split table RW_N.
+struct GenStft {
+    const float* win;
+    const float2* tw;
+    const float2* rw;
+    uint32_t n;
+};
+
 struct WaveCtx {
     cudaStream_t stream;
     const float* samples;  // device
@@ -120,6 +128,7 @@ struct WaveCtx {
     uint32_t max_lg_fft;
     uint32_t max_lufs_nb;
     uint32_t max_key_peaks;  // HPCP peak slots a frame may need: (band bins + 1) / 2 over the wave's sample rates
+    GenStft gen_key;         // key STFT frames other than 2048 / 8192 points (n = 0: unused)
     uint32_t kband_stride_common;  // row stride of the compact key band when every live track of the wave has the same one, else 0
 };
 
@@ -135,7 +144,7 @@ void launch_stft_hop(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n
 void launch_stft_key(const WaveCtx& c);
 void stft_upload_constants(const float2* ptw1024_host, const float2* ptw4096_host);  // per device, before the first STFT launch
 void launch_stft_raw(cudaStream_t s, const float* d_samples, uint64_t n, uint32_t frame_size, uint32_t hop, float gain, const Tables& tab,
-                     float* d_out, uint32_t frames);
+                     float* d_out, uint32_t frames, const GenStft* gen = nullptr);
 // k_onset.cu
 void launch_energy_onsets(const WaveCtx& c);
 void launch_spec_features(const WaveCtx& c, int hop_idx, const int32_t* d_list, int n_list);

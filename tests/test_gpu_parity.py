@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 SR = 44100
 
 
-@pytest.mark.parametrize("frame,hop", [(2048, 512), (2048, 256), (2048, 1024), (8192, 512)])
+# 2048 and 8192 points: the register-fused kernels; every other power of two: the generic shared-memory form of the same DAG
+@pytest.mark.parametrize("frame,hop", [(2048, 512), (2048, 256), (2048, 1024), (8192, 512), (1024, 256), (4096, 512), (512, 100), (256, 256), (64, 32), (16384, 4096)])
 def test_stft_bit_exact(frame, hop):
     rng = np.random.default_rng(frame + hop)
     x = (rng.standard_normal(3 * SR) * 0.25).astype(np.float32)
@@ -421,9 +422,13 @@ def test_key_chroma_variants(cfg):
     {"enable_key_stft_override": 0, "enable_key_beat_synchronous": 1, "enable_key_harmonic_mask": 0},
     {"key_stft_frame_size": 2048, "key_stft_hop_size": 1024, "enable_key_hpss_harmonic": 1, "enable_key_hpcp": 0},
     {"key_stft_hop_size": 2048, "enable_key_log_frequency": 1, "enable_key_multi_scale": 1},
+    {"key_stft_frame_size": 4096},                                        # other powers of two: the generic STFT kernel in front of the same key kernels
+    {"key_stft_frame_size": 1024, "key_stft_hop_size": 256},
+    {"key_stft_frame_size": 4096, "key_stft_hop_size": 1024, "enable_key_harmonic_mask": 0, "enable_key_hpcp": 0},
+    {"key_stft_frame_size": 100},                                         # clamped to 256 (lib.rs:986)
 ])
 def test_key_stft_geometry(cfg):
-    # key STFT frame 2048 / 8192 at any hop, or no override at all: every key kernel takes the geometry from the configuration
+    # key STFT frames of any power of two from 256 to 8192 at any hop, or no override at all: every key kernel takes the geometry from the configuration
     xs = [synth.render_progression(6, 26, SR, tonic=5, minor=True, bpm=118, detune_cents=15), synth.render(synth.c2_params(44, 14 * 48000, 48000))]
     srs = [SR, 48000]
     for i, (x, sr) in enumerate(zip(xs, srs)):
