@@ -101,9 +101,38 @@ __global__ void __launch_bounds__(256) energy_onset_kernel(TrackDev* tr, float* 
 //     run of 32 consecutive frames, lanes stride the bins (coalesced), ln(1+x) is evaluated once per
 //     (frame, bin) and kept in shared memory for the next frame's max filter; reductions are warp trees.
 //     Mel bands are folded by one lane per band in ascending-bin order (the reference's order).
+// Rows of slot h's spectrogram and their maxima.  The multi-resolution slots share frames with the hop-512 slot (k_stft.cu:
+// launch_stft_hop): frame f of the hop-1024 sequence is hop-512 frame 2f, an even frame f of the hop-256 sequence is hop-512 frame f/2,
+// bit for bit — only the odd hop-256 frames have rows (and maxima) of their own.  MODE: 0 = the slot's own rows (hop 512, percussive
+// component), 1 = hop 256, 2 = hop 1024; a template parameter, with the base pointers hoisted by the caller — a run-time slot test in
+// the row loops cost the feature kernels 20 %.
+struct SpecRows {
+    const float* own;   // the slot's spectrogram
+    const float* base;  // the hop-512 spectrogram
+    const float* own_max;
+    const float* base_max;
+};
+__device__ __forceinline__ SpecRows spec_rows(const TrackDev& T, const float* fa, int h) {
+    return SpecRows{fa + T.hop[h].spec, fa + T.hop[0].spec, fa + T.hop[h].frame + (uint64_t)FQ_ROWMAX * T.hop[h].fmax,
+                    fa + T.hop[0].frame + (uint64_t)FQ_ROWMAX * T.hop[0].fmax};
+}
+template <int MODE>
+__device__ __forceinline__ const float* spec_row(const SpecRows& R, uint32_t f) {
+    if (MODE == 1) return (f & 1u) ? R.own + (uint64_t)f * 1025 : R.base + (uint64_t)(f >> 1) * 1025;
+    if (MODE == 2) return R.base + (uint64_t)(2 * f) * 1025;
+    return R.own + (uint64_t)f * 1025;
+}
+template <int MODE>
+__device__ __forceinline__ float spec_rowmax(const SpecRows& R, uint32_t f) {
+    if (MODE == 1) return (f & 1u) ? R.own_max[f] : R.base_max[f >> 1];
+    if (MODE == 2) return R.base_max[2 * f];
+    return R.own_max[f];
+}
+
 constexpr int FEAT_RUN = 32;
 constexpr int HALO = 8;  // superflux radius upper bound (the ABI rejects larger values)
 
+template <int MODE>
 __global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, int h, float* fa) {
     // A warp owns 32 consecutive frames f0 .. f0+31 and produces the flux of the 31 pairs inside them: the normalised value
     // x[f][k] / max[f] that frame f contributes as "current" is the same number frame f+1 needs as "previous", so every lane
@@ -119,12 +148,12 @@ __global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const
     if (f0 >= F || T.status != 0) return;
     float(*tile)[33] = tiles[w];
     const HopLayout& HL = T.hop[h];
-    const float* spec = fa + HL.spec;
     float* fr = fa + HL.frame;
     const uint64_t fm = HL.fmax;
     const uint32_t f = f0 + lane;
     const bool valid = f < F;
-    const float maxc = valid ? fr[FQ_ROWMAX * fm + f] : 0.0f;
+    const SpecRows R = spec_rows(T, fa, h);
+    const float maxc = valid ? spec_rowmax<MODE>(R, f) : 0.0f;
     const bool nc = maxc > 1e-10f;
     // x / max with the frame-constant divisor's correctly rounded reciprocal and one Markstein correction (common.cuh): three
     // instructions per bin instead of the generic division's ten.  x <= max, so the quotient is in [0, 1]; the result is the IEEE
@@ -145,14 +174,14 @@ __global__ void __launch_bounds__(128) seq_feat_kernel(const TrackDev* tr, const
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
             const uint32_t fr_ = f0 + r;
-            tile[r][lane] = fr_ < F ? spec[(uint64_t)fr_ * 1025 + jb * 32 + lane] : 0.0f;
+            tile[r][lane] = fr_ < F ? spec_row<MODE>(R, fr_)[jb * 32 + lane] : 0.0f;
         }
         __syncwarp();
 #pragma unroll 4
         for (int j = 0; j < 32; ++j) step(jb * 32 + j, tile[lane][j]);
         __syncwarp();
     }
-    step(1024, valid ? spec[(uint64_t)f * 1025 + 1024] : 0.0f);  // all lanes: the shuffle inside is warp-wide
+    step(1024, valid ? spec_row<MODE>(R, f)[1024] : 0.0f);  // all lanes: the shuffle inside is warp-wide
     if (valid) {
         fr[FQ_E * fm + f] = E;
         fr[FQ_H * fm + f] = H;
@@ -171,7 +200,7 @@ struct ParSmem {
 // six values common to all windows (17 FMNMX for four bins instead of 36 loads + 36 FMNMX, and a quarter of the shared-memory
 // instructions: ncu had the L1/shared pipe at 73 % on the lane-strided version).  Sums are warp trees either way (tolerance-level
 // consumers), so only their association changes.
-template <bool K4>
+template <bool K4, int MODE>
 __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const int32_t* __restrict__ list, const SrTables* srtab,
                                                        const int32_t* sr_index, int h, float* fa, DevCfg cfg) {
     __shared__ __align__(16) ParSmem sm[4];
@@ -184,10 +213,10 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
     ParSmem& S = sm[w];
     const SrTables& st = srtab[sr_index[t]];
     const HopLayout& HL = T.hop[h];
-    const float* spec = fa + HL.spec;
     float* fr = fa + HL.frame;
     float* pr = fa + HL.pair;
     const uint64_t fm = HL.fmax;
+    const SpecRows R = spec_rows(T, fa, h);
     const int K = K4 ? 4 : (int)min(max(cfg.sf_k, 1u), (uint32_t)HALO);
     const int MK = (int)max(cfg.mel_k, 1u);
     const int nm = (int)st.n_mels;
@@ -200,7 +229,7 @@ __global__ void __launch_bounds__(128) par_feat_kernel(const TrackDev* tr, const
     for (uint32_t f = f_first; f < f_last; ++f, cur ^= 1) {
         float* Lc = S.L[cur] + HALO;
         const float* Lp = S.L[cur ^ 1] + HALO;
-        const float* row = spec + (uint64_t)f * 1025;
+        const float* row = spec_row<MODE>(R, f);
         const bool emit = f >= f0;           // this warp owns the outputs of frame f
         const bool pair = emit && f >= 1;    // pair (f-1, f) -> index f-1
         // per-band accumulators are selected with predicates, never indexed: a run-time index would put the arrays in local
@@ -566,21 +595,33 @@ void launch_hpss_onsets(const WaveCtx& c) {
     count_launch("hpss");
 }
 
+static void launch_seq(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
+    const dim3 grid((c.max_F[h] + 123) / 124, n_list);  // 4 warps x 31 new frames
+    if (h == 1) seq_feat_kernel<1><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
+    else if (h == 2) seq_feat_kernel<2><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
+    else seq_feat_kernel<0><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
+    count_launch("spec_features");
+}
+
 void launch_seq_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (c.max_F[h] == 0 || n_list == 0) return;
-    dim3 grid((c.max_F[h] + 123) / 124, n_list);  // 4 warps x 31 new frames
-    seq_feat_kernel<<<grid, 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
+    launch_seq(c, h, d_list, n_list);
+}
+
+template <bool K4>
+static void launch_par(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
+    const dim3 grid((c.max_F[h] + 127) / 128, n_list);
+    if (h == 1) par_feat_kernel<K4, 1><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
+    else if (h == 2) par_feat_kernel<K4, 2><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
+    else par_feat_kernel<K4, 0><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
     count_launch("spec_features");
 }
 
 void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_list) {
     if (c.max_F[h] == 0 || n_list == 0) return;
-    dim3 grid((c.max_F[h] + 127) / 128, n_list);
-    seq_feat_kernel<<<dim3((c.max_F[h] + 123) / 124, n_list), 128, 0, c.stream>>>(c.tracks, d_list, h, c.fa);
-    count_launch("spec_features");
-    if (std::min(std::max(c.cfg.sf_k, 1u), (uint32_t)HALO) == 4u) par_feat_kernel<true><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
-    else par_feat_kernel<false><<<grid, 128, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg);
-    count_launch("spec_features");
+    launch_seq(c, h, d_list, n_list);
+    if (std::min(std::max(c.cfg.sf_k, 1u), (uint32_t)HALO) == 4u) launch_par<true>(c, h, d_list, n_list);
+    else launch_par<false>(c, h, d_list, n_list);
 }
 
 void launch_spectral_onsets_consensus(const WaveCtx& c) {
