@@ -2085,8 +2085,9 @@ static int32_t analyze_host_batch(const void* src, const uint64_t* boff, const u
         std::lock_guard<std::recursive_mutex> lk(ctx->mu);
         if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(STRATUM_PROCESSING_ERROR, "cudaSetDevice failed");
         // Chunk sizes ramp up: a small first chunk keeps the un-overlapped first upload short, later chunks grow to
-        // STRATUM_B200_STAGE_MB of mono f32 (default 3876 MB = 128 three-minute tracks, the most efficient wave size measured:
-        // 999 tracks/s device-resident in waves of 128 vs 933 in waves of 64); at least one track per chunk
+        // STRATUM_B200_STAGE_MB of mono f32 (default 3876 MB = 128 three-minute tracks: its 74 ms upload at 55 GB/s still hides behind the
+        // ~85 ms the chunk's wave takes, and larger chunks lengthen the ramp; device-resident batches use waves of up to 208); at least
+        // one track per chunk
         uint64_t chunk_frames = (uint64_t)128 * 7938000;  // = the wave cap of a session: one full-size chunk is one wave
         if (const char* e = getenv("STRATUM_B200_STAGE_MB")) chunk_frames = std::max<uint64_t>((uint64_t)(atof(e) * 1024 * 1024 / 4), 1u << 16);
         static const bool no_ramp = getenv("STRATUM_B200_STAGE_NO_RAMP") != nullptr;

@@ -27,9 +27,9 @@ constexpr int HPCP_MAX_HARM = 8;     // key_hpcp_num_harmonics upper bound accep
 // The reference builds `prefix[t+1] = prefix[t] + x[t]` per bin and takes window sums as prefix
 // differences (extractor.rs:1274-1287); the cancellation noise of that formulation is part of its
 // output, so the scan is reproduced term by term.  Adjacent threads own adjacent bins, so every
-// load and store of a frame row is coalesced.  Frames are consumed in groups of 16 whose loads are
-// issued together (16 independent requests in flight per thread); stores only touch rows already
-// consumed, so the mask is written in place.  MG > 0: margin known at compile time, the delayed sample
+// load and store of a frame row is coalesced.  Frames are consumed in half-steps of 8 whose loads are
+// issued one half-step ahead (see the frame loop); stores only touch rows already consumed, so the
+// non-compact variant writes the mask in place.  MG > 0: margin known at compile time, the delayed sample
 // x[t - MG] is then a register; MG = 0: run-time margin with a shared-memory ring for the samples.
 constexpr int MASK_G = 16;
 
