@@ -133,7 +133,9 @@ Error analyze_audio(const float* samples, size_t n, uint32_t sr, const Config& c
                 if (ambiguous) {
                     BpmEstimate mr;
                     std::vector<TempoCand> mc;
-                    if (!multi_resolution_tempogram(x, m, sr, c, &S, mr, mc, dump)) {
+                    // multi_resolution_tempogram_from_samples (lib.rs:493-509) recomputes the STFT at hops 256 / 512 / 1024 from the samples; the base
+                    // spectrogram is the hop-512 one only when hop_size is 512
+                    if (!multi_resolution_tempogram(x, m, sr, c, c.hop_size == 512 ? &S : nullptr, mr, mc, dump)) {
                         float rel = base.bpm > 1e-6f ? fmax_rs(mr.bpm / base.bpm, base.bpm / mr.bpm) : 1.0f;
                         bool fam_rel = fabsf(rel - 2.0f) < 0.05f || fabsf(rel - 1.5f) < 0.05f || fabsf(rel - (4.0f / 3.0f)) < 0.05f;
                         bool forbid = base.bpm <= 180.0f && mr.bpm > 180.0f;

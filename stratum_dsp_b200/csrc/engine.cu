@@ -908,7 +908,12 @@ static int config_validate(const StratumConfig& c) {
     }
     if ((c.enable_hpss_onsets || c.enable_tempogram_percussive_fallback) && c.hpss_margin > 10) return ni("hpss_margin > 10");
     if (c.emit_tempogram_candidates && c.tempogram_candidates_top_n > 200) return ni("tempogram_candidates_top_n > 200");
-    if (c.frame_size != 2048 || c.hop_size != 512) return ni("frame_size/hop_size other than 2048/512");
+    if (c.frame_size != 2048) return ni("frame_size other than 2048");
+    if (c.hop_size == 0) {
+        set_error("Hop size must be > 0");
+        return STRATUM_INVALID_INPUT;
+    }
+    if (c.hop_size < 32 || c.hop_size > 16384) return ni("hop_size outside 32..16384");  // (work areas are sized by the frame count)
     if (c.enable_key_stft_override) {  // any power of two from 256 (lib.rs:986 clamps below) to 8192; 2048 and 8192 have fused kernels
         const uint32_t kf = std::max<uint32_t>(c.key_stft_frame_size, 256);
         if ((kf & (kf - 1)) != 0 || kf > 8192) return ni("key_stft_frame_size that is not a power of two between 256 and 8192");
@@ -1022,6 +1027,8 @@ static DevCfg make_devcfg(const StratumConfig& c) {
     d.hpcp_decay = c.key_hpcp_harmonic_decay;
     d.hpcp_pow = c.key_hpcp_mag_power;
     d.hpcp_sigma = c.soft_mapping_sigma;
+    d.hop = c.hop_size;
+    d.bs = c.hop_size == 512 ? 0 : SLOT_BASE_ALT;  // the base path shares slot 0 with the multi-resolution pass only at hop 512
     d.key_frame = c.enable_key_stft_override ? std::max<uint32_t>(c.key_stft_frame_size, 256) : c.frame_size;  // lib.rs:984-995
     d.key_hop = c.enable_key_stft_override ? std::max<uint32_t>(c.key_stft_hop_size, 1) : c.hop_size;
     d.key_bins = d.key_frame / 2 + 1;
@@ -1099,12 +1106,17 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     const DevCfg kd = make_devcfg(cfg);
     const uint32_t Fk = frames_of(n, kd.key_frame, kd.key_hop);
     const uint32_t Fsil = n >= 2048 ? frames_of(n, 2048, 1024) : 1;
-    T.fall = std::max(std::max(F256, F512), std::max(F1024, 1u));
+    const uint32_t Fb = frames_of(n, 2048, kd.hop);  // frames of the base path (= F512 at the default hop_size)
+    T.fall = std::max(std::max(std::max(F256, F512), std::max(F1024, 1u)), Fb);
     T.fkmax = Fk;
     plan_hop(fa, T.hop[0], std::max(F512, 1u), 512);
     T.cands[0] = fa.take((uint64_t)MAX_CANDS * 4);
+    if (kd.bs != 0) {  // hop_size other than 512: the base path gets a slot of its own
+        plan_hop(fa, T.hop[SLOT_BASE_ALT], std::max(Fb, 1u), kd.hop);
+        T.cands[SLOT_BASE_ALT] = fa.take((uint64_t)MAX_CANDS * 4);
+    }
     T.sil_rms = fa.take(Fsil + 1);
-    T.erms = fa.take(F512 + 2);
+    T.erms = fa.take(std::max(F512, Fb) + 2);
     T.scratch = fa.take((uint64_t)12 * T.fall);
     T.keyspec = fa.take((uint64_t)Fk * kd.key_stride + 8, 32);
     T.keymask = T.keyspec;  // the mask is applied in place (or, key_compact: only its HPCP band is kept, in kband)
@@ -1137,7 +1149,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.seg_avg = fa.take((uint64_t)T.seg_cap * 13);
     T.seg_rank = fa.take((uint64_t)T.seg_cap * 28);
     // onsets: each detector yields at most every other flux sample
-    const uint32_t on_cap = F512 / 2 + 8;
+    const uint32_t on_cap = std::max(F512, Fb) / 2 + 8;
     T.on_energy = ia.take(on_cap);
     T.on_spectral = ia.take(on_cap);
     T.on_hfc = ia.take(on_cap);
@@ -1147,10 +1159,10 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     if (hpss) {  // HPSS work areas (onset/hpss.rs): two ping-pong pairs of F x 1025 and the feature slot of the percussive part
         T.on_hpss = ia.take(on_cap);
         for (int q = 0; q < 2; ++q) {
-            T.hpss_h[q] = fa.take((uint64_t)std::max(F512, 1u) * 1025);
-            T.hpss_p[q] = fa.take((uint64_t)std::max(F512, 1u) * 1025);
+            T.hpss_h[q] = fa.take((uint64_t)std::max(Fb, 1u) * 1025);
+            T.hpss_p[q] = fa.take((uint64_t)std::max(Fb, 1u) * 1025);
         }
-        plan_hop(fa, T.hop[SLOT_PERC], std::max(F512, 1u), 512, false);
+        plan_hop(fa, T.hop[SLOT_PERC], std::max(Fb, 1u), kd.hop, false);
         T.cands[SLOT_PERC] = fa.take((uint64_t)MAX_CANDS * 4);
     }
     T.on_final = ia.take((uint64_t)(hpss ? 4 : 3) * on_cap);
@@ -1169,7 +1181,7 @@ static void plan_track(Bump& fa, Bump& oa, Bump& ia, TrackDev& T, const StratumC
     T.cand_out = cfg.emit_tempogram_candidates ? oa.take((uint64_t)5 * MAX_TOPC) : 0;
     T.n_cand_out = -1;
     // legacy ACF: next_pow2(2 * (max_frame + 1)), max_frame <= n / 512
-    T.lg_fft = next_pow2_u32((uint32_t)(2 * (n / 512 + 1)));
+    T.lg_fft = next_pow2_u32((uint32_t)(2 * (n / kd.hop + 1)));
     T.lg_work = fa.take((uint64_t)4 * T.lg_fft);
     T.lg_tw = nullptr;
     T.lg_pad = 0;
@@ -1442,6 +1454,7 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
         if (T.status == 0 && T.kband_stride != w.kband_stride_common) w.kband_stride_common = kband_seen ? 0u : T.kband_stride;
         if (T.status == 0) kband_seen = true;
         T.hop[0].tgtw = get_tw(c, T.hop[0].fft_cap);
+        if (dcfg.bs != 0) T.hop[SLOT_BASE_ALT].tgtw = get_tw(c, T.hop[SLOT_BASE_ALT].fft_cap);
         if (dcfg.hpss_onsets || dcfg.perc_fallback) T.hop[SLOT_PERC].tgtw = get_tw(c, T.hop[SLOT_PERC].fft_cap);
         T.lg_tw = get_tw(c, T.lg_fft);
         if (mr_on) {  // escalation work areas, relative to the start of whichever arena slot escalation_compact_kernel assigns
@@ -1450,7 +1463,7 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
             T.hop[1].tgtw = get_tw(c, T.hop[1].fft_cap);
             T.hop[2].tgtw = get_tw(c, T.hop[2].fft_cap);
         }
-        if (!T.hop[0].tgtw || !T.lg_tw || (mr_on && (!T.hop[1].tgtw || !T.hop[2].tgtw))) {
+        if (!T.hop[0].tgtw || !T.hop[dcfg.bs].tgtw || !T.lg_tw || (mr_on && (!T.hop[1].tgtw || !T.hop[2].tgtw))) {
             set_error("twiddle table allocation failed");
             return STRATUM_PROCESSING_ERROR;
         }
@@ -1463,7 +1476,8 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
         w.max_F[0] = std::max(w.max_F[0], frames_of(T.n, 2048, 512));
         w.max_F[1] = std::max(w.max_F[1], frames_of(T.n, 2048, 256));
         w.max_F[2] = std::max(w.max_F[2], frames_of(T.n, 2048, 1024));
-        w.max_F[SLOT_PERC] = w.max_F[0];
+        w.max_F[SLOT_BASE_ALT] = std::max(w.max_F[SLOT_BASE_ALT], frames_of(T.n, 2048, dcfg.hop));
+        w.max_F[SLOT_PERC] = w.max_F[dcfg.bs];
         w.max_Fk = std::max(w.max_Fk, frames_of(T.n, dcfg.key_frame, dcfg.key_hop));
         w.max_Fsil = std::max(w.max_Fsil, Fsil);
         w.max_n = std::max<uint64_t>(w.max_n, T.n);
@@ -1604,8 +1618,9 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
         StageTimer t(s, "onsets_energy");
         launch_energy_onsets(w);
     }
-    { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, 0, nullptr, nt); }
-    { StageTimer t(s, "spec_features"); launch_spec_features(w, 0, nullptr, nt); }
+    const int bs = dcfg.bs;  // the base path's slot
+    { StageTimer t(s, "stft_2048_hop512"); launch_stft_hop(w, bs, nullptr, nt); }
+    { StageTimer t(s, "spec_features"); launch_spec_features(w, bs, nullptr, nt); }
     if (dcfg.hpss_onsets) {  // lib.rs:222-235: onsets of the percussive component as the fourth detector
         StageTimer t(s, "hpss");
         launch_hpss(w, nullptr, nt);
@@ -1617,7 +1632,7 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
     const bool want_tempogram = !dcfg.force_legacy;
     if (want_tempogram) {
         StageTimer t(s, "tempogram");
-        launch_tempogram(w, 0, nullptr, nt);
+        launch_tempogram(w, bs, nullptr, nt);
         launch_escalation_gate(w);
         if (dcfg.mr_enabled) launch_escalation_compact(w, c.d_list, c.d_count, fa_base_end, esc_each, (uint32_t)esc_slots);
     }
@@ -1665,17 +1680,20 @@ static int wave_begin(DeviceCtx& c, const float* d_samples, const uint64_t* samp
             const int32_t* lst = c.d_list + p0;
             {
                 StageTimer t(s, "stft_multires");
+                if (bs != 0) launch_stft_hop(w, 0, lst, nl);  // hop_size is not 512: the pass needs its own hop-512 spectrogram (lib.rs:493-509)
                 launch_stft_hop(w, 1, lst, nl);
                 launch_stft_hop(w, 2, lst, nl);
             }
             {
                 StageTimer t(s, "multires_features");
+                if (bs != 0) launch_spec_features(w, 0, lst, nl);
                 launch_spec_features(w, 1, lst, nl);
                 launch_spec_features(w, 2, lst, nl);
             }
             if (late && p1 == n_esc) fork_key_path();  // last heavy kernel of the tempo path is queued: the key path starts behind it
             {
                 StageTimer t(s, "multires_tempogram");
+                if (bs != 0) launch_tempogram(w, 0, lst, nl);
                 launch_tempogram(w, 1, lst, nl);
                 launch_tempogram(w, 2, lst, nl);
                 launch_multires_fusion(w, lst, nl);
@@ -1759,8 +1777,9 @@ static void debug_dump_wave(DeviceCtx& c, const WaveJob& job) {
     const DevCfg& dcfg = job.dcfg;
     const TrackDev& T = static_cast<const TrackDev*>(job.h_tracks.p)[0];
     if (T.status != 0) return;
-    const HopLayout& H = T.hop[0];
-    const uint32_t F = T.F[0], L = F > 0 ? F - 1 : 0;
+    const int bs = dcfg.bs;
+    const HopLayout& H = T.hop[bs];
+    const uint32_t F = T.F[bs], L = F > 0 ? F - 1 : 0;
     const uint64_t fm = H.fmax;
     debug_put("gain", &c.d_tracks[0].gain, 1, s);
     debug_put("spec512_head", c.fa + H.spec, (size_t)std::min<uint32_t>(F, 64) * 1025, s);
@@ -1783,8 +1802,8 @@ static void debug_dump_wave(DeviceCtx& c, const WaveJob& job) {
     for (int v = 0; v < 5; ++v) debug_put(vn[v], c.fa + H.nov + (uint64_t)v * fm, L, s);
     debug_put("base.tg.fft.full", c.fa + H.tgfft, H.fft_cap / 2 + 1, s);
     debug_put("base.tg.ac.full", c.fa + H.tgac, AC_CAP, s);
-    debug_put("base.cands", c.fa + T.cands[0], (size_t)MAX_CANDS * 4, s);
-    float est[12] = {T.est[0].bpm, T.est[0].confidence, (float)T.est[0].agreement, (float)T.est[0].ok, (float)T.est[0].n_cands,
+    debug_put("base.cands", c.fa + T.cands[bs], (size_t)MAX_CANDS * 4, s);
+    float est[12] = {T.est[bs].bpm, T.est[bs].confidence, (float)T.est[bs].agreement, (float)T.est[bs].ok, (float)T.est[bs].n_cands,
                      T.legacy.bpm, T.legacy.confidence, (float)T.legacy.ok, (float)T.escalate, T.est[1].bpm, T.est[2].bpm, 0.0f};
     {
         std::lock_guard<std::mutex> lk(g_debug_mu);

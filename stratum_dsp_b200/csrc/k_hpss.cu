@@ -49,17 +49,17 @@ __device__ __forceinline__ bool hpss_converged_before(const TrackDev& T, int it)
     return false;
 }
 
-__global__ void __launch_bounds__(256) hpss_iter_kernel(TrackDev* tr, const int32_t* __restrict__ list, float* fa, int it, uint32_t margin) {
+__global__ void __launch_bounds__(256) hpss_iter_kernel(TrackDev* tr, const int32_t* __restrict__ list, float* fa, int it, uint32_t margin, int bs) {
     __shared__ float Ht[HP_T + 2 * HP_MAXM][HP_B + 1];
     __shared__ float Pt[HP_T][HP_B + 2 * HP_MAXM + 1];
     __shared__ float sred[8];
     const int t = list ? list[blockIdx.z] : blockIdx.z;
     TrackDev& T = tr[t];
-    const int F = (int)T.F[0];
+    const int F = (int)T.F[bs];  // the base path's spectrogram (slot 0 unless hop_size is not 512)
     const int f0 = blockIdx.y * HP_T, b0 = blockIdx.x * HP_B;
     if (T.status != 0 || f0 >= F) return;
     if (hpss_converged_before(T, it)) return;
-    const float* S = fa + T.hop[0].spec;
+    const float* S = fa + T.hop[bs].spec;
     const float* Hs = it == 0 ? S : fa + T.hpss_h[it & 1];
     const float* Ps = it == 0 ? S : fa + T.hpss_p[it & 1];
     float* Hd = fa + T.hpss_h[(it + 1) & 1];
@@ -143,10 +143,10 @@ __global__ void hpss_finish_kernel(TrackDev* tr, const int32_t* __restrict__ lis
 }
 
 void launch_hpss(const WaveCtx& c, const int32_t* d_list, int n_list) {
-    if (n_list == 0 || c.max_F[0] == 0) return;
-    const dim3 grid((HP_BINS + HP_B - 1) / HP_B, (c.max_F[0] + HP_T - 1) / HP_T, n_list);
+    if (n_list == 0 || c.max_F[c.cfg.bs] == 0) return;
+    const dim3 grid((HP_BINS + HP_B - 1) / HP_B, (c.max_F[c.cfg.bs] + HP_T - 1) / HP_T, n_list);
     for (int it = 0; it < 10; ++it) {  // DEFAULT_ITERATIONS, hpss.rs:20
-        hpss_iter_kernel<<<grid, 256, 0, c.stream>>>(c.tracks, d_list, c.fa, it, c.cfg.hpss_margin);
+        hpss_iter_kernel<<<grid, 256, 0, c.stream>>>(c.tracks, d_list, c.fa, it, c.cfg.hpss_margin, c.cfg.bs);
         count_launch("hpss");
     }
     hpss_finish_kernel<<<(n_list + 127) / 128, 128, 0, c.stream>>>(c.tracks, d_list, n_list, 10);

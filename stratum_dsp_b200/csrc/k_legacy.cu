@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) legacy_kernel(TrackDev* tr, float* fa, co
     const uint32_t n_on = T.n_on_final;
     if (n_on < 2) return;  // lib.rs:299-307: legacy skipped
     const int32_t* on = ia + T.on_final;
-    const uint32_t hop = 512;
+    const uint32_t hop = cfg.hop;  // lib.rs:310: config.hop_size
     const uint32_t sr = T.sr;
     // ---- autocorrelation candidates ----
     const uint32_t max_frame = (uint32_t)on[n_on - 1] / hop;

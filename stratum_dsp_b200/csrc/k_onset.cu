@@ -21,6 +21,16 @@ constexpr int MEL_MAX = 40;
 
 // ---- energy flux onsets ------------------------------------------------------------------------
 constexpr int ERMS_SEG = 32;  // hop-blocks per segment of the streamed frame-RMS (framed.cuh)
+// hop_size other than 512: the tile form (one lane per frame, any hop), same per-frame sums in the same order
+__global__ void __launch_bounds__(128) energy_rms_any_kernel(const float* __restrict__ x, const TrackDev* tr, float* fa, uint32_t hop, int bs) {
+    __shared__ float tiles[4][32][33];
+    const TrackDev& T = tr[blockIdx.y];
+    const uint32_t nf = T.F[bs];
+    const uint32_t f0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 32;
+    if (f0 >= nf || T.status != 0) return;
+    framed_rms_warp<2048>(x + T.off + T.trim_start, T.m, T.gain, hop, f0, nf, tiles[threadIdx.x >> 5], fa + T.erms);
+}
+
 __global__ void __launch_bounds__(128) energy_rms_kernel(const float* __restrict__ x, const TrackDev* tr, float* fa) {
     __shared__ float tiles[4][2][8][33];
     const TrackDev& T = tr[blockIdx.y];
@@ -59,7 +69,7 @@ __global__ void __launch_bounds__(256) energy_onset_kernel(TrackDev* tr, float* 
     __shared__ float smax[32];
     TrackDev& T = tr[blockIdx.x];
     if (T.status != 0) return;
-    const uint32_t nf = T.F[0];
+    const uint32_t nf = T.F[cfg.bs];
     if (threadIdx.x == 0) {
         T.n_on_energy = 0;
         T.onset_method_consensus = 0.0f;
@@ -79,12 +89,12 @@ __global__ void __launch_bounds__(256) energy_onset_kernel(TrackDev* tr, float* 
     if (mx <= 1e-10f) return;
     const float thr = __fmul_rn(mx, cfg.energy_thr_mul);
     int32_t* out = ia + T.on_energy;
-    uint32_t total = compact_peaks(flux, L, thr, 512, T.m, out, sc);
+    uint32_t total = compact_peaks(flux, L, thr, cfg.hop, T.m, out, sc);
     __syncthreads();
     if (threadIdx.x == 0) {  // dedupe within hop/2 (energy_flux.rs:224-238)
         uint32_t w = 0;
         for (uint32_t i = 0; i < total; ++i)
-            if (w == 0 || out[i] >= out[w - 1] + 256) out[w++] = out[i];
+            if (w == 0 || out[i] >= out[w - 1] + (int32_t)(cfg.hop / 2)) out[w++] = out[i];
         T.n_on_energy = w;
         T.onset_method_consensus = w > 0 ? 1.0f : 0.0f;
     }
@@ -393,10 +403,10 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
     if (threadIdx.x == 0) {
         if (which == 0) T.n_on_spectral = 0; else if (which == 1) T.n_on_hfc = 0; else T.n_on_hpss = 0;
     }
-    const uint32_t F = T.F[0];
+    const uint32_t F = T.F[cfg.bs];
     if (F < 2) return;
     const uint32_t L = F - 1;
-    const HopLayout& HL = T.hop[0];
+    const HopLayout& HL = T.hop[cfg.bs];
     const uint64_t fm = HL.fmax;
     const float* flux;
     if (which == 0) {
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(256) spectral_onset_kernel(TrackDev* tr, float
     idx = min(idx, L - 1);
     const float thr = block_select_kth(flux, L, idx, hist, bc);
     int32_t* out = ia + (which == 0 ? T.on_spectral : (which == 1 ? T.on_hfc : T.on_hpss));
-    uint32_t total = compact_peaks(flux, L, thr, 512, T.m, out, sc);  // frame i+1 -> sample (i+1)*hop, kept if < m (lib.rs:181-190)
+    uint32_t total = compact_peaks(flux, L, thr, cfg.hop, T.m, out, sc);  // frame i+1 -> sample (i+1)*hop, kept if < m (lib.rs:181-190)
     if (threadIdx.x == 0) {
         if (which == 0) T.n_on_spectral = total; else if (which == 1) T.n_on_hfc = total; else T.n_on_hpss = total;
     }
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
     const int32_t* G0 = ia + T.on_energy;
     int32_t* gfin = ia + T.on_final;
     const uint32_t n0 = T.n_on_energy;
-    if (!cfg.enable_consensus || T.F[0] == 0) {
+    if (!cfg.enable_consensus || T.F[cfg.bs] == 0) {
         for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) gfin[i] = G0[i];
         if (threadIdx.x == 0) T.n_on_final = n0;
         return;
@@ -580,8 +590,9 @@ __global__ void __launch_bounds__(256) consensus_kernel(TrackDev* tr, int32_t* i
 }
 
 void launch_energy_onsets(const WaveCtx& c) {
-    if (c.max_F[0] > 0) {
-        energy_rms_kernel<<<dim3((c.max_F[0] + ERMS_SEG * 32 - 1) / (ERMS_SEG * 32), c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
+    if (c.max_F[c.cfg.bs] > 0) {
+        if (c.cfg.bs == 0) energy_rms_kernel<<<dim3((c.max_F[0] + ERMS_SEG * 32 - 1) / (ERMS_SEG * 32), c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa);
+        else energy_rms_any_kernel<<<dim3((c.max_F[c.cfg.bs] + 127) / 128, c.n_tracks), 128, 0, c.stream>>>(c.samples, c.tracks, c.fa, c.cfg.hop, c.cfg.bs);
         count_launch("onsets");
     }
     energy_onset_kernel<<<c.n_tracks, 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg);
@@ -590,7 +601,7 @@ void launch_energy_onsets(const WaveCtx& c) {
 
 // Percussive-component onsets (lib.rs:222-235): frame energies come from seq_feat_kernel on the percussive slot.
 void launch_hpss_onsets(const WaveCtx& c) {
-    if (c.max_F[0] == 0) return;
+    if (c.max_F[c.cfg.bs] == 0) return;
     spectral_onset_kernel<<<dim3(c.n_tracks, 1), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg, 2);
     count_launch("hpss");
 }
@@ -625,7 +636,7 @@ void launch_spec_features(const WaveCtx& c, int h, const int32_t* d_list, int n_
 }
 
 void launch_spectral_onsets_consensus(const WaveCtx& c) {
-    if (c.cfg.enable_consensus && c.max_F[0] > 0) {
+    if (c.cfg.enable_consensus && c.max_F[c.cfg.bs] > 0) {
         spectral_onset_kernel<<<dim3(c.n_tracks, 2), 256, 0, c.stream>>>(c.tracks, c.fa, c.ia, c.cfg, 0);
         count_launch("onsets");
     }

@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(256) trim_kernel(TrackDev* tr, const float* fa
     T.m = m;
     const uint32_t hops[N_HOPS] = {512, 256, 1024};
     for (int h = 0; h < N_HOPS; ++h) T.F[h] = m >= 2048 ? (uint32_t)((m - 2048) / hops[h] + 1) : 0;
-    T.F[SLOT_PERC] = T.F[0];
+    T.F[SLOT_BASE_ALT] = m >= 2048 ? (uint32_t)((m - 2048) / cfg.hop + 1) : 0;
+    T.F[SLOT_PERC] = T.F[cfg.bs];
     T.Fk = m >= cfg.key_frame ? (uint32_t)((m - cfg.key_frame) / cfg.key_hop + 1) : 0;
     if (m == 0 && T.status == 0) {
         T.status = STRATUM_PROCESSING_ERROR;

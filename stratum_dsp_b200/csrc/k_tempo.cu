@@ -539,11 +539,11 @@ __global__ void escalation_gate_kernel(TrackDev* tr, const float* fa, int n_trac
     T.mr_used = -1;
     T.perc_triggered = -1;
     T.perc_used = -1;
-    T.chosen_agree = T.est[0].ok ? T.est[0].agreement : 0;
+    T.chosen_agree = T.est[cfg.bs].ok ? T.est[cfg.bs].agreement : 0;
     T.trap_low = T.trap_high = 0;
-    if (T.status != 0 || !T.est[0].ok || !cfg.mr_enabled || cfg.force_legacy) return;
-    const TempoEstDev& b = T.est[0];
-    const TempoCandDev* c = reinterpret_cast<const TempoCandDev*>(fa + T.cands[0]);
+    if (T.status != 0 || !T.est[cfg.bs].ok || !cfg.mr_enabled || cfg.force_legacy) return;
+    const TempoEstDev& b = T.est[cfg.bs];  // the base estimate (slot 0 unless hop_size is not 512)
+    const TempoCandDev* c = reinterpret_cast<const TempoCandDev*>(fa + T.cands[cfg.bs]);
     const bool trap_low = b.bpm >= 55.0f && b.bpm <= 80.0f;
     const bool trap_high = b.bpm >= 170.0f && b.bpm <= 200.0f;
     const float tol = fmaxf(2.0f, cfg.bpm_resolution);
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(128) multires_fusion_kernel(TrackDev* tr, cons
         if (mr_lookup(c512, n512, bb, tol) > 0.0f) ++agree;
         if (mr_lookup(c1024, n1024, bb, tol) > 0.0f) ++agree;
         // acceptance rule (lib.rs:515-545)
-        const TempoEstDev& base = T.est[0];
+        const TempoEstDev& base = T.est[cfg.bs];
         float rel = base.bpm > 1e-6f ? fmaxf(__fdiv_rn(bb, base.bpm), __fdiv_rn(base.bpm, bb)) : 1.0f;
         bool fam_rel = fabsf(__fsub_rn(rel, 2.0f)) < 0.05f || fabsf(__fsub_rn(rel, 1.5f)) < 0.05f || fabsf(__fsub_rn(rel, 4.0f / 3.0f)) < 0.05f;
         bool forbid = base.bpm <= 180.0f && bb > 180.0f;
@@ -893,16 +893,16 @@ __global__ void final_bpm_kernel(TrackDev* tr, int n_tracks, DevCfg cfg) {
     float bpm = 0.0f, conf = 0.0f;
     if (cfg.force_legacy) {
         if (T.legacy.ok) { bpm = T.legacy.bpm; conf = T.legacy.confidence; }
-    } else if (T.est[0].ok) {
+    } else if (T.est[cfg.bs].ok) {
         if (T.perc_used == 1) { bpm = T.perc_bpm; conf = T.perc_conf; }
         else if (T.mr_used == 1) { bpm = T.bpm; conf = T.bpm_confidence; }
-        else { bpm = T.est[0].bpm; conf = T.est[0].confidence; }
+        else { bpm = T.est[cfg.bs].bpm; conf = T.est[cfg.bs].confidence; }
     } else if (T.legacy.ok) {
         bpm = T.legacy.bpm;
         conf = T.legacy.confidence;
     }
     if (!cfg.force_legacy && cfg.bpm_fusion) {  // lib.rs:819-892: validator mode — the tempogram BPM is never overridden
-        if (T.est[0].ok && bpm > 0.0f) {
+        if (T.est[cfg.bs].ok && bpm > 0.0f) {
             const float l_bpm = T.legacy.ok ? T.legacy.bpm : 0.0f;
             const float l_conf = clamp_rs(T.legacy.ok ? T.legacy.confidence : 0.0f, 0.0f, 1.0f);
             float cf = clamp_rs(conf, 0.0f, 1.0f);
@@ -922,15 +922,15 @@ __global__ void final_bpm_kernel(TrackDev* tr, int n_tracks, DevCfg cfg) {
 }
 
 // ---- percussive tempogram fallback: acceptance rule of lib.rs:621-662, one thread per listed track ------------
-__global__ void perc_accept_kernel(TrackDev* tr, const int32_t* __restrict__ list, int n) {
+__global__ void perc_accept_kernel(TrackDev* tr, const int32_t* __restrict__ list, int n, int bs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     TrackDev& T = tr[list[i]];
-    if (T.status != 0 || !T.est[0].ok) return;
+    if (T.status != 0 || !T.est[bs].ok) return;
     T.perc_used = 0;
     const TempoEstDev& pe = T.est[SLOT_PERC];
     if (!pe.ok) return;  // "Percussive tempogram fallback failed"
-    const TempoEstDev& base = T.est[0];
+    const TempoEstDev& base = T.est[bs];
     const float cb = T.mr_used == 1 ? T.bpm : base.bpm;  // chosen_est after the multi-resolution decision
     const float cc = T.mr_used == 1 ? T.bpm_confidence : base.confidence;
     const uint32_t ca = T.chosen_agree;
@@ -952,7 +952,7 @@ __global__ void perc_accept_kernel(TrackDev* tr, const int32_t* __restrict__ lis
 
 void launch_perc_accept(const WaveCtx& c, const int32_t* d_list, int n_list) {
     if (n_list == 0) return;
-    perc_accept_kernel<<<(n_list + 127) / 128, 128, 0, c.stream>>>(c.tracks, d_list, n_list);
+    perc_accept_kernel<<<(n_list + 127) / 128, 128, 0, c.stream>>>(c.tracks, d_list, n_list, c.cfg.bs);
     count_launch("hpss");
 }
 
@@ -963,16 +963,17 @@ __global__ void emit_candidates_kernel(TrackDev* tr, const float* fa, float* oa,
     TrackDev& T = tr[blockIdx.x];
     if ((int)blockIdx.x >= n_tracks) return;
     if (threadIdx.x == 0) T.n_cand_out = -1;
-    if (T.status != 0 || !T.est[0].ok || cfg.force_legacy || !cfg.emit_cands) return;
-    int slot = 0;
-    uint32_t n = T.est[0].n_cands;
-    float best = T.est[0].bpm;
+    if (T.status != 0 || !T.est[cfg.bs].ok || cfg.force_legacy || !cfg.emit_cands) return;
+    int slot = cfg.bs;
+    uint32_t n = T.est[cfg.bs].n_cands;
+    float best = T.est[cfg.bs].bpm;
     if (T.perc_used == 1) {
         slot = SLOT_PERC;
         n = T.est[SLOT_PERC].n_cands;
         best = T.est[SLOT_PERC].bpm;
     } else if (T.mr_used == 1) {
-        n = min(n, max(cfg.mr_top_k, 1u));
+        slot = 0;  // the hop-512 list of the multi-resolution pass
+        n = min(T.est[0].n_cands, max(cfg.mr_top_k, 1u));
         best = T.bpm;  // multi-resolution winner (written by multires_fusion_kernel)
     }
     const TempoCandDev* c = reinterpret_cast<const TempoCandDev*>(fa + T.cands[slot]);
@@ -1013,7 +1014,7 @@ void launch_tempogram(const WaveCtx& c, int h, const int32_t* d_list, int n_list
         tgac_kernel<<<g5, 256, smem_floats * sizeof(float), c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg, smem_floats);
     }
     count_launch("tempogram");
-    const uint32_t top_n = (h == 0 || h == SLOT_PERC) ? c.cfg.base_top_n : c.cfg.mr_aux_k;
+    const uint32_t top_n = (h == c.cfg.bs || h == SLOT_PERC) ? c.cfg.base_top_n : c.cfg.mr_aux_k;
     score_kernel<<<n_list, 256, 0, c.stream>>>(c.tracks, d_list, c.srtab, c.sr_index, h, c.fa, c.cfg, top_n);
     count_launch("tempogram");
 }

@@ -18,6 +18,8 @@ struct DevCfg {
     float cons_w[4];
     int32_t hpss_onsets, perc_fallback, emit_cands;
     uint32_t hpss_margin;
+    uint32_t hop;                 // hop_size of the base path (config.rs: 512); frame_size is 2048
+    int32_t bs;                   // slot of the base path: 0 (hop 512, shared with the multi-resolution pass) or SLOT_BASE_ALT
     uint32_t sf_k, mel_k;
     float nov_ws, nov_we, nov_wh;
     uint32_t nov_lmw, nov_smw;

@@ -146,13 +146,16 @@ def test_no_cpu_fallback():
 
 def test_config_validation_happens_before_any_device_work():
     # rejected switches give NotImplemented even on a box without a GPU
-    for kw in ({"enable_hpss_onsets": 1, "hpss_margin": 11}, {"key_multi_scale_n_lengths": 9}, {"key_hpcp_peaks_per_frame": 64}, {"frame_size": 1024}, {"key_stft_frame_size": 3000}, {"key_stft_frame_size": 16384}, {"tempogram_multi_res_top_k": 64},
+    for kw in ({"enable_hpss_onsets": 1, "hpss_margin": 11}, {"key_multi_scale_n_lengths": 9}, {"key_hpcp_peaks_per_frame": 64}, {"frame_size": 1024}, {"hop_size": 16}, {"hop_size": 40000}, {"key_stft_frame_size": 3000}, {"key_stft_frame_size": 16384}, {"tempogram_multi_res_top_k": 64},
                {"key_hpss_time_margin": 11, "enable_key_hpss_harmonic": 1}):
         with pytest.raises(S.AnalysisError) as e:
             S.analyze_batch([np.ones(4096, np.float32)], 44100, S.AnalysisConfig(**kw))
         assert e.value.kind == "NotImplemented", kw
     with pytest.raises(S.AnalysisError) as e:
         S.analyze_batch([np.ones(4096, np.float32)], 44100, S.AnalysisConfig(min_bpm=200.0, max_bpm=100.0))
+    assert e.value.kind == "InvalidInput"
+    with pytest.raises(S.AnalysisError) as e:
+        S.analyze_batch([np.ones(4096, np.float32)], 44100, S.AnalysisConfig(hop_size=0))
     assert e.value.kind == "InvalidInput"
 
 

@@ -436,6 +436,25 @@ def test_key_stft_geometry(cfg):
         assert_parity(g, O.analyze(x, sr, _oracle_cfg(cfg), fast=True), f"{cfg} track {i}")
 
 
+@pytest.mark.parametrize("cfg", [
+    {"hop_size": 256},
+    {"hop_size": 1024},
+    {"hop_size": 400},                                                    # not a divisor of the frame: unaligned frame starts, generic frame-RMS kernel
+    {"hop_size": 384, "enable_hpss_onsets": 1, "enable_tempogram_percussive_fallback": 1},
+    {"hop_size": 256, "enable_key_stft_override": 0, "enable_bpm_fusion": 1},  # key path on the shared 2048 / hop_size geometry
+])
+def test_hop_size_variants(cfg):
+    # hop_size other than 512 (config.rs; lib.rs:156-166, 181-190, 310, 391): the base path runs in a slot of its own at that hop — energy
+    # flux, STFT, spectral flux / HFC / HPSS onsets, frame -> sample conversion, legacy estimator, base tempogram — while the
+    # multi-resolution pass keeps recomputing hops 256 / 512 / 1024 from the samples (lib.rs:493-509).  76 BPM sits in the low trap zone, so
+    # the first track escalates.
+    xs = [synth.render(synth.TrackParams(76.0, 3, 0, 0.3, 0.1, SR, 20 * SR)), synth.render(synth.c2_params(45, 13 * 48000, 48000))]
+    srs = [SR, 48000]
+    res = S.analyze_batch(xs, srs, S.AnalysisConfig(**cfg))
+    for i, (x, sr, g) in enumerate(zip(xs, srs, res)):
+        assert_parity(g, O.analyze(x, sr, _oracle_cfg(cfg), fast=True), f"{cfg} track {i}")
+
+
 def test_key_variants_in_a_ragged_batch():
     # per-track decisions (beat grid present or not, tuned or untuned lists, window counts) inside one wave
     cfg = {"enable_key_beat_synchronous": 1, "enable_key_tuning_compensation": 1, "key_tuning_max_abs_semitones": 0.5, "enable_key_mode_heuristic": 1,
