@@ -288,6 +288,11 @@ int32_t stratum_b200_debug_check_divisions(uint64_t n, uint32_t seed, uint64_t* 
 uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg, double budget_gb,
                                        uint32_t* wave_of_track);
 
+/* Host-side schedule of the mel-band fold of the novelty features on its own (no device work; csrc/engine.cu: mel_fold_schedule):
+ * mel_off = n_mels + 1 entry offsets (n_mels <= 40), schedule256 = 64 chunk starts, 64 chunk ends, 64 partial-sum positions, 41 band
+ * starts (padded to 256).  Lets the chunking be tested without a GPU. */
+void stratum_b200_debug_mel_schedule(const int32_t* mel_off, uint32_t n_mels, int32_t* schedule256);
+
 /* Per-stage device time (ms) accumulated since the last reset; names newline separated. */
 int32_t stratum_b200_stage_times(char* names, size_t cap, double* ms, int32_t max_stages);
 void stratum_b200_stage_times_reset(void);

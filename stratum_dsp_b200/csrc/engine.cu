@@ -323,6 +323,43 @@ static const float2* get_tw(DeviceCtx& c, uint32_t M) {
     return p;
 }
 
+// Mel fold schedule for par_feat_kernel: the bands' entry lists cut into at most 64 chunks of near-equal length (two per lane), a
+// band's chunks consecutive in `pos` order so that one lane per band can add their partial sums in order afterwards.  Layout of ck[256]:
+// [0..64) first entry, [64..128) end entry, [128..192) position of the chunk's partial sum, [192..233) first position of each band.
+// Slots are sorted by length (longest first: the first 32 go to the lanes' first round); idle slots are empty and point at positions
+// no band reads.  mel_off = n_mels + 1 entry offsets (n_mels <= 40).
+static void mel_fold_schedule(const int32_t* mel_off, uint32_t nm, int32_t* ck) {
+    for (int i = 0; i < 256; ++i) ck[i] = 0;
+    uint32_t C = 1;
+    for (;; ++C) {
+        uint32_t k = 0;
+        for (uint32_t m = 0; m < nm; ++m) k += ((uint32_t)(mel_off[m + 1] - mel_off[m]) + C - 1) / C;
+        if (k <= 64) break;
+    }
+    struct Chunk { int32_t a, e, pos; };
+    std::vector<Chunk> chunks;
+    int32_t pos = 0;
+    for (uint32_t m = 0; m < nm; ++m) {
+        ck[192 + m] = pos;
+        const uint32_t n = (uint32_t)(mel_off[m + 1] - mel_off[m]);
+        const uint32_t k = (n + C - 1) / C;
+        int32_t a = mel_off[m];
+        for (uint32_t j = 0; j < k; ++j) {
+            const int32_t len = (int32_t)(n / k + (j < n % k ? 1 : 0));
+            chunks.push_back({a, a + len, pos++});
+            a += len;
+        }
+    }
+    for (uint32_t m = nm; m <= 40; ++m) ck[192 + m] = pos;
+    std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.e - x.a > y.e - y.a; });
+    for (size_t i = 0; i < 64; ++i) {
+        const Chunk ch = i < chunks.size() ? chunks[i] : Chunk{0, 0, (int32_t)std::min<size_t>(i, 63)};  // idle slots write a partial nobody reads (positions >= the chunk count)
+        ck[i] = ch.a;
+        ck[64 + i] = ch.e;
+        ck[128 + i] = ch.pos;
+    }
+}
+
 // tables of the generic STFT for frame size n (a power of two); win == nullptr on allocation failure
 static GenStft get_gen_stft(DeviceCtx& c, uint32_t n) {
     GenStft g{};
@@ -576,40 +613,9 @@ static int sr_slot(DeviceCtx& c, uint32_t sr, const StratumConfig& cfg, int* slo
     mel_off.resize(42, mel_off.back());
     if (mel_bin.empty()) { mel_bin.push_back(0); mel_w.push_back(0.0f); }
     st.variant_mask = vm;
-    // Mel fold schedule for par_feat_kernel: the bands' entry lists cut into at most 64 chunks of near-equal length (two per lane), a
-    // band's chunks consecutive in `pos` order so that one lane per band can add their partial sums in order afterwards.  Layout:
-    // [0..64) first entry, [64..128) end entry, [128..192) position of the chunk's partial sum, [192..233) first position of each band.
     {
         std::vector<int32_t> ck(256, 0);
-        const uint32_t nm = st.n_mels;
-        uint32_t C = 1;
-        for (;; ++C) {
-            uint32_t k = 0;
-            for (uint32_t m = 0; m < nm; ++m) k += ((uint32_t)(mel_off[m + 1] - mel_off[m]) + C - 1) / C;
-            if (k <= 64) break;
-        }
-        struct Chunk { int32_t a, e, pos; };
-        std::vector<Chunk> chunks;
-        int32_t pos = 0;
-        for (uint32_t m = 0; m < nm; ++m) {
-            ck[192 + m] = pos;
-            const uint32_t n = (uint32_t)(mel_off[m + 1] - mel_off[m]);
-            const uint32_t k = (n + C - 1) / C;
-            int32_t a = mel_off[m];
-            for (uint32_t j = 0; j < k; ++j) {
-                const int32_t len = (int32_t)(n / k + (j < n % k ? 1 : 0));
-                chunks.push_back({a, a + len, pos++});
-                a += len;
-            }
-        }
-        for (uint32_t m = nm; m <= 40; ++m) ck[192 + m] = pos;
-        std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.e - x.a > y.e - y.a; });
-        for (size_t i = 0; i < 64; ++i) {
-            const Chunk ch = i < chunks.size() ? chunks[i] : Chunk{0, 0, (int32_t)std::min<size_t>(i, 63)};  // idle slots write a partial nobody reads (positions >= the chunk count)
-            ck[i] = ch.a;
-            ck[64 + i] = ch.e;
-            ck[128 + i] = ch.pos;
-        }
+        mel_fold_schedule(mel_off.data(), st.n_mels, ck.data());
         st.mel_chunks = dev_upload(c, ck);
     }
     st.mel_off = dev_upload(c, mel_off);
@@ -2268,6 +2274,11 @@ static int32_t analyze_host_batch(const void* src, const uint64_t* boff, const u
             return status[d];
         }
     return STRATUM_OK;
+}
+
+void stratum_b200_debug_mel_schedule(const int32_t* mel_off, uint32_t n_mels, int32_t* schedule256) {
+    if (!mel_off || !schedule256 || n_mels > 40) return;
+    mel_fold_schedule(mel_off, n_mels, schedule256);
 }
 
 uint32_t stratum_b200_debug_plan_waves(const uint64_t* offsets, const uint32_t* sample_rates, uint32_t n_tracks, const StratumConfig* cfg, double budget_gb,

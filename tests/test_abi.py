@@ -219,6 +219,40 @@ def test_wave_planner_balances_and_respects_the_budget():
     assert nw == 1
 
 
+def test_mel_fold_schedule_partitions_every_band():
+    # par_feat_kernel folds the mel triangles as <= 64 chunks of the bands' entry lists, two per lane, then adds each band's partial sums
+    # in order (period/novelty.rs:172-189 accumulates per band in ascending-bin order; the curve is a tolerance-level quantity)
+    L = S.lib()
+    L.stratum_b200_debug_mel_schedule.restype = None
+    rng = np.random.RandomState(11)
+    cases = [np.array([0] + list(np.cumsum(rng.randint(1, 120, nm))), np.int32) for nm in (4, 17, 40, 40)]
+    cases.append(np.array([0] + list(np.cumsum([2, 2, 3, 3] + list(range(3, 39)))), np.int32))   # the shape of a real filterbank: widening triangles
+    cases.append(np.zeros(1, np.int32))                                                            # mel novelty off
+    for off in cases:
+        nm = len(off) - 1
+        ck = np.full(256, -7, np.int32)
+        L.stratum_b200_debug_mel_schedule(off.ctypes.data_as(C.POINTER(C.c_int32)), nm, ck.ctypes.data_as(C.POINTER(C.c_int32)))
+        a, e, pos, band0 = ck[:64], ck[64:128], ck[128:192], ck[192:233]
+        live = [i for i in range(64) if e[i] > a[i]]
+        assert sorted(pos.tolist()) == list(range(64)) or len(set(pos[live].tolist())) == len(live)   # one partial-sum slot per live chunk
+        lens = (e - a)[live]
+        assert np.all(np.diff(lens) <= 0)                                                          # longest first: the first 32 are round one
+        n_chunks = len(live)
+        assert n_chunks <= 64 and band0[nm] == n_chunks and np.all(band0[nm:] == n_chunks)
+        by_pos = {int(pos[i]): (int(a[i]), int(e[i])) for i in live}
+        for m in range(nm):                                                                        # a band's chunks, in position order, tile its entry range
+            cur = int(off[m])
+            for p in range(int(band0[m]), int(band0[m + 1])):
+                assert by_pos[p][0] == cur
+                cur = by_pos[p][1]
+            assert cur == int(off[m + 1])
+        if n_chunks:
+            total = int(off[-1])
+            assert lens.max() <= -(-total // 64) * 2 + max(1, int(np.diff(off).min()))              # balanced: no chunk much longer than the mean
+        idle = [i for i in range(64) if i not in live]
+        assert all(int(pos[i]) >= n_chunks for i in idle)                                          # idle slots write where no band reads
+
+
 def test_division_by_25_is_exact_for_every_float(tmp_path):
     # tools/check_div_by_const.c: RN(a * RN(1/25)) corrected once (csrc/common.cuh div_by_25_rn) equals a / 25.0f for every finite
     # float with |a| >= 1e-30 — exhaustive over all 2^32 bit patterns (about 20 s on 8 threads)
