@@ -217,6 +217,11 @@ def test_wave_planner_balances_and_respects_the_budget():
     assert max(per) <= 1.5 * 208 * T3 and (nw == 1 or min(per) >= 0.3 * max(per))          # no tiny tail wave
     nw, w = _plan([200 * T3])                       # one 10-hour track: still planned (the budget is raised for a single track)
     assert nw == 1
+    # hop_size other than 512 gives the base path a slot of its own (more frames at a smaller hop): the same budget holds fewer tracks
+    nw512, _ = _plan([T3] * 200, budget_gb=20.0)
+    nw128, w = _plan([T3] * 200, budget_gb=20.0, cfg=S.AnalysisConfig(hop_size=128))
+    nw2048, _ = _plan([T3] * 200, budget_gb=20.0, cfg=S.AnalysisConfig(hop_size=2048))
+    assert nw128 > nw2048 >= nw512 and np.all(np.diff(w) >= 0)
 
 
 def test_mel_fold_schedule_partitions_every_band():
